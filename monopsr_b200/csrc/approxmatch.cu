@@ -1,0 +1,538 @@
+// monopsr_b200/csrc/approxmatch.cu -- approximate-EMD ops for sm_100a.
+//
+// Replaces approxmatch / matchcost / matchcostgrad{1,2} and their launchers
+// (reference: src/tf_ops/approxmatch/tf_approxmatch_g.cu:1-295).  Same mathematics as
+// the reference GPU kernel (10 annealing levels level=-4^j, j=7..-2; three n x m sweeps
+// per level; match stored (b,m,n) with [l,k] at l*n+k), different machine mapping:
+//
+//   * one THREAD-BLOCK CLUSTER per batch element instead of one CTA (the reference keeps
+//     at most 32 of 148 SMs busy).  Each CTA of the cluster owns a slice of the dataset
+//     points (k) and a slice of the query points (l); per-level ratios are all-gathered
+//     through distributed shared memory, two cluster barriers per level;
+//   * both clouds live in shared memory as float4 {x,y,z,weight} for the whole kernel;
+//     the per-point state (remainL/remainR/ratioL/ratioR) never touches HBM -- the
+//     caller's `temp` scratch is unused;
+//   * `match` is written exactly ONCE: the per-level ratioL/ratioR are kept on chip and
+//     the final pass evaluates  match[l,k] = sum_j exp(level_j d_kl) ratioL_j[k] ratioR_j[l]
+//     (the reference zero-fills match and read-modify-writes it in HBM ten times);
+//   * the level-0 pass (exp == 1) has no third sweep (nothing consumes remainL after it).
+//
+// The op is MUFU(ex2)/FP32 bound with a 10-deep serial dependency chain; HBM only
+// matters for the single match write.  See DESIGN.md "approxmatch roofline".
+#include "common.cuh"
+#include "../../include/monopsr_b200_tfops.h"
+#include <cooperative_groups.h>
+#include <math.h>
+
+namespace cg = cooperative_groups;
+
+namespace mpb {
+
+constexpr int kAmThreads = 512;
+constexpr int kAmLevels = 10;   // j = 7 .. -2  (tf_approxmatch_g.cu:21)
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float am_d2(const float4& a, const float4& b) {
+    float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+}
+
+struct AmSmem {
+    // carve-up of dynamic shared memory; all sizes in floats
+    int n_pad, m_pad, own_n, own_m;
+    __host__ __device__ size_t p1() const { return 0; }                                   // float4[n_pad]
+    __host__ __device__ size_t p2() const { return p1() + 4 * (size_t)n_pad; }            // float4[m_pad]
+    __host__ __device__ size_t rr() const { return p2() + 4 * (size_t)m_pad; }            // remainR full [m_pad]
+    __host__ __device__ size_t hl() const { return rr() + m_pad; }                        // ratioL history [levels][n_pad]
+    __host__ __device__ size_t hr() const { return hl() + (size_t)kAmLevels * n_pad; }    // ratioR history own [own_m][12]
+    __host__ __device__ size_t rl() const { return hr() + 12 * (size_t)own_m; }           // remainL own [own_n]
+    __host__ __device__ size_t total() const { return rl() + own_n; }
+};
+
+// Pick S (lanes sharing one owner point) so that owners*S fills the CTA in whole rounds.
+__host__ __device__ inline int am_pick_split(int owners) {
+    int best_s = 1;
+    float best_w = 1e30f;
+    for (int s = 1; s <= 32; s <<= 1) {
+        float units = (float)owners * s / kAmThreads;
+        float w = ceilf(units) / units;
+        if (w < best_w - 1e-3f) {
+            best_w = w;
+            best_s = s;
+        }
+    }
+    return best_s;
+}
+
+// sum over `cnt` candidates (weights in .w), strided by S lanes, of exp2(c*d2)*w
+__device__ __forceinline__ float am_sweep(const float4 me, const float4* __restrict__ other, int cnt,
+                                          int s, int S, float c) {
+    float acc0 = 0.f, acc1 = 0.f;
+    int l = s;
+    for (; l + S < cnt; l += 2 * S) {
+        float4 o0 = other[l], o1 = other[l + S];
+        acc0 = fmaf(ex2_approx(c * am_d2(me, o0)), o0.w, acc0);
+        acc1 = fmaf(ex2_approx(c * am_d2(me, o1)), o1.w, acc1);
+    }
+    if (l < cnt) {
+        float4 o0 = other[l];
+        acc0 = fmaf(ex2_approx(c * am_d2(me, o0)), o0.w, acc0);
+    }
+    return acc0 + acc1;
+}
+
+__device__ __forceinline__ float group_sum(float v, int S) {
+    for (int o = S >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kAmThreads, 1)
+approxmatch_cluster_kernel(int n, int m, const float* __restrict__ xyz1,
+                           const float* __restrict__ xyz2, float* __restrict__ match) {
+    extern __shared__ __align__(16) float smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = cluster.num_blocks();
+    const int rank = cluster.block_rank();
+    const int bi = blockIdx.x / C;
+    const int tid = threadIdx.x;
+
+    AmSmem L;
+    L.n_pad = (n + 3) & ~3;
+    L.m_pad = (m + 3) & ~3;
+    L.own_n = ceil_div(n, C);
+    L.own_m = ceil_div(m, C);
+    float4* P1 = reinterpret_cast<float4*>(smem + L.p1());
+    float4* P2 = reinterpret_cast<float4*>(smem + L.p2());
+    float* RR = smem + L.rr();
+    float* HL = smem + L.hl();
+    float* HR = smem + L.hr();
+    float* RL = smem + L.rl();
+
+    const int k0 = min(n, rank * L.own_n), k1 = min(n, k0 + L.own_n);
+    const int l0 = min(m, rank * L.own_m), l1 = min(m, l0 + L.own_m);
+
+    float multiL, multiR;   // integer division as in tf_approxmatch_g.cu:4-10 (quirk Q5)
+    if (n >= m) { multiL = 1.f; multiR = (float)(n / m); }
+    else        { multiL = (float)(m / n); multiR = 1.f; }
+
+    const float* g1 = xyz1 + (size_t)bi * n * 3;
+    const float* g2 = xyz2 + (size_t)bi * m * 3;
+    for (int t = tid; t < n * 3; t += kAmThreads) smem[L.p1() + (t / 3) * 4 + (t % 3)] = g1[t];
+    for (int t = tid; t < m * 3; t += kAmThreads) smem[L.p2() + (t / 3) * 4 + (t % 3)] = g2[t];
+    for (int t = tid; t < m; t += kAmThreads) { RR[t] = multiR; P2[t].w = multiR; }
+    for (int t = tid; t < k1 - k0; t += kAmThreads) RL[t] = multiL;
+    __syncthreads();
+    cluster.sync();   // every CTA's smem is initialised before any remote write lands
+
+    const int SL = am_pick_split(L.own_n);   // lanes per owned dataset point
+    const int SR = am_pick_split(L.own_m);   // lanes per owned query point
+
+    for (int lev = 0; lev < kAmLevels; lev++) {
+        const int j = 7 - lev;
+        const float level = (j == -2) ? 0.f : -exp2f(2.f * (float)j);   // -4^j
+        const float c = level * kLog2e;
+        // ---- sweep 1: ratioL[k] = remainL[k] / (1e-9 + sum_l exp(level d) remainR[l]) ----
+        for (int u = tid; u < ((k1 - k0) * SL + 31) / 32 * 32; u += kAmThreads) {
+            int o = u / SL, s = u % SL;
+            bool act = o < k1 - k0;
+            float sum = 0.f;
+            if (act) sum = am_sweep(P1[k0 + o], P2, m, s, SL, c);
+            sum = group_sum(sum, SL);
+            if (act && s == 0) {
+                float ratio = RL[o] / (1e-9f + sum);
+                for (int r = 0; r < C; r++) {   // all-gather through DSMEM
+                    float* rs = cluster.map_shared_rank(smem, r);
+                    rs[L.p1() + (size_t)(k0 + o) * 4 + 3] = ratio;
+                    rs[L.hl() + (size_t)lev * L.n_pad + k0 + o] = ratio;
+                }
+            }
+        }
+        cluster.sync();
+        // ---- sweep 2: per query l ----
+        for (int u = tid; u < ((l1 - l0) * SR + 31) / 32 * 32; u += kAmThreads) {
+            int o = u / SR, s = u % SR;
+            bool act = o < l1 - l0;
+            float sum = 0.f;
+            if (act) sum = am_sweep(P2[l0 + o], P1, n, s, SR, c);
+            sum = group_sum(sum, SR);
+            if (act && s == 0) {
+                float rem = RR[l0 + o];
+                float sumr = sum * rem;
+                float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
+                float ratio = consumption * rem;
+                float nrem = fmaxf(0.0f, rem - sumr);
+                HR[o * 12 + lev] = ratio;
+                for (int r = 0; r < C; r++) {
+                    float* rs = cluster.map_shared_rank(smem, r);
+                    rs[L.p2() + (size_t)(l0 + o) * 4 + 3] = ratio;
+                    rs[L.rr() + l0 + o] = nrem;
+                }
+            }
+        }
+        cluster.sync();
+        if (lev == kAmLevels - 1) break;   // nothing consumes remainL after the last level
+        // ---- sweep 3: remainL[k] -= ratioL[k] * sum_l exp(level d) ratioR[l] ----
+        for (int u = tid; u < ((k1 - k0) * SL + 31) / 32 * 32; u += kAmThreads) {
+            int o = u / SL, s = u % SL;
+            bool act = o < k1 - k0;
+            float sum = 0.f;
+            if (act) sum = am_sweep(P1[k0 + o], P2, m, s, SL, c);
+            sum = group_sum(sum, SL);
+            if (act && s == 0) RL[o] = fmaxf(0.0f, RL[o] - sum * P1[k0 + o].w);
+        }
+        __syncthreads();
+        for (int t = tid; t < m; t += kAmThreads) P2[t].w = RR[t];   // weights for next sweep 1
+        __syncthreads();
+    }
+
+    // ---- final pass: write match[l, :] for own query rows, once, coalesced over k ----
+    float* mout = match + (size_t)bi * n * m;
+    float cl[kAmLevels];
+#pragma unroll
+    for (int q = 0; q < kAmLevels; q++) {
+        int j = 7 - q;
+        cl[q] = (j == -2) ? 0.f : -exp2f(2.f * (float)j) * kLog2e;
+    }
+    for (int kb = 0; kb < n; kb += kAmThreads) {
+        const int k = kb + tid;
+        const bool act = k < n;
+        float4 me = act ? P1[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float rl[kAmLevels];
+#pragma unroll
+        for (int q = 0; q < kAmLevels; q++) rl[q] = act ? HL[(size_t)q * L.n_pad + k] : 0.f;
+        for (int l = l0; l < l1; l++) {
+            const float4 o = P2[l];
+            const float4* hr4 = reinterpret_cast<const float4*>(HR + (size_t)(l - l0) * 12);
+            float4 ra = hr4[0], rb = hr4[1], rc = hr4[2];
+            float rr[12] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x, rc.y, rc.z, rc.w};
+            float d = am_d2(me, o);
+            float acc = rl[kAmLevels - 1] * rr[kAmLevels - 1];   // level 0: exp == 1
+#pragma unroll
+            for (int q = 0; q < kAmLevels - 1; q++)
+                acc = fmaf(ex2_approx(cl[q] * d), rl[q] * rr[q], acc);
+            if (act) __stcs(&mout[(size_t)l * n + k], acc);   // streaming: written once, not re-read here
+        }
+    }
+    cluster.sync();   // keep smem alive until all remote accesses in the cluster are done
+}
+
+// ---- generic fallback (clouds too large for the on-chip path): one CTA per batch
+// element, state in global scratch, match read-modify-written per level.  Correctness
+// path only; same sweeps as above.
+__global__ void __launch_bounds__(kAmThreads)
+approxmatch_fallback_kernel(int b, int n, int m, const float* __restrict__ xyz1,
+                            const float* __restrict__ xyz2, float* __restrict__ match,
+                            float* __restrict__ scratch) {
+    const int tid = threadIdx.x;
+    float multiL, multiR;
+    if (n >= m) { multiL = 1.f; multiR = (float)(n / m); }
+    else        { multiL = (float)(m / n); multiR = 1.f; }
+    for (int bi = blockIdx.x; bi < b; bi += gridDim.x) {
+        float* remainL = scratch + (size_t)bi * (n + m) * 2;
+        float* remainR = remainL + n;
+        float* ratioL = remainR + m;
+        float* ratioR = ratioL + n;
+        const float* p1 = xyz1 + (size_t)bi * n * 3;
+        const float* p2 = xyz2 + (size_t)bi * m * 3;
+        float* mt = match + (size_t)bi * n * m;
+        for (size_t t = tid; t < (size_t)n * m; t += kAmThreads) mt[t] = 0.f;
+        for (int t = tid; t < n; t += kAmThreads) remainL[t] = multiL;
+        for (int t = tid; t < m; t += kAmThreads) remainR[t] = multiR;
+        __syncthreads();
+        for (int lev = 0; lev < kAmLevels; lev++) {
+            const int j = 7 - lev;
+            const float c = ((j == -2) ? 0.f : -exp2f(2.f * (float)j)) * kLog2e;
+            for (int k = tid; k < n; k += kAmThreads) {
+                float4 me = make_float4(p1[k * 3], p1[k * 3 + 1], p1[k * 3 + 2], 0.f);
+                float sum = 1e-9f;
+                for (int l = 0; l < m; l++) {
+                    float4 o = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
+                    sum = fmaf(ex2_approx(c * am_d2(me, o)), remainR[l], sum);
+                }
+                ratioL[k] = remainL[k] / sum;
+            }
+            __syncthreads();
+            for (int l = tid; l < m; l += kAmThreads) {
+                float4 me = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
+                float sum = 0.f;
+                for (int k = 0; k < n; k++) {
+                    float4 o = make_float4(p1[k * 3], p1[k * 3 + 1], p1[k * 3 + 2], 0.f);
+                    sum = fmaf(ex2_approx(c * am_d2(me, o)), ratioL[k], sum);
+                }
+                float rem = remainR[l];
+                float sumr = sum * rem;
+                float consumption = fminf(rem / (sumr + 1e-9f), 1.0f);
+                ratioR[l] = consumption * rem;
+                remainR[l] = fmaxf(0.0f, rem - sumr);
+            }
+            __syncthreads();
+            for (int k = tid; k < n; k += kAmThreads) {
+                float4 me = make_float4(p1[k * 3], p1[k * 3 + 1], p1[k * 3 + 2], 0.f);
+                float rl = ratioL[k];
+                float sum = 0.f;
+                for (int l = 0; l < m; l++) {
+                    float4 o = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
+                    float w = ex2_approx(c * am_d2(me, o)) * rl * ratioR[l];
+                    mt[(size_t)l * n + k] += w;
+                    sum += w;
+                }
+                remainL[k] = fmaxf(0.0f, remainL[k] - sum);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- matchcost: cost[b] = sum_{l,k} sqrt(d2) * match[l,k]  (tf_approxmatch_g.cu:183-225)
+// Grid (row tiles, b); a CTA streams kMcRows rows of match once (coalesced over k),
+// block-reduces, and writes one partial; a second tiny kernel sums the partials in a
+// fixed order (deterministic, no atomics).
+constexpr int kMcThreads = 256;
+constexpr int kMcRows = 16;
+
+__global__ void __launch_bounds__(kMcThreads)
+matchcost_partial_kernel(int n, int m, const float* __restrict__ xyz1,
+                         const float* __restrict__ xyz2, const float* __restrict__ match,
+                         float* __restrict__ partial) {
+    __shared__ float4 q[kMcRows];
+    __shared__ float red[kMcThreads / 32];
+    const int bi = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int l0 = tile * kMcRows, rows = min(kMcRows, m - l0);
+    const float* p1 = xyz1 + (size_t)bi * n * 3;
+    const float* p2 = xyz2 + (size_t)bi * m * 3;
+    const float* mt = match + (size_t)bi * n * m + (size_t)l0 * n;
+    if (tid < kMcRows) {
+        int l = l0 + min(tid, rows - 1);
+        q[tid] = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
+    }
+    __syncthreads();
+    float acc = 0.f;
+    for (int k = tid; k < n; k += kMcThreads) {
+        float4 me = make_float4(p1[k * 3], p1[k * 3 + 1], p1[k * 3 + 2], 0.f);
+        float w[kMcRows];
+#pragma unroll
+        for (int r = 0; r < kMcRows; r++) w[r] = r < rows ? __ldcs(&mt[(size_t)r * n + k]) : 0.f;
+#pragma unroll
+        for (int r = 0; r < kMcRows; r++) acc = fmaf(sqrtf(am_d2(me, q[r])), w[r], acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < kMcThreads / 32; w++) s += red[w];
+        partial[(size_t)bi * gridDim.x + tile] = s;
+    }
+}
+
+__global__ void matchcost_final_kernel(int tiles, const float* __restrict__ partial,
+                                       float* __restrict__ out) {
+    const int bi = blockIdx.x;
+    float acc = 0.f;
+    for (int t = threadIdx.x; t < tiles; t += 32) acc += partial[(size_t)bi * tiles + t];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) out[bi] = acc;
+}
+
+// ---- matchcostgrad (tf_approxmatch_g.cu:229-291) ----
+// grad1[k] = sum_l match[l,k] (p1_k - p2_l) rsqrt(max(d2,1e-20)): thread owns k, a CTA
+//   is 64 k-columns x 4 row groups, rows strided over the groups, smem-reduced (fixed order).
+// grad2[l] = sum_k match[l,k] (p2_l - p1_k) rsqrt(...): one warp per row, float4 loads.
+constexpr int kG1Cols = 64, kG1Groups = 4;
+
+__global__ void __launch_bounds__(kG1Cols * kG1Groups)
+matchcostgrad1_kernel(int n, int m, const float* __restrict__ xyz1,
+                      const float* __restrict__ xyz2, const float* __restrict__ match,
+                      float* __restrict__ grad1) {
+    extern __shared__ __align__(16) float sm[];
+    float4* q = reinterpret_cast<float4*>(sm);                 // [chunk]
+    const int bi = blockIdx.y, tid = threadIdx.x;
+    const int col = tid % kG1Cols, grp = tid / kG1Cols;
+    const int k = blockIdx.x * kG1Cols + col;
+    const float* p1 = xyz1 + (size_t)bi * n * 3;
+    const float* p2 = xyz2 + (size_t)bi * m * 3;
+    const float* mt = match + (size_t)bi * n * m;
+    const bool act = k < n;
+    float x = act ? p1[k * 3] : 0.f, y = act ? p1[k * 3 + 1] : 0.f, z = act ? p1[k * 3 + 2] : 0.f;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    constexpr int kChunk = 1024;
+    for (int c0 = 0; c0 < m; c0 += kChunk) {
+        int cnt = min(kChunk, m - c0);
+        __syncthreads();
+        for (int t = tid; t < cnt; t += kG1Cols * kG1Groups)
+            q[t] = make_float4(p2[(c0 + t) * 3], p2[(c0 + t) * 3 + 1], p2[(c0 + t) * 3 + 2], 0.f);
+        __syncthreads();
+        if (act) {
+#pragma unroll 4
+            for (int l = grp; l < cnt; l += kG1Groups) {
+                float4 o = q[l];
+                float dx = x - o.x, dy = y - o.y, dz = z - o.z;
+                float w = __ldcs(&mt[(size_t)(c0 + l) * n + k]) *
+                          rsqrtf(fmaxf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)), 1e-20f));
+                ax = fmaf(dx, w, ax);
+                ay = fmaf(dy, w, ay);
+                az = fmaf(dz, w, az);
+            }
+        }
+    }
+    __syncthreads();
+    float* red = sm;   // reuse: [groups][cols][3]
+    red[(grp * kG1Cols + col) * 3 + 0] = ax;
+    red[(grp * kG1Cols + col) * 3 + 1] = ay;
+    red[(grp * kG1Cols + col) * 3 + 2] = az;
+    __syncthreads();
+    if (grp == 0 && act) {
+        for (int c = 0; c < 3; c++) {
+            float s = 0.f;
+            for (int g = 0; g < kG1Groups; g++) s += red[(g * kG1Cols + col) * 3 + c];
+            grad1[((size_t)bi * n + k) * 3 + c] = s;
+        }
+    }
+}
+
+constexpr int kG2Warps = 8;
+
+__global__ void __launch_bounds__(kG2Warps * 32)
+matchcostgrad2_kernel(int n, int m, const float* __restrict__ xyz1,
+                      const float* __restrict__ xyz2, const float* __restrict__ match,
+                      float* __restrict__ grad2) {
+    const int bi = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = blockIdx.x * kG2Warps + warp;
+    if (l >= m) return;
+    const float* p1 = xyz1 + (size_t)bi * n * 3;
+    const float* p2 = xyz2 + ((size_t)bi * m + l) * 3;
+    const float* row = match + (size_t)bi * n * m + (size_t)l * n;
+    const float x = p2[0], y = p2[1], z = p2[2];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll 4
+    for (int k = lane; k < n; k += 32) {
+        float dx = x - p1[k * 3], dy = y - p1[k * 3 + 1], dz = z - p1[k * 3 + 2];
+        float w = __ldcs(&row[k]) * rsqrtf(fmaxf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)), 1e-20f));
+        ax = fmaf(dx, w, ax);
+        ay = fmaf(dy, w, ay);
+        az = fmaf(dz, w, az);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        az += __shfl_xor_sync(0xffffffffu, az, o);
+    }
+    if (lane == 0) {
+        float* g = grad2 + ((size_t)bi * m + l) * 3;
+        g[0] = ax;
+        g[1] = ay;
+        g[2] = az;
+    }
+}
+
+}  // namespace mpb
+
+MPB_API int mpb_approxmatch(int b, int n, int m, const float* xyz1, const float* xyz2,
+                            float* match, float* temp, void* stream) {
+    using namespace mpb;
+    (void)temp;
+    if (b < 0 || n < 0 || m < 0) return -1;
+    if (b == 0 || n == 0 || m == 0) return 0;
+    if (!xyz1 || !xyz2 || !match) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int sms = num_sms();
+    // largest power-of-two cluster (<= 8, portable) that still fits b clusters on the chip
+    int C = 1;
+    while (C < 8 && (long)b * (C * 2) <= sms) C *= 2;
+    // do not slice a cloud thinner than 64 points per CTA
+    while (C > 1 && (ceil_div(n, C) < 64 || ceil_div(m, C) < 64)) C /= 2;
+    static int max_smem = -1;
+    if (max_smem < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    for (; C >= 1; C /= 2) {
+        AmSmem L;
+        L.n_pad = (n + 3) & ~3;
+        L.m_pad = (m + 3) & ~3;
+        L.own_n = ceil_div(n, C);
+        L.own_m = ceil_div(m, C);
+        size_t bytes = L.total() * sizeof(float);
+        if (bytes > (size_t)max_smem) {
+            if (C == 1) break;
+            continue;
+        }
+        MPB_CUDA_TRY(cudaFuncSetAttribute(approxmatch_cluster_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)b * C);
+        cfg.blockDim = dim3(kAmThreads);
+        cfg.dynamicSmemBytes = bytes;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        MPB_CUDA_TRY(cudaLaunchKernelEx(&cfg, approxmatch_cluster_kernel, n, m, xyz1, xyz2, match));
+        count_launch();
+        return 0;
+    }
+    // fallback: stream-ordered scratch, one CTA per batch element
+    float* scratch = nullptr;
+    MPB_CUDA_TRY(cudaMallocAsync(&scratch, sizeof(float) * (size_t)b * (n + m) * 2, s));
+    approxmatch_fallback_kernel<<<min(b, 4 * sms), kAmThreads, 0, s>>>(b, n, m, xyz1, xyz2, match, scratch);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, s);
+    return cuda_status(e);
+}
+
+MPB_API int mpb_matchcost(int b, int n, int m, const float* xyz1, const float* xyz2,
+                          const float* match, float* out, void* stream) {
+    using namespace mpb;
+    if (b < 0 || n < 0 || m < 0) return -1;
+    if (b == 0) return 0;
+    if (!out) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0 || m == 0) return cuda_status(cudaMemsetAsync(out, 0, sizeof(float) * b, s));
+    if (!xyz1 || !xyz2 || !match) return -1;
+    if (b > 65535) return -1;
+    const int tiles = ceil_div(m, kMcRows);
+    float* partial = nullptr;
+    MPB_CUDA_TRY(cudaMallocAsync(&partial, sizeof(float) * (size_t)b * tiles, s));
+    matchcost_partial_kernel<<<dim3(tiles, b), kMcThreads, 0, s>>>(n, m, xyz1, xyz2, match, partial);
+    count_launch();
+    matchcost_final_kernel<<<b, 32, 0, s>>>(tiles, partial, out);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(partial, s);
+    return cuda_status(e);
+}
+
+MPB_API int mpb_matchcostgrad(int b, int n, int m, const float* xyz1, const float* xyz2,
+                              const float* match, float* grad1, float* grad2, void* stream) {
+    using namespace mpb;
+    if (b < 0 || n < 0 || m < 0) return -1;
+    if (b == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0 || m == 0) {
+        if (n && grad1) MPB_CUDA_TRY(cudaMemsetAsync(grad1, 0, sizeof(float) * (size_t)b * n * 3, s));
+        if (m && grad2) MPB_CUDA_TRY(cudaMemsetAsync(grad2, 0, sizeof(float) * (size_t)b * m * 3, s));
+        return 0;
+    }
+    if (!xyz1 || !xyz2 || !match || !grad1 || !grad2) return -1;
+    if (b > 65535) return -1;
+    size_t sm1 = sizeof(float) * 4 * 1024;   // float4[1024] >= [4][64][3] floats
+    matchcostgrad1_kernel<<<dim3(ceil_div(n, kG1Cols), b), kG1Cols * kG1Groups, sm1, s>>>(
+        n, m, xyz1, xyz2, match, grad1);
+    MPB_LAUNCH_CHECK();
+    matchcostgrad2_kernel<<<dim3(ceil_div(m, kG2Warps), b), kG2Warps * 32, 0, s>>>(
+        n, m, xyz1, xyz2, match, grad2);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,251 @@
+"""GPU parity tests of the point-set ops (run on a B200: pytest -m gpu).
+
+Every test calls the product through its public op module (which goes through the C ABI
+in include/monopsr_b200_tfops.h) and compares with
+  * the CPU oracle in GPU rounding order (oracle/tfops_oracle.c)        -- always
+  * the reference's own CUDA kernels compiled for sm_100a (oracle/_ref) -- when present
+Bars: nearest-neighbour idx AND dist bit-exact; gradients / EMD within 1e-3 relative
+(fp32 atomics in the reference make its own gradient order-dependent; the reference EMD
+uses ex2.approx / rsqrt.approx).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import refgpu, tfops
+
+pytestmark = pytest.mark.gpu
+
+from monopsr_b200.tf_ops.approxmatch import tf_approxmatch  # noqa: E402
+from monopsr_b200.tf_ops.nn_distance import tf_nndistance  # noqa: E402
+
+
+def _t(a, dev):
+    return torch.as_tensor(np.asarray(a, np.float32), device=dev)
+
+
+def _clouds(b, n, m, seed, masked=0.0, scale=1.0):
+    rng = np.random.RandomState(seed)
+    x = (rng.randn(b, n, 3) * scale).astype(np.float32)
+    y = (rng.randn(b, m, 3) * scale).astype(np.float32)
+    if masked:
+        k = min(n, m)
+        mask = rng.rand(b, k, 1) < masked
+        x[:, :k] = np.where(mask, 0, x[:, :k])
+        y[:, :k] = np.where(mask, 0, y[:, :k])
+    return x, y
+
+
+# ------------------------------------------------------------------ nn_distance
+
+def test_nn_kats(cuda):
+    pc = [[[1., 1., 1.], [2., 2., 2.], [3., 3., 3.]]]
+    d1, i1, _, _ = tf_nndistance.nn_distance(_t(pc, cuda), _t(pc, cuda))
+    assert float(d1.sum()) == 0 and i1.cpu().tolist() == [[0, 1, 2]]
+    d1, i1, _, _ = tf_nndistance.nn_distance(_t(pc, cuda), _t([[[1., 1., 1.], [2., 2., 2.]]], cuda))
+    assert float(d1.sum()) == 3.0 and i1.cpu().tolist() == [[0, 1, 1]]
+    d1, _, _, _ = tf_nndistance.nn_distance(_t([[[-2., 2., -2.], [1., 3., 4.]]], cuda),
+                                            _t([[[2., 0., 2.], [3., -5., 7.]]], cuda))
+    assert float(d1.sum()) == 50.0
+    pc2 = [[[1., 0., 1.], [2., 0., 2.], [3., 0., 3.]], [[4., 4., 4.], [2., 2., 2.], [3., 3., 3.]]]
+    d1, _, _, _ = tf_nndistance.nn_distance(_t(pc * 2, cuda), _t(pc2, cuda))
+    np.testing.assert_almost_equal(d1.sum(1).cpu().numpy(), [14.0, 3.0])
+
+
+@pytest.mark.parametrize("b,n,m,seed,masked", [
+    (1, 1, 1, 0, 0), (2, 3, 2, 1, 0), (3, 37, 53, 2, 0), (2, 257, 1000, 3, 0),
+    (4, 2048, 2048, 100, 0), (2, 2304, 2304, 4, 0.4), (1, 5000, 300, 5, 0),
+    (2, 64, 4500, 6, 0.3), (32, 2048, 2048, 101, 0),
+])
+def test_nn_bit_exact_vs_oracle(cuda, b, n, m, seed, masked):
+    x, y = _clouds(b, n, m, seed, masked)
+    got = tf_nndistance.nn_distance(_t(x, cuda), _t(y, cuda))
+    if b * n * m <= 4 * 2304 * 2304:
+        exp = tfops.nn_distance(x, y, "gpu")
+        for g, e in zip(got, exp):
+            np.testing.assert_array_equal(g.cpu().numpy(), e)
+    if refgpu.available():
+        ref = refgpu.nn_distance(_t(x, cuda), _t(y, cuda))
+        for g, r in zip(got, ref):
+            assert torch.equal(g, r)
+
+
+def test_nn_golden(cuda, golden):
+    # golden vectors come from the reference CPU nnsearch (different rounding order, Q1):
+    # distances agree to fp32 rounding; where the CPU result is unambiguous so do indices
+    for case in "abc":
+        x, y = golden[f"{case}_x"], golden[f"{case}_y"]
+        d1, i1, d2, i2 = tf_nndistance.nn_distance(_t(x, cuda), _t(y, cuda))
+        np.testing.assert_allclose(d1.cpu().numpy(), golden[f"{case}_d1"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(d2.cpu().numpy(), golden[f"{case}_d2"], rtol=1e-5, atol=1e-7)
+        agree = (i1.cpu().numpy() == golden[f"{case}_i1"]).mean()
+        assert agree > 0.99
+
+
+def test_nn_ties_lowest_index_wins(cuda):
+    # quirk Q8: duplicated points -> exact ties; lowest index must win, also across the
+    # 8-candidate groups and the 2048-candidate shared-memory passes
+    rng = np.random.RandomState(9)
+    base = rng.randn(1, 50, 3).astype(np.float32)
+    y = np.concatenate([base] * 100, axis=1)          # 5000 candidates, each point 100 times
+    x = base.copy()
+    d1, i1, _, _ = tf_nndistance.nn_distance(_t(x, cuda), _t(y, cuda))
+    assert i1.cpu().tolist() == [list(range(50))]
+    assert float(d1.abs().max()) == 0.0
+    z = np.zeros((2, 3000, 3), np.float32)
+    d1, i1, d2, i2 = tf_nndistance.nn_distance(_t(z, cuda), _t(z, cuda))
+    assert int(i1.max()) == 0 and int(i2.max()) == 0
+
+
+@pytest.mark.parametrize("b,n,m,seed,masked", [(2, 9, 7, 5, 0), (3, 300, 170, 6, 0), (4, 2304, 2304, 7, 0.4)])
+def test_nn_grad_vs_oracle(cuda, b, n, m, seed, masked):
+    x, y = _clouds(b, n, m, seed, masked)
+    rng = np.random.RandomState(seed + 50)
+    w1 = rng.rand(b, n).astype(np.float32)
+    w2 = rng.rand(b, m).astype(np.float32)
+    xt, yt = _t(x, cuda).requires_grad_(), _t(y, cuda).requires_grad_()
+    d1, i1, d2, i2 = tf_nndistance.nn_distance(xt, yt)
+    ((d1 * _t(w1, cuda)).sum() + (d2 * _t(w2, cuda)).sum()).backward()
+    e1, e2 = tfops.nn_distance_grad(x, y, w1, i1.cpu().numpy(), w2, i2.cpu().numpy())
+    scale = max(np.abs(e1).max(), np.abs(e2).max())
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), e1, rtol=1e-3, atol=1e-5 * scale)
+    np.testing.assert_allclose(yt.grad.cpu().numpy(), e2, rtol=1e-3, atol=1e-5 * scale)
+    if refgpu.available():
+        r1, r2 = refgpu.nn_distance_grad(_t(x, cuda), _t(y, cuda), _t(w1, cuda), i1, _t(w2, cuda), i2)
+        np.testing.assert_allclose(xt.grad.cpu().numpy(), r1.cpu().numpy(), rtol=1e-3, atol=1e-5 * scale)
+        np.testing.assert_allclose(yt.grad.cpu().numpy(), r2.cpu().numpy(), rtol=1e-3, atol=1e-5 * scale)
+
+
+def test_nn_shape_errors(cuda):
+    with pytest.raises(ValueError):
+        tf_nndistance.nn_distance(torch.zeros(2, 4, 2, device=cuda), torch.zeros(2, 4, 3, device=cuda))
+    with pytest.raises(ValueError):
+        tf_nndistance.nn_distance(torch.zeros(2, 4, 3, device=cuda), torch.zeros(3, 4, 3, device=cuda))
+    with pytest.raises(ValueError):
+        tf_nndistance.nn_distance(torch.zeros(4, 3, device=cuda), torch.zeros(1, 4, 3, device=cuda))
+
+
+def test_nn_chamfer_symmetry_property_full_size(cuda):
+    # size-independent property at BASELINE size b=256: swapping the clouds swaps the outputs
+    x, y = _clouds(256, 2048, 2048, 42)
+    a = tf_nndistance.nn_distance(_t(x, cuda), _t(y, cuda))
+    bb = tf_nndistance.nn_distance(_t(y, cuda), _t(x, cuda))
+    assert torch.equal(a[0], bb[2]) and torch.equal(a[1], bb[3])
+    assert torch.equal(a[2], bb[0]) and torch.equal(a[3], bb[1])
+    # dist equals the distance to the reported index
+    xt, yt = _t(x, cuda), _t(y, cuda)
+    nbr = torch.gather(yt, 1, a[1].long().unsqueeze(-1).expand(-1, -1, 3))
+    np.testing.assert_allclose(((xt - nbr) ** 2).sum(-1).cpu().numpy(), a[0].cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------ approxmatch
+
+def _emd_ops(x, y, dev):
+    xt, yt = _t(x, dev), _t(y, dev)
+    mt = tf_approxmatch.approx_match(xt, yt)
+    return mt, tf_approxmatch.match_cost(xt, yt, mt)
+
+
+def test_emd_kats(cuda):
+    pc = [[[1., 1., 1.], [2., 2., 2.], [3., 3., 3.]]]
+    _, c = _emd_ops(pc, pc, cuda)
+    np.testing.assert_almost_equal(float(c.mean()), 0, decimal=5)
+    pc2 = [[[1., 0., 1.], [2., 0., 2.], [3., 0., 3.]]]
+    mt, c = _emd_ops(pc, pc2, cuda)
+    assert np.argmax(mt[0].cpu().numpy(), axis=1).tolist() == [0, 1, 2]
+    np.testing.assert_almost_equal(float(c.mean()), 6.0, decimal=2)
+    _, c = _emd_ops([[[-2., 2., -2.]]], [[[2., 0., 2.]]], cuda)
+    np.testing.assert_almost_equal(float(c.mean()), 6.0, decimal=2)
+    pcb = [[[1., 0., 1.], [2., 0., 2.], [3., 0., 3.]], [[4., 4., 4.], [2., 2., 2.], [3., 3., 3.]]]
+    _, c = _emd_ops(pc * 2, pcb, cuda)
+    np.testing.assert_almost_equal(c.cpu().numpy(), [6.0, 5.196152], decimal=2)
+
+
+def _match_close(got, exp, what):
+    # match entries span many decades; the contract is 1e-3 relative on the mass that
+    # matters: compare against the row scale (each query row sums to ~its capacity)
+    err = np.abs(got - exp)
+    tol = 1e-3 * np.maximum(np.abs(exp), 1e-2 * np.abs(exp).max(axis=-1, keepdims=True)) + 1e-6
+    bad = err > tol
+    assert bad.mean() < 1e-4, "%s: %.3g of entries off, worst %.3g" % (what, bad.mean(), (err / tol).max())
+
+
+@pytest.mark.parametrize("b,n,m,seed,masked", [
+    (1, 1, 1, 0, 0), (2, 3, 3, 1, 0), (3, 37, 53, 11, 0), (2, 64, 64, 12, 0.4), (2, 128, 256, 13, 0),
+    (4, 512, 512, 14, 0), (32, 200, 200, 15, 0), (1, 1024, 1024, 200, 0), (3, 700, 100, 16, 0),
+])
+def test_emd_vs_oracle(cuda, b, n, m, seed, masked):
+    x, y = _clouds(b, n, m, seed, masked)
+    mt, cost = _emd_ops(x, y, cuda)
+    exp = tfops.approx_match(x, y, "gpu")
+    _match_close(mt.cpu().numpy(), exp, "match vs oracle")
+    np.testing.assert_allclose(cost.cpu().numpy(), tfops.match_cost(x, y, exp, "gpu"), rtol=1e-3, atol=1e-4)
+    # cost / grad kernels on the SAME match as the oracle: tight tolerance
+    expt = _t(exp, cuda)
+    np.testing.assert_allclose(tf_approxmatch.match_cost(_t(x, cuda), _t(y, cuda), expt).cpu().numpy(),
+                               tfops.match_cost(x, y, exp, "gpu"), rtol=2e-5, atol=1e-5)
+    g1, g2 = tf_approxmatch.match_cost_grad(_t(x, cuda), _t(y, cuda), expt)
+    e1, e2 = tfops.match_cost_grad(x, y, exp, "gpu")
+    s = max(np.abs(e1).max(), np.abs(e2).max(), 1e-6)
+    np.testing.assert_allclose(g1.cpu().numpy(), e1, rtol=1e-3, atol=2e-5 * s)
+    np.testing.assert_allclose(g2.cpu().numpy(), e2, rtol=1e-3, atol=2e-5 * s)
+    if refgpu.available():
+        r = refgpu.approx_match(_t(x, cuda), _t(y, cuda))
+        _match_close(mt.cpu().numpy(), r.cpu().numpy(), "match vs reference GPU kernel")
+        rc = refgpu.match_cost(_t(x, cuda), _t(y, cuda), r)
+        np.testing.assert_allclose(cost.cpu().numpy(), rc.cpu().numpy(), rtol=1e-3, atol=1e-4)
+        rg1, rg2 = refgpu.match_cost_grad(_t(x, cuda), _t(y, cuda), expt)
+        np.testing.assert_allclose(g1.cpu().numpy(), rg1.cpu().numpy(), rtol=1e-3, atol=2e-5 * s)
+        np.testing.assert_allclose(g2.cpu().numpy(), rg2.cpu().numpy(), rtol=1e-3, atol=2e-5 * s)
+
+
+def test_emd_golden(cuda, golden):
+    for case in "ab":
+        x, y = golden[f"{case}_x"], golden[f"{case}_y"]
+        mt, cost = _emd_ops(x, y, cuda)
+        ref_t = golden[f"{case}_match"].transpose(0, 2, 1)
+        assert np.abs(mt.cpu().numpy() - ref_t).max() < 2e-3
+        np.testing.assert_allclose(cost.cpu().numpy(), golden[f"{case}_cost"], rtol=2e-3)
+
+
+def test_emd_match_cost_autograd(cuda):
+    x, y = _clouds(2, 96, 96, 21)
+    xt, yt = _t(x, cuda).requires_grad_(), _t(y, cuda).requires_grad_()
+    mt = tf_approxmatch.approx_match(xt, yt)
+    assert not mt.requires_grad                       # ops.NoGradient('ApproxMatch')
+    w = torch.tensor([2.0, -0.5], device=cuda)
+    (tf_approxmatch.match_cost(xt, yt, mt) * w).sum().backward()
+    e1, e2 = tfops.match_cost_grad(x, y, mt.cpu().numpy(), "gpu")
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), e1 * np.array([2.0, -0.5], np.float32)[:, None, None],
+                               rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(yt.grad.cpu().numpy(), e2 * np.array([2.0, -0.5], np.float32)[:, None, None],
+                               rtol=1e-3, atol=1e-5)
+
+
+def test_emd_full_size_properties(cuda):
+    # BASELINE cfg4 (32 x 1024 x 1024) and the in-model size (32 x 2304 x 2304):
+    # mass conservation -- every query row and dataset column carries (almost) unit mass
+    for (b, n, seed) in [(32, 1024, 200), (32, 2304, 201)]:
+        x, y = _clouds(b, n, n, seed)
+        xt, yt = _t(x, cuda), _t(y, cuda)
+        mt = tf_approxmatch.approx_match(xt, yt)
+        assert bool(torch.isfinite(mt).all()) and float(mt.min()) >= 0.0
+        rows, cols = mt.sum(2), mt.sum(1)
+        assert float((rows - 1).abs().max()) < 2e-2 and float((cols - 1).abs().max()) < 2e-2
+        cost = tf_approxmatch.match_cost(xt, yt, mt)
+        # EMD upper-bounds nothing smaller than the NN matching cost: cost >= sum_k min_l ||.||
+        d1, _, d2, _ = tf_nndistance.nn_distance(xt, yt)
+        assert bool((cost >= 0.99 * torch.maximum(d1.sqrt().sum(1), d2.sqrt().sum(1)) * 0.98).all())
+        if refgpu.available() and n == 1024:
+            r = refgpu.approx_match(xt, yt)
+            _match_close(mt.cpu().numpy(), r.cpu().numpy(), "cfg4 match vs reference GPU kernel")
+            np.testing.assert_allclose(cost.cpu().numpy(), refgpu.match_cost(xt, yt, r).cpu().numpy(), rtol=1e-3)
+
+
+def test_emd_large_fallback_path(cuda):
+    # clouds too large for the on-chip path take the generic kernel
+    x, y = _clouds(1, 6000, 3000, 31)
+    mt = tf_approxmatch.approx_match(_t(x, cuda), _t(y, cuda))
+    assert bool(torch.isfinite(mt).all())
+    rows = mt.sum(2)           # each of the 3000 queries has capacity n/m = 2
+    assert float((rows - 2).abs().max()) < 5e-2
