@@ -484,11 +484,11 @@ MPB_API int mpb_approxmatch(int b, int n, int m, const float* xyz1, const float*
     }
     // fallback: stream-ordered scratch, one CTA per batch element
     float* scratch = nullptr;
-    MPB_CUDA_TRY(cudaMallocAsync(&scratch, sizeof(float) * (size_t)b * (n + m) * 2, s));
+    MPB_CUDA_TRY(scratch_alloc((void**)&scratch, sizeof(float) * (size_t)b * (n + m) * 2, s));
     approxmatch_fallback_kernel<<<min(b, 4 * sms), kAmThreads, 0, s>>>(b, n, m, xyz1, xyz2, match, scratch);
     count_launch();
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(scratch, s);
+    scratch_free(scratch, s);
     return cuda_status(e);
 }
 
@@ -504,13 +504,13 @@ MPB_API int mpb_matchcost(int b, int n, int m, const float* xyz1, const float* x
     if (b > 65535) return -1;
     const int tiles = ceil_div(m, kMcRows);
     float* partial = nullptr;
-    MPB_CUDA_TRY(cudaMallocAsync(&partial, sizeof(float) * (size_t)b * tiles, s));
+    MPB_CUDA_TRY(scratch_alloc((void**)&partial, sizeof(float) * (size_t)b * tiles, s));
     matchcost_partial_kernel<<<dim3(tiles, b), kMcThreads, 0, s>>>(n, m, xyz1, xyz2, match, partial);
     count_launch();
     matchcost_final_kernel<<<b, 32, 0, s>>>(tiles, partial, out);
     count_launch();
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(partial, s);
+    scratch_free(partial, s);
     return cuda_status(e);
 }
 

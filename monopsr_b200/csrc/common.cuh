@@ -39,6 +39,31 @@ inline int num_sms() {
     return sms;
 }
 
+// Stream-ordered scratch from a library-private pool (no effect on the process's default
+// pool; memory is cached across calls, so an allocation costs ~1 us after the first use).
+inline cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool;
+        e = cudaMemPoolCreate(&pool, &props);
+        if (e != cudaSuccess) return e;
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        pools[dev] = pool;
+    }
+    return cudaMallocFromPoolAsync(p, bytes, pools[dev], s);
+}
+inline cudaError_t scratch_free(void* p, cudaStream_t s) { return cudaFreeAsync(p, s); }
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace mpb
