@@ -1,0 +1,394 @@
+// monopsr_b200/csrc/tc_gemm.cu -- see tc_gemm.cuh for the design.
+#include "tc_gemm.cuh"
+
+namespace mpb {
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // bounded spin: a protocol bug must trap, not hang the GPU box
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    int sz = valid ? 16 : 0;   // src-size 0 => 16 zero bytes are written
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
+//  K-major : rows of 128 B (32 tf32 of K), 8-row groups 1024 B apart (SBO); LBO unused (=1)
+//  MN-major: K-rows of 128 B (32 tf32 of M/N), 8-K-row groups SBO apart, 32-element MN groups LBO apart
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) |
+           ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ int tap_delta(int tap, int kh, int kw, int dil, int W) {
+    int th = tap / kw - kh / 2, tw = tap % kw - kw / 2;
+    return (th * W + tw) * dil;
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int BN, int OP>
+__global__ void __launch_bounds__(kTcThreads)
+tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024 B alignment
+    constexpr uint32_t kStage = kTcABytes + BN * 128;
+    const uint32_t bar_base = base + kTcStages * kStage;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * kTcStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kTcStages) + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int taps = p.kh * p.kw;
+
+    // ---- K range of this CTA
+    int nkb;
+    if (OP == TC_FWD) nkb = taps * (p.Cin / kTcBK);
+    else if (OP == TC_DGRAD) nkb = taps * (p.Cout / kTcBK);
+    else nkb = (p.M + kTcBK - 1) / kTcBK;
+    const int per = (nkb + p.ksplit - 1) / p.ksplit;
+    const int kb0 = blockIdx.z * per;
+    const int kb1 = min(nkb, kb0 + per);
+    const int nk = kb1 - kb0;
+    if (nk <= 0) return;   // uniform per CTA (only possible with split-K)
+
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; s++) {
+            mbar_init(full_bar(s), 128);   // one deferred arrive per producer thread
+            mbar_init(empty_bar(s), 1);    // one tcgen05.commit
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "n"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot_ptr;
+
+    const int m0 = blockIdx.x * kTcBM;   // FWD/DGRAD: first pixel; WGRAD: first output channel
+    const int n0 = blockIdx.y * BN;      // FWD: co0; DGRAD: ci0; WGRAD: column in (tap,ci)
+
+    if (warp < 4) {
+        // =========================== PRODUCERS ===========================
+        int stage = 0;
+        uint32_t phase = 0;
+        if (OP == TC_FWD || OP == TC_DGRAD) {
+            // A rows are fixed per thread: chunk = tid&7, rows (tid>>3)+16j
+            const int chunk = tid & 7;
+            const int rbase = tid >> 3;
+            const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;   // channels of the gathered tensor
+            const int cblocks = Ck / kTcBK;
+            unsigned rowmask[8];
+            bool rowok[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int m = m0 + rbase + 16 * j;
+                rowok[j] = m < p.M;
+                rowmask[j] = (p.tapmask && rowok[j]) ? p.tapmask[m] : 0xFFFFu;
+            }
+            for (int i = 0; i < nk; i++) {
+                const int kb = kb0 + i;
+                const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
+                int delta = (taps > 1) ? tap_delta(tap, p.kh, p.kw, p.dil, p.W) : 0;
+                int mtap = tap;
+                if (OP == TC_DGRAD) { delta = -delta; mtap = taps - 1 - tap; }
+                const float* xsrc = p.X + (size_t)cb * kTcBK + chunk * 4;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int r = rbase + 16 * j;
+                    const bool ok = rowok[j] && ((rowmask[j] >> mtap) & 1u);
+                    const long pix = ok ? (long)(m0 + r + delta) : 0;
+                    cp_async16(sA + r * 128 + ((chunk ^ (r & 7)) << 4), xsrc + pix * p.ldx, ok);
+                }
+                if (OP == TC_FWD) {
+                    // B: BN weight rows, K-major
+                    const float* wsrc = p.Wt + (size_t)kb * kTcBK + chunk * 4;
+#pragma unroll
+                    for (int j = 0; j < BN / 16; j++) {
+                        const int r = rbase + 16 * j;
+                        cp_async16(sB + r * 128 + ((chunk ^ (r & 7)) << 4),
+                                   wsrc + (size_t)(n0 + r) * p.ldw, true);
+                    }
+                } else {
+                    // B: 32 K-rows (co) x BN contiguous ci, MN-major
+                    constexpr int cpr = BN / 4;
+                    const float* wsrc = p.Wt + (size_t)tap * p.Cin + n0;
+#pragma unroll
+                    for (int j = 0; j < cpr / 4; j++) {
+                        const int idx = tid + 128 * j;
+                        const int r = idx / cpr, c = idx % cpr;
+                        cp_async16(sB + (c >> 3) * 4096 + r * 128 + (((c & 7) ^ (r & 7)) << 4),
+                                   wsrc + (size_t)(cb * kTcBK + r) * p.ldw + c * 4, true);
+                    }
+                }
+                cp_async_arrive_noinc(full_bar(stage));
+                if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+            }
+        } else {
+            // WGRAD: K = pixels.  A: dY rows (MN-major, 128 co wide); B: gathered X (MN-major, BN ci wide)
+            const int tap = n0 / p.Cin, ci0 = n0 - tap * p.Cin;
+            const int delta = (taps > 1) ? tap_delta(tap, p.kh, p.kw, p.dil, p.W) : 0;
+            constexpr int cpr = BN / 4;
+            for (int i = 0; i < nk; i++) {
+                const int k0 = (kb0 + i) * kTcBK;
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int idx = tid + 128 * j;
+                    const int r = idx >> 5, c = idx & 31;
+                    const int m = k0 + r, co = m0 + c * 4;
+                    const bool ok = m < p.M && co < p.Cout;
+                    cp_async16(sA + (c >> 3) * 4096 + r * 128 + (((c & 7) ^ (r & 7)) << 4),
+                               p.Y + (ok ? (size_t)m * p.ldy + co : 0), ok);
+                }
+#pragma unroll
+                for (int j = 0; j < cpr / 4; j++) {
+                    const int idx = tid + 128 * j;
+                    const int r = idx / cpr, c = idx % cpr;
+                    const int m = k0 + r;
+                    bool ok = m < p.M;
+                    if (ok && p.tapmask) ok = (p.tapmask[m] >> tap) & 1u;
+                    cp_async16(sB + (c >> 3) * 4096 + r * 128 + (((c & 7) ^ (r & 7)) << 4),
+                               p.X + (ok ? (size_t)(m + delta) * p.ldx + ci0 + c * 4 : 0), ok);
+                }
+                cp_async_arrive_noinc(full_bar(stage));
+                if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+
+        // =========================== EPILOGUE ===========================
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;          // TMEM lane == accumulator row
+        const int grow = m0 + row;                 // pixel (FWD/DGRAD) or output channel (WGRAD)
+        const int nrows = (OP == TC_WGRAD) ? p.Cout : p.M;
+        const bool rok = grow < nrows;
+        const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
+        const int ldo = (OP == TC_WGRAD) ? p.ldw : p.ldo;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(trow + c0, v);
+            const int gc = n0 + c0;
+            if (p.scale) {
+#pragma unroll
+                for (int q = 0; q < 32; q++) v[q] *= __ldg(p.scale + gc + q);
+            }
+            if (p.shift) {
+#pragma unroll
+                for (int q = 0; q < 32; q++) v[q] += __ldg(p.shift + gc + q);
+            }
+            if (p.res && rok) {
+                const float4* rp = reinterpret_cast<const float4*>(p.res + (size_t)grow * p.ldr + gc);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    float4 t = __ldg(rp + q);
+                    v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                }
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int q = 0; q < 32; q++) v[q] = fmaxf(v[q], 0.f);
+            }
+            if (p.mask && rok) {
+                const float4* mp = reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ldm + gc);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    float4 t = __ldg(mp + q);
+                    v[4 * q] = t.x > 0.f ? v[4 * q] : 0.f;
+                    v[4 * q + 1] = t.y > 0.f ? v[4 * q + 1] : 0.f;
+                    v[4 * q + 2] = t.z > 0.f ? v[4 * q + 2] : 0.f;
+                    v[4 * q + 3] = t.w > 0.f ? v[4 * q + 3] : 0.f;
+                }
+            }
+            if (p.scale2) {
+#pragma unroll
+                for (int q = 0; q < 32; q++) v[q] *= __ldg(p.scale2 + gc + q);
+            }
+            if (p.round_tf32) {
+#pragma unroll
+                for (int q = 0; q < 32; q++) v[q] = round_tf32(v[q]);
+            }
+            if (p.colsum) {
+                // per-column sums over this warp's 32 rows, one RED per column per warp
+#pragma unroll
+                for (int q = 0; q < 32; q++) {
+                    float s = rok ? v[q] : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == q) atomicAdd(p.colsum + gc + q, s);
+                }
+            }
+            if (rok) {
+                float4* op = reinterpret_cast<float4*>(p.out + (size_t)grow * ldo + gc);
+                if (p.atomic) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        atomicAdd(op + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // =========================== MMA ISSUER (warp 4) ===========================
+        constexpr bool a_mn = (OP == TC_WGRAD);
+        constexpr bool b_mn = (OP != TC_FWD);
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) |
+                                   ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(kTcBM >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < nk; i++) {
+            mbar_wait(full_bar(stage), phase);
+            // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
+#pragma unroll
+                for (int k = 0; k < kTcBK / 8; k++) {
+                    const uint64_t ad = a_mn ? desc_mnmajor(sA + k * 1024) : desc_kmajor(sA + k * 32);
+                    const uint64_t bd = b_mn ? desc_mnmajor(sB + k * 1024) : desc_kmajor(sB + k * 32);
+                    umma_tf32(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(stage));               // frees the smem stage when the MMAs retire
+                if (i == nk - 1) umma_commit(tmem_full_bar);  // accumulator complete
+            }
+            __syncwarp();
+            if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN)
+                     : "memory");
+    }
+}
+
+template <int BN, int OP>
+static int launch_one(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
+    constexpr int smem = tc_smem_bytes<BN>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<BN, OP>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    tc_gemm_kernel<BN, OP><<<grid, kTcThreads, smem, s>>>(p);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+
+int tc_gemm_launch(const TcGemmParams& p, int BN, cudaStream_t s) {
+    const int taps = p.kh * p.kw;
+    if (p.M <= 0 || p.Cin <= 0 || p.Cout <= 0) return -1;
+    if (p.ksplit < 1) return -1;
+    dim3 grid;
+    if (p.op == TC_FWD) {
+        if (p.Cin % kTcBK || p.Cout % BN || p.ldo % 4 || p.ldx % 4 || p.ldw % 4) return -1;
+        grid = dim3(ceil_div(p.M, kTcBM), p.Cout / BN, p.ksplit);
+    } else if (p.op == TC_DGRAD) {
+        if (p.Cout % kTcBK || p.Cin % BN || p.ldo % 4 || p.ldx % 4 || p.ldw % 4) return -1;
+        grid = dim3(ceil_div(p.M, kTcBM), p.Cin / BN, p.ksplit);
+    } else if (p.op == TC_WGRAD) {
+        if (p.Cin % BN || p.Cout % 4 || p.ldy % 4 || p.ldx % 4 || p.ldw % 4) return -1;
+        grid = dim3(ceil_div(p.Cout, kTcBM), taps * p.Cin / BN, p.ksplit);
+    } else {
+        return -1;
+    }
+    if (grid.y > 65535 || grid.z > 65535) return -1;
+#define MPB_TC_CASE(bn)                                                       \
+    if (BN == bn) {                                                           \
+        if (p.op == TC_FWD) return launch_one<bn, TC_FWD>(p, grid, s);        \
+        if (p.op == TC_DGRAD) return launch_one<bn, TC_DGRAD>(p, grid, s);    \
+        return launch_one<bn, TC_WGRAD>(p, grid, s);                          \
+    }
+    MPB_TC_CASE(64)
+    MPB_TC_CASE(128)
+    MPB_TC_CASE(256)
+#undef MPB_TC_CASE
+    return -1;
+}
+
+}  // namespace mpb
