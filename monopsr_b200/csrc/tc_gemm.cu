@@ -74,14 +74,20 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 // Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
 //  K-major : rows of 128 B (32 tf32 of K), 8-row groups 1024 B apart (SBO); LBO unused (=1)
-//  MN-major: K-rows of 128 B (32 tf32 of M/N), 8-K-row groups SBO apart, 32-element MN groups LBO apart
+//  MN-major: K-rows of 128 B (32 tf32 of M/N), 4-K-row groups SBO apart, 32-element MN groups LBO apart
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// tf32 MN-major operands only exist as SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 K-rows x
+// 128 B, the 32-byte chunk index XORed with (K-row % 4)  [cute Layout_MN_SW128_32B_Atom]
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) |
-           ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+           ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// byte offset of 16-byte chunk c (0..7) inside K-row r of an MN-major group
+__device__ __forceinline__ uint32_t mn_swz(int c, int r) {
+    return (uint32_t)((((((c & 7) >> 1) ^ (r & 3)) << 1) | (c & 1)) << 4);
 }
 
 __device__ __forceinline__ int tap_delta(int tap, int kh, int kw, int dil, int W) {
@@ -191,7 +197,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
                     for (int j = 0; j < cpr / 4; j++) {
                         const int idx = tid + 128 * j;
                         const int r = idx / cpr, c = idx % cpr;
-                        cp_async16(sB + (c >> 3) * 4096 + r * 128 + (((c & 7) ^ (r & 7)) << 4),
+                        cp_async16(sB + (c >> 3) * 4096 + r * 128 + mn_swz(c, r),
                                    wsrc + (size_t)(cb * kTcBK + r) * p.ldw + c * 4, true);
                     }
                 }
@@ -213,7 +219,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
                     const int r = idx >> 5, c = idx & 31;
                     const int m = k0 + r, co = m0 + c * 4;
                     const bool ok = m < p.M && co < p.Cout;
-                    cp_async16(sA + (c >> 3) * 4096 + r * 128 + (((c & 7) ^ (r & 7)) << 4),
+                    cp_async16(sA + (c >> 3) * 4096 + r * 128 + mn_swz(c, r),
                                p.Y + (ok ? (size_t)m * p.ldy + co : 0), ok);
                 }
 #pragma unroll
@@ -223,7 +229,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
                     const int m = k0 + r;
                     bool ok = m < p.M;
                     if (ok && p.tapmask) ok = (p.tapmask[m] >> tap) & 1u;
-                    cp_async16(sB + (c >> 3) * 4096 + r * 128 + (((c & 7) ^ (r & 7)) << 4),
+                    cp_async16(sB + (c >> 3) * 4096 + r * 128 + mn_swz(c, r),
                                p.X + (ok ? (size_t)(m + delta) * p.ldx + ci0 + c * 4 : 0), ok);
                 }
                 cp_async_arrive_noinc(full_bar(stage));

@@ -116,7 +116,7 @@ def test_dgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN):
 @pytest.mark.parametrize("nimg,H,W,k,dil,Cin,Cout,BN,ksplit", [
     (1, 8, 16, 1, 1, 64, 128, 64, 1), (2, 12, 12, 1, 1, 256, 128, 128, 2), (3, 12, 12, 3, 1, 64, 64, 64, 3),
     (2, 12, 12, 3, 2, 128, 128, 64, 1), (4, 12, 12, 3, 4, 256, 256, 128, 4), (1, 40, 152, 3, 4, 64, 64, 64, 8),
-    (32, 1, 1, 1, 1, 1056, 1024, 64, 1),
+    (32, 1, 1, 1, 1, 1088, 1024, 64, 1),
 ])
 def test_wgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit):
     g = torch.Generator(device="cpu").manual_seed(3)
