@@ -35,7 +35,7 @@ typedef struct mpb_tc_gemm_params {
     float* out;          /* FWD [M][ldo] (Cout cols); DGRAD [M][ldo] (Cin cols); WGRAD dW [Cout][ldw] */
     int ldo;
     const unsigned short* tapmask;   /* [M], bit t <=> tap t in bounds at that pixel; NULL for 1x1 */
-    /* fused epilogue: v=acc; v*=scale[c]; v+=shift[c]; v+=res[r][c]; relu; v = mask[r][c]>0 ? v : 0;
+    /* fused epilogue: v=acc; v*=rowscale[r]; v*=scale[c]; v+=shift[c]; v+=res[r][c]; relu; v = mask[r][c]>0 ? v : 0;
      *                 v*=scale2[c]; round-to-tf32; colsum[c]+=v; store | atomic add */
     const float* scale;
     const float* shift;
@@ -44,6 +44,7 @@ typedef struct mpb_tc_gemm_params {
     const float* mask;
     int ldm;
     const float* scale2;
+    const float* rowscale;  /* per output ROW factor (WGRAD: folded-BN scale of each output channel) */
     float* colsum;
     int relu;
     int round_tf32;
@@ -56,6 +57,115 @@ int mpb_tc_gemm(const mpb_tc_gemm_params* p, int BN, void* stream);
 
 /* tapmask[m] for an (nimg,H,W) pixel grid and a kh x kw filter with atrous rate dil. */
 int mpb_build_tapmask(int nimg, int H, int W, int kh, int kw, int dil, unsigned short* out, void* stream);
+
+/* ---- weight preparation -------------------------------------------------------------------
+ * Frozen (inference-mode) batch norm of the two ResNet towers (feature_extractor.py:228-242:
+ * is_training=False, eps=1e-5, scale=True) folded into the conv weights:
+ *   wf = tf32(w * s), s = gamma*rsqrt(var+eps), shift = beta - mean*s.   w is [cout][K]. */
+int mpb_fold_bn(int cout, int K, const float* w, const float* gamma, const float* beta, const float* mean,
+                const float* var, float eps, float* wf, float* scale, float* shift, void* stream);
+int mpb_round_copy(long n, const float* src, float* dst, void* stream);   /* dst = tf32(src) */
+/* d(gamma) of a frozen BN from the conv weight gradient: rowdot(w,dw)/gamma - mean*dbeta*rsqrt(var+eps) */
+int mpb_bn_param_grad(int cout, int K, const float* w, const float* dw, const float* gamma, const float* mean,
+                      const float* var, float eps, const float* dbeta, float* dgamma, void* stream);
+
+/* ---- stem: conv2d_same(7x7, stride 2) + frozen BN + ReLU  (nets/resnet_v1.py:234) ---- */
+int mpb_stem_fwd(int nimg, int Hin, int Win, const float* x, const float* wf, const float* shift, float* y, void* stream);
+int mpb_stem_wgrad(int nimg, int Hin, int Win, const float* x, const float* g, const float* scale, float* dw, void* stream);
+
+/* ---- pools: slim.max_pool2d([3,3],2,'SAME') (resnet_v1.py:235); slim.max_pool2d([2,2]) (net_builder.py:60,68) */
+int mpb_maxpool3s2_fwd(int nimg, int H, int W, int C, const float* x, float* y, void* stream);
+int mpb_maxpool3s2_bwd(int nimg, int H, int W, int C, const float* x, const float* dy, float* dx, void* stream); /* dx also masked by x>0 */
+int mpb_maxpool2_fwd(int nimg, int H, int W, int C, const float* x, int ldx, float* y, int ldy, void* stream);
+int mpb_maxpool2_bwd(int nimg, int H, int W, int C, const float* x, int ldx, const float* dy, int ldy,
+                     float* dx, int lddx, int accumulate, void* stream);
+
+/* ---- tf.image.crop_and_resize(feat, boxes, 0, (crop,crop)) + max_pool2d([2,2]) fused (net_builder.py:54-60) */
+int mpb_crop_pool_fwd(int H, int W, int C, const float* feat, int nbox, const float* boxes_norm, int crop,
+                      float* out, int ldo, void* stream);
+int mpb_crop_pool_bwd(int H, int W, int C, const float* feat, int nbox, const float* boxes_norm, int crop,
+                      const float* dout, int ldd, float* dfeat, void* stream);   /* zeroes dfeat itself */
+
+/* ---- tf.image.resize_images(align_corners=True) (net_builder.py:73-75,82-84) ---- */
+int mpb_resize_ac_fwd(int nimg, int H, int W, int C, const float* x, int OH, int OW, float* y, void* stream);
+int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, int OH, int OW, float* dx, void* stream); /* zeroes dx */
+
+/* ---- slim.batch_norm(is_training=True) + ReLU of the map decoder (net_builder.py:77-89) ----
+ * scratch: 2*C doubles.  moving_mean/var may be NULL (no UPDATE_OPS). */
+int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, float eps, float* y, float* mean, float* var,
+                     float* moving_mean, float* moving_var, float decay, double* scratch, void* stream);
+int mpb_bn_train_bwd(int M, int C, const float* z, const float* mean, const float* var, float eps, const float* y,
+                     const float* dy, float* dz, float* dbeta, double* scratch, void* stream);
+
+/* ---- xyz head: conv3x3 128->3 + bias (monopsr_output_builder.py:95-108); w is [3][3][3][128] ---- */
+int mpb_xyzhead_fwd(int nimg, int H, int W, const float* x, const float* w, const float* bias, float* y, void* stream);
+int mpb_xyzhead_bwd(int nimg, int H, int W, const float* x, const float* w, const float* dy, float* dx, float* dw,
+                    float* db, void* stream);   /* dw, db accumulate */
+
+/* ---- small dense heads, N<=32 outputs (monopsr_output_builder.py:283,469,580,633); w is [N][K] ---- */
+int mpb_fc_small_fwd(int B, int K, int N, const float* x, int ldx, const float* w, const float* bias, float* y, int ldy,
+                     void* stream);
+int mpb_fc_small_bwd(int B, int K, int N, const float* x, int ldx, const float* w, const float* dy, int ldy, float* dx,
+                     int lddx, int accumulate_dx, float* dw, float* db, void* stream);
+
+/* ---- elementwise helpers ---- */
+int mpb_bias_relu(long rows, int C, const float* x, int ldx, const float* bias, int relu, int round, float* y, int ldy, void* stream);
+int mpb_relu_bwd_colsum(int M, int C, const float* y, int ldy, const float* dy, int lddy, float* g, int ldg,
+                        float* colsum, void* stream);
+int mpb_add_inplace(long n, float* a, const float* b, void* stream);
+
+/* ---- box heads, geometric projections, losses and their gradients (csrc/heads.cu) ----------
+ * Replaces monopsr_output_builder.py:126-274,407-488,551-746, monopsr_model.py:416-461,554-958
+ * and the tf_* geometry helpers (instance_utils.py:567-681,738-788,907-953; calib_utils.py:263-280). */
+typedef struct mpb_heads_io {
+    int nbox;
+    /* per-box inputs (placeholders of monopsr_model.py:70-126) */
+    const float* boxes_2d;            /* [N][4] y1,x1,y2,x2 px */
+    const float* cam_p;               /* [3][4] */
+    const int* class_indices;         /* [N] */
+    const float* mean_lwh;            /* [N][3] */
+    const float* prop_cen_z_offset;   /* [N] */
+    const float* est_view_angs;       /* [N] */
+    /* ground truth */
+    const float* boxes_3d;            /* [N][7] x,y,z,l,w,h,ry */
+    const int* gt_alpha_bins;         /* [N] */
+    const float* gt_alpha_regs;       /* [N][12] */
+    const float* gt_alpha_valid_bins; /* [N][12] */
+    const float* gt_view_angs;        /* [N] */
+    const float* gt_xyz_local;        /* [N][48][48][3] */
+    const float* gt_xyz_global;       /* [N][48][48][3] (z used) */
+    const float* valid_mask;          /* [N][48][48] */
+    /* network outputs (read) */
+    const float* lwh_offs;            /* [N][3] */
+    const float* alpha;               /* [N][24] bins | regs */
+    const float* cen_y_offs;          /* [N] */
+    const float* cen_z_offs;          /* [N] */
+    const float* xyz_local;           /* [N][48][48][3] */
+    /* derived outputs (written) */
+    float* lwh; float* prop_cen_z; float* prop_cen_y; float* cen_x; float* cen_y; float* cen_z; float* centroids;
+    float* proj_err_norm;             /* [N] */
+    float* depth_global;              /* [N][48][48] */
+    float* feat1; int ld1;            /* proposal concat buffer [N][ld1]: cols 0..1023 img_fc, tail written here */
+    float* feat2; int ld2;            /* regression concat buffer */
+    /* losses and gradients */
+    float* losses;                    /* [9] xyz, lwh, alpha_bins, alpha_regs, cen_z, cen_y, proj_err, depth, total */
+    float* d_lwh_offs; float* d_alpha; float* d_cen_y_offs; float* d_cen_z_offs; float* d_xyz_local;
+    float* d_prop_y; float* d_prop_z; /* scratch [N] */
+    const float* d_feat2; int ldd2;   /* gradient of the regression concat buffer (from the fc0 data-gradient) */
+    float* maskstats;                 /* [N+1]: valid pixels per box, total */
+} mpb_heads_io;
+int mpb_heads_static(const mpb_heads_io* io, void* stream);        /* once per sample */
+int mpb_heads_mid(const mpb_heads_io* io, void* stream);           /* after lwh / alpha heads */
+int mpb_heads_final(const mpb_heads_io* io, int train, void* stream); /* after cen_y / cen_z heads */
+int mpb_heads_bwd_mid(const mpb_heads_io* io, void* stream);       /* after the regression fc0 data-gradient */
+
+/* ---- fused train-op: per-variable clip_by_norm + Adam + EMA (csrc/optimizer.cu) ----
+ * Replaces slim.learning.create_train_op(..., clip_gradient_norm=1.0) (core/trainer.py:76-81) with
+ * AdamOptimizer + MovingAverageOptimizer (builders/optimizer_builder.py:56-82). */
+typedef struct mpb_opt_chunk { long start; int len; int tensor; } mpb_opt_chunk;
+int mpb_opt_step(int nchunks, const mpb_opt_chunk* chunks, int ntensors, float* param, const float* grad,
+                 float* m, float* v, float* ema, float* norm2, const float* hyper, float grad_scale,
+                 float clip_norm, float beta1, float beta2, float eps, float ema_decay, void* stream);
 
 #ifdef __cplusplus
 }

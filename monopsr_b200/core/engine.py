@@ -1,0 +1,707 @@
+"""B200 execution engine of the MonoPSR per-instance network (forward, backward, train-op).
+
+Host-side orchestration only: every arithmetic operation is a hand-written sm_100a kernel
+reached through the C ABI of ``include/monopsr_b200_net.h``; torch tensors are device-memory
+containers (plus ``torch.distributed`` for the one gradient all-reduce).  The op sequence
+restates the reference graph:
+
+  builders/net_builder.py:30-96                         two ResNet-101 towers, squash, map decoder
+  core/models/monopsr/monopsr_output_builder.py          FC stacks and heads
+  core/models/monopsr/monopsr_model.py:138-492,554-958   wiring and losses
+  core/trainer.py:76-81, builders/optimizer_builder.py   train-op
+
+One ``Engine`` = one sample in flight (num_boxes crops + one full image), matching the
+reference's ``batch_size: 1`` (configs/monopsr_model_000.yaml:14-17).  The whole step is
+captured into a CUDA graph after the first call.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from .. import lib as _lib
+from ..lib_net import TC_DGRAD, TC_FWD, TC_WGRAD, HeadsIO, OptChunk, TcGemmParams
+from . import model_spec as ms
+
+BN_EPS_RESNET = 1e-5
+BN_EPS_DECODER = 1e-3
+BN_DECAY_DECODER = 0.999
+KPAD = 1088          # 1043 / 1060 concat widths padded to a multiple of 64
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, device, params=None, num_boxes=ms.NUM_BOXES, seed=0, sms=148):
+        self.dev = torch.device(device)
+        self.N = num_boxes
+        self.L = _lib.load()
+        self.sms = sms
+        self._launch_checks = True
+        with torch.cuda.device(self.dev):
+            self._build_param_layout()
+            self._alloc_state()
+            self.load_params(params if params is not None else ms.init_params(seed))
+            self._alloc_activations()
+        self.step_count = 0
+        self.world = 1
+
+    # ------------------------------------------------------------------ parameters
+    def _dev_shape(self, name, shape, kind):
+        if kind == "weights":
+            if len(shape) == 4:
+                k, _, cin, cout = shape
+                return (cout, k * k * cin)
+            kin, kout = shape
+            if kin in (1043, 1060):
+                kin = KPAD
+            return (kout, kin)
+        return tuple(shape)
+
+    def _build_param_layout(self):
+        table = ms.param_table()
+        self.ptable = {n: (s, k) for n, s, k in table}
+        self.layout = {}          # name -> (arena, offset, dev_shape)
+        off = 0
+        self.trainable_names = []
+        for n, s, k in table:
+            if k in ms.TRAINABLE_KINDS:
+                ds = self._dev_shape(n, s, k)
+                self.layout[n] = ("T", off, ds)
+                off += int(np.prod(ds))
+                off = (off + 3) & ~3          # 16-byte alignment of every tensor
+                self.trainable_names.append(n)
+        self.n_train = off
+        off = 0
+        for n, s, k in table:
+            if k not in ms.TRAINABLE_KINDS:
+                self.layout[n] = ("S", off, tuple(s))
+                off += int(np.prod(s))
+                off = (off + 3) & ~3
+        self.n_state = off
+
+    def _alloc_state(self):
+        z = lambda n, dt=torch.float32: torch.zeros(n, dtype=dt, device=self.dev)
+        self.params = z(self.n_train)
+        self.state = z(self.n_state)
+        self.grads = z(self.n_train)
+        self.adam_m = z(self.n_train)
+        self.adam_v = z(self.n_train)
+        self.ema = z(self.n_train)
+        self.prep = z(self.n_train)            # folded / tf32-rounded weights (same offsets as params)
+        self.hyper = z(4)
+        # optimizer chunk table
+        chunks = []
+        CH = 1 << 16
+        for ti, n in enumerate(self.trainable_names):
+            _, off, ds = self.layout[n]
+            size = int(np.prod(ds))
+            for s in range(0, size, CH):
+                chunks.append((off + s, min(CH, size - s), ti))
+        arr = (OptChunk * len(chunks))()
+        for i, (a, b, c) in enumerate(chunks):
+            arr[i].start, arr[i].len, arr[i].tensor = a, b, c
+        raw = bytes(arr)
+        self.opt_chunks = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.dev)
+        self.n_chunks = len(chunks)
+        self.norm2 = z(len(self.trainable_names))
+
+    def view(self, name, arena=None):
+        a, off, ds = self.layout[name]
+        base = {"T": self.params, "S": self.state}[a] if arena is None else arena
+        return base[off:off + int(np.prod(ds))].view(ds)
+
+    def gview(self, name):
+        return self.view(name, self.grads)
+
+    def pview(self, name):
+        return self.view(name, self.prep)
+
+    def load_params(self, P):
+        """P: name -> numpy array in TF layout (conv HWIO, fc [in,out])."""
+        for n, (s, k) in self.ptable.items():
+            a = np.asarray(P[n], np.float32)
+            assert tuple(a.shape) == tuple(s), (n, a.shape, s)
+            if k == "weights":
+                if a.ndim == 4:
+                    a = a.transpose(3, 0, 1, 2).reshape(a.shape[3], -1)       # HWIO -> O,(H,W,I)
+                else:
+                    a = a.T                                                     # [in,out] -> [out,in]
+                    ds = self.layout[n][2]
+                    if a.shape[1] != ds[1]:
+                        a = np.concatenate([a, np.zeros((a.shape[0], ds[1] - a.shape[1]), np.float32)], 1)
+            self.view(n).copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        self.ema.copy_(self.params)
+        self.adam_m.zero_()
+        self.adam_v.zero_()
+        self._prepared = False
+
+    def export_params(self, arena=None):
+        out = {}
+        for n, (s, k) in self.ptable.items():
+            t = self.view(n, arena if (arena is not None and self.layout[n][0] == "T") else None).detach().cpu().numpy()
+            if k == "weights":
+                if len(s) == 4:
+                    kk, _, cin, cout = s
+                    t = t.reshape(cout, kk, kk, cin).transpose(1, 2, 3, 0)
+                else:
+                    t = t[:, :s[0]].T
+            out[n] = np.ascontiguousarray(t)
+        return out
+
+    def export_grads(self):
+        return self.export_params(self.grads)
+
+    # ------------------------------------------------------------------ activations
+    def _alloc_activations(self):
+        N = self.N
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.dev)
+        self.towers = {}
+        for enc, nimg, Hin, Win in ((ms.ENCODERS[0], N, ms.CROP, ms.CROP), (ms.ENCODERS[1], 1, ms.FULL_H, ms.FULL_W)):
+            H2, W2 = Hin // 2, Win // 2
+            h, w = H2 // 2, W2 // 2
+            M = nimg * h * w
+            T = dict(enc=enc, nimg=nimg, Hin=Hin, Win=Win, H2=H2, W2=W2, h=h, w=w, M=M)
+            T["stem"] = e(nimg * H2 * W2, 64)
+            T["pool"] = e(M, 64)
+            T["g_stem"] = e(nimg * H2 * W2, 64)
+            T["g_pool"] = e(M, 64)
+            T["tapmask"] = {}
+            for rate in (1, 2, 4):
+                tm = torch.empty(M, dtype=torch.int16, device=self.dev)
+                self._chk(self.L.mpb_build_tapmask(nimg, h, w, 3, 3, rate, _ptr(tm), self._st()), "tapmask")
+                T["tapmask"][rate] = tm
+            units = []
+            cin = 64
+            for name, base, nunits, rate in ms.BLOCKS:
+                for u in range(1, nunits + 1):
+                    scope = "%s/resnet_v1_101/%s/unit_%d/bottleneck_v1" % (enc, name, u)
+                    U = dict(scope=scope, cin=cin, base=base, cout=base * 4, rate=rate, proj=(cin != base * 4))
+                    U["y1"], U["y2"] = e(M, base), e(M, base)
+                    U["g1"], U["g2"] = e(M, base), e(M, base)
+                    U["sc"] = e(M, base * 4) if U["proj"] else None
+                    U["t"] = e(M, cin) if U["proj"] else None
+                    last = (name == "block3" and u == nunits)
+                    if last and nimg > 1:
+                        U["out"] = None          # written into the concat buffer (crop tower)
+                    else:
+                        U["out"] = e(M, base * 4)
+                    U["g_out"] = e(M, base * 4)
+                    units.append(U)
+                    cin = base * 4
+            T["units"] = units
+            self.towers[enc] = T
+        Mc = self.towers[ms.ENCODERS[0]]["M"]          # N*12*12
+        self.Mc = Mc
+        self.concat = e(Mc, 2048)
+        self.towers[ms.ENCODERS[0]]["units"][-1]["out_view"] = (self.concat, 2048)
+        self.squashed = e(Mc, 512)
+        self.pooled = e(N * 36, 512)
+        self.r1 = e(N * 576, 512)
+        self.dec = []
+        for (blk, cin, cout, M) in (("conv2", 512, 256, N * 576), ("conv3", 256, 128, N * 2304)):
+            for i in (1, 2):
+                sc = "map_decoder/%s/%s_%d" % (blk, blk, i)
+                D = dict(scope=sc, cin=cin if i == 1 else cout, cout=cout, M=M, side=24 if blk == "conv2" else 48)
+                D["z"], D["y"] = e(M, cout), e(M, cout)
+                D["mean"], D["var"] = e(cout), e(cout)
+                D["dz"], D["dy"] = e(M, cout), e(M, cout)
+                self.dec.append(D)
+        self.r2 = e(N * 2304, 256)
+        self.d_r2 = e(N * 2304, 256)
+        self.d_r1 = e(N * 576, 512)
+        self.bn_scratch = torch.zeros(2 * 512, dtype=torch.float64, device=self.dev)
+        self.tm24 = torch.empty(N * 576, dtype=torch.int16, device=self.dev)
+        self.tm48 = torch.empty(N * 2304, dtype=torch.int16, device=self.dev)
+        self._chk(self.L.mpb_build_tapmask(N, 24, 24, 3, 3, 1, _ptr(self.tm24), self._st()), "tapmask")
+        self._chk(self.L.mpb_build_tapmask(N, 48, 48, 3, 3, 1, _ptr(self.tm48), self._st()), "tapmask")
+        self.xyz = e(N * 2304, 3)
+        self.d_xyz = e(N * 2304, 3)
+        # FC stacks
+        self.fc = {}
+        for key in ("proposal", "regression"):
+            F = dict(acc=e(N, 1024), feat=torch.zeros(N, KPAD, dtype=torch.float32, device=self.dev),
+                     h0=e(N, 1024), h1=e(N, 1024), d_h1=e(N, 1024), g_h1=e(N, 1024), d_h0=e(N, 1024),
+                     g_h0=e(N, 1024), d_feat=e(N, KPAD), g_img=e(N, 1024))
+            self.fc[key] = F
+        self.d_flat = e(N, 18432)
+        self.d_squashed = e(Mc, 512)
+        self.g_squashed = e(Mc, 512)
+        self.g_fullcrop = e(Mc, 1024)
+        self.d_fullfeat = e(self.towers[ms.ENCODERS[1]]["M"], 1024)
+        # heads
+        self.h = {k: e(*s) for k, s in dict(
+            lwh_offs=(N, 3), alpha=(N, 24), cen_y_offs=(N,), cen_z_offs=(N,), lwh=(N, 3), prop_cen_z=(N,),
+            prop_cen_y=(N,), cen_x=(N,), cen_y=(N,), cen_z=(N,), centroids=(N, 3), proj_err_norm=(N,),
+            depth_global=(N, 2304), losses=(9,), d_lwh_offs=(N, 3), d_alpha=(N, 24), d_cen_y_offs=(N,),
+            d_cen_z_offs=(N,), d_prop_y=(N,), d_prop_z=(N,), maskstats=(N + 1,)).items()}
+        self.inputs = {}
+        torch.cuda.synchronize(self.dev)
+
+    # ------------------------------------------------------------------ helpers
+    def _st(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _chk(self, status, what):
+        if status != 0:
+            _lib.check(status, what)
+
+    def _pick_bn(self, mtiles, ncols, allowed=(256, 128, 64)):
+        for bn in allowed:
+            if ncols % bn == 0 and mtiles * (ncols // bn) >= int(0.9 * self.sms):
+                return bn
+        for bn in reversed(allowed):
+            if ncols % bn == 0:
+                return bn
+        raise ValueError("no tile width divides %d" % ncols)
+
+    def gemm(self, op, M, H, W, k, dil, Cin, Cout, X, ldx, Wt, ldw, out, ldo, Y=None, ldy=0, tapmask=None,
+             shift=None, res=None, ldr=0, mask=None, ldm=0, rowscale=None, colsum=None, relu=0, round_tf32=0,
+             atomic=0, ksplit=1, bn=None):
+        p = TcGemmParams()
+        p.op, p.H, p.W, p.kh, p.kw, p.dil, p.M, p.Cin, p.Cout = op, H, W, k, k, dil, M, Cin, Cout
+        p.X, p.ldx, p.Y, p.ldy, p.Wt, p.ldw, p.out, p.ldo = _ptr(X), ldx, _ptr(Y), ldy, _ptr(Wt), ldw, _ptr(out), ldo
+        p.tapmask = _ptr(tapmask)
+        p.shift, p.res, p.ldr, p.mask, p.ldm = _ptr(shift), _ptr(res), ldr, _ptr(mask), ldm
+        p.rowscale, p.colsum = _ptr(rowscale), _ptr(colsum)
+        p.relu, p.round_tf32, p.atomic, p.ksplit = relu, round_tf32, atomic, ksplit
+        mt = (M + 127) // 128
+        if bn is None:
+            if op == TC_FWD:
+                bn = self._pick_bn(mt, Cout)
+            elif op == TC_DGRAD:
+                bn = self._pick_bn(mt, Cin)
+            else:
+                bn = 128 if Cin % 128 == 0 else 64
+        self._chk(self.L.mpb_tc_gemm(ctypes.byref(p), bn, self._st()), "mpb_tc_gemm")
+
+    def wgrad(self, M, H, W, k, dil, Cin, Cout, X, ldx, dY, ldy, dW, tapmask=None, rowscale=None):
+        bn = 128 if Cin % 128 == 0 else 64
+        tiles = ((Cout + 127) // 128) * (k * k * Cin // bn)
+        nkb = (M + 31) // 32
+        ksplit = max(1, min((self.sms + tiles - 1) // tiles, max(1, nkb // 4)))
+        self.gemm(TC_WGRAD, M, H, W, k, dil, Cin, Cout, X, ldx, None, k * k * Cin, dW, 0, Y=dY, ldy=ldy,
+                  tapmask=tapmask, rowscale=rowscale, atomic=1, ksplit=ksplit, bn=bn)
+
+    # ------------------------------------------------------------------ weight preparation
+    def prepare_weights(self):
+        """fold frozen BN into the tower convs, tf32-round every GEMM weight (run after each update)."""
+        L, st = self.L, self._st()
+        self.bnfold = getattr(self, "bnfold", {})
+        for enc in ms.ENCODERS:
+            for scope, k, cin, cout, _ in ms.conv_layers(enc):
+                if scope not in self.bnfold:
+                    self.bnfold[scope] = (torch.empty(cout, device=self.dev), torch.empty(cout, device=self.dev))
+                sc, sh = self.bnfold[scope]
+                b = scope + "/BatchNorm/"
+                self._chk(L.mpb_fold_bn(cout, k * k * cin, _ptr(self.view(scope + "/weights")),
+                                        _ptr(self.view(b + "gamma")), _ptr(self.view(b + "beta")),
+                                        _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
+                                        BN_EPS_RESNET, _ptr(self.pview(scope + "/weights")), _ptr(sc), _ptr(sh), st),
+                          "fold_bn")
+        for n in self.trainable_names:
+            if self.ptable[n][1] == "weights" and not n.startswith("FirstStage"):
+                v = self.view(n)
+                self._chk(L.mpb_round_copy(v.numel(), _ptr(v), _ptr(self.pview(n)), st), "round_copy")
+        self._prepared = True
+
+    # ------------------------------------------------------------------ inputs
+    def set_inputs(self, S):
+        """S: dict of numpy arrays / torch tensors (model_spec.synthetic_sample keys); host->device copy."""
+        for k, v in S.items():
+            t = torch.as_tensor(np.asarray(v)) if not isinstance(v, torch.Tensor) else v
+            if t.dtype == torch.float64:
+                t = t.float()
+            if k in self.inputs and self.inputs[k].shape == t.shape:
+                self.inputs[k].copy_(t, non_blocking=True)
+            else:
+                self.inputs[k] = t.to(self.dev).contiguous()
+        self._heads_io = None
+
+    def heads_io(self):
+        if getattr(self, "_heads_io", None) is not None:
+            return self._heads_io
+        I, h = self.inputs, self.h
+        io = HeadsIO()
+        io.nbox = self.N
+        for k in ("boxes_2d", "cam_p", "class_indices", "mean_lwh", "prop_cen_z_offset", "est_view_angs", "boxes_3d",
+                  "gt_alpha_bins", "gt_alpha_regs", "gt_alpha_valid_bins", "gt_view_angs"):
+            if k in I:
+                setattr(io, k, I[k].data_ptr())
+        for k, src in (("gt_xyz_local", "gt_inst_xyz_maps_local"), ("gt_xyz_global", "gt_inst_xyz_maps_global"),
+                       ("valid_mask", "gt_valid_mask_maps")):
+            if src in I:
+                setattr(io, k, I[src].data_ptr())
+        for k in ("lwh_offs", "alpha", "cen_y_offs", "cen_z_offs", "lwh", "prop_cen_z", "prop_cen_y", "cen_x", "cen_y",
+                  "cen_z", "centroids", "proj_err_norm", "depth_global", "losses", "d_lwh_offs", "d_alpha",
+                  "d_cen_y_offs", "d_cen_z_offs", "d_prop_y", "d_prop_z", "maskstats"):
+            setattr(io, k, h[k].data_ptr())
+        io.xyz_local, io.d_xyz_local = self.xyz.data_ptr(), self.d_xyz.data_ptr()
+        io.feat1, io.ld1 = self.fc["proposal"]["feat"].data_ptr(), KPAD
+        io.feat2, io.ld2 = self.fc["regression"]["feat"].data_ptr(), KPAD
+        io.d_feat2, io.ldd2 = self.fc["regression"]["d_feat"].data_ptr(), KPAD
+        self._heads_io = io
+        return io
+
+    # ------------------------------------------------------------------ forward
+    def _tower_fwd(self, T, x_in):
+        L, st = self.L, self._st()
+        enc = T["enc"]
+        s0 = enc + "/resnet_v1_101/conv1"
+        self._chk(L.mpb_stem_fwd(T["nimg"], T["Hin"], T["Win"], _ptr(x_in), _ptr(self.pview(s0 + "/weights")),
+                                 _ptr(self.bnfold[s0][1]), _ptr(T["stem"]), st), "stem_fwd")
+        self._chk(L.mpb_maxpool3s2_fwd(T["nimg"], T["H2"], T["W2"], 64, _ptr(T["stem"]), _ptr(T["pool"]), st), "pool1")
+        x, ldx = T["pool"], 64
+        M, h, w = T["M"], T["h"], T["w"]
+        for U in T["units"]:
+            s, cin, base, cout, rate = U["scope"], U["cin"], U["base"], U["cout"], U["rate"]
+            if U["out"] is not None:
+                out, ldo = U["out"], cout
+            else:
+                out, ldo = U["out_view"]
+            if U["proj"]:
+                self.gemm(TC_FWD, M, h, w, 1, 1, cin, cout, x, ldx, self.pview(s + "/shortcut/weights"), cin,
+                          U["sc"], cout, shift=self.bnfold[s + "/shortcut"][1])
+                res, ldr = U["sc"], cout
+            else:
+                res, ldr = x, ldx
+            self.gemm(TC_FWD, M, h, w, 1, 1, cin, base, x, ldx, self.pview(s + "/conv1/weights"), cin, U["y1"], base,
+                      shift=self.bnfold[s + "/conv1"][1], relu=1, round_tf32=1)
+            self.gemm(TC_FWD, M, h, w, 3, rate, base, base, U["y1"], base, self.pview(s + "/conv2/weights"), 9 * base,
+                      U["y2"], base, tapmask=T["tapmask"][rate], shift=self.bnfold[s + "/conv2"][1], relu=1, round_tf32=1)
+            self.gemm(TC_FWD, M, h, w, 1, 1, base, cout, U["y2"], base, self.pview(s + "/conv3/weights"), base, out, ldo,
+                      shift=self.bnfold[s + "/conv3"][1], res=res, ldr=ldr, relu=1, round_tf32=1)
+            U["x"], U["ldx"], U["o"], U["ldo"] = x, ldx, out, ldo
+            x, ldx = out, ldo
+        return x, ldx
+
+    def _fc_layer(self, x, ldx, K, wname, out, ldo, acc):
+        """relu(x @ W^T + b): split-K tcgen05 GEMM into a zeroed accumulator, then bias+ReLU."""
+        N = self.N
+        acc.zero_()
+        nkb = K // 32
+        ksplit = max(1, min(8, nkb // 8))
+        self.gemm(TC_FWD, N, 1, 1, 1, 1, K, 1024, x, ldx, self.pview(wname + "/weights"), K, acc, 1024, atomic=1,
+                  ksplit=ksplit, bn=64)
+        self._chk(self.L.mpb_bias_relu(N, 1024, _ptr(acc), 1024, _ptr(self.view(wname + "/biases")), 1, 1, _ptr(out), ldo,
+                                       self._st()), "bias_relu")
+
+    def forward(self, train=True):
+        if not self._prepared:
+            self.prepare_weights()
+        L, st, N, I = self.L, self._st(), self.N, self.inputs
+        Tc, Tf = self.towers[ms.ENCODERS[0]], self.towers[ms.ENCODERS[1]]
+        self._tower_fwd(Tc, I["rgb_crops"])
+        ff, _ = self._tower_fwd(Tf, I["full_img"])
+        self._chk(L.mpb_crop_pool_fwd(Tf["h"], Tf["w"], 1024, _ptr(ff), N, _ptr(I["boxes_2d_norm"]), 24,
+                                      _ptr(self.concat[:, 1024:]), 2048, st), "crop_pool_fwd")
+        Mc = self.Mc
+        self.gemm(TC_FWD, Mc, 12, 12, 1, 1, 2048, 512, self.concat, 2048, self.pview("squash/1x1_conv/weights"), 2048,
+                  self.squashed, 512, shift=self.view("squash/1x1_conv/biases"), relu=1, round_tf32=1)
+        self._chk(L.mpb_maxpool2_fwd(N, 12, 12, 512, _ptr(self.squashed), 512, _ptr(self.pooled), 512, st), "pool")
+        self._chk(L.mpb_resize_ac_fwd(N, 12, 12, 512, _ptr(self.squashed), 24, 24, _ptr(self.r1), st), "resize1")
+        x = self.r1
+        for i, D in enumerate(self.dec):
+            if i == 2:
+                self._chk(L.mpb_resize_ac_fwd(N, 24, 24, 256, _ptr(x), 48, 48, _ptr(self.r2), st), "resize2")
+                x = self.r2
+            side = D["side"]
+            self.gemm(TC_FWD, D["M"], side, side, 3, 1, D["cin"], D["cout"], x, D["cin"], self.pview(D["scope"] + "/weights"),
+                      9 * D["cin"], D["z"], D["cout"], tapmask=self.tm24 if side == 24 else self.tm48)
+            b = D["scope"] + "/BatchNorm/"
+            mm = self.view(b + "moving_mean") if train else None
+            mv = self.view(b + "moving_variance") if train else None
+            self._chk(L.mpb_bn_train_fwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")), BN_EPS_DECODER,
+                                         _ptr(D["y"]), _ptr(D["mean"]), _ptr(D["var"]), _ptr(mm), _ptr(mv),
+                                         BN_DECAY_DECODER, _ptr(self.bn_scratch), st), "bn_train_fwd")
+            D["x"] = x
+            x = D["y"]
+        sx = "output/inst_xyz_map_local/inst_xyz_map_local"
+        self._chk(L.mpb_xyzhead_fwd(N, 48, 48, _ptr(x), _ptr(self.view(sx + "/weights")), _ptr(self.view(sx + "/biases")),
+                                    _ptr(self.xyz), st), "xyzhead_fwd")
+        # ---- FC stacks and heads
+        io = self.heads_io()
+        self._chk(L.mpb_heads_static(ctypes.byref(io), st), "heads_static")
+        P, R = self.fc["proposal"], self.fc["regression"]
+        p = "output/proposal_fc/proposal_fc"
+        self._fc_layer(self.pooled, 18432, 18432, p + "/img_fc", P["feat"], KPAD, P["acc"])
+        self._fc_layer(P["feat"], KPAD, KPAD, p + "/fc0", P["h0"], 1024, P["acc"])
+        self._fc_layer(P["h0"], 1024, 1024, p + "/fc1", P["h1"], 1024, P["acc"])
+        h = self.h
+        for nm, n, out in (("output/lwh/lwh", 3, h["lwh_offs"]), ("output/alpha", 24, h["alpha"])):
+            self._chk(L.mpb_fc_small_fwd(N, 1024, n, _ptr(P["h1"]), 1024, _ptr(self.view(nm + "/weights")),
+                                         _ptr(self.view(nm + "/biases")), _ptr(out), n, st), "fc_small_fwd")
+        self._chk(L.mpb_heads_mid(ctypes.byref(io), st), "heads_mid")
+        r = "output/regression_fc/regression_fc"
+        self._fc_layer(self.pooled, 18432, 18432, r + "/img_fc", R["feat"], KPAD, R["acc"])
+        self._fc_layer(R["feat"], KPAD, KPAD, r + "/fc0", R["h0"], 1024, R["acc"])
+        self._fc_layer(R["h0"], 1024, 1024, r + "/fc1", R["h1"], 1024, R["acc"])
+        for nm, out in (("output/cen_y/cen_y", h["cen_y_offs"]), ("output/cen_z_offs/cen_z", h["cen_z_offs"])):
+            self._chk(L.mpb_fc_small_fwd(N, 1024, 1, _ptr(R["h1"]), 1024, _ptr(self.view(nm + "/weights")),
+                                         _ptr(self.view(nm + "/biases")), _ptr(out), 1, st), "fc_small_fwd")
+        self._chk(L.mpb_heads_final(ctypes.byref(io), 1 if train else 0, st), "heads_final")
+
+    def outputs(self):
+        """output_dict (core/constants.py KEY_*) as device tensors."""
+        N, h = self.N, self.h
+        o = {
+            "inst_xyz_map_local": self.xyz.view(N, 48, 48, 3),
+            "valid_mask_maps": self.inputs.get("gt_valid_mask_maps"),
+            "lwh": h["lwh"], "lwh_offs": h["lwh_offs"], "alpha_bins": h["alpha"][:, :12], "alpha_regs": h["alpha"][:, 12:],
+            "view_ang": self.inputs["est_view_angs"].view(N, 1), "prop_cen_z": h["prop_cen_z"].view(N, 1),
+            "cen_x": h["cen_x"].view(N, 1), "cen_y": h["cen_y"].view(N, 1), "cen_y_offs": h["cen_y_offs"].view(N, 1),
+            "cen_z": h["cen_z"].view(N, 1), "cen_z_offs": h["cen_z_offs"].view(N, 1), "centroids": h["centroids"],
+            "proj_err_norm": h["proj_err_norm"], "inst_depth_map_global": h["depth_global"].view(N, 48, 48, 1),
+        }
+        return o
+
+    def losses(self):
+        names = ["inst_xyz_map_local", "lwh_offs", "alpha_bins", "alpha_regs", "cen_z_offs", "cen_y_offs", "proj_err",
+                 "inst_depth_map_global", "total_loss"]
+        v = self.h["losses"].detach().cpu().numpy()
+        return {n: float(x) for n, x in zip(names, v)}
+
+    # ------------------------------------------------------------------ backward
+    def _fc_bwd(self, y, ldy, dy, lddy, g, x, ldx, K, wname, dx, lddx, res=None, ldr=0, want_dx=True):
+        """backward of relu(x W^T + b): g = relu'(y)*dy; db = colsum(g); dW += g^T x; dx = g W (+res)."""
+        N = self.N
+        self._chk(self.L.mpb_relu_bwd_colsum(N, 1024, _ptr(y), ldy, _ptr(dy), lddy, _ptr(g), 1024,
+                                             _ptr(self.gview(wname + "/biases")), self._st()), "relu_bwd")
+        self.wgrad(N, 1, 1, 1, 1, K, 1024, x, ldx, g, 1024, self.gview(wname + "/weights"))
+        if want_dx:
+            self.gemm(TC_DGRAD, N, 1, 1, 1, 1, K, 1024, g, 1024, self.pview(wname + "/weights"), K, dx, lddx,
+                      res=res, ldr=ldr, bn=64 if K % 256 else 256)
+
+    def _tower_bwd(self, T, x_in):
+        """T['units'][-1]['g_out'] holds g = dL/d(out)*(out>0) of the last unit (and its d(beta3) is set)."""
+        L, st = self.L, self._st()
+        M, h, w = T["M"], T["h"], T["w"]
+        units = T["units"]
+        for ui in range(len(units) - 1, -1, -1):
+            U = units[ui]
+            s, cin, base, cout, rate = U["scope"], U["cin"], U["base"], U["cout"], U["rate"]
+            g = U["g_out"]
+            x, ldx = U["x"], U["ldx"]
+            f = self.bnfold
+            # conv3
+            self.wgrad(M, h, w, 1, 1, base, cout, U["y2"], base, g, cout, self.gview(s + "/conv3/weights"),
+                       rowscale=f[s + "/conv3"][0])
+            self.gemm(TC_DGRAD, M, h, w, 1, 1, base, cout, g, cout, self.pview(s + "/conv3/weights"), base, U["g2"], base,
+                      mask=U["y2"], ldm=base, colsum=self.gview(s + "/conv2/BatchNorm/beta"), round_tf32=1)
+            # conv2
+            tm = T["tapmask"][rate]
+            self.wgrad(M, h, w, 3, rate, base, base, U["y1"], base, U["g2"], base, self.gview(s + "/conv2/weights"),
+                       tapmask=tm, rowscale=f[s + "/conv2"][0])
+            self.gemm(TC_DGRAD, M, h, w, 3, rate, base, base, U["g2"], base, self.pview(s + "/conv2/weights"), 9 * base,
+                      U["g1"], base, tapmask=tm, mask=U["y1"], ldm=base, colsum=self.gview(s + "/conv1/BatchNorm/beta"),
+                      round_tf32=1)
+            # conv1 (+ shortcut)
+            self.wgrad(M, h, w, 1, 1, cin, base, x, ldx, U["g1"], base, self.gview(s + "/conv1/weights"),
+                       rowscale=f[s + "/conv1"][0])
+            if U["proj"]:
+                self.gview(s + "/shortcut/BatchNorm/beta").copy_(self.gview(s + "/conv3/BatchNorm/beta"))
+                self.wgrad(M, h, w, 1, 1, cin, cout, x, ldx, g, cout, self.gview(s + "/shortcut/weights"),
+                           rowscale=f[s + "/shortcut"][0])
+                self.gemm(TC_DGRAD, M, h, w, 1, 1, cin, cout, g, cout, self.pview(s + "/shortcut/weights"), cin, U["t"], cin)
+                res, ldr = U["t"], cin
+            else:
+                res, ldr = g, cout
+            if ui > 0:
+                prev = units[ui - 1]
+                dst, colsum = prev["g_out"], self.gview(prev["scope"] + "/conv3/BatchNorm/beta")
+            else:
+                dst, colsum = T["g_pool"], None
+            self.gemm(TC_DGRAD, M, h, w, 1, 1, cin, base, U["g1"], base, self.pview(s + "/conv1/weights"), cin, dst, cin,
+                      res=res, ldr=ldr, mask=x, ldm=ldx, colsum=colsum, round_tf32=1)
+        # stem
+        s0 = T["enc"] + "/resnet_v1_101/conv1"
+        self._chk(L.mpb_maxpool3s2_bwd(T["nimg"], T["H2"], T["W2"], 64, _ptr(T["stem"]), _ptr(T["g_pool"]),
+                                       _ptr(T["g_stem"]), st), "pool1_bwd")
+        Ms = T["nimg"] * T["H2"] * T["W2"]
+        self._chk(L.mpb_relu_bwd_colsum(Ms, 64, _ptr(T["stem"]), 64, _ptr(T["g_stem"]), 64, _ptr(T["g_stem"]), 64,
+                                        _ptr(self.gview(s0 + "/BatchNorm/beta")), st), "stem_colsum")
+        self._chk(L.mpb_stem_wgrad(T["nimg"], T["Hin"], T["Win"], _ptr(x_in), _ptr(T["g_stem"]), _ptr(self.bnfold[s0][0]),
+                                   _ptr(self.gview(s0 + "/weights")), st), "stem_wgrad")
+        # d(gamma) of every frozen BN from (w, dw, dbeta)
+        for scope, k, cin, cout, _ in ms.conv_layers(T["enc"]):
+            b = scope + "/BatchNorm/"
+            self._chk(L.mpb_bn_param_grad(cout, k * k * cin, _ptr(self.view(scope + "/weights")),
+                                          _ptr(self.gview(scope + "/weights")), _ptr(self.view(b + "gamma")),
+                                          _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
+                                          BN_EPS_RESNET, _ptr(self.gview(b + "beta")), _ptr(self.gview(b + "gamma")), st),
+                      "bn_param_grad")
+
+    def backward(self):
+        L, st, N, I, h = self.L, self._st(), self.N, self.inputs, self.h
+        self.grads.zero_()
+        io = self.heads_io()
+        P, R = self.fc["proposal"], self.fc["regression"]
+        # ---- regression stack
+        r = "output/regression_fc/regression_fc"
+        first = True
+        for nm, dy in (("output/cen_y/cen_y", h["d_cen_y_offs"]), ("output/cen_z_offs/cen_z", h["d_cen_z_offs"])):
+            self._chk(L.mpb_fc_small_bwd(N, 1024, 1, _ptr(R["h1"]), 1024, _ptr(self.view(nm + "/weights")), _ptr(dy), 1,
+                                         _ptr(R["d_h1"]), 1024, 0 if first else 1, _ptr(self.gview(nm + "/weights")),
+                                         _ptr(self.gview(nm + "/biases")), st), "fc_small_bwd")
+            first = False
+        self._fc_bwd(R["h1"], 1024, R["d_h1"], 1024, R["g_h1"], R["h0"], 1024, 1024, r + "/fc1", R["d_h0"], 1024)
+        self._fc_bwd(R["h0"], 1024, R["d_h0"], 1024, R["g_h0"], R["feat"], KPAD, KPAD, r + "/fc0", R["d_feat"], KPAD)
+        self._chk(L.mpb_heads_bwd_mid(ctypes.byref(io), st), "heads_bwd_mid")
+        self._fc_bwd(R["feat"], KPAD, R["d_feat"], KPAD, R["g_img"], self.pooled, 18432, 18432, r + "/img_fc",
+                     self.d_flat, 18432)
+        # ---- proposal stack
+        p = "output/proposal_fc/proposal_fc"
+        first = True
+        for nm, n, dy in (("output/lwh/lwh", 3, h["d_lwh_offs"]), ("output/alpha", 24, h["d_alpha"])):
+            self._chk(L.mpb_fc_small_bwd(N, 1024, n, _ptr(P["h1"]), 1024, _ptr(self.view(nm + "/weights")), _ptr(dy), n,
+                                         _ptr(P["d_h1"]), 1024, 0 if first else 1, _ptr(self.gview(nm + "/weights")),
+                                         _ptr(self.gview(nm + "/biases")), st), "fc_small_bwd")
+            first = False
+        self._fc_bwd(P["h1"], 1024, P["d_h1"], 1024, P["g_h1"], P["h0"], 1024, 1024, p + "/fc1", P["d_h0"], 1024)
+        self._fc_bwd(P["h0"], 1024, P["d_h0"], 1024, P["g_h0"], P["feat"], KPAD, KPAD, p + "/fc0", P["d_feat"], KPAD)
+        self._fc_bwd(P["feat"], KPAD, P["d_feat"], KPAD, P["g_img"], self.pooled, 18432, 18432, p + "/img_fc",
+                     self.d_flat, 18432, res=self.d_flat, ldr=18432)
+        # ---- map decoder
+        sx = "output/inst_xyz_map_local/inst_xyz_map_local"
+        D = self.dec[3]
+        self._chk(L.mpb_xyzhead_bwd(N, 48, 48, _ptr(D["y"]), _ptr(self.view(sx + "/weights")), _ptr(self.d_xyz),
+                                    _ptr(D["dy"]), _ptr(self.gview(sx + "/weights")), _ptr(self.gview(sx + "/biases")), st),
+                  "xyzhead_bwd")
+        for i in (3, 2, 1, 0):
+            D = self.dec[i]
+            side, b = D["side"], D["scope"] + "/BatchNorm/"
+            tm = self.tm24 if side == 24 else self.tm48
+            self._chk(L.mpb_bn_train_bwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(D["mean"]), _ptr(D["var"]), BN_EPS_DECODER,
+                                         _ptr(D["y"]), _ptr(D["dy"]), _ptr(D["dz"]), _ptr(self.gview(b + "beta")),
+                                         _ptr(self.bn_scratch), st), "bn_train_bwd")
+            self.wgrad(D["M"], side, side, 3, 1, D["cin"], D["cout"], D["x"], D["cin"], D["dz"], D["cout"],
+                       self.gview(D["scope"] + "/weights"), tapmask=tm)
+            if i in (3, 1):
+                dst = self.dec[i - 1]["dy"]
+            elif i == 2:
+                dst = self.d_r2
+            else:
+                dst = self.d_r1
+            self.gemm(TC_DGRAD, D["M"], side, side, 3, 1, D["cin"], D["cout"], D["dz"], D["cout"],
+                      self.pview(D["scope"] + "/weights"), 9 * D["cin"], dst, D["cin"], tapmask=tm)
+            if i == 2:
+                self._chk(L.mpb_resize_ac_bwd(N, 24, 24, 256, _ptr(self.d_r2), 48, 48, _ptr(self.dec[1]["dy"]), st), "resize2_bwd")
+        self._chk(L.mpb_resize_ac_bwd(N, 12, 12, 512, _ptr(self.d_r1), 24, 24, _ptr(self.d_squashed), st), "resize1_bwd")
+        self._chk(L.mpb_maxpool2_bwd(N, 12, 12, 512, _ptr(self.squashed), 512, _ptr(self.d_flat), 512, _ptr(self.d_squashed),
+                                     512, 1, st), "pool_bwd")
+        # ---- squash
+        Mc = self.Mc
+        self._chk(L.mpb_relu_bwd_colsum(Mc, 512, _ptr(self.squashed), 512, _ptr(self.d_squashed), 512, _ptr(self.g_squashed),
+                                        512, _ptr(self.gview("squash/1x1_conv/biases")), st), "squash_relu_bwd")
+        self.wgrad(Mc, 12, 12, 1, 1, 2048, 512, self.concat, 2048, self.g_squashed, 512, self.gview("squash/1x1_conv/weights"))
+        Tc, Tf = self.towers[ms.ENCODERS[0]], self.towers[ms.ENCODERS[1]]
+        lastc, lastf = Tc["units"][-1], Tf["units"][-1]
+        wsq = self.pview("squash/1x1_conv/weights")
+        self.gemm(TC_DGRAD, Mc, 12, 12, 1, 1, 1024, 512, self.g_squashed, 512, wsq, 2048, lastc["g_out"], 1024,
+                  mask=self.concat, ldm=2048, colsum=self.gview(lastc["scope"] + "/conv3/BatchNorm/beta"), round_tf32=1)
+        self.gemm(TC_DGRAD, Mc, 12, 12, 1, 1, 1024, 512, self.g_squashed, 512, wsq.view(-1)[1024:], 2048,
+                  self.g_fullcrop, 1024)
+        self._chk(L.mpb_crop_pool_bwd(Tf["h"], Tf["w"], 1024, _ptr(lastf["o"]), N, _ptr(I["boxes_2d_norm"]), 24,
+                                      _ptr(self.g_fullcrop), 1024, _ptr(self.d_fullfeat), st), "crop_pool_bwd")
+        self._chk(L.mpb_relu_bwd_colsum(Tf["M"], 1024, _ptr(lastf["o"]), 1024, _ptr(self.d_fullfeat), 1024,
+                                        _ptr(lastf["g_out"]), 1024, _ptr(self.gview(lastf["scope"] + "/conv3/BatchNorm/beta")),
+                                        st), "full_relu_bwd")
+        self._tower_bwd(Tc, I["rgb_crops"])
+        self._tower_bwd(Tf, I["full_img"])
+
+    # ------------------------------------------------------------------ train-op
+    def learning_rate(self, step):
+        return 0.00008 * (0.8 ** (step // 10000))        # exponential_decay, staircase (yaml:145-150)
+
+    def set_hyper(self, step):
+        t = step + 1
+        lr_t = self.learning_rate(step) * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        self.hyper_host = getattr(self, "hyper_host", torch.zeros(4, pin_memory=True))
+        self.hyper_host[0] = lr_t
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+
+    def optimizer_step(self, grad_scale=1.0):
+        self._chk(self.L.mpb_opt_step(self.n_chunks, _ptr(self.opt_chunks), len(self.trainable_names), _ptr(self.params),
+                                      _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.ema),
+                                      _ptr(self.norm2), _ptr(self.hyper), grad_scale, 1.0, 0.9, 0.999, 1e-8, 0.9999,
+                                      self._st()), "opt_step")
+        self._prepared = False
+
+    def allreduce_grads(self):
+        """the one collective of the path: sum the flat fp32 gradient arena over the NVLink domain"""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+            return dist.get_world_size()
+        return 1
+
+    def train_step_eager(self):
+        """forward + backward + (all-reduce) + train-op, launched kernel by kernel."""
+        self.forward(train=True)
+        self.backward()
+        world = self.allreduce_grads()
+        self.optimizer_step(1.0 / world)
+        self.prepare_weights()
+
+    def train_step(self, S=None):
+        """One training step on sample S (host arrays are copied in).  The kernel sequence is captured
+        into a CUDA graph on first use and replayed afterwards."""
+        if S is not None:
+            self.set_inputs(S)
+        self.set_hyper(self.step_count)
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if distributed:
+            # two graphs around the NCCL all-reduce (kept out of capture for portability)
+            if getattr(self, "_g_fb", None) is None:
+                self._capture_split()
+            self._g_fb.replay()
+            world = self.allreduce_grads()
+            self._g_opt.replay()
+        else:
+            if getattr(self, "_graph", None) is None:
+                self._capture()
+            self._graph.replay()
+        self.step_count += 1
+
+    def _warm(self):
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self.forward(train=True)
+            self.backward()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+
+    def _capture(self):
+        if not self._prepared:
+            self.prepare_weights()
+        self._warm()
+        g = torch.cuda.CUDAGraph()
+        c0 = _lib.launch_count()
+        with torch.cuda.graph(g):
+            self.forward(train=True)
+            self.backward()
+            self.optimizer_step(1.0)
+            self.prepare_weights()
+        self.launches_per_step = _lib.launch_count() - c0
+        self._graph = g
+
+    def _capture_split(self):
+        import torch.distributed as dist
+        if not self._prepared:
+            self.prepare_weights()
+        self._warm()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        c0 = _lib.launch_count()
+        with torch.cuda.graph(g1):
+            self.forward(train=True)
+            self.backward()
+        with torch.cuda.graph(g2):
+            self.optimizer_step(1.0 / dist.get_world_size())
+            self.prepare_weights()
+        self.launches_per_step = _lib.launch_count() - c0
+        self._g_fb, self._g_opt = g1, g2

@@ -1,0 +1,826 @@
+// monopsr_b200/csrc/net_kernels.cu -- the bandwidth-bound layers around the tcgen05 GEMM core.
+//
+// NHWC fp32 everywhere.  Each kernel cites the reference graph op it replaces (the reference
+// obtains all of these from TensorFlow 1.8 / TF-slim; semantics restated from TF defaults).
+#include "common.cuh"
+#include "../../include/monopsr_b200_net.h"
+#include <math.h>
+
+namespace mpb {
+
+__device__ __forceinline__ float rtf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------- weight preparation
+// Frozen (inference-mode) BN folded into the conv weights (feature_extractor.py:228-242:
+// is_training=False, eps 1e-5, scale=True):  wf = tf32(w * s), s = gamma*rsqrt(var+eps),
+// shift = beta - mean*s.  The GEMM then needs only "+ shift" in its epilogue, and the
+// data-gradient pass can use wf directly.
+__global__ void fold_bn_kernel(int cout, int K, const float* __restrict__ w, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, float eps, float* __restrict__ wf,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+    const int co = blockIdx.x;
+    const float s = gamma[co] * rsqrtf(var[co] + eps);
+    if (threadIdx.x == 0) {
+        scale[co] = s;
+        shift[co] = beta[co] - mean[co] * s;
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) wf[(size_t)co * K + k] = rtf32(w[(size_t)co * K + k] * s);
+}
+
+__global__ void round_copy_kernel(size_t n, const float* __restrict__ src, float* __restrict__ dst) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = rtf32(src[i]);
+}
+
+// d(gamma), d(beta) of a frozen BN from the conv's weight gradient:
+//   dbeta[c] = colsum(g)[c];  dgamma[c] = rowdot(w, dw)[c]/gamma[c] - mean[c]*dbeta[c]*rsqrt(var+eps)
+__global__ void bn_param_grad_kernel(int cout, int K, const float* __restrict__ w, const float* __restrict__ dw,
+                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                     const float* __restrict__ var, float eps, const float* __restrict__ dbeta,
+                                     float* __restrict__ dgamma) {
+    const int co = blockIdx.x;
+    float acc = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) acc += w[(size_t)co * K + k] * dw[(size_t)co * K + k];
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) s += red[i];
+        dgamma[co] = s / gamma[co] - mean[co] * dbeta[co] * rsqrtf(var[co] + eps);
+    }
+}
+
+// ---------------------------------------------------------------- stem: conv 7x7/2 + BN + ReLU
+// resnet_utils.conv2d_same(net, 64, 7, stride=2) (nets/resnet_v1.py:234): pad 3|3, VALID.
+// Cin=3 -> K=147: bandwidth-bound, kept off the tensor cores.  One thread = one output pixel x
+// 16 channels; folded weights in shared memory.
+constexpr int kStemK = 147;
+__global__ void __launch_bounds__(256)
+stem_fwd_kernel(int nimg, int Hin, int Win, int Ho, int Wo, const float* __restrict__ x,
+                const float* __restrict__ wf, const float* __restrict__ shift, float* __restrict__ y) {
+    __shared__ float sw[64 * kStemK];
+    for (int i = threadIdx.x; i < 64 * kStemK; i += blockDim.x) sw[i] = wf[i];
+    __syncthreads();
+    const int cg = threadIdx.x & 3;                       // 4 groups of 16 output channels
+    const long pix = (long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
+    const long total = (long)nimg * Ho * Wo;
+    if (pix >= total) return;
+    const int n = (int)(pix / (Ho * Wo)), rem = (int)(pix % (Ho * Wo)), oh = rem / Wo, ow = rem % Wo;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) acc[c] = 0.f;
+    for (int kh = 0; kh < 7; kh++) {
+        const int ih = oh * 2 - 3 + kh;
+        if (ih < 0 || ih >= Hin) continue;
+        for (int kw = 0; kw < 7; kw++) {
+            const int iw = ow * 2 - 3 + kw;
+            if (iw < 0 || iw >= Win) continue;
+            const float* xp = x + (((size_t)n * Hin + ih) * Win + iw) * 3;
+            const float x0 = xp[0], x1 = xp[1], x2 = xp[2];
+            const float* wp = sw + (cg * 16) * kStemK + (kh * 7 + kw) * 3;
+#pragma unroll
+            for (int c = 0; c < 16; c++)
+                acc[c] = fmaf(x2, wp[c * kStemK + 2], fmaf(x1, wp[c * kStemK + 1], fmaf(x0, wp[c * kStemK], acc[c])));
+        }
+    }
+    float* yp = y + (size_t)pix * 64 + cg * 16;
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+        float4 o;
+        o.x = rtf32(fmaxf(acc[c] + shift[cg * 16 + c], 0.f));
+        o.y = rtf32(fmaxf(acc[c + 1] + shift[cg * 16 + c + 1], 0.f));
+        o.z = rtf32(fmaxf(acc[c + 2] + shift[cg * 16 + c + 2], 0.f));
+        o.w = rtf32(fmaxf(acc[c + 3] + shift[cg * 16 + c + 3], 0.f));
+        *reinterpret_cast<float4*>(yp + c) = o;
+    }
+}
+
+// dW[co][kh][kw][ci] += scale[co] * sum_pix g[pix][co] * x[pix*2-3+k][ci].  A CTA owns a strip of
+// output pixels, accumulates the 64x147 products in registers (thread = (co, 9..10 k's)), one
+// RED per weight per CTA.
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(int nimg, int Hin, int Win, int Ho, int Wo, const float* __restrict__ x,
+                  const float* __restrict__ g, const float* __restrict__ scale, float* __restrict__ dw,
+                  int pix_per_cta) {
+    __shared__ float sg[64];
+    __shared__ float sx[kStemK];
+    const long total = (long)nimg * Ho * Wo;
+    const long p0 = (long)blockIdx.x * pix_per_cta;
+    const int co = threadIdx.x & 63, part = threadIdx.x >> 6;   // 4 parts over the 147 taps
+    float acc[37];
+#pragma unroll
+    for (int i = 0; i < 37; i++) acc[i] = 0.f;
+    for (long pix = p0; pix < min(total, p0 + pix_per_cta); pix++) {
+        const int n = (int)(pix / (Ho * Wo)), rem = (int)(pix % (Ho * Wo)), oh = rem / Wo, ow = rem % Wo;
+        __syncthreads();
+        if (threadIdx.x < 64) sg[threadIdx.x] = g[(size_t)pix * 64 + threadIdx.x];
+        if (threadIdx.x < kStemK) {
+            const int t = threadIdx.x / 3, ci = threadIdx.x % 3;
+            const int ih = oh * 2 - 3 + t / 7, iw = ow * 2 - 3 + t % 7;
+            sx[threadIdx.x] = (ih >= 0 && ih < Hin && iw >= 0 && iw < Win)
+                                  ? x[(((size_t)n * Hin + ih) * Win + iw) * 3 + ci] : 0.f;
+        }
+        __syncthreads();
+        const float gv = sg[co];
+        if (gv != 0.f) {
+#pragma unroll
+            for (int i = 0; i < 37; i++) {
+                const int k = part * 37 + i;
+                if (k < kStemK) acc[i] = fmaf(gv, sx[k], acc[i]);
+            }
+        }
+    }
+    const float s = scale[co];
+#pragma unroll
+    for (int i = 0; i < 37; i++) {
+        const int k = part * 37 + i;
+        if (k < kStemK && acc[i] != 0.f) atomicAdd(&dw[(size_t)co * kStemK + k], acc[i] * s);
+    }
+}
+
+// ---------------------------------------------------------------- max pools
+// slim.max_pool2d([3,3], stride=2, padding='SAME') (nets/resnet_v1.py:235): even H,W -> window
+// rows 2o..2o+2 clipped at the bottom/right edge.
+__global__ void maxpool3s2_fwd_kernel(int nimg, int H, int W, int C4, int Ho, int Wo,
+                                      const float4* __restrict__ x, float4* __restrict__ y) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)nimg * Ho * Wo * C4;
+    if (i >= total) return;
+    const int c = (int)(i % C4);
+    long p = i / C4;
+    const int ow = (int)(p % Wo); p /= Wo;
+    const int oh = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dh = 0; dh < 3; dh++) {
+        const int ih = oh * 2 + dh;
+        if (ih >= H) break;
+        for (int dw = 0; dw < 3; dw++) {
+            const int iw = ow * 2 + dw;
+            if (iw >= W) break;
+            const float4 v = x[(((size_t)n * H + ih) * W + iw) * C4 + c];
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    y[i] = m;
+}
+
+// gather form (deterministic): dx[in] = (x[in]>0) * sum over the <=4 windows containing `in` whose
+// FIRST maximum is `in`.  The (x>0) factor is the ReLU of the stem that produced x.
+__global__ void maxpool3s2_bwd_kernel(int nimg, int H, int W, int C, int Ho, int Wo,
+                                      const float* __restrict__ x, const float* __restrict__ dy,
+                                      float* __restrict__ dx) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)nimg * H * W * C;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long p = i / C;
+    const int iw = (int)(p % W); p /= W;
+    const int ih = (int)(p % H);
+    const int n = (int)(p / H);
+    const float xv = x[i];
+    float acc = 0.f;
+    if (xv > 0.f) {
+        for (int oh = max(0, (ih - 1) / 2); oh <= min(Ho - 1, ih / 2); oh++) {
+            if (ih < oh * 2 || ih > oh * 2 + 2) continue;
+            for (int ow = max(0, (iw - 1) / 2); ow <= min(Wo - 1, iw / 2); ow++) {
+                if (iw < ow * 2 || iw > ow * 2 + 2) continue;
+                // is (ih,iw) the first max of window (oh,ow)?
+                bool first = true;
+                for (int dh = 0; dh < 3 && first; dh++) {
+                    const int jh = oh * 2 + dh;
+                    if (jh >= H) break;
+                    for (int dw = 0; dw < 3; dw++) {
+                        const int jw = ow * 2 + dw;
+                        if (jw >= W) break;
+                        const float v = x[(((size_t)n * H + jh) * W + jw) * C + c];
+                        const bool before = (jh < ih) || (jh == ih && jw < iw);
+                        if (v > xv || (before && v == xv)) { first = false; break; }
+                    }
+                }
+                if (first) acc += dy[(((size_t)n * Ho + oh) * Wo + ow) * C + c];
+            }
+        }
+    }
+    dx[i] = acc;
+}
+
+// slim.max_pool2d([2,2]) (builders/net_builder.py:60,68): VALID, stride 2
+__global__ void maxpool2_fwd_kernel(int nimg, int H, int W, int C4, const float* __restrict__ x, int ldx,
+                                    float* __restrict__ y, int ldy) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)nimg * Ho * Wo * C4;
+    if (i >= total) return;
+    const int c = (int)(i % C4) * 4;
+    long p = i / C4;
+    const int ow = (int)(p % Wo); p /= Wo;
+    const int oh = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    const float* b = x + (((size_t)n * H + oh * 2) * W + ow * 2) * ldx + c;
+    const float4 a0 = *reinterpret_cast<const float4*>(b), a1 = *reinterpret_cast<const float4*>(b + ldx);
+    const float4 a2 = *reinterpret_cast<const float4*>(b + (size_t)W * ldx),
+                 a3 = *reinterpret_cast<const float4*>(b + (size_t)W * ldx + ldx);
+    float4 m;
+    m.x = fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x));
+    m.y = fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y));
+    m.z = fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z));
+    m.w = fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w));
+    *reinterpret_cast<float4*>(y + (((size_t)n * Ho + oh) * Wo + ow) * ldy + c) = m;
+}
+
+// dx (same geometry as x) = or += dy routed to the first maximum of each 2x2 window
+__global__ void maxpool2_bwd_kernel(int nimg, int H, int W, int C, const float* __restrict__ x, int ldx,
+                                    const float* __restrict__ dy, int ldy, float* __restrict__ dx, int lddx,
+                                    int accumulate) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)nimg * Ho * Wo * C;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long p = i / C;
+    const int ow = (int)(p % Wo); p /= Wo;
+    const int oh = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    const size_t b = (((size_t)n * H + oh * 2) * W + ow * 2);
+    float v[4] = {x[b * ldx + c], x[(b + 1) * ldx + c], x[(b + W) * ldx + c], x[(b + W + 1) * ldx + c]};
+    int best = 0;
+    for (int k = 1; k < 4; k++)
+        if (v[k] > v[best]) best = k;
+    const float g = dy[(((size_t)n * Ho + oh) * Wo + ow) * ldy + c];
+    const size_t off[4] = {b, b + 1, b + W, b + W + 1};
+    for (int k = 0; k < 4; k++) {
+        const float t = (k == best) ? g : 0.f;
+        float* d = dx + off[k] * lddx + c;
+        *d = accumulate ? (*d + t) : t;
+    }
+}
+
+// ---------------------------------------------------------------- crop_and_resize + 2x2 max pool
+// tf.image.crop_and_resize(full_img_encoder_out, boxes_2d_norm, box_ind=0, (24,24)) followed by
+// slim.max_pool2d([2,2]) (builders/net_builder.py:54-60), fused: the (nbox,24,24,C) intermediate
+// never exists.  Sample coordinate: in_y = y1 (H-1) + i (y2-y1)(H-1)/(crop-1); outside [0,H-1]
+// -> 0 (extrapolation_value); bilinear between floor and ceil.
+struct CropCoord { int y0, y1i, x0, x1i; float ly, lx; bool valid; };
+__device__ __forceinline__ CropCoord crop_coord(const float* box, int i, int j, int crop, int H, int W) {
+    CropCoord c;
+    const float y1 = box[0], x1 = box[1], y2 = box[2], x2 = box[3];
+    const float in_y = y1 * (H - 1) + i * ((y2 - y1) * (H - 1) / (crop - 1));
+    const float in_x = x1 * (W - 1) + j * ((x2 - x1) * (W - 1) / (crop - 1));
+    c.valid = in_y >= 0.f && in_y <= (float)(H - 1) && in_x >= 0.f && in_x <= (float)(W - 1);
+    const float fy = floorf(in_y), fx = floorf(in_x);
+    c.y0 = min(max((int)fy, 0), H - 1);
+    c.y1i = min(max((int)ceilf(in_y), 0), H - 1);
+    c.x0 = min(max((int)fx, 0), W - 1);
+    c.x1i = min(max((int)ceilf(in_x), 0), W - 1);
+    c.ly = in_y - fy;
+    c.lx = in_x - fx;
+    return c;
+}
+__device__ __forceinline__ float crop_sample(const float* feat, int W, int C, int ch, const CropCoord& c) {
+    if (!c.valid) return 0.f;
+    const float tl = feat[((size_t)c.y0 * W + c.x0) * C + ch], tr = feat[((size_t)c.y0 * W + c.x1i) * C + ch];
+    const float bl = feat[((size_t)c.y1i * W + c.x0) * C + ch], br = feat[((size_t)c.y1i * W + c.x1i) * C + ch];
+    const float top = tl + (tr - tl) * c.lx, bot = bl + (br - bl) * c.lx;
+    return top + (bot - top) * c.ly;
+}
+
+__global__ void crop_pool_fwd_kernel(int H, int W, int C, const float* __restrict__ feat, int nbox,
+                                     const float* __restrict__ boxes, int crop, float* __restrict__ out, int ldo) {
+    const int P = crop / 2;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)nbox * P * P * C;
+    if (i >= total) return;
+    const int ch = (int)(i % C);
+    long p = i / C;
+    const int pw = (int)(p % P); p /= P;
+    const int ph = (int)(p % P);
+    const int b = (int)(p / P);
+    float m = -INFINITY;
+    for (int k = 0; k < 4; k++) {
+        CropCoord c = crop_coord(boxes + b * 4, ph * 2 + (k >> 1), pw * 2 + (k & 1), crop, H, W);
+        m = fmaxf(m, crop_sample(feat, W, C, ch, c));
+    }
+    out[(((size_t)b * P + ph) * P + pw) * ldo + ch] = rtf32(m);
+}
+
+__global__ void crop_pool_bwd_kernel(int H, int W, int C, const float* __restrict__ feat, int nbox,
+                                     const float* __restrict__ boxes, int crop, const float* __restrict__ dout,
+                                     int ldd, float* __restrict__ dfeat) {
+    const int P = crop / 2;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)nbox * P * P * C;
+    if (i >= total) return;
+    const int ch = (int)(i % C);
+    long p = i / C;
+    const int pw = (int)(p % P); p /= P;
+    const int ph = (int)(p % P);
+    const int b = (int)(p / P);
+    const float g = dout[(((size_t)b * P + ph) * P + pw) * ldd + ch];
+    if (g == 0.f) return;
+    float m = -INFINITY;
+    int best = 0;
+    CropCoord bc;
+    for (int k = 0; k < 4; k++) {
+        CropCoord c = crop_coord(boxes + b * 4, ph * 2 + (k >> 1), pw * 2 + (k & 1), crop, H, W);
+        const float v = crop_sample(feat, W, C, ch, c);
+        if (v > m) { m = v; best = k; bc = c; }
+    }
+    (void)best;
+    if (!bc.valid) return;
+    atomicAdd(&dfeat[((size_t)bc.y0 * W + bc.x0) * C + ch], g * (1.f - bc.ly) * (1.f - bc.lx));
+    atomicAdd(&dfeat[((size_t)bc.y0 * W + bc.x1i) * C + ch], g * (1.f - bc.ly) * bc.lx);
+    atomicAdd(&dfeat[((size_t)bc.y1i * W + bc.x0) * C + ch], g * bc.ly * (1.f - bc.lx));
+    atomicAdd(&dfeat[((size_t)bc.y1i * W + bc.x1i) * C + ch], g * bc.ly * bc.lx);
+}
+
+// ---------------------------------------------------------------- bilinear resize, align_corners=True
+// tf.image.resize_images(x, (OH,OW), align_corners=True) (builders/net_builder.py:73-75,82-84)
+__global__ void resize_ac_fwd_kernel(int nimg, int H, int W, int C4, int OH, int OW,
+                                     const float4* __restrict__ x, float4* __restrict__ y) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)nimg * OH * OW * C4;
+    if (i >= total) return;
+    const int c = (int)(i % C4);
+    long p = i / C4;
+    const int ow = (int)(p % OW); p /= OW;
+    const int oh = (int)(p % OH);
+    const int n = (int)(p / OH);
+    const float sy = oh * ((float)(H - 1) / (float)(OH - 1)), sx = ow * ((float)(W - 1) / (float)(OW - 1));
+    const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    const float4 tl = x[(((size_t)n * H + y0) * W + x0) * C4 + c], tr = x[(((size_t)n * H + y0) * W + x1) * C4 + c];
+    const float4 bl = x[(((size_t)n * H + y1) * W + x0) * C4 + c], br = x[(((size_t)n * H + y1) * W + x1) * C4 + c];
+    float4 o;
+#define MPB_LERP(f) { float t = tl.f + (tr.f - tl.f) * lx, b = bl.f + (br.f - bl.f) * lx; o.f = rtf32(t + (b - t) * ly); }
+    MPB_LERP(x) MPB_LERP(y) MPB_LERP(z) MPB_LERP(w)
+#undef MPB_LERP
+    y[i] = o;
+}
+
+__global__ void resize_ac_bwd_kernel(int nimg, int H, int W, int C, int OH, int OW, const float* __restrict__ dy,
+                                     float* __restrict__ dx) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)nimg * OH * OW * C;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long p = i / C;
+    const int ow = (int)(p % OW); p /= OW;
+    const int oh = (int)(p % OH);
+    const int n = (int)(p / OH);
+    const float g = dy[i];
+    if (g == 0.f) return;
+    const float sy = oh * ((float)(H - 1) / (float)(OH - 1)), sx = ow * ((float)(W - 1) / (float)(OW - 1));
+    const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    atomicAdd(&dx[(((size_t)n * H + y0) * W + x0) * C + c], g * (1.f - ly) * (1.f - lx));
+    atomicAdd(&dx[(((size_t)n * H + y0) * W + x1) * C + c], g * (1.f - ly) * lx);
+    atomicAdd(&dx[(((size_t)n * H + y1) * W + x0) * C + c], g * ly * (1.f - lx));
+    atomicAdd(&dx[(((size_t)n * H + y1) * W + x1) * C + c], g * ly * lx);
+}
+
+// ---------------------------------------------------------------- train-mode batch norm (+beta, ReLU)
+// slim.batch_norm(is_training=True) defaults (center, no scale, eps 1e-3, decay 0.999) on the
+// decoder convs (builders/net_builder.py:77-89): statistics over all M = nimg*H*W rows.
+// stats: CTA = 32 channels x 8 row-groups, fp32 partials, final combine in double.
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(int M, int C, const float* __restrict__ z, double* __restrict__ psum, double* __restrict__ psq) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rg = threadIdx.x >> 5;
+    const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+    float s = 0.f, q = 0.f;
+    if (c < C)
+        for (int r = r0 + rg; r < r1; r += 8) {
+            const float v = z[(size_t)r * C + c];
+            s += v;
+            q = fmaf(v, v, q);
+        }
+    __shared__ float ss[8][32], sq[8][32];
+    ss[rg][threadIdx.x & 31] = s;
+    sq[rg][threadIdx.x & 31] = q;
+    __syncthreads();
+    if (rg == 0 && c < C) {
+        double a = 0, b = 0;
+        for (int k = 0; k < 8; k++) { a += ss[k][threadIdx.x]; b += sq[k][threadIdx.x]; }
+        atomicAdd(&psum[c], a);
+        atomicAdd(&psq[c], b);
+    }
+}
+__global__ void bn_finalize_kernel(int M, int C, const double* __restrict__ psum, const double* __restrict__ psq,
+                                   float* __restrict__ mean, float* __restrict__ var,
+                                   float* __restrict__ mmean, float* __restrict__ mvar, float decay) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = psum[c] / M;
+    const double v = fmax(psq[c] / M - m * m, 0.0);
+    mean[c] = (float)m;
+    var[c] = (float)v;
+    if (mmean) {   // UPDATE_OPS: moving = moving*decay + batch*(1-decay)  (batch var as TF: biased)
+        mmean[c] = mmean[c] * decay + (float)m * (1.f - decay);
+        mvar[c] = mvar[c] * decay + (float)v * (1.f - decay);
+    }
+}
+__global__ void bn_apply_kernel(long total4, int C4, const float4* __restrict__ z, const float* __restrict__ mean,
+                                const float* __restrict__ var, const float* __restrict__ beta, float eps,
+                                float4* __restrict__ y) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int c = (int)(i % C4) * 4;
+    const float4 v = z[i];
+    float4 o;
+    o.x = rtf32(fmaxf((v.x - mean[c]) * rsqrtf(var[c] + eps) + beta[c], 0.f));
+    o.y = rtf32(fmaxf((v.y - mean[c + 1]) * rsqrtf(var[c + 1] + eps) + beta[c + 1], 0.f));
+    o.z = rtf32(fmaxf((v.z - mean[c + 2]) * rsqrtf(var[c + 2] + eps) + beta[c + 2], 0.f));
+    o.w = rtf32(fmaxf((v.w - mean[c + 3]) * rsqrtf(var[c + 3] + eps) + beta[c + 3], 0.f));
+    y[i] = o;
+}
+// backward: g = dy*(y>0); s1 = sum g; s2 = sum g*xhat; dz = rstd*(g - s1/M - xhat*s2/M); dbeta = s1
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(int M, int C, const float* __restrict__ z, const float* __restrict__ y,
+                     const float* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ var,
+                     float eps, double* __restrict__ s1, double* __restrict__ s2) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rg = threadIdx.x >> 5;
+    const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+    float a = 0.f, b = 0.f;
+    if (c < C) {
+        const float mu = mean[c], rs = rsqrtf(var[c] + eps);
+        for (int r = r0 + rg; r < r1; r += 8) {
+            const size_t o = (size_t)r * C + c;
+            const float g = y[o] > 0.f ? dy[o] : 0.f;
+            a += g;
+            b = fmaf(g, (z[o] - mu) * rs, b);
+        }
+    }
+    __shared__ float sa[8][32], sb[8][32];
+    sa[rg][threadIdx.x & 31] = a;
+    sb[rg][threadIdx.x & 31] = b;
+    __syncthreads();
+    if (rg == 0 && c < C) {
+        double p = 0, q = 0;
+        for (int k = 0; k < 8; k++) { p += sa[k][threadIdx.x]; q += sb[k][threadIdx.x]; }
+        atomicAdd(&s1[c], p);
+        atomicAdd(&s2[c], q);
+    }
+}
+__global__ void bn_bwd_apply_kernel(long total, int M, int C, const float* __restrict__ z, const float* __restrict__ y,
+                                    const float* __restrict__ dy, const float* __restrict__ mean,
+                                    const float* __restrict__ var, float eps, const double* __restrict__ s1,
+                                    const double* __restrict__ s2, float* __restrict__ dz, float* __restrict__ dbeta) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const float rs = rsqrtf(var[c] + eps);
+    const float xh = (z[i] - mean[c]) * rs;
+    const float g = y[i] > 0.f ? dy[i] : 0.f;
+    const float m1 = (float)(s1[c] / M), m2 = (float)(s2[c] / M);
+    dz[i] = rtf32(rs * (g - m1 - xh * m2));
+    if (i < C) dbeta[i] = (float)s1[i];
+}
+
+// ---------------------------------------------------------------- xyz head: conv3x3 128 -> 3 (+bias)
+// add_inst_xyz_maps_local (monopsr_output_builder.py:95-108).  N=3 output channels: bandwidth
+// bound on the (32,48,48,128) map features; one warp per output pixel, lanes over the 128
+// channels (float4 each), weights [3][9][128] in shared memory.
+__global__ void __launch_bounds__(256)
+xyzhead_fwd_kernel(int nimg, int H, int W, const float* __restrict__ x, const float* __restrict__ w,
+                   const float* __restrict__ bias, float* __restrict__ y) {
+    __shared__ float4 sw[3 * 9 * 32];
+    for (int i = threadIdx.x; i < 3 * 9 * 32; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= (long)nimg * H * W) return;
+    const int n = (int)(pix / (H * W)), rem = (int)(pix % (H * W)), h = rem / W, ww = rem % W;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int t = 0; t < 9; t++) {
+        const int ih = h + t / 3 - 1, iw = ww + t % 3 - 1;
+        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+        const float4 v = reinterpret_cast<const float4*>(x + (((size_t)n * H + ih) * W + iw) * 128)[lane];
+        const float4 w0 = sw[(0 * 9 + t) * 32 + lane], w1 = sw[(1 * 9 + t) * 32 + lane], w2 = sw[(2 * 9 + t) * 32 + lane];
+        a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
+        a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
+        a2 += v.x * w2.x + v.y * w2.y + v.z * w2.z + v.w * w2.w;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        y[pix * 3 + 0] = a0 + bias[0];
+        y[pix * 3 + 1] = a1 + bias[1];
+        y[pix * 3 + 2] = a2 + bias[2];
+    }
+}
+// dX[p][ci] = sum_{t,co} dY[p - off(t)][co] * w[co][t][ci]   (thread = (pixel, 4 channels))
+__global__ void __launch_bounds__(256)
+xyzhead_dgrad_kernel(int nimg, int H, int W, const float* __restrict__ dy, const float* __restrict__ w,
+                     float* __restrict__ dx) {
+    __shared__ float4 sw[3 * 9 * 32];
+    for (int i = threadIdx.x; i < 3 * 9 * 32; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= (long)nimg * H * W) return;
+    const int n = (int)(pix / (H * W)), rem = (int)(pix % (H * W)), h = rem / W, ww = rem % W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < 9; t++) {
+        const int ih = h - (t / 3 - 1), iw = ww - (t % 3 - 1);
+        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+        const float* g = dy + (((size_t)n * H + ih) * W + iw) * 3;
+        const float g0 = g[0], g1 = g[1], g2 = g[2];
+        const float4 w0 = sw[(0 * 9 + t) * 32 + lane], w1 = sw[(1 * 9 + t) * 32 + lane], w2 = sw[(2 * 9 + t) * 32 + lane];
+        acc.x += g0 * w0.x + g1 * w1.x + g2 * w2.x;
+        acc.y += g0 * w0.y + g1 * w1.y + g2 * w2.y;
+        acc.z += g0 * w0.z + g1 * w1.z + g2 * w2.z;
+        acc.w += g0 * w0.w + g1 * w1.w + g2 * w2.w;
+    }
+    reinterpret_cast<float4*>(dx + (size_t)pix * 128)[lane] = acc;
+}
+// dW[co][t][ci] += sum_p dY[p][co] * x[p + off(t)][ci];  db[co] += sum_p dY[p][co]
+// CTA = 128 threads (ci) x a strip of pixels; 27 accumulators per thread.
+__global__ void __launch_bounds__(128)
+xyzhead_wgrad_kernel(int nimg, int H, int W, const float* __restrict__ x, const float* __restrict__ dy,
+                     float* __restrict__ dw, float* __restrict__ db, int pix_per_cta) {
+    const int ci = threadIdx.x;
+    const long total = (long)nimg * H * W;
+    const long p0 = (long)blockIdx.x * pix_per_cta, p1 = min(total, p0 + pix_per_cta);
+    float acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; i++) acc[i] = 0.f;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    for (long pix = p0; pix < p1; pix++) {
+        const int n = (int)(pix / (H * W)), rem = (int)(pix % (H * W)), h = rem / W, ww = rem % W;
+        const float g0 = dy[pix * 3], g1 = dy[pix * 3 + 1], g2 = dy[pix * 3 + 2];
+        b0 += g0; b1 += g1; b2 += g2;
+        if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const int ih = h + t / 3 - 1, iw = ww + t % 3 - 1;
+            if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+            const float v = x[(((size_t)n * H + ih) * W + iw) * 128 + ci];
+            acc[t] = fmaf(g0, v, acc[t]);
+            acc[9 + t] = fmaf(g1, v, acc[9 + t]);
+            acc[18 + t] = fmaf(g2, v, acc[18 + t]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 27; i++) atomicAdd(&dw[(size_t)i * 128 + ci], acc[i]);
+    if (ci == 0) { atomicAdd(&db[0], b0); atomicAdd(&db[1], b1); atomicAdd(&db[2], b2); }
+}
+
+// ---------------------------------------------------------------- small dense heads (N <= 32 outputs)
+// slim.fully_connected(features, n, activation_fn=None) for lwh / alpha / cen_y / cen_z
+// (monopsr_output_builder.py:283,469,580,633).  w is [n][K].
+__global__ void fc_small_fwd_kernel(int B, int K, int N, const float* __restrict__ x, int ldx,
+                                    const float* __restrict__ w, const float* __restrict__ bias,
+                                    float* __restrict__ y, int ldy) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B * N) return;
+    const int b = warp / N, n = warp % N;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(x[(size_t)b * ldx + k], w[(size_t)n * K + k], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[(size_t)b * ldy + n] = acc + bias[n];
+}
+// dx[b][k] (+)= sum_n dy[b][n] w[n][k];  dw[n][k] += sum_b dy[b][n] x[b][k];  db[n] += sum_b dy[b][n]
+__global__ void fc_small_bwd_kernel(int B, int K, int N, const float* __restrict__ x, int ldx,
+                                    const float* __restrict__ w, const float* __restrict__ dy, int ldy,
+                                    float* __restrict__ dx, int lddx, int accumulate_dx,
+                                    float* __restrict__ dw, float* __restrict__ db) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) {
+        for (int b = 0; b < B; b++) {
+            float acc = 0.f;
+            for (int n = 0; n < N; n++) acc = fmaf(dy[(size_t)b * ldy + n], w[(size_t)n * K + k], acc);
+            float* d = dx + (size_t)b * lddx + k;
+            *d = accumulate_dx ? (*d + acc) : acc;
+        }
+        for (int n = 0; n < N; n++) {
+            float acc = 0.f;
+            for (int b = 0; b < B; b++) acc = fmaf(dy[(size_t)b * ldy + n], x[(size_t)b * ldx + k], acc);
+            dw[(size_t)n * K + k] += acc;
+        }
+    }
+    if (k < N) {
+        float acc = 0.f;
+        for (int b = 0; b < B; b++) acc += dy[(size_t)b * ldy + k];
+        db[k] += acc;
+    }
+}
+
+// ---------------------------------------------------------------- elementwise helpers
+// y = relu(x + bias[c]) (optionally tf32-rounded): finishes split-K FC layers
+__global__ void bias_relu_kernel(long total, int C, const float* __restrict__ x, int ldx, const float* __restrict__ bias,
+                                 int relu, int round, float* __restrict__ y, int ldy) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const long r = i / C;
+    float v = x[r * ldx + c] + (bias ? bias[c] : 0.f);
+    if (relu) v = fmaxf(v, 0.f);
+    y[r * ldy + c] = round ? rtf32(v) : v;
+}
+// g = (y>0 ? dy : 0) (tf32-rounded), colsum[c] += sum_r g   (ReLU + bias backward)
+__global__ void __launch_bounds__(256)
+relu_bwd_colsum_kernel(int M, int C, const float* __restrict__ y, int ldy, const float* __restrict__ dy, int lddy,
+                       float* __restrict__ g, int ldg, float* __restrict__ colsum) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rg = threadIdx.x >> 5;
+    const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+    float s = 0.f;
+    if (c < C)
+        for (int r = r0 + rg; r < r1; r += 8) {
+            const float v = y[(size_t)r * ldy + c] > 0.f ? dy[(size_t)r * lddy + c] : 0.f;
+            const float rv = rtf32(v);
+            g[(size_t)r * ldg + c] = rv;
+            s += rv;
+        }
+    __shared__ float ss[8][32];
+    ss[rg][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (rg == 0 && c < C && colsum) {
+        float a = 0.f;
+        for (int k = 0; k < 8; k++) a += ss[k][threadIdx.x];
+        atomicAdd(&colsum[c], a);
+    }
+}
+__global__ void add_inplace_kernel(long n, float* __restrict__ a, const float* __restrict__ b) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += b[i];
+}
+
+}  // namespace mpb
+
+// =================================================================== C ABI
+using namespace mpb;
+#define ST ((cudaStream_t)stream)
+static inline unsigned nblk(long total, int t) { return (unsigned)((total + t - 1) / t); }
+
+MPB_API int mpb_fold_bn(int cout, int K, const float* w, const float* gamma, const float* beta, const float* mean,
+                        const float* var, float eps, float* wf, float* scale, float* shift, void* stream) {
+    fold_bn_kernel<<<cout, 256, 0, ST>>>(cout, K, w, gamma, beta, mean, var, eps, wf, scale, shift);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_round_copy(long n, const float* src, float* dst, void* stream) {
+    round_copy_kernel<<<nblk(n, 256), 256, 0, ST>>>((size_t)n, src, dst);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_bn_param_grad(int cout, int K, const float* w, const float* dw, const float* gamma, const float* mean,
+                              const float* var, float eps, const float* dbeta, float* dgamma, void* stream) {
+    bn_param_grad_kernel<<<cout, 256, 0, ST>>>(cout, K, w, dw, gamma, mean, var, eps, dbeta, dgamma);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_stem_fwd(int nimg, int Hin, int Win, const float* x, const float* wf, const float* shift, float* y,
+                         void* stream) {
+    const int Ho = (Hin + 6 - 7) / 2 + 1, Wo = (Win + 6 - 7) / 2 + 1;
+    stem_fwd_kernel<<<nblk((long)nimg * Ho * Wo, 64), 256, 0, ST>>>(nimg, Hin, Win, Ho, Wo, x, wf, shift, y);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_stem_wgrad(int nimg, int Hin, int Win, const float* x, const float* g, const float* scale, float* dw,
+                           void* stream) {
+    const int Ho = (Hin + 6 - 7) / 2 + 1, Wo = (Win + 6 - 7) / 2 + 1;
+    const long total = (long)nimg * Ho * Wo;
+    const int ppc = 64;
+    stem_wgrad_kernel<<<nblk(total, ppc), 256, 0, ST>>>(nimg, Hin, Win, Ho, Wo, x, g, scale, dw, ppc);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_maxpool3s2_fwd(int nimg, int H, int W, int C, const float* x, float* y, void* stream) {
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    maxpool3s2_fwd_kernel<<<nblk((long)nimg * Ho * Wo * (C / 4), 256), 256, 0, ST>>>(
+        nimg, H, W, C / 4, Ho, Wo, (const float4*)x, (float4*)y);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_maxpool3s2_bwd(int nimg, int H, int W, int C, const float* x, const float* dy, float* dx, void* stream) {
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    maxpool3s2_bwd_kernel<<<nblk((long)nimg * H * W * C, 256), 256, 0, ST>>>(nimg, H, W, C, Ho, Wo, x, dy, dx);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_maxpool2_fwd(int nimg, int H, int W, int C, const float* x, int ldx, float* y, int ldy, void* stream) {
+    maxpool2_fwd_kernel<<<nblk((long)nimg * (H / 2) * (W / 2) * (C / 4), 256), 256, 0, ST>>>(nimg, H, W, C / 4, x, ldx, y, ldy);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_maxpool2_bwd(int nimg, int H, int W, int C, const float* x, int ldx, const float* dy, int ldy,
+                             float* dx, int lddx, int accumulate, void* stream) {
+    maxpool2_bwd_kernel<<<nblk((long)nimg * (H / 2) * (W / 2) * C, 256), 256, 0, ST>>>(nimg, H, W, C, x, ldx, dy, ldy, dx,
+                                                                                      lddx, accumulate);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_crop_pool_fwd(int H, int W, int C, const float* feat, int nbox, const float* boxes_norm, int crop,
+                              float* out, int ldo, void* stream) {
+    crop_pool_fwd_kernel<<<nblk((long)nbox * (crop / 2) * (crop / 2) * C, 256), 256, 0, ST>>>(H, W, C, feat, nbox,
+                                                                                            boxes_norm, crop, out, ldo);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_crop_pool_bwd(int H, int W, int C, const float* feat, int nbox, const float* boxes_norm, int crop,
+                              const float* dout, int ldd, float* dfeat, void* stream) {
+    MPB_CUDA_TRY(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)H * W * C, ST));
+    crop_pool_bwd_kernel<<<nblk((long)nbox * (crop / 2) * (crop / 2) * C, 256), 256, 0, ST>>>(H, W, C, feat, nbox,
+                                                                                            boxes_norm, crop, dout, ldd, dfeat);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_resize_ac_fwd(int nimg, int H, int W, int C, const float* x, int OH, int OW, float* y, void* stream) {
+    resize_ac_fwd_kernel<<<nblk((long)nimg * OH * OW * (C / 4), 256), 256, 0, ST>>>(nimg, H, W, C / 4, OH, OW,
+                                                                                  (const float4*)x, (float4*)y);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, int OH, int OW, float* dx, void* stream) {
+    MPB_CUDA_TRY(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)nimg * H * W * C, ST));
+    resize_ac_bwd_kernel<<<nblk((long)nimg * OH * OW * C, 256), 256, 0, ST>>>(nimg, H, W, C, OH, OW, dy, dx);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, float eps, float* y, float* mean,
+                             float* var, float* moving_mean, float* moving_var, float decay, double* scratch,
+                             void* stream) {
+    MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, ST));
+    dim3 g(ceil_div(C, 32), min(256, ceil_div(M, 64)));
+    bn_stats_kernel<<<g, 256, 0, ST>>>(M, C, z, scratch, scratch + C);
+    MPB_LAUNCH_CHECK();
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(M, C, scratch, scratch + C, mean, var, moving_mean, moving_var, decay);
+    MPB_LAUNCH_CHECK();
+    bn_apply_kernel<<<nblk((long)M * C / 4, 256), 256, 0, ST>>>((long)M * C / 4, C / 4, (const float4*)z, mean, var, beta, eps,
+                                                              (float4*)y);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_bn_train_bwd(int M, int C, const float* z, const float* mean, const float* var, float eps, const float* y,
+                             const float* dy, float* dz, float* dbeta, double* scratch, void* stream) {
+    MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, ST));
+    dim3 g(ceil_div(C, 32), min(256, ceil_div(M, 64)));
+    bn_bwd_reduce_kernel<<<g, 256, 0, ST>>>(M, C, z, y, dy, mean, var, eps, scratch, scratch + C);
+    MPB_LAUNCH_CHECK();
+    bn_bwd_apply_kernel<<<nblk((long)M * C, 256), 256, 0, ST>>>((long)M * C, M, C, z, y, dy, mean, var, eps, scratch,
+                                                              scratch + C, dz, dbeta);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_xyzhead_fwd(int nimg, int H, int W, const float* x, const float* w, const float* bias, float* y, void* stream) {
+    xyzhead_fwd_kernel<<<nblk((long)nimg * H * W, 8), 256, 0, ST>>>(nimg, H, W, x, w, bias, y);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_xyzhead_bwd(int nimg, int H, int W, const float* x, const float* w, const float* dy, float* dx, float* dw,
+                            float* db, void* stream) {
+    xyzhead_dgrad_kernel<<<nblk((long)nimg * H * W, 8), 256, 0, ST>>>(nimg, H, W, dy, w, dx);
+    MPB_LAUNCH_CHECK();
+    const int ppc = 128;
+    xyzhead_wgrad_kernel<<<nblk((long)nimg * H * W, ppc), 128, 0, ST>>>(nimg, H, W, x, dy, dw, db, ppc);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_fc_small_fwd(int B, int K, int N, const float* x, int ldx, const float* w, const float* bias, float* y,
+                             int ldy, void* stream) {
+    fc_small_fwd_kernel<<<nblk((long)B * N * 32, 256), 256, 0, ST>>>(B, K, N, x, ldx, w, bias, y, ldy);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_fc_small_bwd(int B, int K, int N, const float* x, int ldx, const float* w, const float* dy, int ldy,
+                             float* dx, int lddx, int accumulate_dx, float* dw, float* db, void* stream) {
+    fc_small_bwd_kernel<<<nblk(K > N ? K : N, 128), 128, 0, ST>>>(B, K, N, x, ldx, w, dy, ldy, dx, lddx, accumulate_dx, dw, db);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_bias_relu(long rows, int C, const float* x, int ldx, const float* bias, int relu, int round, float* y,
+                          int ldy, void* stream) {
+    bias_relu_kernel<<<nblk(rows * C, 256), 256, 0, ST>>>(rows * C, C, x, ldx, bias, relu, round, y, ldy);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_relu_bwd_colsum(int M, int C, const float* y, int ldy, const float* dy, int lddy, float* g, int ldg,
+                                float* colsum, void* stream) {
+    dim3 grid(ceil_div(C, 32), min(256, ceil_div(M, 64)));
+    relu_bwd_colsum_kernel<<<grid, 256, 0, ST>>>(M, C, y, ldy, dy, lddy, g, ldg, colsum);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_add_inplace(long n, float* a, const float* b, void* stream) {
+    add_inplace_kernel<<<nblk(n, 256), 256, 0, ST>>>(n, a, b);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}

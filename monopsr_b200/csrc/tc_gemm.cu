@@ -251,6 +251,11 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
             float v[32];
             tmem_ld32(trow + c0, v);
             const int gc = n0 + c0;
+            if (p.rowscale && rok) {
+                const float rs = __ldg(p.rowscale + grow);
+#pragma unroll
+                for (int q = 0; q < 32; q++) v[q] *= rs;
+            }
             if (p.scale) {
 #pragma unroll
                 for (int q = 0; q < 32; q++) v[q] *= __ldg(p.scale + gc + q);
