@@ -276,7 +276,40 @@ class Engine:
                 bn = self._pick_bn(mt, Cin)
             else:
                 bn = 128 if Cin % 128 == 0 else 64
+        if getattr(self, "_record", None) is not None:
+            self._record.append((p, bn, 2.0 * M * Cin * Cout * k * k))
         self._chk(self.L.mpb_tc_gemm(ctypes.byref(p), bn, self._st()), "mpb_tc_gemm")
+
+    def gemm_only_roofline(self, flush=None, iters=10):
+        """Time ONLY the tcgen05 GEMM launches of one training step (same arguments, replayed as a CUDA
+        graph) and return their algorithmic FLOP rate (2*M*N*K, full-tap convention of SURVEY.md 8d)."""
+        self._record = []
+        self.forward(train=True)
+        self.backward()
+        rec, self._record = self._record, None
+        torch.cuda.synchronize(self.dev)
+        s = torch.cuda.Stream(device=self.dev)
+        with torch.cuda.stream(s):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for p, bn, _ in rec:
+                    self._chk(self.L.mpb_tc_gemm(ctypes.byref(p), bn, self._st()), "mpb_tc_gemm")
+        torch.cuda.synchronize(self.dev)
+        g.replay()
+        torch.cuda.synchronize(self.dev)
+        ts = []
+        for _ in range(iters):
+            if flush is not None:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g.replay()
+            b.record()
+            torch.cuda.synchronize(self.dev)
+            ts.append(a.elapsed_time(b))
+        ms_ = float(np.median(ts))
+        flop = float(sum(r[2] for r in rec))
+        return {"ms": ms_, "gflop": flop / 1e9, "tflops": flop / (ms_ * 1e-3) / 1e12, "launches": len(rec)}
 
     def wgrad(self, M, H, W, k, dil, Cin, Cout, X, ldx, dY, ldy, dW, tapmask=None, rowscale=None):
         bn = 128 if Cin % 128 == 0 else 64

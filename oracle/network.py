@@ -33,6 +33,31 @@ BN_EPS_DECODER = 1e-3     # slim.batch_norm default
 MAX_DEPTH = 45.0          # dataset_config.obj_filter_config.depth_range[1] (yaml:31)
 
 
+# ----------------------------------------------------------------------------- tf32 emulation
+# The product feeds fp32 operands to tcgen05 kind::tf32 and rounds them to tf32 (cvt.rna: 10
+# mantissa bits, ties away from zero) where they are produced.  With EMULATE_TF32 the oracle
+# applies the same rounding at the same points (straight-through gradient), so the remaining
+# product-vs-oracle difference is fp32-vs-fp64 accumulation only; with it off the oracle is the
+# plain fp64 restatement and the difference measures the tf32 effect itself.
+EMULATE_TF32 = False
+
+
+class _RoundTF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        i = x.detach().to(torch.float32).contiguous().view(torch.int32)
+        i = (i + 0x1000) & ~0x1FFF
+        return i.view(torch.float32).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def Q(x):
+    return _RoundTF32.apply(x) if EMULATE_TF32 else x
+
+
 # ----------------------------------------------------------------------------- layers
 def conv_hwio(x, w, stride=1, rate=1, pad="SAME"):
     """x NHWC, w HWIO (TF).  SAME for stride 1 == symmetric pad rate*(k-1)/2 (k odd)."""
@@ -66,6 +91,18 @@ def frozen_bn(x, P, scope):
     return (x - m) / torch.sqrt(v + BN_EPS_RESNET) * g + b
 
 
+def conv_bn(x, P, scope, stride=1, rate=1):
+    """conv (no bias) + inference-mode BN.  Emulation mode mirrors the product: BN scale folded
+    into the weights, folded weights rounded to tf32, then '+ shift'."""
+    w = P[scope + "/weights"]
+    bn = scope + "/BatchNorm"
+    if not EMULATE_TF32:
+        return frozen_bn(conv2d_same(x, w, stride, rate), P, bn)
+    sc = P[bn + "/gamma"] / torch.sqrt(P[bn + "/moving_variance"] + BN_EPS_RESNET)
+    wf = Q(w * sc)           # HWIO: scale broadcasts over the output-channel axis
+    return conv2d_same(x, wf, stride, rate) + (P[bn + "/beta"] - P[bn + "/moving_mean"] * sc)
+
+
 def max_pool_same_3x3_s2(x):
     """slim.max_pool2d([3,3], stride=2, padding='SAME'): even input => one pad row/col at the end."""
     xn = x.permute(0, 3, 1, 2)
@@ -86,11 +123,11 @@ def bottleneck(x, P, scope, depth, depth_bottleneck, rate):
     if x.shape[-1] == depth:
         shortcut = x
     else:
-        shortcut = frozen_bn(conv_hwio(x, P[s + "/shortcut/weights"]), P, s + "/shortcut/BatchNorm")
-    r = torch.relu(frozen_bn(conv_hwio(x, P[s + "/conv1/weights"]), P, s + "/conv1/BatchNorm"))
-    r = torch.relu(frozen_bn(conv2d_same(r, P[s + "/conv2/weights"], 1, rate), P, s + "/conv2/BatchNorm"))
-    r = frozen_bn(conv_hwio(r, P[s + "/conv3/weights"]), P, s + "/conv3/BatchNorm")
-    return torch.relu(shortcut + r)
+        shortcut = conv_bn(x, P, s + "/shortcut")
+    r = Q(torch.relu(conv_bn(x, P, s + "/conv1")))
+    r = Q(torch.relu(conv_bn(r, P, s + "/conv2", 1, rate)))
+    r = conv_bn(r, P, s + "/conv3")
+    return Q(torch.relu(shortcut + r))
 
 
 BLOCKS = [("block1", 64, 3), ("block2", 128, 4), ("block3", 256, 23)]   # block4 is never consumed
@@ -100,7 +137,7 @@ def resnet101_block3(x, P, scope):
     """feature_extractor.py:197-245 with output_stride=4: stem /2, pool /2, every unit stride 1,
     atrous rate 1/2/4 in block1/2/3 (resnet_utils.py:181-200)."""
     s = scope + "/resnet_v1_101"
-    x = torch.relu(frozen_bn(conv2d_same(x, P[s + "/conv1/weights"], 2), P, s + "/conv1/BatchNorm"))
+    x = Q(torch.relu(conv_bn(x, P, s + "/conv1", 2)))
     x = max_pool_same_3x3_s2(x)
     rate = 1
     for name, base, units in BLOCKS:
@@ -149,12 +186,15 @@ def train_bn_relu(x, P, scope):
     """slim.batch_norm defaults, is_training=True: batch statistics (biased variance), beta only."""
     mean = x.mean((0, 1, 2))
     var = x.var((0, 1, 2), unbiased=False)
-    return torch.relu((x - mean) / torch.sqrt(var + BN_EPS_DECODER) + P[scope + "/beta"]), mean, var
+    return Q(torch.relu((x - mean) / torch.sqrt(var + BN_EPS_DECODER) + P[scope + "/beta"])), mean, var
 
 
 def fc(x, P, scope, relu=True):
-    y = x @ P[scope + "/weights"] + P[scope + "/biases"]
-    return torch.relu(y) if relu else y
+    """slim.fully_connected; the 1024-wide ReLU layers run on the tensor cores in the product
+    (weights and outputs tf32-rounded), the small linear heads run in plain fp32."""
+    if relu:
+        return Q(torch.relu(x @ Q(P[scope + "/weights"]) + P[scope + "/biases"]))
+    return x @ P[scope + "/weights"] + P[scope + "/biases"]
 
 
 # ----------------------------------------------------------------------------- losses
@@ -192,20 +232,20 @@ def forward(P, S, train=True):
     crop_feat = resnet101_block3(S["rgb_crops"], P, "FirstStageFeatureExtractor_crop")
     full_feat = resnet101_block3(S["full_img"], P, "FirstStageFeatureExtractor_full")
     large = crop_and_resize(full_feat, S["boxes_2d_norm"], 24, 24)
-    full_crop = max_pool_2x2(large)
+    full_crop = Q(max_pool_2x2(large))
     concat = torch.cat([crop_feat, full_crop], dim=3)
-    squashed = torch.relu(conv_hwio(concat, P["squash/1x1_conv/weights"]) + P["squash/1x1_conv/biases"])
+    squashed = Q(torch.relu(conv_hwio(concat, Q(P["squash/1x1_conv/weights"])) + P["squash/1x1_conv/biases"]))
     pooled = max_pool_2x2(squashed)
-    x = resize_bilinear_ac(squashed, 24, 24)
+    x = Q(resize_bilinear_ac(squashed, 24, 24))
     bn_stats = {}
     for i in (1, 2):
         sc = "map_decoder/conv2/conv2_%d" % i
-        x, m, v = train_bn_relu(conv_hwio(x, P[sc + "/weights"]), P, sc + "/BatchNorm")
+        x, m, v = train_bn_relu(conv_hwio(x, Q(P[sc + "/weights"])), P, sc + "/BatchNorm")
         bn_stats[sc] = (m, v)
-    x = resize_bilinear_ac(x, 48, 48)
+    x = Q(resize_bilinear_ac(x, 48, 48))
     for i in (1, 2):
         sc = "map_decoder/conv3/conv3_%d" % i
-        x, m, v = train_bn_relu(conv_hwio(x, P[sc + "/weights"]), P, sc + "/BatchNorm")
+        x, m, v = train_bn_relu(conv_hwio(x, Q(P[sc + "/weights"])), P, sc + "/BatchNorm")
         bn_stats[sc] = (m, v)
     map_features = x
 

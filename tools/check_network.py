@@ -29,6 +29,7 @@ def main():
     eng.forward(train=True)
     torch.cuda.synchronize()
     print("engine fwd (eager, first) %.3fs" % (time.time() - t))
+    onet.EMULATE_TF32 = "--emu" in sys.argv
     Pt = onet.to_torch(P, torch.float64, dev)
     for v in Pt.values():
         v.requires_grad_(v.dtype == torch.float64)
