@@ -103,6 +103,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024 B alignment
     constexpr uint32_t kStage = kTcABytes + BN * 128;
+    constexpr int kTcStages = tc_stages<BN>();
     const uint32_t bar_base = base + kTcStages * kStage;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };

@@ -30,13 +30,15 @@ using TcGemmParams = mpb_tc_gemm_params;
 
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 32;          // floats per k-block = one 128B swizzle row
-constexpr int kTcStages = 4;
+// pipeline depth: cp.async round trips are long (about 2 us under load), so keep as many
+// stages in flight as shared memory allows (one CTA per SM): 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
+template <int BN> constexpr int tc_stages() { return BN == 64 ? 8 : (BN == 128 ? 6 : 4); }
 constexpr int kTcThreads = 160;    // 4 producer/epilogue warps + 1 MMA warp
 constexpr int kTcABytes = kTcBM * 128;
 
 template <int BN>
 constexpr int tc_smem_bytes() {
-    return kTcStages * (kTcABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+    return tc_stages<BN>() * (kTcABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 int tc_gemm_launch(const TcGemmParams& p, int BN, cudaStream_t s);

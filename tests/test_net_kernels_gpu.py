@@ -1,0 +1,375 @@
+"""GPU unit tests of the bandwidth-bound network kernels (csrc/net_kernels.cu, heads.cu,
+optimizer.cu) through the C ABI, each against a torch fp64 restatement of the TF op it
+replaces (test-side reference; torch autograd supplies the expected gradients)."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from monopsr_b200 import lib as mlib  # noqa: E402
+from monopsr_b200.lib_net import HeadsIO, OptChunk  # noqa: E402
+from oracle import network as onet  # noqa: E402
+
+
+def P(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def ok(st, what="call"):
+    mlib.check(st, what)
+    torch.cuda.synchronize()
+
+
+def close(a, b, rtol=1e-4, atol=None):
+    a, b = a.double(), b.double()
+    atol = atol if atol is not None else 1e-5 * max(1.0, float(b.abs().max()))
+    err = (a - b).abs()
+    assert bool((err <= atol + rtol * b.abs()).all()), "max err %.3e (ref max %.3e)" % (float(err.max()), float(b.abs().max()))
+
+
+def rnd(*shape, seed=0, scale=1.0, dev="cuda:0"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dev)
+
+
+def test_fold_bn_and_param_grad(cuda):
+    L = mlib.load()
+    co, K = 64, 147
+    w, g, b, m = rnd(co, K, seed=1), rnd(co, seed=2).abs() + 0.5, rnd(co, seed=3), rnd(co, seed=4)
+    v = rnd(co, seed=5).abs() + 0.5
+    wf, sc, sh = torch.empty_like(w), torch.empty(co, device=cuda), torch.empty(co, device=cuda)
+    ok(L.mpb_fold_bn(co, K, P(w), P(g), P(b), P(m), P(v), 1e-5, P(wf), P(sc), P(sh), mlib.stream_ptr()))
+    s = g.double() / torch.sqrt(v.double() + 1e-5)
+    close(sc, s, 1e-5)
+    close(sh, b.double() - m.double() * s, 1e-5)
+    assert float(((wf.double() - w.double() * s[:, None]).abs() / (w.double() * s[:, None]).abs().clamp(min=1e-6)).max()) < 6e-4
+    assert bool(((wf.view(torch.int32) & 0x1FFF) == 0).all())          # exactly representable in tf32
+    dw, dbeta, dgamma = rnd(co, K, seed=6), rnd(co, seed=7), torch.empty(co, device=cuda)
+    ok(L.mpb_bn_param_grad(co, K, P(w), P(dw), P(g), P(m), P(v), 1e-5, P(dbeta), P(dgamma), mlib.stream_ptr()))
+    ref = (w.double() * dw.double()).sum(1) / g.double() - m.double() * dbeta.double() / torch.sqrt(v.double() + 1e-5)
+    close(dgamma, ref, 1e-4)
+
+
+@pytest.mark.parametrize("nimg,H,W", [(3, 48, 48), (1, 160, 608)])
+def test_stem(cuda, nimg, H, W):
+    L = mlib.load()
+    x = rnd(nimg, H, W, 3, seed=1, scale=50)
+    w = rnd(64, 7, 7, 3, seed=2, scale=0.01)
+    shift = rnd(64, seed=3, scale=0.1)
+    Ho, Wo = H // 2, W // 2
+    y = torch.empty(nimg, Ho, Wo, 64, device=cuda)
+    ok(L.mpb_stem_fwd(nimg, H, W, P(x), P(w), P(shift), P(y), mlib.stream_ptr()))
+    wt = w.double().permute(0, 3, 1, 2).clone().requires_grad_()
+    ref = torch.relu(F.conv2d(F.pad(x.double().permute(0, 3, 1, 2), (3, 3, 3, 3)), wt, stride=2).permute(0, 2, 3, 1) + shift.double())
+    assert ref.shape == y.shape
+    close(y, ref, 1.5e-3)            # output is tf32-rounded
+    g = rnd(nimg, Ho, Wo, 64, seed=4) * (ref > 0)
+    scale = rnd(64, seed=5).abs() + 0.5
+    dw = torch.zeros(64, 7, 7, 3, device=cuda)
+    ok(L.mpb_stem_wgrad(nimg, H, W, P(x), P(g.float().contiguous()), P(scale), P(dw), mlib.stream_ptr()))
+    conv = F.conv2d(F.pad(x.double().permute(0, 3, 1, 2), (3, 3, 3, 3)), wt, stride=2)
+    conv.backward(g.double().permute(0, 3, 1, 2))
+    refw = wt.grad.permute(0, 2, 3, 1) * scale.double()[:, None, None, None]
+    close(dw, refw, 1e-3, atol=1e-4 * float(refw.abs().max()))
+
+
+def test_maxpool3s2(cuda):
+    L = mlib.load()
+    n, H, W, C = 2, 24, 24, 64
+    x = torch.relu(rnd(n, H, W, C, seed=1))
+    y = torch.empty(n, 12, 12, C, device=cuda)
+    ok(L.mpb_maxpool3s2_fwd(n, H, W, C, P(x), P(y), mlib.stream_ptr()))
+    xx = x.double().clone().requires_grad_()
+    ref = onet.max_pool_same_3x3_s2(xx)
+    close(y, ref, 0, atol=0)
+    dy = rnd(n, 12, 12, C, seed=2)
+    dx = torch.empty_like(x)
+    ok(L.mpb_maxpool3s2_bwd(n, H, W, C, P(x), P(dy), P(dx), mlib.stream_ptr()))
+    ref.backward(dy.double())
+    # zero activations carry no gradient in the product (ReLU of the producer fused in)
+    close(dx, xx.grad * (x > 0), 1e-6)
+
+
+def test_maxpool2_and_crop_pool(cuda):
+    L = mlib.load()
+    n, H, W, C = 3, 12, 12, 64
+    x = torch.relu(rnd(n, H, W, C, seed=1) + 0.5)
+    y = torch.empty(n, 6, 6, C, device=cuda)
+    ok(L.mpb_maxpool2_fwd(n, H, W, C, P(x), C, P(y), C, mlib.stream_ptr()))
+    xx = x.double().clone().requires_grad_()
+    ref = onet.max_pool_2x2(xx)
+    close(y, ref, 0, atol=0)
+    dy = rnd(n, 6, 6, C, seed=2)
+    dx = torch.ones_like(x)
+    ok(L.mpb_maxpool2_bwd(n, H, W, C, P(x), C, P(dy), C, P(dx), C, 1, mlib.stream_ptr()))
+    ref.backward(dy.double())
+    close(dx, xx.grad + 1.0, 1e-6)
+    # crop_and_resize(24x24) + maxpool2 on a (1,40,152,C) map
+    Hf, Wf, C = 40, 152, 32
+    feat = torch.relu(rnd(1, Hf, Wf, C, seed=3) + 0.3)
+    rng = np.random.RandomState(0)
+    y1, x1 = rng.uniform(-0.05, 0.7, 8), rng.uniform(-0.05, 0.7, 8)
+    boxes = torch.tensor(np.stack([y1, x1, y1 + rng.uniform(0.1, 0.4, 8), x1 + rng.uniform(0.1, 0.4, 8)], 1),
+                         dtype=torch.float32, device=cuda)
+    out = torch.empty(8, 12, 12, C, device=cuda)
+    ok(L.mpb_crop_pool_fwd(Hf, Wf, C, P(feat), 8, P(boxes), 24, P(out), C, mlib.stream_ptr()))
+    ff = feat.double().clone().requires_grad_()
+    ref = onet.max_pool_2x2(onet.crop_and_resize(ff, boxes.double(), 24, 24))
+    close(out, ref, 1.5e-3, atol=2e-4)          # fp32 coordinates + tf32 rounding of the output
+    dy = rnd(8, 12, 12, C, seed=4)
+    dfeat = torch.empty_like(feat)
+    ok(L.mpb_crop_pool_bwd(Hf, Wf, C, P(feat), 8, P(boxes), 24, P(dy), C, P(dfeat), mlib.stream_ptr()))
+    ref.backward(dy.double())
+    err = (dfeat.double() - ff.grad).abs()
+    assert float(err.max()) < 2e-3 * float(ff.grad.abs().max()) or float((err > 1e-4).double().mean()) < 1e-3
+
+
+def test_resize_ac(cuda):
+    L = mlib.load()
+    n, H, W, C = 2, 12, 12, 32
+    x = rnd(n, H, W, C, seed=1)
+    y = torch.empty(n, 24, 24, C, device=cuda)
+    ok(L.mpb_resize_ac_fwd(n, H, W, C, P(x), 24, 24, P(y), mlib.stream_ptr()))
+    xx = x.double().clone().requires_grad_()
+    ref = onet.resize_bilinear_ac(xx, 24, 24)
+    close(y, ref, 1e-3, atol=1e-5)
+    dy = rnd(n, 24, 24, C, seed=2)
+    dx = torch.empty_like(x)
+    ok(L.mpb_resize_ac_bwd(n, H, W, C, P(dy), 24, 24, P(dx), mlib.stream_ptr()))
+    ref.backward(dy.double())
+    close(dx, xx.grad, 1e-4, atol=1e-5)
+
+
+def test_bn_train(cuda):
+    L = mlib.load()
+    M, C = 2048, 128
+    z = rnd(M, C, seed=1) * 2 + 0.7
+    beta = rnd(C, seed=2, scale=0.3)
+    y, mean, var = torch.empty_like(z), torch.empty(C, device=cuda), torch.empty(C, device=cuda)
+    mm, mv = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
+    scr = torch.zeros(2 * C, dtype=torch.float64, device=cuda)
+    ok(L.mpb_bn_train_fwd(M, C, P(z), P(beta), 1e-3, P(y), P(mean), P(var), P(mm), P(mv), 0.999, P(scr), mlib.stream_ptr()))
+    zz = z.double().clone().requires_grad_()
+    m_ref, v_ref = zz.mean(0), zz.var(0, unbiased=False)
+    ref = torch.relu((zz - m_ref) / torch.sqrt(v_ref + 1e-3) + beta.double())
+    close(mean, m_ref, 1e-5)
+    close(var, v_ref, 1e-4)
+    close(y, ref, 1.5e-3, atol=1e-5)
+    close(mm, m_ref * 0.001, 1e-4, atol=1e-7)
+    close(mv, 0.999 + v_ref * 0.001, 1e-5)
+    dy = rnd(M, C, seed=3)
+    dz, dbeta = torch.empty_like(z), torch.empty(C, device=cuda)
+    ok(L.mpb_bn_train_bwd(M, C, P(z), P(mean), P(var), 1e-3, P(y), P(dy), P(dz), P(dbeta), P(scr), mlib.stream_ptr()))
+    ref.backward(dy.double())
+    close(dz, zz.grad, 2e-3, atol=2e-4 * float(zz.grad.abs().max()))
+    close(dbeta, (dy.double() * (ref > 0)).sum(0), 1e-4, atol=1e-3)
+
+
+def test_xyzhead(cuda):
+    L = mlib.load()
+    n, H, W = 2, 48, 48
+    x = rnd(n, H, W, 128, seed=1)
+    w = rnd(3, 3, 3, 128, seed=2, scale=0.05)
+    b = rnd(3, seed=3)
+    y = torch.empty(n, H, W, 3, device=cuda)
+    ok(L.mpb_xyzhead_fwd(n, H, W, P(x), P(w), P(b), P(y), mlib.stream_ptr()))
+    xx = x.double().permute(0, 3, 1, 2).clone().requires_grad_()
+    wt = w.double().permute(0, 3, 1, 2).clone().requires_grad_()
+    ref = F.conv2d(xx, wt, padding=1).permute(0, 2, 3, 1) + b.double()
+    close(y, ref, 1e-4)
+    dy = rnd(n, H, W, 3, seed=4)
+    dx, dw, db = torch.empty_like(x), torch.zeros_like(w), torch.zeros(3, device=cuda)
+    ok(L.mpb_xyzhead_bwd(n, H, W, P(x), P(w), P(dy), P(dx), P(dw), P(db), mlib.stream_ptr()))
+    ref.backward(dy.double())
+    close(dx, xx.grad.permute(0, 2, 3, 1), 1e-4)
+    close(dw, wt.grad.permute(0, 2, 3, 1), 1e-3, atol=1e-4 * float(wt.grad.abs().max()))
+    close(db, dy.double().sum((0, 1, 2)), 1e-4, atol=1e-3)
+
+
+def test_fc_small_and_helpers(cuda):
+    L = mlib.load()
+    B, K, N = 32, 1024, 24
+    x, w, b = rnd(B, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    y = torch.empty(B, N, device=cuda)
+    ok(L.mpb_fc_small_fwd(B, K, N, P(x), K, P(w), P(b), P(y), N, mlib.stream_ptr()))
+    close(y, x.double() @ w.double().T + b.double(), 1e-4)
+    dy = rnd(B, N, seed=4)
+    dx, dw, db = torch.ones(B, K, device=cuda), torch.zeros(N, K, device=cuda), torch.zeros(N, device=cuda)
+    ok(L.mpb_fc_small_bwd(B, K, N, P(x), K, P(w), P(dy), N, P(dx), K, 1, P(dw), P(db), mlib.stream_ptr()))
+    close(dx, dy.double() @ w.double() + 1.0, 1e-4)
+    close(dw, dy.double().T @ x.double(), 1e-4)
+    close(db, dy.double().sum(0), 1e-4)
+    # bias+relu and relu-backward+colsum
+    M, C = 300, 96
+    a, bias = rnd(M, C, seed=5), rnd(C, seed=6)
+    o = torch.empty(M, C, device=cuda)
+    ok(L.mpb_bias_relu(M, C, P(a), C, P(bias), 1, 0, P(o), C, mlib.stream_ptr()))
+    close(o, torch.relu(a.double() + bias.double()), 1e-6)
+    g, cs = torch.empty(M, C, device=cuda), torch.zeros(C, device=cuda)
+    d = rnd(M, C, seed=7)
+    ok(L.mpb_relu_bwd_colsum(M, C, P(o), C, P(d), C, P(g), C, P(cs), mlib.stream_ptr()))
+    ref = d.double() * (o > 0)
+    close(g, ref, 1e-3, atol=1e-6)
+    close(cs, ref.sum(0), 1e-3, atol=1e-3)
+
+
+def test_optimizer_step_matches_tf_adam_semantics(cuda):
+    L = mlib.load()
+    sizes = [1000, 70000, 3]
+    total = sum(sizes)
+    chunks, off = [], 0
+    for ti, s in enumerate(sizes):
+        for a in range(0, s, 1 << 16):
+            chunks.append((off + a, min(1 << 16, s - a), ti))
+        off += s
+    arr = (OptChunk * len(chunks))()
+    for i, (a, b, c) in enumerate(chunks):
+        arr[i].start, arr[i].len, arr[i].tensor = a, b, c
+    dchunks = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(cuda)
+    p, g = rnd(total, seed=1), rnd(total, seed=2, scale=0.01)
+    g[1000:71000] *= 100          # this tensor's norm exceeds the clip threshold, the others do not
+    m, v = rnd(total, seed=3, scale=0.01), rnd(total, seed=4, scale=0.01).abs()
+    ema = p.clone() + 0.01
+    p0, m0, v0, e0 = p.double().clone(), m.double().clone(), v.double().clone(), ema.double().clone()
+    lr_t = 8e-5 * math.sqrt(1 - 0.999 ** 3) / (1 - 0.9 ** 3)
+    hyper = torch.tensor([lr_t, 0, 0, 0], dtype=torch.float32, device=cuda)
+    norm2 = torch.empty(len(sizes), device=cuda)
+    ok(L.mpb_opt_step(len(chunks), P(dchunks), len(sizes), P(p), P(g), P(m), P(v), P(ema), P(norm2), P(hyper), 0.5, 1.0,
+                      0.9, 0.999, 1e-8, 0.9999, mlib.stream_ptr()))
+    off = 0
+    for s in sizes:
+        gg = g.double()[off:off + s] * 0.5
+        nrm = gg.norm()
+        gg = gg * 1.0 / max(float(nrm), 1.0)                     # tf.clip_by_norm per variable
+        mr = 0.9 * m0[off:off + s] + 0.1 * gg
+        vr = 0.999 * v0[off:off + s] + 0.001 * gg * gg
+        pr = p0[off:off + s] - lr_t * mr / (vr.sqrt() + 1e-8)
+        er = e0[off:off + s] - (1 - 0.9999) * (e0[off:off + s] - pr)
+        close(p[off:off + s], pr, 1e-5, atol=1e-7)
+        close(m[off:off + s], mr, 1e-5, atol=1e-9)
+        close(v[off:off + s], vr, 1e-5, atol=1e-12)
+        close(ema[off:off + s], er, 1e-6, atol=1e-7)
+        off += s
+
+
+def test_heads_losses_and_gradients_vs_oracle(cuda):
+    """heads.cu against autograd of the oracle's head/geometry/loss code on random head outputs."""
+    from monopsr_b200.core import model_spec as ms
+    L = mlib.load()
+    N = 32
+    S = ms.synthetic_sample(3)
+    St = {k: torch.as_tensor(v).to(cuda) for k, v in S.items()}
+    e = lambda *s: torch.zeros(*s, device=cuda)
+    lwh_offs, alpha = rnd(N, 3, seed=1, scale=0.3), rnd(N, 24, seed=2)
+    cy, cz = rnd(N, seed=3, scale=0.5), rnd(N, seed=4, scale=1.5)
+    xyz = rnd(N, 48, 48, 3, seed=5)
+    bufs = {k: e(*s) for k, s in dict(lwh=(N, 3), prop_cen_z=(N,), prop_cen_y=(N,), cen_x=(N,), cen_y=(N,), cen_z=(N,),
+                                        centroids=(N, 3), proj_err_norm=(N,), depth_global=(N, 2304), losses=(9,),
+                                        d_lwh_offs=(N, 3), d_alpha=(N, 24), d_cen_y_offs=(N,), d_cen_z_offs=(N,),
+                                        d_xyz_local=(N, 48, 48, 3), d_prop_y=(N,), d_prop_z=(N,), maskstats=(N + 1,)).items()}
+    feat1, feat2 = e(N, 1088), e(N, 1088)
+    d_feat2 = rnd(N, 1088, seed=6, scale=0.01)
+    io = HeadsIO()
+    io.nbox = N
+    for k in ("boxes_2d", "cam_p", "class_indices", "mean_lwh", "prop_cen_z_offset", "est_view_angs", "boxes_3d",
+              "gt_alpha_bins", "gt_alpha_regs", "gt_alpha_valid_bins", "gt_view_angs"):
+        setattr(io, k, St[k].data_ptr())
+    io.gt_xyz_local, io.gt_xyz_global = St["gt_inst_xyz_maps_local"].data_ptr(), St["gt_inst_xyz_maps_global"].data_ptr()
+    io.valid_mask = St["gt_valid_mask_maps"].data_ptr()
+    io.lwh_offs, io.alpha, io.cen_y_offs, io.cen_z_offs, io.xyz_local = (lwh_offs.data_ptr(), alpha.data_ptr(), cy.data_ptr(),
+                                                                       cz.data_ptr(), xyz.data_ptr())
+    for k, t in bufs.items():
+        setattr(io, k, t.data_ptr())
+    io.feat1, io.ld1, io.feat2, io.ld2, io.d_feat2, io.ldd2 = feat1.data_ptr(), 1088, feat2.data_ptr(), 1088, d_feat2.data_ptr(), 1088
+    st = mlib.stream_ptr()
+    ok(L.mpb_heads_static(ctypes.byref(io), st))
+    ok(L.mpb_heads_mid(ctypes.byref(io), st))
+    ok(L.mpb_heads_final(ctypes.byref(io), 1, st))
+    ok(L.mpb_heads_bwd_mid(ctypes.byref(io), st))
+
+    # ---- the same computation with the oracle's formulas, fp64 + autograd
+    D = {k: v.double() if v.dtype.is_floating_point else v for k, v in St.items()}
+    lo = lwh_offs.double().clone().requires_grad_()
+    al = alpha.double().clone().requires_grad_()
+    cyo, czo = cy.double().clone().requires_grad_(), cz.double().clone().requires_grad_()
+    xl = xyz.double().clone().requires_grad_()
+    cam, b2 = D["cam_p"], D["boxes_2d"]
+    f, cv = cam[0, 0], cam[1, 2]
+    lwh = D["mean_lwh"] + lo
+    pz = (f * lwh[:, 2] / (b2[:, 2] - b2[:, 0]) + D["prop_cen_z_offset"]).reshape(N, 1)
+    py = ((b2[:, 2] + b2[:, 0]) / 2 - cv).reshape(N, 1) * (pz / f) - 0.0648
+    # the regression-concat tail consumes lwh_offs, alpha, prop_y/1.666754, prop_z/45: emulate its
+    # upstream gradient d_feat2 with a linear functional
+    tail = torch.cat([lo, al, py / 1.666754, pz / 45.0], 1)
+    extra = (tail * d_feat2.double()[:, 1031:1060]).sum()
+    out = {"inst_xyz_map_local": xl, "lwh": lwh, "lwh_offs": lo, "alpha_bins": al[:, :12], "alpha_regs": al[:, 12:],
+           "prop_cen_z": pz, "cen_y_offs": cyo.reshape(N, 1), "cen_z_offs": czo.reshape(N, 1)}
+    out["cen_y"], out["cen_z"] = py + out["cen_y_offs"], pz + out["cen_z_offs"]
+    # reuse the oracle's projection / depth / loss code by calling its forward tail through a shim
+    full = _oracle_tail(out, D)
+    Ls, tot = onet.loss(full, D)
+    (tot + extra).backward()
+    names = ["inst_xyz_map_local", "lwh_offs", "alpha_bins", "alpha_regs", "cen_z_offs", "cen_y_offs", "proj_err",
+             "inst_depth_map_global"]
+    got = bufs["losses"].cpu().numpy()
+    for i, n in enumerate(names):
+        assert abs(got[i] - float(Ls[n])) <= 2e-4 * max(1.0, abs(float(Ls[n]))), (n, got[i], float(Ls[n]))
+    close(bufs["proj_err_norm"], full["proj_err_norm"], 1e-3, atol=1e-5)
+    close(bufs["depth_global"].view(N, 48, 48, 1), full["inst_depth_map_global"], 1e-4)
+    close(bufs["centroids"], torch.cat([full["cen_x"], full["cen_y"], full["cen_z"]], 1), 1e-4)
+    for a, b, nm in ((bufs["d_xyz_local"], xl.grad, "d_xyz"), (bufs["d_cen_y_offs"], cyo.grad, "d_cy"),
+                     (bufs["d_cen_z_offs"], czo.grad, "d_cz"), (bufs["d_lwh_offs"], lo.grad, "d_lwh"),
+                     (bufs["d_alpha"], al.grad, "d_alpha")):
+        err = (a.double() - b).abs().max() / b.abs().max()
+        assert float(err) < 2e-3, (nm, float(err))
+
+
+def _oracle_tail(out, S):
+    """projection error + global depth exactly as oracle/network.py computes them (copied call path:
+    we run oracle.forward's tail by monkey-free re-implementation through its own helpers)."""
+    N = 32
+    dt, dev = torch.float64, out["cen_z"].device
+    cam_p, boxes_2d = S["cam_p"], S["boxes_2d"]
+    est_view = S["est_view_angs"].reshape(N, 1)
+    cen_y, cen_z, xyz_local = out["cen_y"], out["cen_z"], out["inst_xyz_map_local"]
+    valid = S["gt_valid_mask_maps"]
+    x_offset = -cam_p[0, 3] / cam_p[0, 0]
+    f, centre_u = cam_p[0, 0], cam_p[0, 2]
+    out = dict(out)
+    out["cen_x"] = cen_z * torch.tan(est_view) + x_offset
+    gt_view = S["gt_view_angs"].reshape(N, 1)
+    proj_cen = torch.cat([cen_z * torch.tan(gt_view) + x_offset, cen_y, cen_z], dim=1)
+    c, s = torch.cos(gt_view)[:, :, None], torch.sin(gt_view)[:, :, None]
+    lx, ly, lz = xyz_local[..., 0], xyz_local[..., 1], xyz_local[..., 2]
+    gx = c * lx + s * lz + proj_cen[:, 0, None, None]
+    gy = ly + proj_cen[:, 1, None, None]
+    gz = -s * lx + c * lz + proj_cen[:, 2, None, None]
+    pu = cam_p[0, 0] * gx + cam_p[0, 1] * gy + cam_p[0, 2] * gz + cam_p[0, 3]
+    pv = cam_p[1, 0] * gx + cam_p[1, 1] * gy + cam_p[1, 2] * gz + cam_p[1, 3]
+    pw = cam_p[2, 0] * gx + cam_p[2, 1] * gy + cam_p[2, 2] * gz + cam_p[2, 3]
+    lin = torch.arange(48, dtype=dt, device=dev) / 47.0
+    v1, u1, v2, u2 = [boxes_2d[:, i] for i in range(4)]
+    hu, hv = (u2 - u1) / 48 / 2.0, (v2 - v1) / 48 / 2.0
+    grid_u = (u1 + hu)[:, None] + ((u2 - hu) - (u1 + hu))[:, None] * lin[None, :]
+    grid_v = (v1 + hv)[:, None] + ((v2 - hv) - (v1 + hv))[:, None] * lin[None, :]
+    vm = valid[..., 0]
+    eu = torch.clamp((grid_u[:, None, :] - pu / pw) / (u2 - u1)[:, None, None] * vm, -2.0, 2.0)
+    ev = torch.clamp((grid_v[:, :, None] - pv / pw) / (v2 - v1)[:, None, None] * vm, -2.0, 2.0)
+    nvalid = vm.sum((1, 2))
+    nvalid = torch.where(nvalid < 1.0, torch.ones_like(nvalid), nvalid)
+    out["proj_err_norm"] = (eu.sum((1, 2)) + ev.sum((1, 2))) / nvalid
+    x1b, x2b = boxes_2d[:, 1], boxes_2d[:, 3]
+    sp = (x2b - x1b) / 48 / 2.0
+    va_l = torch.atan2((x1b + sp - centre_u) / f, torch.ones_like(x1b)).reshape(N, 1)
+    va_r = torch.atan2((x2b - sp - centre_u) / f, torch.ones_like(x1b)).reshape(N, 1)
+    inst_xz = cen_z / torch.cos(est_view)
+    off_l = (inst_xz / torch.cos(va_l - est_view) * torch.sin(va_l - est_view) * torch.sin(est_view)).reshape(N)
+    off_r = (inst_xz / torch.cos(va_r - est_view) * torch.sin(va_r - est_view) * torch.sin(est_view)).reshape(N)
+    off = (-off_l)[:, None] + ((-off_r) - (-off_l))[:, None] * lin[None, :]
+    out["inst_depth_map_global"] = xyz_local[..., 2:3] + cen_z.reshape(N, 1, 1, 1) + off.reshape(N, 48, 1, 1)
+    return out
