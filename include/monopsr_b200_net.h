@@ -55,6 +55,10 @@ typedef struct mpb_tc_gemm_params {
 /* BN: tile width in output columns (64, 128 or 256). */
 int mpb_tc_gemm(const mpb_tc_gemm_params* p, int BN, void* stream);
 
+/* operand staging of the GEMM core: 1 = TMA (cp.async.bulk.tensor, default), 0 = cp.async (LSU) producers.
+ * Returns the mode in effect (TMA falls back to 0 when the driver lacks cuTensorMapEncode*). */
+int mpb_tc_set_producer(int mode);
+
 /* tapmask[m] for an (nimg,H,W) pixel grid and a kh x kw filter with atrous rate dil. */
 int mpb_build_tapmask(int nimg, int H, int W, int kh, int kw, int dil, unsigned short* out, void* stream);
 

@@ -28,3 +28,8 @@ MPB_API int mpb_build_tapmask(int nimg, int H, int W, int kh, int kw, int dil, u
     MPB_LAUNCH_CHECK();
     return 0;
 }
+
+MPB_API int mpb_tc_set_producer(int mode) {
+    mpb::tc_gemm_set_mode(mode);
+    return mpb::tc_gemm_mode();
+}

@@ -1,5 +1,7 @@
 // monopsr_b200/csrc/tc_gemm.cu -- see tc_gemm.cuh for the design.
 #include "tc_gemm.cuh"
+#include <cuda.h>
+#include <stdlib.h>
 
 namespace mpb {
 
@@ -93,6 +95,96 @@ __device__ __forceinline__ uint32_t mn_swz(int c, int r) {
 __device__ __forceinline__ int tap_delta(int tap, int kh, int kw, int dil, int W) {
     int th = tap / kw - kh / 2, tw = tap % kw - kw / 2;
     return (th * W + tw) * dil;
+}
+
+// ------------------------------------------------------------------ fused epilogue
+// Called by 4 warps; `quad` (= warp index % 4) selects the 32 TMEM lanes (= accumulator rows) a
+// warp may read.
+template <int BN, int OP>
+__device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem_full_bar, uint32_t tmem_acc,
+                                            int quad, int lane, int m0, int n0) {
+    const int warp = quad;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;          // TMEM lane == accumulator row
+    const int grow = m0 + row;                 // pixel (FWD/DGRAD) or output channel (WGRAD)
+    const int nrows = (OP == TC_WGRAD) ? p.Cout : p.M;
+    const bool rok = grow < nrows;
+    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const int ldo = (OP == TC_WGRAD) ? p.ldw : p.ldo;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(trow + c0, v);
+        const int gc = n0 + c0;
+        if (p.rowscale && rok) {
+            const float rs = __ldg(p.rowscale + grow);
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] *= rs;
+        }
+        if (p.scale) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] *= __ldg(p.scale + gc + q);
+        }
+        if (p.shift) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] += __ldg(p.shift + gc + q);
+        }
+        if (p.res && rok) {
+            const float4* rp = reinterpret_cast<const float4*>(p.res + (size_t)grow * p.ldr + gc);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                float4 t = __ldg(rp + q);
+                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+            }
+        }
+        if (p.relu) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = fmaxf(v[q], 0.f);
+        }
+        if (p.mask && rok) {
+            const float4* mp = reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ldm + gc);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                float4 t = __ldg(mp + q);
+                v[4 * q] = t.x > 0.f ? v[4 * q] : 0.f;
+                v[4 * q + 1] = t.y > 0.f ? v[4 * q + 1] : 0.f;
+                v[4 * q + 2] = t.z > 0.f ? v[4 * q + 2] : 0.f;
+                v[4 * q + 3] = t.w > 0.f ? v[4 * q + 3] : 0.f;
+            }
+        }
+        if (p.scale2) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] *= __ldg(p.scale2 + gc + q);
+        }
+        if (p.round_tf32) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = round_tf32(v[q]);
+        }
+        if (p.colsum) {
+            // per-column sums over this warp's 32 rows, one RED per column per warp
+#pragma unroll
+            for (int q = 0; q < 32; q++) {
+                float s = rok ? v[q] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == q) atomicAdd(p.colsum + gc + q, s);
+            }
+        }
+        if (rok) {
+            float4* op = reinterpret_cast<float4*>(p.out + (size_t)grow * ldo + gc);
+            if (p.atomic) {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    atomicAdd(op + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+        }
+    }
+    tc_fence_before();
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -238,88 +330,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
             }
         }
 
-        // =========================== EPILOGUE ===========================
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const int row = warp * 32 + lane;          // TMEM lane == accumulator row
-        const int grow = m0 + row;                 // pixel (FWD/DGRAD) or output channel (WGRAD)
-        const int nrows = (OP == TC_WGRAD) ? p.Cout : p.M;
-        const bool rok = grow < nrows;
-        const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
-        const int ldo = (OP == TC_WGRAD) ? p.ldw : p.ldo;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-            tmem_ld32(trow + c0, v);
-            const int gc = n0 + c0;
-            if (p.rowscale && rok) {
-                const float rs = __ldg(p.rowscale + grow);
-#pragma unroll
-                for (int q = 0; q < 32; q++) v[q] *= rs;
-            }
-            if (p.scale) {
-#pragma unroll
-                for (int q = 0; q < 32; q++) v[q] *= __ldg(p.scale + gc + q);
-            }
-            if (p.shift) {
-#pragma unroll
-                for (int q = 0; q < 32; q++) v[q] += __ldg(p.shift + gc + q);
-            }
-            if (p.res && rok) {
-                const float4* rp = reinterpret_cast<const float4*>(p.res + (size_t)grow * p.ldr + gc);
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    float4 t = __ldg(rp + q);
-                    v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
-                }
-            }
-            if (p.relu) {
-#pragma unroll
-                for (int q = 0; q < 32; q++) v[q] = fmaxf(v[q], 0.f);
-            }
-            if (p.mask && rok) {
-                const float4* mp = reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ldm + gc);
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    float4 t = __ldg(mp + q);
-                    v[4 * q] = t.x > 0.f ? v[4 * q] : 0.f;
-                    v[4 * q + 1] = t.y > 0.f ? v[4 * q + 1] : 0.f;
-                    v[4 * q + 2] = t.z > 0.f ? v[4 * q + 2] : 0.f;
-                    v[4 * q + 3] = t.w > 0.f ? v[4 * q + 3] : 0.f;
-                }
-            }
-            if (p.scale2) {
-#pragma unroll
-                for (int q = 0; q < 32; q++) v[q] *= __ldg(p.scale2 + gc + q);
-            }
-            if (p.round_tf32) {
-#pragma unroll
-                for (int q = 0; q < 32; q++) v[q] = round_tf32(v[q]);
-            }
-            if (p.colsum) {
-                // per-column sums over this warp's 32 rows, one RED per column per warp
-#pragma unroll
-                for (int q = 0; q < 32; q++) {
-                    float s = rok ? v[q] : 0.f;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == q) atomicAdd(p.colsum + gc + q, s);
-                }
-            }
-            if (rok) {
-                float4* op = reinterpret_cast<float4*>(p.out + (size_t)grow * ldo + gc);
-                if (p.atomic) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++)
-                        atomicAdd(op + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; q++)
-                        op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                }
-            }
-        }
-        tc_fence_before();
+        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp, lane, m0, n0);
     } else {
         // =========================== MMA ISSUER (warp 4) ===========================
         constexpr bool a_mn = (OP == TC_WGRAD);
@@ -358,6 +369,284 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     }
 }
 
+
+// =====================================================================================
+// TMA-fed variant: every operand tile is brought in by the Tensor Memory Accelerator
+// (cp.async.bulk.tensor), so the whole producer side is ONE thread and no LSU issue slots
+// are spent on operand traffic:
+//   K-major tiles   : tiled 2-D maps (box 32 floats x rows, SWIZZLE_128B)            -- 1x1 / FC / weights
+//   gathered pixels : im2col 4-D maps over the NHWC tensor (C,W,H,N); the filter tap is the
+//                     per-instruction {offW,offH}; padding taps are zero-filled by the TMA
+//   MN-major tiles  : 32x32 boxes with SWIZZLE_128B_ATOM_32B, one per 32-column group
+// Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue.
+// =====================================================================================
+constexpr int kTmaThreads = 192;
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w,
+                                                int h, int n, int offw, int offh) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n),
+          "h"((unsigned short)offw), "h"((unsigned short)offh)
+        : "memory");
+}
+
+template <int BN, int OP>
+__global__ void __launch_bounds__(kTmaThreads)
+tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant__ CUtensorMap mapA,
+                   const __grid_constant__ CUtensorMap mapB) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    constexpr uint32_t kStage = kTcABytes + BN * 128;
+    constexpr int kTcStages = tc_stages<BN>();
+    const uint32_t bar_base = base + kTcStages * kStage;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * kTcStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kTcStages) + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int taps = p.kh * p.kw;
+    int nkb;
+    if (OP == TC_FWD) nkb = taps * (p.Cin / kTcBK);
+    else if (OP == TC_DGRAD) nkb = taps * (p.Cout / kTcBK);
+    else nkb = (p.M + kTcBK - 1) / kTcBK;
+    const int per = (nkb + p.ksplit - 1) / p.ksplit;
+    const int kb0 = blockIdx.z * per;
+    const int nk = min(nkb, kb0 + per) - kb0;
+    if (nk <= 0) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; s++) {
+            mbar_init(full_bar(s), 1);    // the producer's arrive.expect_tx (+ TMA byte count)
+            mbar_init(empty_bar(s), 1);   // one tcgen05.commit
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot_ptr;
+    const int m0 = blockIdx.x * kTcBM;
+    const int n0 = blockIdx.y * BN;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // =========================== TMA PRODUCER ===========================
+            int stage = 0;
+            uint32_t phase = 0;
+            constexpr uint32_t kBytes = kTcABytes + BN * 128;
+            const int r = p.dil;
+            if (OP == TC_FWD || OP == TC_DGRAD) {
+                const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;
+                const int cblocks = Ck / kTcBK;
+                // first pixel of this tile in (w,h,n) -- base coordinate of the im2col walk
+                const int hw = p.H * p.W;
+                const int img0 = m0 / hw, rem0 = m0 - img0 * hw, ph0 = rem0 / p.W, pw0 = rem0 - ph0 * p.W;
+                for (int i = 0; i < nk; i++) {
+                    const int kb = kb0 + i;
+                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
+                    mbar_expect_tx(full_bar(stage), kBytes);
+                    if (taps == 1) {
+                        tma_load_2d(sA, &mapA, full_bar(stage), cb * kTcBK, m0);
+                    } else {
+                        int th = tap / p.kw, tw = tap - th * p.kw;
+                        if (OP == TC_DGRAD) { th = p.kh - 1 - th; tw = p.kw - 1 - tw; }   // dX[p] needs dY[p - off]
+                        tma_load_im2col(sA, &mapA, full_bar(stage), cb * kTcBK, pw0 - r * (p.kw / 2),
+                                        ph0 - r * (p.kh / 2), img0, tw * r, th * r);
+                    }
+                    if (OP == TC_FWD) {
+                        tma_load_2d(sB, &mapB, full_bar(stage), kb * kTcBK, n0);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BN / 32; g++)
+                            tma_load_2d(sB + g * 4096, &mapB, full_bar(stage), tap * p.Cin + n0 + 32 * g, cb * kTcBK);
+                    }
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+                }
+            } else {
+                const int tap = n0 / p.Cin, ci0 = n0 - tap * p.Cin;
+                const int th = tap / p.kw, tw = tap - th * p.kw;
+                const int hw = p.H * p.W;
+                for (int i = 0; i < nk; i++) {
+                    const int k0 = (kb0 + i) * kTcBK;
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
+                    mbar_expect_tx(full_bar(stage), kBytes);
+#pragma unroll
+                    for (int g = 0; g < 4; g++) tma_load_2d(sA + g * 4096, &mapA, full_bar(stage), m0 + 32 * g, k0);
+                    if (taps == 1) {
+#pragma unroll
+                        for (int g = 0; g < BN / 32; g++)
+                            tma_load_2d(sB + g * 4096, &mapB, full_bar(stage), ci0 + 32 * g, k0);
+                    } else {
+                        const int img = k0 / hw, rem = k0 - img * hw, ph = rem / p.W, pw = rem - ph * p.W;
+#pragma unroll
+                        for (int g = 0; g < BN / 32; g++)
+                            tma_load_im2col(sB + g * 4096, &mapB, full_bar(stage), ci0 + 32 * g, pw - r * (p.kw / 2),
+                                            ph - r * (p.kh / 2), img, tw * r, th * r);
+                    }
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA ISSUER ===========================
+        constexpr bool a_mn = (OP == TC_WGRAD);
+        constexpr bool b_mn = (OP != TC_FWD);
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) |
+                                   ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(kTcBM >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < nk; i++) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
+#pragma unroll
+                for (int k = 0; k < kTcBK / 8; k++) {
+                    const uint64_t ad = a_mn ? desc_mnmajor(sA + k * 1024) : desc_kmajor(sA + k * 32);
+                    const uint64_t bd = b_mn ? desc_mnmajor(sB + k * 1024) : desc_kmajor(sB + k * 32);
+                    umma_tf32(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(stage));
+                if (i == nk - 1) umma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+            if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
+        tc_fence_before();
+    } else {
+        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, lane, m0, n0);
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+
+static bool tma_api_ready() {
+    if (g_encode_tiled && g_encode_im2col) return true;
+    cudaDriverEntryPointQueryResult q;
+    void* f = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return false;
+    g_encode_tiled = (EncodeTiledFn)f;
+    f = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return false;
+    g_encode_im2col = (EncodeIm2colFn)f;
+    cudaDriverGetVersion(&g_driver_version);
+    return true;
+}
+
+// rows x inner fp32 matrix with a row pitch of `pitch` floats; box = 32 floats x box_rows
+static bool make_map_2d(CUtensorMap* m, const float* ptr, long inner, long rows, long pitch, int box_rows, bool mn_major) {
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    return g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// NHWC tensor (C channels used, pixel pitch `pitch` floats) walked in im2col order for a kh x kw filter
+// with atrous rate r and SAME padding; box = 32 channels x `pixels` consecutive output pixels
+static bool make_map_im2col(CUtensorMap* m, const float* ptr, int C, int W, int H, int N, long pitch, int kh, int kw,
+                            int r, int pixels, bool mn_major) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * W, (cuuint64_t)pitch * 4 * W * H};
+    // base pixel range [-pad, dim + upper): pad = r*(k/2); upper = pad - (k-1)*r   (WHD order: {W, H})
+    int lower[2] = {-r * (kw / 2), -r * (kh / 2)};
+    int upper[2] = {r * (kw / 2) - (kw - 1) * r, r * (kh / 2) - (kh - 1) * r};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult res = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, lower, upper, 32,
+                                   (cuuint32_t)pixels, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (res != CUDA_SUCCESS) return false;
+    // driver workaround also applied by CUTLASS (copy_traits_sm90_im2col.hpp): small tensors
+    if (g_driver_version <= 13010 && (size_t)pitch * 4 * W * H * N < 131072)
+        reinterpret_cast<uint64_t*>(m)[1] &= ~(1llu << 21);
+    return true;
+}
+
+template <int BN, int OP>
+static int launch_tma(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
+    alignas(64) CUtensorMap mapA, mapB;
+    const int taps = p.kh * p.kw;
+    const int nimg = p.M / (p.H * p.W);
+    bool ok = true;
+    if (OP == TC_FWD || OP == TC_DGRAD) {
+        const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;
+        if (taps == 1) ok &= make_map_2d(&mapA, p.X, Ck, p.M, p.ldx, kTcBM, false);
+        else ok &= make_map_im2col(&mapA, p.X, Ck, p.W, p.H, nimg, p.ldx, p.kh, p.kw, p.dil, kTcBM, false);
+        if (OP == TC_FWD) ok &= make_map_2d(&mapB, p.Wt, (long)taps * p.Cin, p.Cout, p.ldw, BN, false);
+        else ok &= make_map_2d(&mapB, p.Wt, (long)taps * p.Cin, p.Cout, p.ldw, 32, true);
+    } else {
+        ok &= make_map_2d(&mapA, p.Y, p.Cout, p.M, p.ldy, 32, true);
+        if (taps == 1) ok &= make_map_2d(&mapB, p.X, p.Cin, p.M, p.ldx, 32, true);
+        else ok &= make_map_im2col(&mapB, p.X, p.Cin, p.W, p.H, nimg, p.ldx, p.kh, p.kw, p.dil, 32, true);
+    }
+    if (!ok) return -2;
+    constexpr int smem = tc_smem_bytes<BN>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    tc_gemm_tma_kernel<BN, OP><<<grid, kTmaThreads, smem, s>>>(p, mapA, mapB);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int g_tc_mode = -1;   // 0 = cp.async producers, 1 = TMA producers
+int tc_gemm_mode() {
+    if (g_tc_mode < 0) {
+        const char* e = getenv("MPB_TC_PRODUCER");
+        g_tc_mode = (e && e[0] == 'c') ? 0 : 1;    // MPB_TC_PRODUCER=cpasync selects the LSU-fed variant
+        if (g_tc_mode == 1 && !tma_api_ready()) g_tc_mode = 0;
+    }
+    return g_tc_mode;
+}
+void tc_gemm_set_mode(int m) { g_tc_mode = m; if (m == 1 && !tma_api_ready()) g_tc_mode = 0; }
+
 template <int BN, int OP>
 static int launch_one(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     constexpr int smem = tc_smem_bytes<BN>();
@@ -390,8 +679,15 @@ int tc_gemm_launch(const TcGemmParams& p, int BN, cudaStream_t s) {
         return -1;
     }
     if (grid.y > 65535 || grid.z > 65535) return -1;
+    // the TMA path needs whole images in the pixel grid (im2col walk) and 16-byte aligned pitches
+    const bool tma = tc_gemm_mode() == 1 && (p.M % (p.H * p.W) == 0);
 #define MPB_TC_CASE(bn)                                                       \
     if (BN == bn) {                                                           \
+        if (tma) {                                                            \
+            if (p.op == TC_FWD) return launch_tma<bn, TC_FWD>(p, grid, s);    \
+            if (p.op == TC_DGRAD) return launch_tma<bn, TC_DGRAD>(p, grid, s);\
+            return launch_tma<bn, TC_WGRAD>(p, grid, s);                      \
+        }                                                                     \
         if (p.op == TC_FWD) return launch_one<bn, TC_FWD>(p, grid, s);        \
         if (p.op == TC_DGRAD) return launch_one<bn, TC_DGRAD>(p, grid, s);    \
         return launch_one<bn, TC_WGRAD>(p, grid, s);                          \

@@ -51,6 +51,7 @@ class OptChunk(ctypes.Structure):
 
 _SIGS = {
     "mpb_tc_gemm": [ctypes.POINTER(TcGemmParams), c_i, c_p],
+    "mpb_tc_set_producer": [c_i],
     "mpb_build_tapmask": [c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "mpb_fold_bn": [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
     "mpb_round_copy": [c_l, c_p, c_p, c_p],

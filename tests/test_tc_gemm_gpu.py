@@ -19,6 +19,16 @@ from monopsr_b200 import lib as mlib  # noqa: E402
 from monopsr_b200.lib_net import TC_DGRAD, TC_FWD, TC_WGRAD, TcGemmParams  # noqa: E402
 
 
+@pytest.fixture(autouse=True, params=["tma", "cpasync"])
+def producer(request):
+    """run every case with both operand-staging variants of the kernel"""
+    mode = mlib.load().mpb_tc_set_producer(1 if request.param == "tma" else 0)
+    if request.param == "tma" and mode != 1:
+        pytest.skip("driver lacks cuTensorMapEncode*")
+    yield request.param
+    mlib.load().mpb_tc_set_producer(1)
+
+
 def tf32_round(t):
     """round-to-nearest-even-ish to 10 mantissa bits (matches cvt.rna up to ties)"""
     i = t.contiguous().view(torch.int32)
