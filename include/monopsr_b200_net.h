@@ -73,6 +73,17 @@ int mpb_round_copy(long n, const float* src, float* dst, void* stream);   /* dst
 int mpb_bn_param_grad(int cout, int K, const float* w, const float* dw, const float* gamma, const float* mean,
                       const float* var, float eps, const float* dbeta, float* dgamma, void* stream);
 
+/* whole-model variants of the two calls above: one launch over all (layer, output channel) rows.
+ * layers / row2layer are DEVICE arrays; row2layer[r] = layer index of global row r, layers[i].row0 = first row. */
+typedef struct mpb_bn_layer {
+    const float* w; const float* gamma; const float* beta; const float* mean; const float* var;
+    float* wf; float* scale; float* shift;
+    const float* dw; const float* dbeta; float* dgamma;
+    int cout; int K; int row0; int pad_;
+} mpb_bn_layer;
+int mpb_fold_bn_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream);
+int mpb_bn_param_grad_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream);
+
 /* ---- stem: conv2d_same(7x7, stride 2) + frozen BN + ReLU  (nets/resnet_v1.py:234) ---- */
 int mpb_stem_fwd(int nimg, int Hin, int Win, const float* x, const float* wf, const float* shift, float* y, void* stream);
 int mpb_stem_wgrad(int nimg, int Hin, int Win, const float* x, const float* g, const float* scale, float* dw, void* stream);

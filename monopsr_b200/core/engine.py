@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from .. import lib as _lib
-from ..lib_net import TC_DGRAD, TC_FWD, TC_WGRAD, HeadsIO, OptChunk, TcGemmParams
+from ..lib_net import TC_DGRAD, TC_FWD, TC_WGRAD, BnLayer, HeadsIO, OptChunk, TcGemmParams
 from . import model_spec as ms
 
 BN_EPS_RESNET = 1e-5
@@ -320,25 +320,43 @@ class Engine:
                   tapmask=tapmask, rowscale=rowscale, atomic=1, ksplit=ksplit, bn=bn)
 
     # ------------------------------------------------------------------ weight preparation
+    def _build_bn_table(self):
+        """device table of every frozen-BN conv of both towers (one launch folds / differentiates them all)"""
+        self.bnfold = {}
+        layers = []
+        for enc in ms.ENCODERS:
+            for scope, k, cin, cout, _ in ms.conv_layers(enc):
+                self.bnfold[scope] = (torch.empty(cout, device=self.dev), torch.empty(cout, device=self.dev))
+                layers.append((scope, k * k * cin, cout))
+        arr = (BnLayer * len(layers))()
+        row2layer = []
+        row = 0
+        for i, (scope, K, cout) in enumerate(layers):
+            b = scope + "/BatchNorm/"
+            e = arr[i]
+            e.w, e.gamma, e.beta = self.view(scope + "/weights").data_ptr(), self.view(b + "gamma").data_ptr(), self.view(b + "beta").data_ptr()
+            e.mean, e.var = self.view(b + "moving_mean").data_ptr(), self.view(b + "moving_variance").data_ptr()
+            e.wf, e.scale, e.shift = self.pview(scope + "/weights").data_ptr(), self.bnfold[scope][0].data_ptr(), self.bnfold[scope][1].data_ptr()
+            e.dw, e.dbeta, e.dgamma = self.gview(scope + "/weights").data_ptr(), self.gview(b + "beta").data_ptr(), self.gview(b + "gamma").data_ptr()
+            e.cout, e.K, e.row0 = cout, K, row
+            row2layer += [i] * cout
+            row += cout
+        self.bn_rows = row
+        self.bn_layers = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev)
+        self.bn_row2layer = torch.tensor(row2layer, dtype=torch.int32, device=self.dev)
+        # the non-tower GEMM weights only need tf32 rounding: they are contiguous at the end of the arena
+        first = min(self.layout[n][1] for n in self.trainable_names if not n.startswith("FirstStage"))
+        self.round_off, self.round_len = first, self.n_train - first
+
     def prepare_weights(self):
         """fold frozen BN into the tower convs, tf32-round every GEMM weight (run after each update)."""
         L, st = self.L, self._st()
-        self.bnfold = getattr(self, "bnfold", {})
-        for enc in ms.ENCODERS:
-            for scope, k, cin, cout, _ in ms.conv_layers(enc):
-                if scope not in self.bnfold:
-                    self.bnfold[scope] = (torch.empty(cout, device=self.dev), torch.empty(cout, device=self.dev))
-                sc, sh = self.bnfold[scope]
-                b = scope + "/BatchNorm/"
-                self._chk(L.mpb_fold_bn(cout, k * k * cin, _ptr(self.view(scope + "/weights")),
-                                        _ptr(self.view(b + "gamma")), _ptr(self.view(b + "beta")),
-                                        _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
-                                        BN_EPS_RESNET, _ptr(self.pview(scope + "/weights")), _ptr(sc), _ptr(sh), st),
-                          "fold_bn")
-        for n in self.trainable_names:
-            if self.ptable[n][1] == "weights" and not n.startswith("FirstStage"):
-                v = self.view(n)
-                self._chk(L.mpb_round_copy(v.numel(), _ptr(v), _ptr(self.pview(n)), st), "round_copy")
+        if getattr(self, "bn_layers", None) is None:
+            self._build_bn_table()
+        self._chk(L.mpb_fold_bn_multi(self.bn_rows, _ptr(self.bn_layers), _ptr(self.bn_row2layer), BN_EPS_RESNET, st),
+                  "fold_bn_multi")
+        self._chk(L.mpb_round_copy(self.round_len, _ptr(self.params[self.round_off:]), _ptr(self.prep[self.round_off:]), st),
+                  "round_copy")
         self._prepared = True
 
     # ------------------------------------------------------------------ inputs
@@ -558,14 +576,6 @@ class Engine:
                                         _ptr(self.gview(s0 + "/BatchNorm/beta")), st), "stem_colsum")
         self._chk(L.mpb_stem_wgrad(T["nimg"], T["Hin"], T["Win"], _ptr(x_in), _ptr(T["g_stem"]), _ptr(self.bnfold[s0][0]),
                                    _ptr(self.gview(s0 + "/weights")), st), "stem_wgrad")
-        # d(gamma) of every frozen BN from (w, dw, dbeta)
-        for scope, k, cin, cout, _ in ms.conv_layers(T["enc"]):
-            b = scope + "/BatchNorm/"
-            self._chk(L.mpb_bn_param_grad(cout, k * k * cin, _ptr(self.view(scope + "/weights")),
-                                          _ptr(self.gview(scope + "/weights")), _ptr(self.view(b + "gamma")),
-                                          _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
-                                          BN_EPS_RESNET, _ptr(self.gview(b + "beta")), _ptr(self.gview(b + "gamma")), st),
-                      "bn_param_grad")
 
     def backward(self):
         L, st, N, I, h = self.L, self._st(), self.N, self.inputs, self.h
@@ -644,6 +654,9 @@ class Engine:
                                         st), "full_relu_bwd")
         self._tower_bwd(Tc, I["rgb_crops"])
         self._tower_bwd(Tf, I["full_img"])
+        # d(gamma) of every frozen BN from (w, dw, dbeta), both towers in one launch
+        self._chk(L.mpb_bn_param_grad_multi(self.bn_rows, _ptr(self.bn_layers), _ptr(self.bn_row2layer), BN_EPS_RESNET, st),
+                  "bn_param_grad_multi")
 
     # ------------------------------------------------------------------ train-op
     def learning_rate(self, step):

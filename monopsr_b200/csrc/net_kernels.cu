@@ -57,6 +57,40 @@ __global__ void bn_param_grad_kernel(int cout, int K, const float* __restrict__ 
     }
 }
 
+
+// ---- whole-model variants: one launch over every (layer, output channel) pair instead of
+// one launch per layer (208 frozen-BN convs in the two towers)
+__global__ void fold_bn_multi_kernel(const mpb_bn_layer* __restrict__ layers, const int* __restrict__ row2layer, float eps) {
+    const mpb_bn_layer L = layers[row2layer[blockIdx.x]];
+    const int co = blockIdx.x - L.row0;
+    const float s = L.gamma[co] * rsqrtf(L.var[co] + eps);
+    if (threadIdx.x == 0) {
+        L.scale[co] = s;
+        L.shift[co] = L.beta[co] - L.mean[co] * s;
+    }
+    const float* w = L.w + (size_t)co * L.K;
+    float* wf = L.wf + (size_t)co * L.K;
+    for (int k = threadIdx.x; k < L.K; k += blockDim.x) wf[k] = rtf32(w[k] * s);
+}
+__global__ void bn_param_grad_multi_kernel(const mpb_bn_layer* __restrict__ layers, const int* __restrict__ row2layer,
+                                           float eps) {
+    const mpb_bn_layer L = layers[row2layer[blockIdx.x]];
+    const int co = blockIdx.x - L.row0;
+    const float* w = L.w + (size_t)co * L.K;
+    const float* dw = L.dw + (size_t)co * L.K;
+    float acc = 0.f;
+    for (int k = threadIdx.x; k < L.K; k += blockDim.x) acc = fmaf(w[k], dw[k], acc);
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+        L.dgamma[co] = t / L.gamma[co] - L.mean[co] * L.dbeta[co] * rsqrtf(L.var[co] + eps);
+    }
+}
+
 // ---------------------------------------------------------------- stem: conv 7x7/2 + BN + ReLU
 // resnet_utils.conv2d_same(net, 64, 7, stride=2) (nets/resnet_v1.py:234): pad 3|3, VALID.
 // Cin=3 -> K=147: bandwidth-bound, kept off the tensor cores.  One thread = one output pixel x
@@ -684,6 +718,18 @@ MPB_API int mpb_round_copy(long n, const float* src, float* dst, void* stream) {
 MPB_API int mpb_bn_param_grad(int cout, int K, const float* w, const float* dw, const float* gamma, const float* mean,
                               const float* var, float eps, const float* dbeta, float* dgamma, void* stream) {
     bn_param_grad_kernel<<<cout, 256, 0, ST>>>(cout, K, w, dw, gamma, mean, var, eps, dbeta, dgamma);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_fold_bn_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream) {
+    if (total_rows <= 0 || !layers || !row2layer) return -1;
+    fold_bn_multi_kernel<<<total_rows, 128, 0, ST>>>(layers, row2layer, eps);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_bn_param_grad_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream) {
+    if (total_rows <= 0 || !layers || !row2layer) return -1;
+    bn_param_grad_multi_kernel<<<total_rows, 128, 0, ST>>>(layers, row2layer, eps);
     MPB_LAUNCH_CHECK();
     return 0;
 }

@@ -99,90 +99,66 @@ __device__ __forceinline__ int tap_delta(int tap, int kh, int kw, int dil, int W
 
 // ------------------------------------------------------------------ fused epilogue
 // Called by 4 warps; `quad` (= warp index % 4) selects the 32 TMEM lanes (= accumulator rows) a
-// warp may read.
+// warp may read.  tcgen05.ld hands every thread one ROW (32 consecutive columns); global memory
+// wants a warp on one row.  Each 32x32 chunk is therefore transposed through a padded shared-memory
+// tile (the pipeline stages are free once the accumulator is complete), after which lane = column:
+// residual / mask reads, stores and split-K REDs are 128-byte coalesced, the per-column BN shift
+// lives in a register and the column sums (d beta) need no shuffles.
 template <int BN, int OP>
 __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem_full_bar, uint32_t tmem_acc,
-                                            int quad, int lane, int m0, int n0) {
-    const int warp = quad;
+                                            int quad, int lane, int m0, int n0, float* stg_base) {
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int row = warp * 32 + lane;          // TMEM lane == accumulator row
-    const int grow = m0 + row;                 // pixel (FWD/DGRAD) or output channel (WGRAD)
+    float* stg = stg_base + quad * (32 * 33);
+    const int row0 = m0 + quad * 32;               // first accumulator row of this warp
     const int nrows = (OP == TC_WGRAD) ? p.Cout : p.M;
-    const bool rok = grow < nrows;
-    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const int nvalid = min(32, nrows - row0);      // warp-uniform
+    const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16);
     const int ldo = (OP == TC_WGRAD) ? p.ldw : p.ldo;
+    float rs = 1.f;
+    if (p.rowscale && lane < nvalid) rs = __ldg(p.rowscale + row0 + lane);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int col = n0 + c0 + lane;
+        // issue every global read of this chunk first (32 independent coalesced loads each), so
+        // their latency overlaps the TMEM read and the shared-memory transpose
+        float rv[32], mv[32];
+        if (p.res) {
+            const float* resp = p.res + (size_t)row0 * p.ldr + col;
+#pragma unroll
+            for (int r = 0; r < 32; r++) rv[r] = r < nvalid ? __ldg(resp + (size_t)r * p.ldr) : 0.f;
+        }
+        if (p.mask) {
+            const float* mskp = p.mask + (size_t)row0 * p.ldm + col;
+#pragma unroll
+            for (int r = 0; r < 32; r++) mv[r] = r < nvalid ? __ldg(mskp + (size_t)r * p.ldm) : 0.f;
+        }
+        const float sc = p.scale ? __ldg(p.scale + col) : 1.f;
+        const float sh = p.shift ? __ldg(p.shift + col) : 0.f;
+        const float s2 = p.scale2 ? __ldg(p.scale2 + col) : 1.f;
         float v[32];
         tmem_ld32(trow + c0, v);
-        const int gc = n0 + c0;
-        if (p.rowscale && rok) {
-            const float rs = __ldg(p.rowscale + grow);
+        __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 32; q++) v[q] *= rs;
-        }
-        if (p.scale) {
+        for (int q = 0; q < 32; q++) stg[lane * 33 + q] = v[q] * rs;
+        __syncwarp();
+        float csum = 0.f;
+        float* outp = p.out + (size_t)row0 * ldo + col;
 #pragma unroll
-            for (int q = 0; q < 32; q++) v[q] *= __ldg(p.scale + gc + q);
-        }
-        if (p.shift) {
-#pragma unroll
-            for (int q = 0; q < 32; q++) v[q] += __ldg(p.shift + gc + q);
-        }
-        if (p.res && rok) {
-            const float4* rp = reinterpret_cast<const float4*>(p.res + (size_t)grow * p.ldr + gc);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                float4 t = __ldg(rp + q);
-                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+        for (int r = 0; r < 32; r++) {
+            float x = fmaf(stg[r * 33 + lane], sc, sh);
+            if (p.res) x += rv[r];
+            if (p.relu) x = fmaxf(x, 0.f);
+            if (p.mask) x = mv[r] > 0.f ? x : 0.f;
+            x *= s2;
+            if (p.round_tf32) x = round_tf32(x);
+            if (r < nvalid) {
+                csum += x;
+                if (p.atomic) atomicAdd(outp + (size_t)r * ldo, x);
+                else outp[(size_t)r * ldo] = x;
             }
         }
-        if (p.relu) {
-#pragma unroll
-            for (int q = 0; q < 32; q++) v[q] = fmaxf(v[q], 0.f);
-        }
-        if (p.mask && rok) {
-            const float4* mp = reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ldm + gc);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                float4 t = __ldg(mp + q);
-                v[4 * q] = t.x > 0.f ? v[4 * q] : 0.f;
-                v[4 * q + 1] = t.y > 0.f ? v[4 * q + 1] : 0.f;
-                v[4 * q + 2] = t.z > 0.f ? v[4 * q + 2] : 0.f;
-                v[4 * q + 3] = t.w > 0.f ? v[4 * q + 3] : 0.f;
-            }
-        }
-        if (p.scale2) {
-#pragma unroll
-            for (int q = 0; q < 32; q++) v[q] *= __ldg(p.scale2 + gc + q);
-        }
-        if (p.round_tf32) {
-#pragma unroll
-            for (int q = 0; q < 32; q++) v[q] = round_tf32(v[q]);
-        }
-        if (p.colsum) {
-            // per-column sums over this warp's 32 rows, one RED per column per warp
-#pragma unroll
-            for (int q = 0; q < 32; q++) {
-                float s = rok ? v[q] : 0.f;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == q) atomicAdd(p.colsum + gc + q, s);
-            }
-        }
-        if (rok) {
-            float4* op = reinterpret_cast<float4*>(p.out + (size_t)grow * ldo + gc);
-            if (p.atomic) {
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    atomicAdd(op + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-        }
+        if (p.colsum && nvalid > 0) atomicAdd(p.colsum + col, csum);
     }
     tc_fence_before();
 }
@@ -330,7 +306,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
             }
         }
 
-        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp, lane, m0, n0);
+        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp, lane, m0, n0,
+                            reinterpret_cast<float*>(smem_raw + (base - raw)));
     } else {
         // =========================== MMA ISSUER (warp 4) ===========================
         constexpr bool a_mn = (OP == TC_WGRAD);
@@ -540,7 +517,8 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
         }
         tc_fence_before();
     } else {
-        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, lane, m0, n0);
+        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, lane, m0, n0,
+                            reinterpret_cast<float*>(smem_raw + (base - raw)));
     }
     __syncthreads();
     if (warp == 1) {

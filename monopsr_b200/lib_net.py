@@ -45,6 +45,12 @@ class HeadsIO(ctypes.Structure):
     ]
 
 
+class BnLayer(ctypes.Structure):
+    _fields_ = [("w", c_p), ("gamma", c_p), ("beta", c_p), ("mean", c_p), ("var", c_p), ("wf", c_p), ("scale", c_p),
+                ("shift", c_p), ("dw", c_p), ("dbeta", c_p), ("dgamma", c_p), ("cout", c_i), ("K", c_i), ("row0", c_i),
+                ("pad_", c_i)]
+
+
 class OptChunk(ctypes.Structure):
     _fields_ = [("start", c_l), ("len", c_i), ("tensor", c_i)]
 
@@ -54,6 +60,8 @@ _SIGS = {
     "mpb_tc_set_producer": [c_i],
     "mpb_build_tapmask": [c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "mpb_fold_bn": [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
+    "mpb_fold_bn_multi": [c_i, c_p, c_p, c_f, c_p],
+    "mpb_bn_param_grad_multi": [c_i, c_p, c_p, c_f, c_p],
     "mpb_round_copy": [c_l, c_p, c_p, c_p],
     "mpb_bn_param_grad": [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p],
     "mpb_stem_fwd": [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
