@@ -79,6 +79,12 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def cpu_threads():
+    # torch's CPU convolutions on 12x12 maps stop scaling (and then regress) beyond a few dozen
+    # threads; use what helps and report the count actually used
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def cpu_reference_step(P, S, threads, steps=1):
     """The restated reference graph (oracle/network.py, fp32) fwd+bwd on the host cores.
     TensorFlow 1.8 itself cannot be installed here."""
@@ -105,7 +111,7 @@ def run_reference(args):
     if rank != 0:
         return
     from monopsr_b200.core import model_spec as ms
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     P, S = ms.init_params(0), ms.synthetic_sample(0)
     steps = max(1, min(args.steps, 3))       # one step = 32 crops = ~10-20 s of CPU work
     cpu_reference_step(P, S, threads, 1) if args.warmup > 0 else None
@@ -292,7 +298,7 @@ def main():
     if not args.no_ops:
         line["ops"] = tfops_micro(dev)
     if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         ts = cpu_reference_step(P, S, threads, 1)
         line["cpu_baseline"] = {"value": CROPS_PER_SAMPLE / ts[0], "unit": "crops/s", "cores": threads, "kind": "port",
                                 "sample": "1 full step of 32 crops (restated TF1 graph, torch-CPU fp32)"}

