@@ -58,6 +58,8 @@ int mpb_tc_gemm(const mpb_tc_gemm_params* p, int BN, void* stream);
 /* operand staging of the GEMM core: 1 = TMA (cp.async.bulk.tensor, default), 0 = cp.async (LSU) producers.
  * Returns the mode in effect (TMA falls back to 0 when the driver lacks cuTensorMapEncode*). */
 int mpb_tc_set_producer(int mode);
+/* max CTAs per thread-block cluster sharing (TMA-multicasting) one A tile: 1 (default, off), 2 or 4. */
+int mpb_tc_set_cluster(int max_cluster);
 
 /* tapmask[m] for an (nimg,H,W) pixel grid and a kh x kw filter with atrous rate dil. */
 int mpb_build_tapmask(int nimg, int H, int W, int kh, int kw, int dil, unsigned short* out, void* stream);

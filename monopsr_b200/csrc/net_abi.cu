@@ -33,3 +33,8 @@ MPB_API int mpb_tc_set_producer(int mode) {
     mpb::tc_gemm_set_mode(mode);
     return mpb::tc_gemm_mode();
 }
+
+MPB_API int mpb_tc_set_cluster(int max_cluster) {
+    mpb::tc_gemm_set_cluster(max_cluster);
+    return max_cluster;
+}

@@ -691,8 +691,11 @@ static int g_tc_cluster = -1;   // max CTAs per cluster along N (1 disables mult
 template <int BN, int OP>
 static int launch_tma(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     if (g_tc_cluster < 0) {
+        // Measured on B200 (profiles/r1_notes.md): multicasting A over a cluster of column tiles does
+        // NOT speed these GEMMs up (21.1 vs 19.6 ms of GEMM time per step) -- they are bound by the
+        // bytes each SM must RECEIVE per MMA, which multicast does not change -- so it is off by default.
         const char* e = getenv("MPB_TC_CLUSTER");
-        g_tc_cluster = e ? atoi(e) : 4;
+        g_tc_cluster = e ? atoi(e) : 1;
     }
     if (g_tc_cluster >= 4 && grid.y % 4 == 0) return launch_tma_cn<BN, OP, 4>(p, grid, s);
     if (g_tc_cluster >= 2 && grid.y % 2 == 0) return launch_tma_cn<BN, OP, 2>(p, grid, s);
@@ -708,6 +711,7 @@ int tc_gemm_mode() {
     }
     return g_tc_mode;
 }
+void tc_gemm_set_cluster(int c) { g_tc_cluster = c < 1 ? 1 : c; }
 void tc_gemm_set_mode(int m) { g_tc_mode = m; if (m == 1 && !tma_api_ready()) g_tc_mode = 0; }
 
 template <int BN, int OP>

@@ -44,5 +44,6 @@ constexpr int tc_smem_bytes() {
 int tc_gemm_launch(const TcGemmParams& p, int BN, cudaStream_t s);
 int tc_gemm_mode();            // 0 = cp.async producers, 1 = TMA producers (default)
 void tc_gemm_set_mode(int m);
+void tc_gemm_set_cluster(int c);  // max CTAs per cluster for A-tile multicast (1 = off, default)
 
 }  // namespace mpb

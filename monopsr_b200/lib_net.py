@@ -58,6 +58,7 @@ class OptChunk(ctypes.Structure):
 _SIGS = {
     "mpb_tc_gemm": [ctypes.POINTER(TcGemmParams), c_i, c_p],
     "mpb_tc_set_producer": [c_i],
+    "mpb_tc_set_cluster": [c_i],
     "mpb_build_tapmask": [c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "mpb_fold_bn": [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
     "mpb_fold_bn_multi": [c_i, c_p, c_p, c_f, c_p],

@@ -19,14 +19,18 @@ from monopsr_b200 import lib as mlib  # noqa: E402
 from monopsr_b200.lib_net import TC_DGRAD, TC_FWD, TC_WGRAD, TcGemmParams  # noqa: E402
 
 
-@pytest.fixture(autouse=True, params=["tma", "cpasync"])
+@pytest.fixture(autouse=True, params=["tma", "tma_cluster", "cpasync"])
 def producer(request):
-    """run every case with both operand-staging variants of the kernel"""
-    mode = mlib.load().mpb_tc_set_producer(1 if request.param == "tma" else 0)
-    if request.param == "tma" and mode != 1:
+    """run every case with all operand-staging variants of the kernel: TMA, TMA with the A tile
+    multicast over a thread-block cluster of column tiles, and cp.async (LSU) producers"""
+    L = mlib.load()
+    mode = L.mpb_tc_set_producer(0 if request.param == "cpasync" else 1)
+    if request.param != "cpasync" and mode != 1:
         pytest.skip("driver lacks cuTensorMapEncode*")
+    L.mpb_tc_set_cluster(4 if request.param == "tma_cluster" else 1)
     yield request.param
-    mlib.load().mpb_tc_set_producer(1)
+    L.mpb_tc_set_producer(1)
+    L.mpb_tc_set_cluster(1)
 
 
 def tf32_round(t):
