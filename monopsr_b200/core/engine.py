@@ -48,6 +48,13 @@ class Engine:
             self._alloc_activations()
         self.step_count = 0
         self.world = 1
+        # side streams: the two towers are independent until the concat, and weight gradients are
+        # off the critical path of the data-gradient chain -> they run concurrently (also inside
+        # the captured CUDA graph, where the fork/join become graph edges)
+        self.s_full = torch.cuda.Stream(device=self.dev)
+        self.s_wc = torch.cuda.Stream(device=self.dev)
+        self.s_wf = torch.cuda.Stream(device=self.dev)
+        self.overlap = True
 
     # ------------------------------------------------------------------ parameters
     def _dev_shape(self, name, shape, kind):
@@ -403,7 +410,7 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     def _tower_fwd(self, T, x_in):
-        L, st = self.L, self._st()
+        L, st = self.L, self._st()      # evaluated inside the caller's stream context
         enc = T["enc"]
         s0 = enc + "/resnet_v1_101/conv1"
         self._chk(L.mpb_stem_fwd(T["nimg"], T["Hin"], T["Win"], _ptr(x_in), _ptr(self.pview(s0 + "/weights")),
@@ -449,10 +456,12 @@ class Engine:
             self.prepare_weights()
         L, st, N, I = self.L, self._st(), self.N, self.inputs
         Tc, Tf = self.towers[ms.ENCODERS[0]], self.towers[ms.ENCODERS[1]]
+        with self._side(self.s_full):
+            ff, _ = self._tower_fwd(Tf, I["full_img"])
+            self._chk(L.mpb_crop_pool_fwd(Tf["h"], Tf["w"], 1024, _ptr(ff), N, _ptr(I["boxes_2d_norm"]), 24,
+                                          _ptr(self.concat[:, 1024:]), 2048, self._st()), "crop_pool_fwd")
         self._tower_fwd(Tc, I["rgb_crops"])
-        ff, _ = self._tower_fwd(Tf, I["full_img"])
-        self._chk(L.mpb_crop_pool_fwd(Tf["h"], Tf["w"], 1024, _ptr(ff), N, _ptr(I["boxes_2d_norm"]), 24,
-                                      _ptr(self.concat[:, 1024:]), 2048, st), "crop_pool_fwd")
+        self._join(self.s_full)
         Mc = self.Mc
         self.gemm(TC_FWD, Mc, 12, 12, 1, 1, 2048, 512, self.concat, 2048, self.pview("squash/1x1_conv/weights"), 2048,
                   self.squashed, 512, shift=self.view("squash/1x1_conv/biases"), relu=1, round_tf32=1)
@@ -530,9 +539,10 @@ class Engine:
             self.gemm(TC_DGRAD, N, 1, 1, 1, 1, K, 1024, g, 1024, self.pview(wname + "/weights"), K, dx, lddx,
                       res=res, ldr=ldr, bn=64 if K % 256 else 256)
 
-    def _tower_bwd(self, T, x_in):
-        """T['units'][-1]['g_out'] holds g = dL/d(out)*(out>0) of the last unit (and its d(beta3) is set)."""
-        L, st = self.L, self._st()
+    def _tower_bwd(self, T, x_in, ws):
+        """T['units'][-1]['g_out'] holds g = dL/d(out)*(out>0) of the last unit (and its d(beta3) is set).
+        The data-gradient chain runs on the current stream, the weight gradients on `ws`."""
+        L = self.L
         M, h, w = T["M"], T["h"], T["w"]
         units = T["units"]
         for ui in range(len(units) - 1, -1, -1):
@@ -542,24 +552,28 @@ class Engine:
             x, ldx = U["x"], U["ldx"]
             f = self.bnfold
             # conv3
-            self.wgrad(M, h, w, 1, 1, base, cout, U["y2"], base, g, cout, self.gview(s + "/conv3/weights"),
-                       rowscale=f[s + "/conv3"][0])
+            with self._side(ws):
+                self.wgrad(M, h, w, 1, 1, base, cout, U["y2"], base, g, cout, self.gview(s + "/conv3/weights"),
+                           rowscale=f[s + "/conv3"][0])
+                if U["proj"]:
+                    self.wgrad(M, h, w, 1, 1, cin, cout, x, ldx, g, cout, self.gview(s + "/shortcut/weights"),
+                               rowscale=f[s + "/shortcut"][0])
             self.gemm(TC_DGRAD, M, h, w, 1, 1, base, cout, g, cout, self.pview(s + "/conv3/weights"), base, U["g2"], base,
                       mask=U["y2"], ldm=base, colsum=self.gview(s + "/conv2/BatchNorm/beta"), round_tf32=1)
             # conv2
             tm = T["tapmask"][rate]
-            self.wgrad(M, h, w, 3, rate, base, base, U["y1"], base, U["g2"], base, self.gview(s + "/conv2/weights"),
-                       tapmask=tm, rowscale=f[s + "/conv2"][0])
+            with self._side(ws):
+                self.wgrad(M, h, w, 3, rate, base, base, U["y1"], base, U["g2"], base, self.gview(s + "/conv2/weights"),
+                           tapmask=tm, rowscale=f[s + "/conv2"][0])
             self.gemm(TC_DGRAD, M, h, w, 3, rate, base, base, U["g2"], base, self.pview(s + "/conv2/weights"), 9 * base,
                       U["g1"], base, tapmask=tm, mask=U["y1"], ldm=base, colsum=self.gview(s + "/conv1/BatchNorm/beta"),
                       round_tf32=1)
             # conv1 (+ shortcut)
-            self.wgrad(M, h, w, 1, 1, cin, base, x, ldx, U["g1"], base, self.gview(s + "/conv1/weights"),
-                       rowscale=f[s + "/conv1"][0])
+            with self._side(ws):
+                self.wgrad(M, h, w, 1, 1, cin, base, x, ldx, U["g1"], base, self.gview(s + "/conv1/weights"),
+                           rowscale=f[s + "/conv1"][0])
             if U["proj"]:
                 self.gview(s + "/shortcut/BatchNorm/beta").copy_(self.gview(s + "/conv3/BatchNorm/beta"))
-                self.wgrad(M, h, w, 1, 1, cin, cout, x, ldx, g, cout, self.gview(s + "/shortcut/weights"),
-                           rowscale=f[s + "/shortcut"][0])
                 self.gemm(TC_DGRAD, M, h, w, 1, 1, cin, cout, g, cout, self.pview(s + "/shortcut/weights"), cin, U["t"], cin)
                 res, ldr = U["t"], cin
             else:
@@ -572,6 +586,7 @@ class Engine:
             self.gemm(TC_DGRAD, M, h, w, 1, 1, cin, base, U["g1"], base, self.pview(s + "/conv1/weights"), cin, dst, cin,
                       res=res, ldr=ldr, mask=x, ldm=ldx, colsum=colsum, round_tf32=1)
         # stem
+        st = self._st()
         s0 = T["enc"] + "/resnet_v1_101/conv1"
         self._chk(L.mpb_maxpool3s2_bwd(T["nimg"], T["H2"], T["W2"], 64, _ptr(T["stem"]), _ptr(T["g_pool"]),
                                        _ptr(T["g_stem"]), st), "pool1_bwd")
@@ -651,13 +666,16 @@ class Engine:
                   mask=self.concat, ldm=2048, colsum=self.gview(lastc["scope"] + "/conv3/BatchNorm/beta"), round_tf32=1)
         self.gemm(TC_DGRAD, Mc, 12, 12, 1, 1, 1024, 512, self.g_squashed, 512, wsq.view(-1)[1024:], 2048,
                   self.g_fullcrop, 1024)
-        self._chk(L.mpb_crop_pool_bwd(Tf["h"], Tf["w"], 1024, _ptr(lastf["o"]), N, _ptr(I["boxes_2d_norm"]), 24,
-                                      _ptr(self.g_fullcrop), 1024, _ptr(self.d_fullfeat), st), "crop_pool_bwd")
-        self._chk(L.mpb_relu_bwd_colsum(Tf["M"], 1024, _ptr(lastf["o"]), 1024, _ptr(self.d_fullfeat), 1024,
-                                        _ptr(lastf["g_out"]), 1024, _ptr(self.gview(lastf["scope"] + "/conv3/BatchNorm/beta")),
-                                        st), "full_relu_bwd")
-        self._tower_bwd(Tc, I["rgb_crops"])
-        self._tower_bwd(Tf, I["full_img"])
+        with self._side(self.s_full):
+            self._chk(L.mpb_crop_pool_bwd(Tf["h"], Tf["w"], 1024, _ptr(lastf["o"]), N, _ptr(I["boxes_2d_norm"]), 24,
+                                          _ptr(self.g_fullcrop), 1024, _ptr(self.d_fullfeat), self._st()), "crop_pool_bwd")
+            self._chk(L.mpb_relu_bwd_colsum(Tf["M"], 1024, _ptr(lastf["o"]), 1024, _ptr(self.d_fullfeat), 1024,
+                                            _ptr(lastf["g_out"]), 1024,
+                                            _ptr(self.gview(lastf["scope"] + "/conv3/BatchNorm/beta")), self._st()),
+                      "full_relu_bwd")
+            self._tower_bwd(Tf, I["full_img"], self.s_wf)
+        self._tower_bwd(Tc, I["rgb_crops"], self.s_wc)
+        self._join(self.s_full, self.s_wf, self.s_wc)
         # d(gamma) of every frozen BN from (w, dw, dbeta), both towers in one launch
         self._chk(L.mpb_bn_param_grad_multi(self.bn_rows, _ptr(self.bn_layers), _ptr(self.bn_row2layer), BN_EPS_RESNET, st),
                   "bn_param_grad_multi")
