@@ -256,6 +256,21 @@ class Engine:
         if status != 0:
             _lib.check(status, what)
 
+    def _cur(self):
+        return torch.cuda.current_stream(self.dev)
+
+    def _side(self, stream):
+        """context: run on `stream` after everything issued so far on the current stream"""
+        if not self.overlap:
+            return torch.cuda.stream(self._cur())
+        stream.wait_stream(self._cur())
+        return torch.cuda.stream(stream)
+
+    def _join(self, *streams):
+        if self.overlap:
+            for st_ in streams:
+                self._cur().wait_stream(st_)
+
     def _pick_bn(self, mtiles, ncols, allowed=(256, 128, 64)):
         for bn in allowed:
             if ncols % bn == 0 and mtiles * (ncols // bn) >= int(0.9 * self.sms):
