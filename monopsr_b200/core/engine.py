@@ -55,6 +55,9 @@ class Engine:
         self.s_wc = torch.cuda.Stream(device=self.dev)
         self.s_wf = torch.cuda.Stream(device=self.dev)
         self.overlap = True
+        import os
+        self.fill = float(os.environ.get("MPB_TILE_FILL", "0.9"))   # min fraction of SMs a launch must fill before widening tiles
+        self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
 
     # ------------------------------------------------------------------ parameters
     def _dev_shape(self, name, shape, kind):
@@ -273,7 +276,7 @@ class Engine:
 
     def _pick_bn(self, mtiles, ncols, allowed=(256, 128, 64)):
         for bn in allowed:
-            if ncols % bn == 0 and mtiles * (ncols // bn) >= int(0.9 * self.sms):
+            if ncols % bn == 0 and mtiles * (ncols // bn) >= int(self.fill * self.sms):
                 return bn
         for bn in reversed(allowed):
             if ncols % bn == 0:
@@ -295,7 +298,7 @@ class Engine:
             # short reductions are epilogue (memory) bound: small tiles keep two CTAs per SM so one
             # CTA's epilogue overlaps the other's main loop
             kdepth = k * k * (Cin if op == TC_FWD else Cout)
-            allowed = (64,) if (kdepth <= 512 and op != TC_WGRAD) else (256, 128, 64)
+            allowed = (64,) if (kdepth <= self.shortk and op != TC_WGRAD) else (256, 128, 64)
             if op == TC_FWD:
                 bn = self._pick_bn(mt, Cout, allowed)
             elif op == TC_DGRAD:
