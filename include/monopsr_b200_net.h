@@ -50,6 +50,9 @@ typedef struct mpb_tc_gemm_params {
     int round_tf32;
     int atomic;
     int ksplit;          /* >=1: split the K loop over gridDim.z (needs atomic=1 and a zeroed out) */
+    float* out_r;        /* optional second output [rows][ldor]: the tf32-rounded value (GEMM operand of the next
+                          * layer) while `out` keeps the unrounded one (fp32 residual stream) */
+    int ldor;
 } mpb_tc_gemm_params;
 
 /* BN: tile width in output columns (64, 128 or 256). */

@@ -200,6 +200,9 @@ class Engine:
                     else:
                         U["out"] = e(M, base * 4)
                     U["g_out"] = e(M, base * 4)
+                    # fp32 residual stream: `out` stays unrounded (residual add, ReLU mask), `out_r` is the
+                    # tf32-rounded copy that feeds the next unit's GEMMs (halves the forward error)
+                    U["out_r"] = None if last else e(M, base * 4)
                     units.append(U)
                     cin = base * 4
             T["units"] = units
@@ -285,7 +288,7 @@ class Engine:
 
     def gemm(self, op, M, H, W, k, dil, Cin, Cout, X, ldx, Wt, ldw, out, ldo, Y=None, ldy=0, tapmask=None,
              shift=None, res=None, ldr=0, mask=None, ldm=0, rowscale=None, colsum=None, relu=0, round_tf32=0,
-             atomic=0, ksplit=1, bn=None):
+             atomic=0, ksplit=1, bn=None, out_r=None, ldor=0):
         p = TcGemmParams()
         p.op, p.H, p.W, p.kh, p.kw, p.dil, p.M, p.Cin, p.Cout = op, H, W, k, k, dil, M, Cin, Cout
         p.X, p.ldx, p.Y, p.ldy, p.Wt, p.ldw, p.out, p.ldo = _ptr(X), ldx, _ptr(Y), ldy, _ptr(Wt), ldw, _ptr(out), ldo
@@ -293,6 +296,7 @@ class Engine:
         p.shift, p.res, p.ldr, p.mask, p.ldm = _ptr(shift), _ptr(res), ldr, _ptr(mask), ldm
         p.rowscale, p.colsum = _ptr(rowscale), _ptr(colsum)
         p.relu, p.round_tf32, p.atomic, p.ksplit = relu, round_tf32, atomic, ksplit
+        p.out_r, p.ldor = _ptr(out_r), ldor
         mt = (M + 127) // 128
         if bn is None:
             # short reductions are epilogue (memory) bound: small tiles keep two CTAs per SM so one
@@ -435,6 +439,7 @@ class Engine:
                                  _ptr(self.bnfold[s0][1]), _ptr(T["stem"]), st), "stem_fwd")
         self._chk(L.mpb_maxpool3s2_fwd(T["nimg"], T["H2"], T["W2"], 64, _ptr(T["stem"]), _ptr(T["pool"]), st), "pool1")
         x, ldx = T["pool"], 64
+        xr = x                      # tf32-rounded view of x (the pooled stem output is already rounded)
         M, h, w = T["M"], T["h"], T["w"]
         for U in T["units"]:
             s, cin, base, cout, rate = U["scope"], U["cin"], U["base"], U["cout"], U["rate"]
@@ -443,19 +448,22 @@ class Engine:
             else:
                 out, ldo = U["out_view"]
             if U["proj"]:
-                self.gemm(TC_FWD, M, h, w, 1, 1, cin, cout, x, ldx, self.pview(s + "/shortcut/weights"), cin,
+                self.gemm(TC_FWD, M, h, w, 1, 1, cin, cout, xr, ldx, self.pview(s + "/shortcut/weights"), cin,
                           U["sc"], cout, shift=self.bnfold[s + "/shortcut"][1])
                 res, ldr = U["sc"], cout
             else:
                 res, ldr = x, ldx
-            self.gemm(TC_FWD, M, h, w, 1, 1, cin, base, x, ldx, self.pview(s + "/conv1/weights"), cin, U["y1"], base,
+            self.gemm(TC_FWD, M, h, w, 1, 1, cin, base, xr, ldx, self.pview(s + "/conv1/weights"), cin, U["y1"], base,
                       shift=self.bnfold[s + "/conv1"][1], relu=1, round_tf32=1)
             self.gemm(TC_FWD, M, h, w, 3, rate, base, base, U["y1"], base, self.pview(s + "/conv2/weights"), 9 * base,
                       U["y2"], base, tapmask=T["tapmask"][rate], shift=self.bnfold[s + "/conv2"][1], relu=1, round_tf32=1)
+            last_crop = U["out"] is None       # written straight into the concat buffer: rounded (squash operand)
             self.gemm(TC_FWD, M, h, w, 1, 1, base, cout, U["y2"], base, self.pview(s + "/conv3/weights"), base, out, ldo,
-                      shift=self.bnfold[s + "/conv3"][1], res=res, ldr=ldr, relu=1, round_tf32=1)
-            U["x"], U["ldx"], U["o"], U["ldo"] = x, ldx, out, ldo
+                      shift=self.bnfold[s + "/conv3"][1], res=res, ldr=ldr, relu=1, round_tf32=1 if last_crop else 0,
+                      out_r=U["out_r"], ldor=cout)
+            U["x"], U["ldx"], U["xr"], U["o"], U["ldo"] = x, ldx, xr, out, ldo
             x, ldx = out, ldo
+            xr = U["out_r"] if U["out_r"] is not None else out
         return x, ldx
 
     def _fc_layer(self, x, ldx, K, wname, out, ldo, acc):
@@ -574,7 +582,7 @@ class Engine:
                 self.wgrad(M, h, w, 1, 1, base, cout, U["y2"], base, g, cout, self.gview(s + "/conv3/weights"),
                            rowscale=f[s + "/conv3"][0])
                 if U["proj"]:
-                    self.wgrad(M, h, w, 1, 1, cin, cout, x, ldx, g, cout, self.gview(s + "/shortcut/weights"),
+                    self.wgrad(M, h, w, 1, 1, cin, cout, U["xr"], ldx, g, cout, self.gview(s + "/shortcut/weights"),
                                rowscale=f[s + "/shortcut"][0])
             self.gemm(TC_DGRAD, M, h, w, 1, 1, base, cout, g, cout, self.pview(s + "/conv3/weights"), base, U["g2"], base,
                       mask=U["y2"], ldm=base, colsum=self.gview(s + "/conv2/BatchNorm/beta"), round_tf32=1)
@@ -588,7 +596,7 @@ class Engine:
                       round_tf32=1)
             # conv1 (+ shortcut)
             with self._side(ws):
-                self.wgrad(M, h, w, 1, 1, cin, base, x, ldx, U["g1"], base, self.gview(s + "/conv1/weights"),
+                self.wgrad(M, h, w, 1, 1, cin, base, U["xr"], ldx, U["g1"], base, self.gview(s + "/conv1/weights"),
                            rowscale=f[s + "/conv1"][0])
             if U["proj"]:
                 self.gview(s + "/shortcut/BatchNorm/beta").copy_(self.gview(s + "/conv3/BatchNorm/beta"))

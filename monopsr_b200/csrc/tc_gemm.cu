@@ -144,6 +144,7 @@ __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem
         __syncwarp();
         float csum = 0.f;
         float* outp = p.out + (size_t)row0 * ldo + col;
+        float* outr = p.out_r ? p.out_r + (size_t)row0 * p.ldor + col : nullptr;
 #pragma unroll
         for (int r = 0; r < 32; r++) {
             float x = fmaf(stg[r * 33 + lane], sc, sh);
@@ -152,6 +153,7 @@ __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem
             if (p.mask) x = mv[r] > 0.f ? x : 0.f;
             x *= s2;
             if (p.round_tf32) x = round_tf32(x);
+            if (outr && r < nvalid) outr[(size_t)r * p.ldor] = round_tf32(x);
             if (r < nvalid) {
                 csum += x;
                 if (p.atomic) atomicAdd(outp + (size_t)r * ldo, x);

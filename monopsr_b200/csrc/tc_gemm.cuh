@@ -32,7 +32,10 @@ constexpr int kTcBM = 128;
 constexpr int kTcBK = 32;          // floats per k-block = one 128B swizzle row
 // pipeline depth: cp.async round trips are long (about 2 us under load), so keep as many
 // stages in flight as shared memory allows (one CTA per SM): 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
-template <int BN> constexpr int tc_stages() { return 4; }
+#ifndef MPB_STAGES64
+#define MPB_STAGES64 4
+#endif
+template <int BN> constexpr int tc_stages() { return BN == 64 ? MPB_STAGES64 : 4; }
 constexpr int kTcThreads = 160;    // 4 producer/epilogue warps + 1 MMA warp
 constexpr int kTcABytes = kTcBM * 128;
 

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmonopsr_b200.so")
+LIB_PATH = os.environ.get("MPB_LIB", os.path.join(_HERE, "libmonopsr_b200.so"))
 
 c_f = ctypes.c_void_p   # device pointers travel as integers
 c_i = ctypes.c_int

@@ -23,6 +23,7 @@ class TcGemmParams(ctypes.Structure):
         ("mask", c_p), ("ldm", c_i),
         ("scale2", c_p), ("rowscale", c_p), ("colsum", c_p),
         ("relu", c_i), ("round_tf32", c_i), ("atomic", c_i), ("ksplit", c_i),
+        ("out_r", c_p), ("ldor", c_i),
     ]
 
 

@@ -40,6 +40,9 @@ MAX_DEPTH = 45.0          # dataset_config.obj_filter_config.depth_range[1] (yam
 # product-vs-oracle difference is fp32-vs-fp64 accumulation only; with it off the oracle is the
 # plain fp64 restatement and the difference measures the tf32 effect itself.
 EMULATE_TF32 = False
+# Emulation variant: keep the residual stream in full precision (the product would store an
+# unrounded copy of every unit output next to the tf32-rounded one that feeds the GEMMs).
+RESIDUAL_FULL = False
 
 
 class _RoundTF32(torch.autograd.Function):
@@ -120,14 +123,16 @@ def max_pool_2x2(x):
 def bottleneck(x, P, scope, depth, depth_bottleneck, rate):
     """resnet_v1.py:78-139 with stride forced to 1 (output_stride reached, resnet_utils.py:194-200)."""
     s = scope + "/bottleneck_v1"
+    xin = Q(x) if RESIDUAL_FULL else x          # GEMM operand (x already rounded unless RESIDUAL_FULL)
     if x.shape[-1] == depth:
         shortcut = x
     else:
-        shortcut = conv_bn(x, P, s + "/shortcut")
-    r = Q(torch.relu(conv_bn(x, P, s + "/conv1")))
+        shortcut = conv_bn(xin, P, s + "/shortcut")
+    r = Q(torch.relu(conv_bn(xin, P, s + "/conv1")))
     r = Q(torch.relu(conv_bn(r, P, s + "/conv2", 1, rate)))
     r = conv_bn(r, P, s + "/conv3")
-    return Q(torch.relu(shortcut + r))
+    out = torch.relu(shortcut + r)
+    return out if RESIDUAL_FULL else Q(out)
 
 
 BLOCKS = [("block1", 64, 3), ("block2", 128, 4), ("block3", 256, 23)]   # block4 is never consumed
