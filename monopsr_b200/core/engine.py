@@ -492,6 +492,8 @@ class Engine:
         self.gemm(TC_FWD, Mc, 12, 12, 1, 1, 2048, 512, self.concat, 2048, self.pview("squash/1x1_conv/weights"), 2048,
                   self.squashed, 512, shift=self.view("squash/1x1_conv/biases"), relu=1, round_tf32=1)
         self._chk(L.mpb_maxpool2_fwd(N, 12, 12, 512, _ptr(self.squashed), 512, _ptr(self.pooled), 512, st), "pool")
+        with self._side(self.s_wc):
+            self._fc_forward()
         self._chk(L.mpb_resize_ac_fwd(N, 12, 12, 512, _ptr(self.squashed), 24, 24, _ptr(self.r1), st), "resize1")
         x = self.r1
         for i, D in enumerate(self.dec):
@@ -512,7 +514,13 @@ class Engine:
         sx = "output/inst_xyz_map_local/inst_xyz_map_local"
         self._chk(L.mpb_xyzhead_fwd(N, 48, 48, _ptr(x), _ptr(self.view(sx + "/weights")), _ptr(self.view(sx + "/biases")),
                                     _ptr(self.xyz), st), "xyzhead_fwd")
-        # ---- FC stacks and heads
+        self._join(self.s_wc)            # the FC stacks ran beside the decoder
+        io = self.heads_io()
+        self._chk(L.mpb_heads_final(ctypes.byref(io), 1 if train else 0, st), "heads_final")
+
+    def _fc_forward(self):
+        """heads_static, proposal stack, lwh/alpha heads, heads_mid, regression stack, cen_y/cen_z heads"""
+        L, st, N = self.L, self._st(), self.N
         io = self.heads_io()
         self._chk(L.mpb_heads_static(ctypes.byref(io), st), "heads_static")
         P, R = self.fc["proposal"], self.fc["regression"]
@@ -532,7 +540,6 @@ class Engine:
         for nm, out in (("output/cen_y/cen_y", h["cen_y_offs"]), ("output/cen_z_offs/cen_z", h["cen_z_offs"])):
             self._chk(L.mpb_fc_small_fwd(N, 1024, 1, _ptr(R["h1"]), 1024, _ptr(self.view(nm + "/weights")),
                                          _ptr(self.view(nm + "/biases")), _ptr(out), 1, st), "fc_small_fwd")
-        self._chk(L.mpb_heads_final(ctypes.byref(io), 1 if train else 0, st), "heads_final")
 
     def outputs(self):
         """output_dict (core/constants.py KEY_*) as device tensors."""
@@ -564,6 +571,37 @@ class Engine:
         if want_dx:
             self.gemm(TC_DGRAD, N, 1, 1, 1, 1, K, 1024, g, 1024, self.pview(wname + "/weights"), K, dx, lddx,
                       res=res, ldr=ldr, bn=64 if K % 256 else 256)
+
+    def _fc_backward(self):
+        """regression stack -> heads_bwd_mid -> proposal stack; leaves d(pooled) in self.d_flat"""
+        L, st, N, h = self.L, self._st(), self.N, self.h
+        io = self.heads_io()
+        P, R = self.fc["proposal"], self.fc["regression"]
+        # ---- regression stack
+        r = "output/regression_fc/regression_fc"
+        first = True
+        for nm, dy in (("output/cen_y/cen_y", h["d_cen_y_offs"]), ("output/cen_z_offs/cen_z", h["d_cen_z_offs"])):
+            self._chk(L.mpb_fc_small_bwd(N, 1024, 1, _ptr(R["h1"]), 1024, _ptr(self.view(nm + "/weights")), _ptr(dy), 1,
+                                         _ptr(R["d_h1"]), 1024, 0 if first else 1, _ptr(self.gview(nm + "/weights")),
+                                         _ptr(self.gview(nm + "/biases")), st), "fc_small_bwd")
+            first = False
+        self._fc_bwd(R["h1"], 1024, R["d_h1"], 1024, R["g_h1"], R["h0"], 1024, 1024, r + "/fc1", R["d_h0"], 1024)
+        self._fc_bwd(R["h0"], 1024, R["d_h0"], 1024, R["g_h0"], R["feat"], KPAD, KPAD, r + "/fc0", R["d_feat"], KPAD)
+        self._chk(L.mpb_heads_bwd_mid(ctypes.byref(io), st), "heads_bwd_mid")
+        self._fc_bwd(R["feat"], KPAD, R["d_feat"], KPAD, R["g_img"], self.pooled, 18432, 18432, r + "/img_fc",
+                     self.d_flat, 18432)
+        # ---- proposal stack
+        p = "output/proposal_fc/proposal_fc"
+        first = True
+        for nm, n, dy in (("output/lwh/lwh", 3, h["d_lwh_offs"]), ("output/alpha", 24, h["d_alpha"])):
+            self._chk(L.mpb_fc_small_bwd(N, 1024, n, _ptr(P["h1"]), 1024, _ptr(self.view(nm + "/weights")), _ptr(dy), n,
+                                         _ptr(P["d_h1"]), 1024, 0 if first else 1, _ptr(self.gview(nm + "/weights")),
+                                         _ptr(self.gview(nm + "/biases")), st), "fc_small_bwd")
+            first = False
+        self._fc_bwd(P["h1"], 1024, P["d_h1"], 1024, P["g_h1"], P["h0"], 1024, 1024, p + "/fc1", P["d_h0"], 1024)
+        self._fc_bwd(P["h0"], 1024, P["d_h0"], 1024, P["g_h0"], P["feat"], KPAD, KPAD, p + "/fc0", P["d_feat"], KPAD)
+        self._fc_bwd(P["feat"], KPAD, P["d_feat"], KPAD, P["g_img"], self.pooled, 18432, 18432, p + "/img_fc",
+                     self.d_flat, 18432, res=self.d_flat, ldr=18432)
 
     def _tower_bwd(self, T, x_in, ws):
         """T['units'][-1]['g_out'] holds g = dL/d(out)*(out>0) of the last unit (and its d(beta3) is set).
@@ -627,31 +665,8 @@ class Engine:
         self.grads.zero_()
         io = self.heads_io()
         P, R = self.fc["proposal"], self.fc["regression"]
-        # ---- regression stack
-        r = "output/regression_fc/regression_fc"
-        first = True
-        for nm, dy in (("output/cen_y/cen_y", h["d_cen_y_offs"]), ("output/cen_z_offs/cen_z", h["d_cen_z_offs"])):
-            self._chk(L.mpb_fc_small_bwd(N, 1024, 1, _ptr(R["h1"]), 1024, _ptr(self.view(nm + "/weights")), _ptr(dy), 1,
-                                         _ptr(R["d_h1"]), 1024, 0 if first else 1, _ptr(self.gview(nm + "/weights")),
-                                         _ptr(self.gview(nm + "/biases")), st), "fc_small_bwd")
-            first = False
-        self._fc_bwd(R["h1"], 1024, R["d_h1"], 1024, R["g_h1"], R["h0"], 1024, 1024, r + "/fc1", R["d_h0"], 1024)
-        self._fc_bwd(R["h0"], 1024, R["d_h0"], 1024, R["g_h0"], R["feat"], KPAD, KPAD, r + "/fc0", R["d_feat"], KPAD)
-        self._chk(L.mpb_heads_bwd_mid(ctypes.byref(io), st), "heads_bwd_mid")
-        self._fc_bwd(R["feat"], KPAD, R["d_feat"], KPAD, R["g_img"], self.pooled, 18432, 18432, r + "/img_fc",
-                     self.d_flat, 18432)
-        # ---- proposal stack
-        p = "output/proposal_fc/proposal_fc"
-        first = True
-        for nm, n, dy in (("output/lwh/lwh", 3, h["d_lwh_offs"]), ("output/alpha", 24, h["d_alpha"])):
-            self._chk(L.mpb_fc_small_bwd(N, 1024, n, _ptr(P["h1"]), 1024, _ptr(self.view(nm + "/weights")), _ptr(dy), n,
-                                         _ptr(P["d_h1"]), 1024, 0 if first else 1, _ptr(self.gview(nm + "/weights")),
-                                         _ptr(self.gview(nm + "/biases")), st), "fc_small_bwd")
-            first = False
-        self._fc_bwd(P["h1"], 1024, P["d_h1"], 1024, P["g_h1"], P["h0"], 1024, 1024, p + "/fc1", P["d_h0"], 1024)
-        self._fc_bwd(P["h0"], 1024, P["d_h0"], 1024, P["g_h0"], P["feat"], KPAD, KPAD, p + "/fc0", P["d_feat"], KPAD)
-        self._fc_bwd(P["feat"], KPAD, P["d_feat"], KPAD, P["g_img"], self.pooled, 18432, 18432, p + "/img_fc",
-                     self.d_flat, 18432, res=self.d_flat, ldr=18432)
+        with self._side(self.s_wc):
+            self._fc_backward()
         # ---- map decoder
         sx = "output/inst_xyz_map_local/inst_xyz_map_local"
         D = self.dec[3]
@@ -665,8 +680,9 @@ class Engine:
             self._chk(L.mpb_bn_train_bwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(D["mean"]), _ptr(D["var"]), BN_EPS_DECODER,
                                          _ptr(D["y"]), _ptr(D["dy"]), _ptr(D["dz"]), _ptr(self.gview(b + "beta")),
                                          _ptr(self.bn_scratch), st), "bn_train_bwd")
-            self.wgrad(D["M"], side, side, 3, 1, D["cin"], D["cout"], D["x"], D["cin"], D["dz"], D["cout"],
-                       self.gview(D["scope"] + "/weights"), tapmask=tm)
+            with self._side(self.s_wf):
+                self.wgrad(D["M"], side, side, 3, 1, D["cin"], D["cout"], D["x"], D["cin"], D["dz"], D["cout"],
+                           self.gview(D["scope"] + "/weights"), tapmask=tm)
             if i in (3, 1):
                 dst = self.dec[i - 1]["dy"]
             elif i == 2:
@@ -678,6 +694,7 @@ class Engine:
             if i == 2:
                 self._chk(L.mpb_resize_ac_bwd(N, 24, 24, 256, _ptr(self.d_r2), 48, 48, _ptr(self.dec[1]["dy"]), st), "resize2_bwd")
         self._chk(L.mpb_resize_ac_bwd(N, 12, 12, 512, _ptr(self.d_r1), 24, 24, _ptr(self.d_squashed), st), "resize1_bwd")
+        self._join(self.s_wc)            # d(pooled) from the FC stacks
         self._chk(L.mpb_maxpool2_bwd(N, 12, 12, 512, _ptr(self.squashed), 512, _ptr(self.d_flat), 512, _ptr(self.d_squashed),
                                      512, 1, st), "pool_bwd")
         # ---- squash
