@@ -58,6 +58,7 @@ class Engine:
         import os
         self.fill = float(os.environ.get("MPB_TILE_FILL", "0.9"))   # min fraction of SMs a launch must fill before widening tiles
         self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
+        self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "128"))
 
     # ------------------------------------------------------------------ parameters
     def _dev_shape(self, name, shape, kind):
@@ -345,7 +346,7 @@ class Engine:
         return {"ms": ms_, "gflop": flop / 1e9, "tflops": flop / (ms_ * 1e-3) / 1e12, "launches": len(rec)}
 
     def wgrad(self, M, H, W, k, dil, Cin, Cout, X, ldx, dY, ldy, dW, tapmask=None, rowscale=None):
-        bn = 128 if Cin % 128 == 0 else 64
+        bn = 128 if (Cin % 128 == 0 and self.wgrad_bn >= 128) else 64
         tiles = ((Cout + 127) // 128) * (k * k * Cin // bn)
         nkb = (M + 31) // 32
         ksplit = max(1, min((self.sms + tiles - 1) // tiles, max(1, nkb // 4)))

@@ -20,7 +20,16 @@ opt_sumsq_kernel(const mpb_opt_chunk* __restrict__ chunks, const float* __restri
     const mpb_opt_chunk ch = chunks[blockIdx.x];
     const float* g = grad + ch.start;
     float acc = 0.f;
-    for (int i = threadIdx.x; i < ch.len; i += kOptThreads) {
+    const int n4 = ch.len >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (int i = threadIdx.x; i < n4; i += kOptThreads) {
+        const float4 t = g4[i];
+        acc = fmaf(t.x * gscale, t.x * gscale, acc);
+        acc = fmaf(t.y * gscale, t.y * gscale, acc);
+        acc = fmaf(t.z * gscale, t.z * gscale, acc);
+        acc = fmaf(t.w * gscale, t.w * gscale, acc);
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < ch.len; i += kOptThreads) {
         const float v = g[i] * gscale;
         acc = fmaf(v, v, acc);
     }
@@ -45,7 +54,32 @@ opt_adam_ema_kernel(const mpb_opt_chunk* __restrict__ chunks, float* __restrict_
     const float nrm = sqrtf(norm2[ch.tensor]);
     const float cf = gscale * clip / fmaxf(nrm, clip);
     const float lr_t = hyper[0];
-    for (int i = threadIdx.x; i < ch.len; i += kOptThreads) {
+    // 128-bit main loop (every tensor and chunk starts on a 16-byte boundary), scalar tail
+    const int n4 = ch.len >> 2;
+    {
+        const float4* g4 = reinterpret_cast<const float4*>(grad + ch.start);
+        float4* m4 = reinterpret_cast<float4*>(m + ch.start);
+        float4* v4 = reinterpret_cast<float4*>(v + ch.start);
+        float4* p4 = reinterpret_cast<float4*>(param + ch.start);
+        float4* e4 = reinterpret_cast<float4*>(ema + ch.start);
+#pragma unroll 2
+        for (int i = threadIdx.x; i < n4; i += kOptThreads) {
+            const float4 g = __ldcs(g4 + i);
+            float4 mi = m4[i], vi = v4[i], pi = p4[i], ei = e4[i];
+#define MPB_ADAM(c)                                                   \
+            {                                                         \
+                const float gc = g.c * cf;                            \
+                mi.c = b1 * mi.c + (1.f - b1) * gc;                   \
+                vi.c = b2 * vi.c + (1.f - b2) * gc * gc;              \
+                pi.c = pi.c - lr_t * mi.c / (sqrtf(vi.c) + eps);      \
+                ei.c = ei.c - (1.f - ema_decay) * (ei.c - pi.c);      \
+            }
+            MPB_ADAM(x) MPB_ADAM(y) MPB_ADAM(z) MPB_ADAM(w)
+#undef MPB_ADAM
+            m4[i] = mi; v4[i] = vi; p4[i] = pi; e4[i] = ei;
+        }
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < ch.len; i += kOptThreads) {
         const long j = ch.start + i;
         const float g = grad[j] * cf;
         const float mi = b1 * m[j] + (1.f - b1) * g;
