@@ -58,7 +58,8 @@ class Engine:
         import os
         self.fill = float(os.environ.get("MPB_TILE_FILL", "0.9"))   # min fraction of SMs a launch must fill before widening tiles
         self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
-        self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "128"))
+        self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "64"))
+        self.wgrad_fill = float(os.environ.get("MPB_WGRAD_FILL", "1.0"))   # target CTAs / SMs when choosing split-K
 
     # ------------------------------------------------------------------ parameters
     def _dev_shape(self, name, shape, kind):
@@ -349,7 +350,7 @@ class Engine:
         bn = 128 if (Cin % 128 == 0 and self.wgrad_bn >= 128) else 64
         tiles = ((Cout + 127) // 128) * (k * k * Cin // bn)
         nkb = (M + 31) // 32
-        ksplit = max(1, min((self.sms + tiles - 1) // tiles, max(1, nkb // 4)))
+        ksplit = max(1, min(int(self.wgrad_fill * self.sms + tiles - 1) // tiles, max(1, nkb // 4)))
         self.gemm(TC_WGRAD, M, H, W, k, dil, Cin, Cout, X, ldx, None, k * k * Cin, dW, 0, Y=dY, ldy=ldy,
                   tapmask=tapmask, rowscale=rowscale, atomic=1, ksplit=ksplit, bn=bn)
 
