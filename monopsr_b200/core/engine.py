@@ -59,7 +59,7 @@ class Engine:
         self.fill = float(os.environ.get("MPB_TILE_FILL", "0.9"))   # min fraction of SMs a launch must fill before widening tiles
         self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
         self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "64"))
-        self.wgrad_fill = float(os.environ.get("MPB_WGRAD_FILL", "1.0"))   # target CTAs / SMs when choosing split-K
+        self.wgrad_fill = float(os.environ.get("MPB_WGRAD_FILL", "0.5"))   # target CTAs / SMs when choosing split-K
 
     # ------------------------------------------------------------------ parameters
     def _dev_shape(self, name, shape, kind):
