@@ -43,6 +43,38 @@ __device__ __forceinline__ float am_d2(const float4& a, const float4& b) {
     return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
+// Blackwell packed fp32 (two IEEE operations per instruction): the sweeps are FP32-issue bound
+__device__ __forceinline__ uint64_t pk(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// A cloud in shared memory: points stored in PAIRS, structure-of-arrays inside a pair:
+//   {x0,x1,y0,y1} {z0,z1,w0,w1}   (8 floats per 2 points) so a pair loads as two LDS.128 whose halves
+// are already the packed operands.  Accessors for single points:
+__device__ __forceinline__ int am_ix(int k, int c) { return (k >> 1) * 8 + c * 2 + (k & 1); }   // c: 0 x,1 y,2 z,3 w
+__device__ __forceinline__ float4 am_point(const float* cl, int k) {
+    return make_float4(cl[am_ix(k, 0)], cl[am_ix(k, 1)], cl[am_ix(k, 2)], cl[am_ix(k, 3)]);
+}
+
 struct AmSmem {
     // carve-up of dynamic shared memory; all sizes in floats
     int n_pad, m_pad, own_n, own_m;
@@ -70,21 +102,26 @@ __host__ __device__ inline int am_pick_split(int owners) {
     return best_s;
 }
 
-// sum over `cnt` candidates (weights in .w), strided by S lanes, of exp2(c*d2)*w
-__device__ __forceinline__ float am_sweep(const float4 me, const float4* __restrict__ other, int cnt,
+// sum over the `cnt` points of `other` (pair-SoA, weights in the w slots), pairs strided over S lanes,
+// of exp2(c*d2)*w -- two candidates per packed instruction
+__device__ __forceinline__ float am_sweep(const float4 me, const float* __restrict__ other, int cnt,
                                           int s, int S, float c) {
-    float acc0 = 0.f, acc1 = 0.f;
-    int l = s;
-    for (; l + S < cnt; l += 2 * S) {
-        float4 o0 = other[l], o1 = other[l + S];
-        acc0 = fmaf(ex2_approx(c * am_d2(me, o0)), o0.w, acc0);
-        acc1 = fmaf(ex2_approx(c * am_d2(me, o1)), o1.w, acc1);
+    const float4* o4 = reinterpret_cast<const float4*>(other);
+    const uint64_t mx = pk(me.x, me.x), my = pk(me.y, me.y), mz = pk(me.z, me.z), c2 = pk(c, c);
+    uint64_t acc = pk(0.f, 0.f);
+    const int npairs = (cnt + 1) >> 1;
+#pragma unroll 2
+    for (int j = s; j < npairs; j += S) {
+        const float4 a = o4[2 * j], b = o4[2 * j + 1];      // {x0,x1,y0,y1} {z0,z1,w0,w1}
+        const uint64_t dx = sub2(pk(a.x, a.y), mx), dy = sub2(pk(a.z, a.w), my), dz = sub2(pk(b.x, b.y), mz);
+        const uint64_t d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+        float a0, a1;
+        upk(mul2(c2, d2), a0, a1);
+        acc = fma2(pk(ex2_approx(a0), ex2_approx(a1)), pk(b.z, b.w), acc);
     }
-    if (l < cnt) {
-        float4 o0 = other[l];
-        acc0 = fmaf(ex2_approx(c * am_d2(me, o0)), o0.w, acc0);
-    }
-    return acc0 + acc1;
+    float lo, hi;
+    upk(acc, lo, hi);
+    return lo + hi;
 }
 
 __device__ __forceinline__ float group_sum(float v, int S) {
@@ -107,8 +144,8 @@ approxmatch_cluster_kernel(int n, int m, const float* __restrict__ xyz1,
     L.m_pad = (m + 3) & ~3;
     L.own_n = ceil_div(n, C);
     L.own_m = ceil_div(m, C);
-    float4* P1 = reinterpret_cast<float4*>(smem + L.p1());
-    float4* P2 = reinterpret_cast<float4*>(smem + L.p2());
+    float* P1 = smem + L.p1();     // pair-SoA clouds (see am_ix)
+    float* P2 = smem + L.p2();
     float* RR = smem + L.rr();
     float* HL = smem + L.hl();
     float* HR = smem + L.hr();
@@ -123,9 +160,12 @@ approxmatch_cluster_kernel(int n, int m, const float* __restrict__ xyz1,
 
     const float* g1 = xyz1 + (size_t)bi * n * 3;
     const float* g2 = xyz2 + (size_t)bi * m * 3;
-    for (int t = tid; t < n * 3; t += kAmThreads) smem[L.p1() + (t / 3) * 4 + (t % 3)] = g1[t];
-    for (int t = tid; t < m * 3; t += kAmThreads) smem[L.p2() + (t / 3) * 4 + (t % 3)] = g2[t];
-    for (int t = tid; t < m; t += kAmThreads) { RR[t] = multiR; P2[t].w = multiR; }
+    for (int t = tid; t < 4 * L.n_pad; t += kAmThreads) P1[t] = 0.f;     // pad points: weight 0
+    for (int t = tid; t < 4 * L.m_pad; t += kAmThreads) P2[t] = 0.f;
+    __syncthreads();
+    for (int t = tid; t < n * 3; t += kAmThreads) P1[am_ix(t / 3, t % 3)] = g1[t];
+    for (int t = tid; t < m * 3; t += kAmThreads) P2[am_ix(t / 3, t % 3)] = g2[t];
+    for (int t = tid; t < m; t += kAmThreads) { RR[t] = multiR; P2[am_ix(t, 3)] = multiR; }
     for (int t = tid; t < k1 - k0; t += kAmThreads) RL[t] = multiL;
     __syncthreads();
     cluster.sync();   // every CTA's smem is initialised before any remote write lands
@@ -142,13 +182,13 @@ approxmatch_cluster_kernel(int n, int m, const float* __restrict__ xyz1,
             int o = u / SL, s = u % SL;
             bool act = o < k1 - k0;
             float sum = 0.f;
-            if (act) sum = am_sweep(P1[k0 + o], P2, m, s, SL, c);
+            if (act) sum = am_sweep(am_point(P1, k0 + o), P2, m, s, SL, c);
             sum = group_sum(sum, SL);
             if (act && s == 0) {
                 float ratio = RL[o] / (1e-9f + sum);
                 for (int r = 0; r < C; r++) {   // all-gather through DSMEM
                     float* rs = cluster.map_shared_rank(smem, r);
-                    rs[L.p1() + (size_t)(k0 + o) * 4 + 3] = ratio;
+                    rs[L.p1() + am_ix(k0 + o, 3)] = ratio;
                     rs[L.hl() + (size_t)lev * L.n_pad + k0 + o] = ratio;
                 }
             }
@@ -159,7 +199,7 @@ approxmatch_cluster_kernel(int n, int m, const float* __restrict__ xyz1,
             int o = u / SR, s = u % SR;
             bool act = o < l1 - l0;
             float sum = 0.f;
-            if (act) sum = am_sweep(P2[l0 + o], P1, n, s, SR, c);
+            if (act) sum = am_sweep(am_point(P2, l0 + o), P1, n, s, SR, c);
             sum = group_sum(sum, SR);
             if (act && s == 0) {
                 float rem = RR[l0 + o];
@@ -170,7 +210,7 @@ approxmatch_cluster_kernel(int n, int m, const float* __restrict__ xyz1,
                 HR[o * 12 + lev] = ratio;
                 for (int r = 0; r < C; r++) {
                     float* rs = cluster.map_shared_rank(smem, r);
-                    rs[L.p2() + (size_t)(l0 + o) * 4 + 3] = ratio;
+                    rs[L.p2() + am_ix(l0 + o, 3)] = ratio;
                     rs[L.rr() + l0 + o] = nrem;
                 }
             }
@@ -182,12 +222,12 @@ approxmatch_cluster_kernel(int n, int m, const float* __restrict__ xyz1,
             int o = u / SL, s = u % SL;
             bool act = o < k1 - k0;
             float sum = 0.f;
-            if (act) sum = am_sweep(P1[k0 + o], P2, m, s, SL, c);
+            if (act) sum = am_sweep(am_point(P1, k0 + o), P2, m, s, SL, c);
             sum = group_sum(sum, SL);
-            if (act && s == 0) RL[o] = fmaxf(0.0f, RL[o] - sum * P1[k0 + o].w);
+            if (act && s == 0) RL[o] = fmaxf(0.0f, RL[o] - sum * P1[am_ix(k0 + o, 3)]);
         }
         __syncthreads();
-        for (int t = tid; t < m; t += kAmThreads) P2[t].w = RR[t];   // weights for next sweep 1
+        for (int t = tid; t < m; t += kAmThreads) P2[am_ix(t, 3)] = RR[t];   // weights for next sweep 1
         __syncthreads();
     }
 
@@ -202,12 +242,12 @@ approxmatch_cluster_kernel(int n, int m, const float* __restrict__ xyz1,
     for (int kb = 0; kb < n; kb += kAmThreads) {
         const int k = kb + tid;
         const bool act = k < n;
-        float4 me = act ? P1[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 me = act ? am_point(P1, k) : make_float4(0.f, 0.f, 0.f, 0.f);
         float rl[kAmLevels];
 #pragma unroll
         for (int q = 0; q < kAmLevels; q++) rl[q] = act ? HL[(size_t)q * L.n_pad + k] : 0.f;
         for (int l = l0; l < l1; l++) {
-            const float4 o = P2[l];
+            const float4 o = am_point(P2, l);
             const float4* hr4 = reinterpret_cast<const float4*>(HR + (size_t)(l - l0) * 12);
             float4 ra = hr4[0], rb = hr4[1], rc = hr4[2];
             float rr[12] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w, rc.x, rc.y, rc.z, rc.w};

@@ -25,19 +25,53 @@ namespace mpb {
 constexpr int kNnPass = 2048;   // candidates staged per shared-memory pass (32 KB as float4)
 constexpr int kNnGroup = 8;     // candidates per min-tree group
 
-__device__ __forceinline__ float nn_d2(float qx, float qy, float qz, const float4& c) {
+__device__ __forceinline__ float nn_d2(float qx, float qy, float qz, float cx, float cy, float cz) {
     // exact rounding sequence of the reference kernel (tf_nndistance_g.cu:25-28 under
     // nvcc's contraction): sub, sub, sub, mul, fma, fma
-    float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
+    float dx = __fsub_rn(cx, qx), dy = __fsub_rn(cy, qy), dz = __fsub_rn(cz, qz);
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
+
+// Blackwell packed fp32 (FADD2 / FMUL2 / FFMA2): two independent IEEE round-to-nearest operations
+// per instruction, so the SAME rounding sequence is evaluated for two candidates at once with half
+// the issue slots (the kernel is FP32-issue bound).
+__device__ __forceinline__ uint64_t pk(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t nn_d2x2(uint64_t qx, uint64_t qy, uint64_t qz, uint64_t cx, uint64_t cy, uint64_t cz) {
+    uint64_t dx = sub2(cx, qx), dy = sub2(cy, qy), dz = sub2(cz, qz);
+    return fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+}
+
+// candidates live in shared memory as structure-of-arrays blocks of 4: {x0..x3}{y0..y3}{z0..z3}
+struct Cand4 { float4 x, y, z; };
 
 template <int THREADS, int Q>
 __global__ void __launch_bounds__(THREADS)
 nn_distance_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                    float* __restrict__ dist1, int* __restrict__ idx1,
                    float* __restrict__ dist2, int* __restrict__ idx2) {
-    __shared__ float4 cand[kNnPass];
+    __shared__ Cand4 cand[kNnPass / 4];
     const int dir = blockIdx.z;
     const int bi = blockIdx.y;
     const int nq = dir == 0 ? n : m;   // queries
@@ -50,6 +84,7 @@ nn_distance_kernel(int n, int m, const float* __restrict__ xyz1, const float* __
     int* iout = (dir == 0 ? idx1 : idx2) + (size_t)bi * nq;
 
     float qx[Q], qy[Q], qz[Q], best[Q];
+    uint64_t qx2[Q], qy2[Q], qz2[Q];
     int besti[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) {
@@ -58,23 +93,29 @@ nn_distance_kernel(int n, int m, const float* __restrict__ xyz1, const float* __
         qx[q] = ok ? qp[j * 3 + 0] : 0.f;
         qy[q] = ok ? qp[j * 3 + 1] : 0.f;
         qz[q] = ok ? qp[j * 3 + 2] : 0.f;
+        qx2[q] = pk(qx[q], qx[q]);
+        qy2[q] = pk(qy[q], qy[q]);
+        qz2[q] = pk(qz[q], qz[q]);
         best[q] = INFINITY;
         besti[q] = 0;
     }
+    float* cf = reinterpret_cast<float*>(cand);
 
     for (int c0 = 0; c0 < nc; c0 += kNnPass) {
         const int cnt = min(kNnPass, nc - c0);
         const int cnt_pad = (cnt + kNnGroup - 1) / kNnGroup * kNnGroup;
         __syncthreads();   // previous pass fully consumed
-        // coalesced scalar loads of the AoS stream, scattered into float4 slots
+        // coalesced scalar loads of the AoS stream, scattered into the SoA-of-4 slots
         for (int t = threadIdx.x; t < cnt * 3; t += THREADS) {
             float v = cp[(size_t)c0 * 3 + t];
             int p = t / 3, c = t - p * 3;
-            reinterpret_cast<float*>(&cand[p])[c] = v;
+            cf[(p >> 2) * 12 + c * 4 + (p & 3)] = v;
         }
         // pad the tail group with +inf points: d = inf never beats a real candidate
-        for (int p = cnt + threadIdx.x; p < cnt_pad; p += THREADS)
-            cand[p] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+        for (int t = cnt * 3 + threadIdx.x; t < cnt_pad * 3; t += THREADS) {
+            int p = t / 3, c = t - p * 3;
+            cf[(p >> 2) * 12 + c * 4 + (p & 3)] = INFINITY;
+        }
         __syncthreads();
 
         float pbest[Q];
@@ -87,14 +128,17 @@ nn_distance_kernel(int n, int m, const float* __restrict__ xyz1, const float* __
         const int ngroups = cnt_pad / kNnGroup;
 #pragma unroll 2
         for (int g = 0; g < ngroups; g++) {
-            float4 c[kNnGroup];
-#pragma unroll
-            for (int u = 0; u < kNnGroup; u++) c[u] = cand[g * kNnGroup + u];
+            const Cand4 a = cand[2 * g], b = cand[2 * g + 1];
+            const uint64_t ax0 = pk(a.x.x, a.x.y), ax1 = pk(a.x.z, a.x.w), bx0 = pk(b.x.x, b.x.y), bx1 = pk(b.x.z, b.x.w);
+            const uint64_t ay0 = pk(a.y.x, a.y.y), ay1 = pk(a.y.z, a.y.w), by0 = pk(b.y.x, b.y.y), by1 = pk(b.y.z, b.y.w);
+            const uint64_t az0 = pk(a.z.x, a.z.y), az1 = pk(a.z.z, a.z.w), bz0 = pk(b.z.x, b.z.y), bz1 = pk(b.z.z, b.z.w);
 #pragma unroll
             for (int q = 0; q < Q; q++) {
                 float d[kNnGroup];
-#pragma unroll
-                for (int u = 0; u < kNnGroup; u++) d[u] = nn_d2(qx[q], qy[q], qz[q], c[u]);
+                upk(nn_d2x2(qx2[q], qy2[q], qz2[q], ax0, ay0, az0), d[0], d[1]);
+                upk(nn_d2x2(qx2[q], qy2[q], qz2[q], ax1, ay1, az1), d[2], d[3]);
+                upk(nn_d2x2(qx2[q], qy2[q], qz2[q], bx0, by0, bz0), d[4], d[5]);
+                upk(nn_d2x2(qx2[q], qy2[q], qz2[q], bx1, by1, bz1), d[6], d[7]);
                 float mn = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])),
                                  fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
                 if (mn < pbest[q]) {   // strict: the earliest group keeps ties
@@ -112,7 +156,9 @@ nn_distance_kernel(int n, int m, const float* __restrict__ xyz1, const float* __
                 int sel = kNnGroup - 1;
 #pragma unroll
                 for (int u = kNnGroup - 1; u >= 0; u--) {
-                    float d = nn_d2(qx[q], qy[q], qz[q], cand[base + u]);
+                    const int p = base + u;
+                    const float* s = cf + (p >> 2) * 12 + (p & 3);
+                    float d = nn_d2(qx[q], qy[q], qz[q], s[0], s[4], s[8]);
                     if (d == pbest[q]) sel = u;
                 }
                 best[q] = pbest[q];
@@ -127,8 +173,7 @@ nn_distance_kernel(int n, int m, const float* __restrict__ xyz1, const float* __
             // all-inf / NaN clouds: the reference keeps candidate 0 (k==0 branch); best
             // stays +inf here and besti 0, but dist must be d(query, cand 0)
             float out = best[q];
-            if (!(out < INFINITY)) out = nn_d2(qx[q], qy[q], qz[q],
-                                               make_float4(cp[0], cp[1], cp[2], 0.f));
+            if (!(out < INFINITY)) out = nn_d2(qx[q], qy[q], qz[q], cp[0], cp[1], cp[2]);
             dout[j] = out;
             iout[j] = besti[q];
         }
