@@ -91,7 +91,10 @@ struct AmSmem {
 __host__ __device__ inline int am_pick_split(int owners) {
     int best_s = 1;
     float best_w = 1e30f;
-    for (int s = 1; s <= 32; s <<= 1) {
+#ifndef MPB_AM_MAXS
+#define MPB_AM_MAXS 2    // wider splits make 8 lanes read 32 B-strided pairs (bank conflicts): measured slower
+#endif
+    for (int s = 1; s <= MPB_AM_MAXS; s <<= 1) {
         float units = (float)owners * s / kAmThreads;
         float w = ceilf(units) / units;
         if (w < best_w - 1e-3f) {
