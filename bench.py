@@ -142,7 +142,8 @@ def tfops_micro(dev):
             fn()
         ts = []
         for _ in range(it):
-            flush.zero_()
+            flush.sum()      # READ-flush of L2: a write-flush leaves 126 MB of dirty lines whose write-back
+                             # would be charged to the HBM-bound kernel timed next
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             fn()

@@ -22,7 +22,7 @@ def timeit(fn, iters=20, warmup=5, flush=None):
     ts = []
     for _ in range(iters):
         if flush is not None:
-            flush.zero_()
+            flush.sum()      # READ-flush (a write-flush leaves dirty lines whose write-back is charged to the next kernel)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
