@@ -374,115 +374,6 @@ matchcost_partial_kernel(int n, int m, const float* __restrict__ xyz1,
     }
 }
 
-// 128-bit variant (n % 4 == 0): a thread owns 4 consecutive dataset points per 1024-column sweep and
-// streams kMcRows float4 loads per sweep (256 B in flight per thread) -> HBM-bound
-__global__ void __launch_bounds__(kMcThreads)
-matchcost_partial_v4_kernel(int n, int m, const float* __restrict__ xyz1,
-                            const float* __restrict__ xyz2, const float* __restrict__ match,
-                            float* __restrict__ partial) {
-    __shared__ float4 q[kMcRows];
-    __shared__ float red[kMcThreads / 32];
-    const int bi = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    const int l0 = tile * kMcRows, rows = min(kMcRows, m - l0);
-    const float* p1 = xyz1 + (size_t)bi * n * 3;
-    const float* p2 = xyz2 + (size_t)bi * m * 3;
-    const float* mt = match + (size_t)bi * n * m + (size_t)l0 * n;
-    if (tid < kMcRows) {
-        int l = l0 + min(tid, rows - 1);
-        q[tid] = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
-    }
-    __syncthreads();
-    float acc = 0.f;
-    for (int k = tid * 4; k < n; k += kMcThreads * 4) {
-        float4 w[kMcRows];
-#pragma unroll
-        for (int r = 0; r < kMcRows; r++)
-            w[r] = r < rows ? __ldcs(reinterpret_cast<const float4*>(mt + (size_t)r * n + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 me[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) me[u] = make_float4(p1[(k + u) * 3], p1[(k + u) * 3 + 1], p1[(k + u) * 3 + 2], 0.f);
-#pragma unroll
-        for (int r = 0; r < kMcRows; r++) {
-            acc = fmaf(sqrtf(am_d2(me[0], q[r])), w[r].x, acc);
-            acc = fmaf(sqrtf(am_d2(me[1], q[r])), w[r].y, acc);
-            acc = fmaf(sqrtf(am_d2(me[2], q[r])), w[r].z, acc);
-            acc = fmaf(sqrtf(am_d2(me[3], q[r])), w[r].w, acc);
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((tid & 31) == 0) red[tid >> 5] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        float s = 0.f;
-        for (int w = 0; w < kMcThreads / 32; w++) s += red[w];
-        partial[(size_t)bi * gridDim.x + tile] = s;
-    }
-}
-
-// Fused matchcostgrad (n % 4 == 0): ONE streaming pass over match.  A CTA owns kFgRows query rows
-// and all dataset columns; a thread owns 4 consecutive columns per sweep.  grad2[l] (sum over k) is
-// completed inside the CTA (register partials -> warp shuffles -> shared memory, fixed order);
-// grad1[k] (sum over l) gets one RED.ADD per column per row-tile into the pre-zeroed output.
-constexpr int kFgRows = 8;
-constexpr int kFgThreads = 256;
-__global__ void __launch_bounds__(kFgThreads)
-matchcostgrad_fused_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
-                           const float* __restrict__ match, float* __restrict__ grad1, float* __restrict__ grad2) {
-    __shared__ float4 q[kFgRows];
-    __shared__ float red[kFgThreads / 32][kFgRows * 3];
-    const int bi = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-    const int l0 = tile * kFgRows, rows = min(kFgRows, m - l0);
-    const float* p1 = xyz1 + (size_t)bi * n * 3;
-    const float* p2 = xyz2 + (size_t)bi * m * 3;
-    const float* mt = match + (size_t)bi * n * m + (size_t)l0 * n;
-    float* g1 = grad1 + (size_t)bi * n * 3;
-    if (tid < kFgRows) {
-        int l = l0 + min(tid, rows - 1);
-        q[tid] = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
-    }
-    __syncthreads();
-    float a2[kFgRows][3];
-#pragma unroll
-    for (int r = 0; r < kFgRows; r++) a2[r][0] = a2[r][1] = a2[r][2] = 0.f;
-    for (int k = tid * 4; k < n; k += kFgThreads * 4) {
-        float4 w[kFgRows];
-#pragma unroll
-        for (int r = 0; r < kFgRows; r++)
-            w[r] = r < rows ? __ldcs(reinterpret_cast<const float4*>(mt + (size_t)r * n + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const float x = p1[(k + u) * 3], y = p1[(k + u) * 3 + 1], z = p1[(k + u) * 3 + 2];
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int r = 0; r < kFgRows; r++) {
-                const float dx = x - q[r].x, dy = y - q[r].y, dz = z - q[r].z;
-                const float wv = (u == 0 ? w[r].x : u == 1 ? w[r].y : u == 2 ? w[r].z : w[r].w) *
-                                 rsqrtf(fmaxf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)), 1e-20f));
-                const float cx = dx * wv, cy = dy * wv, cz = dz * wv;
-                s0 += cx; s1 += cy; s2 += cz;                 // d cost / d xyz1[k]
-                a2[r][0] -= cx; a2[r][1] -= cy; a2[r][2] -= cz;   // d cost / d xyz2[l]
-            }
-            if (s0 != 0.f) atomicAdd(&g1[(k + u) * 3 + 0], s0);
-            if (s1 != 0.f) atomicAdd(&g1[(k + u) * 3 + 1], s1);
-            if (s2 != 0.f) atomicAdd(&g1[(k + u) * 3 + 2], s2);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < kFgRows; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            float v = a2[r][c];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((tid & 31) == 0) red[tid >> 5][r * 3 + c] = v;
-        }
-    __syncthreads();
-    if (tid < rows * 3) {
-        float s = 0.f;
-        for (int w = 0; w < kFgThreads / 32; w++) s += red[w][tid];
-        grad2[((size_t)bi * m + l0) * 3 + tid] = s;
-    }
-}
-
 __global__ void matchcost_final_kernel(int tiles, const float* __restrict__ partial,
                                        float* __restrict__ out) {
     const int bi = blockIdx.x;
@@ -657,10 +548,7 @@ MPB_API int mpb_matchcost(int b, int n, int m, const float* xyz1, const float* x
     const int tiles = ceil_div(m, kMcRows);
     float* partial = nullptr;
     MPB_CUDA_TRY(scratch_alloc((void**)&partial, sizeof(float) * (size_t)b * tiles, s));
-    if (n % 4 == 0 && ((uintptr_t)match & 15) == 0)
-        matchcost_partial_v4_kernel<<<dim3(tiles, b), kMcThreads, 0, s>>>(n, m, xyz1, xyz2, match, partial);
-    else
-        matchcost_partial_kernel<<<dim3(tiles, b), kMcThreads, 0, s>>>(n, m, xyz1, xyz2, match, partial);
+    matchcost_partial_kernel<<<dim3(tiles, b), kMcThreads, 0, s>>>(n, m, xyz1, xyz2, match, partial);
     count_launch();
     matchcost_final_kernel<<<b, 32, 0, s>>>(tiles, partial, out);
     count_launch();
@@ -682,12 +570,6 @@ MPB_API int mpb_matchcostgrad(int b, int n, int m, const float* xyz1, const floa
     }
     if (!xyz1 || !xyz2 || !match || !grad1 || !grad2) return -1;
     if (b > 65535) return -1;
-    if (n % 4 == 0 && ((uintptr_t)match & 15) == 0) {
-        MPB_CUDA_TRY(cudaMemsetAsync(grad1, 0, sizeof(float) * (size_t)b * n * 3, s));
-        matchcostgrad_fused_kernel<<<dim3(ceil_div(m, kFgRows), b), kFgThreads, 0, s>>>(n, m, xyz1, xyz2, match, grad1, grad2);
-        MPB_LAUNCH_CHECK();
-        return 0;
-    }
     size_t sm1 = sizeof(float) * 4 * 1024;   // float4[1024] >= [4][64][3] floats
     matchcostgrad1_kernel<<<dim3(ceil_div(n, kG1Cols), b), kG1Cols * kG1Groups, sm1, s>>>(
         n, m, xyz1, xyz2, match, grad1);
