@@ -15,6 +15,7 @@ LIB = os.path.join(HERE, "libmonopsr_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("MPB_NVCC_EXTRA", "").split()     # e.g. -DMPB_TC_TRACE (debug timeline, tools/gemm_trace.py)
 
 
 def sources():

@@ -38,3 +38,8 @@ MPB_API int mpb_tc_set_cluster(int max_cluster) {
     mpb::tc_gemm_set_cluster(max_cluster);
     return max_cluster;
 }
+
+#ifdef MPB_TC_TRACE
+namespace mpb { int tc_gemm_set_trace(void* buf); }
+MPB_API int mpb_tc_set_trace(void* buf) { return mpb::tc_gemm_set_trace(buf); }
+#endif

@@ -5,6 +5,20 @@
 
 namespace mpb {
 
+#ifdef MPB_TC_TRACE
+// debug build only: per-CTA clock64 timeline of the TMA kernel ([cta][64] slots), see tools/gemm_trace.py
+__device__ long long* g_tc_trace = nullptr;
+#define TC_TR(slot) do { if (trc) trc[(slot)] = clock64(); } while (0)
+#define TC_TR_DECL long long* trc = (g_tc_trace && cta_lin < 1024) ? g_tc_trace + cta_lin * 64 : nullptr
+#define TC_TR_ARG , long long* trc
+#define TC_TR_PASS , trc
+#else
+#define TC_TR(slot) do { } while (0)
+#define TC_TR_DECL
+#define TC_TR_ARG
+#define TC_TR_PASS
+#endif
+
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -15,6 +29,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     // bounded spin: a protocol bug must trap, not hang the GPU box
     uint32_t done = 0;
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -98,70 +113,154 @@ __device__ __forceinline__ int tap_delta(int tap, int kh, int kw, int dil, int W
 }
 
 // ------------------------------------------------------------------ fused epilogue
-// Called by 4 warps; `quad` (= warp index % 4) selects the 32 TMEM lanes (= accumulator rows) a
-// warp may read.  tcgen05.ld hands every thread one ROW (32 consecutive columns); global memory
-// wants a warp on one row.  Each 32x32 chunk is therefore transposed through a padded shared-memory
-// tile (the pipeline stages are free once the accumulator is complete), after which lane = column:
-// residual / mask reads, stores and split-K REDs are 128-byte coalesced, the per-column BN shift
-// lives in a register and the column sums (d beta) need no shuffles.
+// Called by 4 or 8 warps; `quad` (= warp index % 4) selects the 32 TMEM lanes (= accumulator rows) a
+// warp may read, `half`/`nhalf` split the 32-column chunks of the tile between the warps of one quad.
+// tcgen05.ld hands every thread one ROW (32 consecutive columns); global memory wants whole 128-byte
+// lines.  Each 32x32 chunk is therefore transposed through a 4 KB XOR-swizzled shared-memory tile
+// (the pipeline stages are free once the accumulator is complete) with 128-bit accesses on both
+// sides (conflict-free: float4 slot j of row r lives at slot j ^ (r & 7)).  Afterwards a lane owns
+// 4 consecutive columns of 8 rows, so every global access (residual / mask reads, the store, the
+// second tf32-rounded store, split-K RED.ADD.v4) is a 16-byte vector access, 4 full lines per warp
+// instruction, the per-column BN shift lives in registers and the column sums (d beta) cost two
+// shuffle stages.  All epilogue options are branch-free selects inside the row loop: a lone warp is
+// bound by branch / issue latency, not by arithmetic (the first version of this loop, with a
+// warp-uniform branch per option and row, took ~7000 clk per chunk; see profiles/r1_notes.md).
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
 template <int BN, int OP>
 __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem_full_bar, uint32_t tmem_acc,
-                                            int quad, int lane, int m0, int n0, float* stg_base) {
+                                            int quad, int half, int nhalf, int lane, int m0, int n0,
+                                            float* stg_warp TC_TR_ARG) {
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    float* stg = stg_base + quad * (32 * 33);
+    if (quad == 0 && half == 0 && lane == 0) TC_TR(52);
+    float4* stg4 = reinterpret_cast<float4*>(stg_warp);
     const int row0 = m0 + quad * 32;               // first accumulator row of this warp
     const int nrows = (OP == TC_WGRAD) ? p.Cout : p.M;
-    const int nvalid = min(32, nrows - row0);      // warp-uniform
     const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16);
     const int ldo = (OP == TC_WGRAD) ? p.ldw : p.ldo;
+    const int g = lane >> 3, q = lane & 7;         // after the transpose: rows 4i+g, columns 4q..4q+3
     float rs = 1.f;
-    if (p.rowscale && lane < nvalid) rs = __ldg(p.rowscale + row0 + lane);
+    if (p.rowscale && row0 + lane < nrows) rs = __ldg(p.rowscale + row0 + lane);
+    const bool has_res = p.res != nullptr, has_mask = p.mask != nullptr, do_round = p.round_tf32 != 0;
+    const bool has_outr = p.out_r != nullptr, is_atomic = p.atomic != 0;
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nvalid = nrows - row0;               // warp-uniform; >= 32 except in the last row tile
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int col = n0 + c0 + lane;
-        // issue every global read of this chunk first (32 independent coalesced loads each), so
-        // their latency overlaps the TMEM read and the shared-memory transpose
-        float rv[32], mv[32];
-        if (p.res) {
-            const float* resp = p.res + (size_t)row0 * p.ldr + col;
+    for (int c0 = half * 32; c0 < BN; c0 += 32 * nhalf) {
+        const int col = n0 + c0 + q * 4;
+        // issue every global read of this chunk first (independent 16-byte loads), so their latency
+        // overlaps the TMEM read and the shared-memory transpose
+        float4 rv[8], mv[8];
+        if (has_res) {
+            const float* rp = p.res + (size_t)(row0 + g) * p.ldr + col;
 #pragma unroll
-            for (int r = 0; r < 32; r++) rv[r] = r < nvalid ? __ldg(resp + (size_t)r * p.ldr) : 0.f;
+            for (int i = 0; i < 8; i++) rv[i] = (4 * i + g < nvalid) ? ldg4(rp + (size_t)(4 * i) * p.ldr) : zero4;
         }
-        if (p.mask) {
-            const float* mskp = p.mask + (size_t)row0 * p.ldm + col;
+        if (has_mask) {
+            const float* mp = p.mask + (size_t)(row0 + g) * p.ldm + col;
 #pragma unroll
-            for (int r = 0; r < 32; r++) mv[r] = r < nvalid ? __ldg(mskp + (size_t)r * p.ldm) : 0.f;
+            for (int i = 0; i < 8; i++) mv[i] = (4 * i + g < nvalid) ? ldg4(mp + (size_t)(4 * i) * p.ldm) : zero4;
         }
-        const float sc = p.scale ? __ldg(p.scale + col) : 1.f;
-        const float sh = p.shift ? __ldg(p.shift + col) : 0.f;
-        const float s2 = p.scale2 ? __ldg(p.scale2 + col) : 1.f;
-        float v[32];
-        tmem_ld32(trow + c0, v);
-        __syncwarp();
+        const float4 sc = p.scale ? ldg4(p.scale + col) : one4;
+        const float4 sh = p.shift ? ldg4(p.shift + col) : zero4;
+        float x[32];
+        tmem_ld32(trow + c0, x);
 #pragma unroll
-        for (int q = 0; q < 32; q++) stg[lane * 33 + q] = v[q] * rs;
+        for (int j = 0; j < 8; j++)
+            stg4[lane * 8 + (j ^ (lane & 7))] =
+                make_float4(x[4 * j] * rs, x[4 * j + 1] * rs, x[4 * j + 2] * rs, x[4 * j + 3] * rs);
         __syncwarp();
-        float csum = 0.f;
-        float* outp = p.out + (size_t)row0 * ldo + col;
-        float* outr = p.out_r ? p.out_r + (size_t)row0 * p.ldor + col : nullptr;
+        // after the transpose x[4i..4i+3] = columns col..col+3 of row 4i+g.  Every option below is ONE
+        // warp-uniform branch around a straight run of 32 independent operations.
 #pragma unroll
-        for (int r = 0; r < 32; r++) {
-            float x = fmaf(stg[r * 33 + lane], sc, sh);
-            if (p.res) x += rv[r];
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (p.mask) x = mv[r] > 0.f ? x : 0.f;
-            x *= s2;
-            if (p.round_tf32) x = round_tf32(x);
-            if (outr && r < nvalid) outr[(size_t)r * p.ldor] = round_tf32(x);
-            if (r < nvalid) {
-                csum += x;
-                if (p.atomic) atomicAdd(outp + (size_t)r * ldo, x);
-                else outp[(size_t)r * ldo] = x;
+        for (int i = 0; i < 8; i++) {
+            const int rl = 4 * i + g;
+            const float4 t = stg4[rl * 8 + (q ^ (rl & 7))];
+            x[4 * i] = fmaf(t.x, sc.x, sh.x);
+            x[4 * i + 1] = fmaf(t.y, sc.y, sh.y);
+            x[4 * i + 2] = fmaf(t.z, sc.z, sh.z);
+            x[4 * i + 3] = fmaf(t.w, sc.w, sh.w);
+        }
+        __syncwarp();                  // the next chunk overwrites the staging tile
+        if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                x[4 * i] += rv[i].x; x[4 * i + 1] += rv[i].y; x[4 * i + 2] += rv[i].z; x[4 * i + 3] += rv[i].w;
             }
         }
-        if (p.colsum && nvalid > 0) atomicAdd(p.colsum + col, csum);
+        if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 32; e++) x[e] = fmaxf(x[e], 0.f);
+        }
+        if (has_mask) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                x[4 * i] = mv[i].x > 0.f ? x[4 * i] : 0.f;
+                x[4 * i + 1] = mv[i].y > 0.f ? x[4 * i + 1] : 0.f;
+                x[4 * i + 2] = mv[i].z > 0.f ? x[4 * i + 2] : 0.f;
+                x[4 * i + 3] = mv[i].w > 0.f ? x[4 * i + 3] : 0.f;
+            }
+        }
+        if (p.scale2) {
+            const float4 s2 = ldg4(p.scale2 + col);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                x[4 * i] *= s2.x; x[4 * i + 1] *= s2.y; x[4 * i + 2] *= s2.z; x[4 * i + 3] *= s2.w;
+            }
+        }
+        if (do_round) {
+#pragma unroll
+            for (int e = 0; e < 32; e++) x[e] = round_tf32(x[e]);
+        }
+        float* op = p.out + (size_t)(row0 + g) * ldo + col;
+        const size_t ostep = (size_t)4 * ldo;
+        if (nvalid >= 32) {
+            if (is_atomic) {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    atomicAdd(reinterpret_cast<float4*>(op + i * ostep), make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    *reinterpret_cast<float4*>(op + i * ostep) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (4 * i + g < nvalid) {
+                    const float4 o = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+                    if (is_atomic) atomicAdd(reinterpret_cast<float4*>(op + i * ostep), o);
+                    else *reinterpret_cast<float4*>(op + i * ostep) = o;
+                } else {
+                    x[4 * i] = x[4 * i + 1] = x[4 * i + 2] = x[4 * i + 3] = 0.f;   // keep tail rows out of colsum
+                }
+            }
+        }
+        if (p.colsum) {
+            float4 cs = zero4;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { cs.x += x[4 * i]; cs.y += x[4 * i + 1]; cs.z += x[4 * i + 2]; cs.w += x[4 * i + 3]; }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+                cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+                cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+            }
+            if (g == 0 && nvalid > 0) atomicAdd(reinterpret_cast<float4*>(p.colsum + col), cs);
+        }
+        if (has_outr) {
+            float* orp = p.out_r + (size_t)(row0 + g) * p.ldor + col;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (4 * i + g < nvalid)
+                    *reinterpret_cast<float4*>(orp + (size_t)(4 * i) * p.ldor) =
+                        make_float4(round_tf32(x[4 * i]), round_tf32(x[4 * i + 1]), round_tf32(x[4 * i + 2]), round_tf32(x[4 * i + 3]));
+        }
+        if (quad == 0 && lane == 0 && c0 == 0) TC_TR(53);
     }
+    if (quad == 0 && half == 0 && lane == 0) TC_TR(54);
     tc_fence_before();
 }
 
@@ -308,8 +407,11 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
             }
         }
 
-        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp, lane, m0, n0,
-                            reinterpret_cast<float*>(smem_raw + (base - raw)));
+#ifdef MPB_TC_TRACE
+        long long* trc = nullptr;
+#endif
+        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp, 0, 1, lane, m0, n0,
+                            reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * 1024 TC_TR_PASS);
     } else {
         // =========================== MMA ISSUER (warp 4) ===========================
         constexpr bool a_mn = (OP == TC_WGRAD);
@@ -359,7 +461,19 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 //   MN-major tiles  : 32x32 boxes with SWIZZLE_128B_ATOM_32B, one per 32-column group
 // Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue.
 // =====================================================================================
-constexpr int kTmaThreads = 192;
+// epilogue warps: 4 for 64-wide tiles (two CTAs per SM keep each other's epilogue hidden), 8 otherwise
+template <int BN> constexpr int tma_epi_warps() { return BN == 64 ? 4 : 8; }
+template <int BN> constexpr int tma_threads() { return 64 + 32 * tma_epi_warps<BN>(); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -417,7 +531,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 // 1/CN of the A tile and the TMA multicasts it into every CTA's shared memory -- L2 -> SM traffic
 // for A drops by CN (the GEMMs of this network are bound by exactly that traffic).
 template <int BN, int OP, int CN>
-__global__ void __launch_bounds__(kTmaThreads)
+__global__ void __launch_bounds__(tma_threads<BN>())
 tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant__ CUtensorMap mapA,
                    const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ uint8_t smem_raw[];
@@ -433,6 +547,10 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    (void)cta_lin;
+    TC_TR_DECL;
+    if (tid == 0) TC_TR(0);
     const int taps = p.kh * p.kw;
     int nkb;
     if (OP == TC_FWD) nkb = taps * (p.Cin / kTcBK);
@@ -463,6 +581,14 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     if (CN > 1) cluster_sync_all();      // every CTA's barriers exist before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot_ptr;
+#ifdef MPB_TC_TRACE
+    if (tid == 0) {
+        TC_TR(1);
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (trc) { trc[2] = smid; trc[56] = nk; }
+    }
+#endif
     const int m0 = blockIdx.x * kTcBM;
     const int n0 = blockIdx.y * BN;
     const int crank = (CN > 1) ? (int)cluster_ctarank() : 0;
@@ -470,23 +596,28 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     constexpr int kSlice = kTcBM / CN;      // A rows (pixels) fetched by this CTA
 
     if (warp == 0) {
-        if (lane == 0) {
-            // =========================== TMA PRODUCER ===========================
-            int stage = 0;
-            uint32_t phase = 0;
-            constexpr uint32_t kBytes = kTcABytes + BN * 128;
-            const int r = p.dil;
-            if (OP == TC_FWD || OP == TC_DGRAD) {
-                const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;
-                const int cblocks = Ck / kTcBK;
-                // first pixel of this tile in (w,h,n) -- base coordinate of the im2col walk
-                const int hw = p.H * p.W;
-                const int ms = m0 + crank * kSlice;     // first pixel of this CTA's slice of the A tile
-                const int img0 = ms / hw, rem0 = ms - img0 * hw, ph0 = rem0 / p.W, pw0 = rem0 - ph0 * p.W;
-                for (int i = 0; i < nk; i++) {
-                    const int kb = kb0 + i;
-                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
+        // =========================== TMA PRODUCER ===========================
+        // The whole warp walks the (warp-uniform) loop and one elected lane issues: loop state stays in
+        // uniform registers and ptxas needs no per-lane wrapper around the UTMALDG / SYNCS instructions.
+        // No integer division inside the loop: (tap, channel block) and the pixel coordinates are carried.
+        int stage = 0;
+        uint32_t phase = 0;
+        constexpr uint32_t kBytes = kTcABytes + BN * 128;
+        const int r = p.dil;
+        if (OP == TC_FWD || OP == TC_DGRAD) {
+            const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;
+            const int cblocks = Ck / kTcBK;
+            // first pixel of this tile in (w,h,n) -- base coordinate of the im2col walk
+            const int hw = p.H * p.W;
+            const int ms = m0 + crank * kSlice;     // first pixel of this CTA's slice of the A tile
+            const int img0 = ms / hw, rem0 = ms - img0 * hw, ph0 = rem0 / p.W, pw0 = rem0 - ph0 * p.W;
+            const int bw = pw0 - r * (p.kw / 2), bh = ph0 - r * (p.kh / 2);
+            int tap = kb0 / cblocks, cb = kb0 - tap * cblocks;
+            int th = tap / p.kw, tw = tap - th * p.kw;
+            for (int i = 0; i < nk; i++) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
+                    if (i < 16) TC_TR(4 + i);
                     const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
                     mbar_expect_tx(full_bar(stage), kBytes);
                     const uint32_t sAs = sA + crank * kSlice * 128;
@@ -494,31 +625,37 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                         if (CN > 1) tma_load_2d_mc(sAs, &mapA, full_bar(stage), cb * kTcBK, ms, kMask);
                         else tma_load_2d(sA, &mapA, full_bar(stage), cb * kTcBK, m0);
                     } else {
-                        int th = tap / p.kw, tw = tap - th * p.kw;
-                        if (OP == TC_DGRAD) { th = p.kh - 1 - th; tw = p.kw - 1 - tw; }   // dX[p] needs dY[p - off]
-                        if (CN > 1)
-                            tma_load_im2col_mc(sAs, &mapA, full_bar(stage), cb * kTcBK, pw0 - r * (p.kw / 2),
-                                               ph0 - r * (p.kh / 2), img0, tw * r, th * r, kMask);
-                        else
-                            tma_load_im2col(sA, &mapA, full_bar(stage), cb * kTcBK, pw0 - r * (p.kw / 2),
-                                            ph0 - r * (p.kh / 2), img0, tw * r, th * r);
+                        // dX[p] needs dY[p - off]: mirrored tap
+                        const int ow = (OP == TC_DGRAD ? p.kw - 1 - tw : tw) * r;
+                        const int oh = (OP == TC_DGRAD ? p.kh - 1 - th : th) * r;
+                        if (CN > 1) tma_load_im2col_mc(sAs, &mapA, full_bar(stage), cb * kTcBK, bw, bh, img0, ow, oh, kMask);
+                        else tma_load_im2col(sA, &mapA, full_bar(stage), cb * kTcBK, bw, bh, img0, ow, oh);
                     }
                     if (OP == TC_FWD) {
-                        tma_load_2d(sB, &mapB, full_bar(stage), kb * kTcBK, n0);
+                        tma_load_2d(sB, &mapB, full_bar(stage), (tap * cblocks + cb) * kTcBK, n0);
                     } else {
 #pragma unroll
                         for (int g = 0; g < BN / 32; g++)
                             tma_load_2d(sB + g * 4096, &mapB, full_bar(stage), tap * p.Cin + n0 + 32 * g, cb * kTcBK);
                     }
-                    if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
                 }
-            } else {
-                const int tap = n0 / p.Cin, ci0 = n0 - tap * p.Cin;
-                const int th = tap / p.kw, tw = tap - th * p.kw;
-                const int hw = p.H * p.W;
-                for (int i = 0; i < nk; i++) {
-                    const int k0 = (kb0 + i) * kTcBK;
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                __syncwarp();
+                if (++cb == cblocks) {
+                    cb = 0; ++tap;
+                    if (++tw == p.kw) { tw = 0; ++th; }
+                }
+                if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+            }
+        } else {
+            const int tap = n0 / p.Cin, ci0 = n0 - tap * p.Cin;
+            const int th = tap / p.kw, tw = tap - th * p.kw;
+            const int hw = p.H * p.W;
+            int k0 = kb0 * kTcBK;
+            int img = k0 / hw, ph = (k0 - img * hw) / p.W, pw = k0 - img * hw - ph * p.W;
+            for (int i = 0; i < nk; i++) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
+                    if (i < 16) TC_TR(4 + i);
                     const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
                     mbar_expect_tx(full_bar(stage), kBytes);
 #pragma unroll
@@ -535,14 +672,20 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                         for (int g = 0; g < BN / 32; g++)
                             tma_load_2d(sB + g * 4096, &mapB, full_bar(stage), ci0 + 32 * g, k0);
                     } else {
-                        const int img = k0 / hw, rem = k0 - img * hw, ph = rem / p.W, pw = rem - ph * p.W;
 #pragma unroll
                         for (int g = 0; g < BN / 32; g++)
                             tma_load_im2col(sB + g * 4096, &mapB, full_bar(stage), ci0 + 32 * g, pw - r * (p.kw / 2),
                                             ph - r * (p.kh / 2), img, tw * r, th * r);
                     }
-                    if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                k0 += kTcBK;
+                pw += kTcBK;
+                while (pw >= p.W) {
+                    pw -= p.W;
+                    if (++ph == p.H) { ph = 0; ++img; }
+                }
+                if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -552,32 +695,40 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) |
                                    ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(kTcBM >> 4) << 24);
+        // descriptors of stage 0 / k-step 0; stages and k-steps only move the 14-bit address field
+        // (16-byte units; every tile lives below 256 KB, so the add never carries out of the field)
+        const uint64_t ad0 = a_mn ? desc_mnmajor(base) : desc_kmajor(base);
+        const uint64_t bd0 = b_mn ? desc_mnmajor(base + kTcABytes) : desc_kmajor(base + kTcABytes);
+        constexpr uint32_t ka = (a_mn ? 1024u : 32u) >> 4, kb_ = (b_mn ? 1024u : 32u) >> 4;
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < nk; i++) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
+            if (elect_one()) {
+                if (i < 16) TC_TR(20 + i);
+                const uint64_t ad = ad0 + (uint64_t)((stage * kStage) >> 4);
+                const uint64_t bd = bd0 + (uint64_t)((stage * kStage) >> 4);
 #pragma unroll
-                for (int k = 0; k < kTcBK / 8; k++) {
-                    const uint64_t ad = a_mn ? desc_mnmajor(sA + k * 1024) : desc_kmajor(sA + k * 32);
-                    const uint64_t bd = b_mn ? desc_mnmajor(sB + k * 1024) : desc_kmajor(sB + k * 32);
-                    umma_tf32(tmem_acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < kTcBK / 8; k++)
+                    umma_tf32(tmem_acc, ad + k * ka, bd + k * kb_, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 if (CN > 1) umma_commit_mc(empty_bar(stage), kMask);   // frees this stage in every CTA
                 else umma_commit(empty_bar(stage));
                 if (i == nk - 1) umma_commit(tmem_full_bar);
+                if (i < 16) TC_TR(36 + i);
             }
             __syncwarp();
             if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
         }
         tc_fence_before();
     } else {
-        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, lane, m0, n0,
-                            reinterpret_cast<float*>(smem_raw + (base - raw)));
+        constexpr int EW = tma_epi_warps<BN>();
+        const int ew = warp - 2;
+        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, ew >> 2, EW / 4, lane, m0, n0,
+                            reinterpret_cast<float*>(smem_raw + (base - raw)) + ew * 1024 TC_TR_PASS);
     }
     __syncthreads();
+    if (tid == 0) TC_TR(55);
     if (CN > 1) cluster_sync_all();      // no CTA leaves while peers may still multicast into it / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
@@ -668,13 +819,13 @@ static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
         attr_set = true;
     }
     if (CN == 1) {
-        tc_gemm_tma_kernel<BN, OP, CN><<<grid, kTmaThreads, smem, s>>>(p, mapA, mapB);
+        tc_gemm_tma_kernel<BN, OP, CN><<<grid, tma_threads<BN>(), smem, s>>>(p, mapA, mapB);
         MPB_LAUNCH_CHECK();
         return 0;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(kTmaThreads);
+    cfg.blockDim = dim3(tma_threads<BN>());
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -714,6 +865,12 @@ int tc_gemm_mode() {
     return g_tc_mode;
 }
 void tc_gemm_set_cluster(int c) { g_tc_cluster = c < 1 ? 1 : c; }
+#ifdef MPB_TC_TRACE
+int tc_gemm_set_trace(void* buf) {
+    long long* b = (long long*)buf;
+    return (int)cudaMemcpyToSymbol(g_tc_trace, &b, sizeof(b));
+}
+#endif
 void tc_gemm_set_mode(int m) { g_tc_mode = m; if (m == 1 && !tma_api_ready()) g_tc_mode = 0; }
 
 template <int BN, int OP>
@@ -748,6 +905,13 @@ int tc_gemm_launch(const TcGemmParams& p, int BN, cudaStream_t s) {
         return -1;
     }
     if (grid.y > 65535 || grid.z > 65535) return -1;
+    // the epilogue moves 16-byte vectors (4 consecutive columns): every per-column / per-element operand
+    // must be 16-byte aligned with a pitch that is a multiple of 4 floats
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    if (!al16(p.out) || !al16(p.out_r) || !al16(p.res) || !al16(p.mask) || !al16(p.scale) || !al16(p.shift) ||
+        !al16(p.scale2) || !al16(p.colsum))
+        return -1;
+    if ((p.res && p.ldr % 4) || (p.mask && p.ldm % 4) || (p.out_r && p.ldor % 4)) return -1;
     // the TMA path needs whole images in the pixel grid (im2col walk) and 16-byte aligned pitches
     const bool tma = tc_gemm_mode() == 1 && (p.M % (p.H * p.W) == 0);
 #define MPB_TC_CASE(bn)                                                       \

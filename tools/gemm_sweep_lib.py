@@ -1,0 +1,63 @@
+"""Helpers: sweep tile width / split-K of the tcgen05 GEMM core on the block3 bottleneck shapes (CUDA events, warm L2)."""
+import ctypes, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from monopsr_b200 import lib as mlib
+from monopsr_b200.lib_net import TC_DGRAD, TC_FWD, TC_WGRAD, TcGemmParams
+
+dev = torch.device("cuda:0")
+L = mlib.load()
+
+
+def time_it(p, bn, n=20):
+    st = mlib.stream_ptr()
+    for _ in range(3):
+        rc = L.mpb_tc_gemm(ctypes.byref(p), bn, st)
+        if rc != 0:
+            return None
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        L.mpb_tc_gemm(ctypes.byref(p), bn, st)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / n
+
+
+def make(op, nimg, H, W, k, dil, Cin, Cout, epi):
+    M = nimg * H * W
+    p = TcGemmParams()
+    p.op, p.H, p.W, p.kh, p.kw, p.dil, p.M, p.Cin, p.Cout = op, H, W, k, k, dil, M, Cin, Cout
+    keep = []
+    def T(*s):
+        t = torch.randn(*s, device=dev)
+        keep.append(t)
+        return t
+    w = T(Cout, k * k * Cin)
+    p.Wt, p.ldw = w.data_ptr(), k * k * Cin
+    if op == TC_FWD:
+        x = T(M, Cin); o = T(M, Cout)
+        p.X, p.ldx, p.out, p.ldo = x.data_ptr(), Cin, o.data_ptr(), Cout
+        ncol = Cout
+    elif op == TC_DGRAD:
+        x = T(M, Cout); o = T(M, Cin)
+        p.X, p.ldx, p.out, p.ldo = x.data_ptr(), Cout, o.data_ptr(), Cin
+        ncol = Cin
+    else:
+        x = T(M, Cin); y = T(M, Cout)
+        p.X, p.ldx, p.Y, p.ldy, p.out = x.data_ptr(), Cin, y.data_ptr(), Cout, w.data_ptr()
+        ncol = 0
+    if k > 1:
+        tm = torch.empty(M, dtype=torch.int16, device=dev)
+        L.mpb_build_tapmask(nimg, H, W, k, k, dil, tm.data_ptr(), mlib.stream_ptr())
+        keep.append(tm)
+        p.tapmask = tm.data_ptr()
+    if epi and op != TC_WGRAD:
+        sh = T(ncol); r = T(M, ncol); o2 = T(M, ncol)
+        p.shift, p.res, p.ldr, p.relu, p.round_tf32 = sh.data_ptr(), r.data_ptr(), ncol, 1, 0
+        p.out_r, p.ldor = o2.data_ptr(), ncol
+    p.ksplit = 1
+    return p, keep
+
+
