@@ -531,7 +531,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 // 1/CN of the A tile and the TMA multicasts it into every CTA's shared memory -- L2 -> SM traffic
 // for A drops by CN (the GEMMs of this network are bound by exactly that traffic).
 template <int BN, int OP, int CN>
-__global__ void __launch_bounds__(tma_threads<BN>())
+__global__ void __launch_bounds__(tma_threads<BN>(), BN == 64 ? 2 : 1)
 tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant__ CUtensorMap mapA,
                    const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ uint8_t smem_raw[];
@@ -586,7 +586,11 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
         TC_TR(1);
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if (trc) { trc[2] = smid; trc[56] = nk; }
+        if (trc) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            trc[2] = smid; trc[56] = nk; trc[3] = (long long)gt;
+        }
     }
 #endif
     const int m0 = blockIdx.x * kTcBM;
@@ -733,6 +737,13 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN) : "memory");
+#ifdef MPB_TC_TRACE
+        if (lane == 0 && trc) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            trc[57] = (long long)gt;
+        }
+#endif
     }
 }
 

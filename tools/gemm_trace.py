@@ -45,7 +45,12 @@ for name, op, nimg, H, W, k, dil, Cin, Cout, epi, bn, ks in CASES:
     m = min(nk, 16)
     print("== %s: %.1f us, %d CTAs traced, nk=%d, SMs used %d" % (name, us, n, nk, len(set(t[:, 2]))))
     rel = lambda s: (t[:, s] - t[:, 0])
-    print("   CTA start spread (clk): med %d max %d" % (np.median(t[:, 0] - t0), (t[:, 0] - t0).max()))
+    g0 = t[:, 3].min()
+    st_ns, en_ns = np.sort(t[:, 3] - g0), t[:, 57] - g0
+    print("   CTA start (ns, globaltimer) pctl 50/75/90/100: %d %d %d %d ; last exit %d ns" % (
+        st_ns[n // 2], st_ns[(3 * n) // 4], st_ns[(9 * n) // 10], st_ns[-1], en_ns.max()))
+    percta = (t[:, 57] - t[:, 3])
+    print("   per-CTA lifetime ns: med %d" % np.median(percta))
     print("   setup            : med %d" % np.median(rel(1)))
     print("   first TMA issue  : med %d" % np.median(rel(4)))
     print("   first full       : med %d  (TMA latency of k-block 0: %d)" % (np.median(rel(20)), np.median(t[:, 20] - t[:, 4])))
@@ -60,4 +65,4 @@ for name, op, nimg, H, W, k, dil, Cin, Cout, epi, bn, ks in CASES:
     print("   first chunk done : med +%d" % np.median(t[:, 53] - t[:, 52]))
     print("   epilogue done    : med +%d" % np.median(t[:, 54] - t[:, 52]))
     print("   exit             : med %d  max %d" % (np.median(rel(55)), rel(55).max()))
-    print("   whole kernel span: %d clk" % (t[:, 55].max() - t0), flush=True)
+    sys.stdout.flush()
