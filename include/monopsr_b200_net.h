@@ -49,7 +49,10 @@ typedef struct mpb_tc_gemm_params {
     int relu;
     int round_tf32;
     int atomic;
-    int ksplit;          /* >=1: split the K loop over gridDim.z (needs atomic=1 and a zeroed out) */
+    int ksplit;          /* >=1: split the K loop over gridDim.z.  atomic=1: slices RED.ADD into a zeroed `out` (no
+                          * other epilogue option makes sense then).  atomic=0: the slices of a tile form one
+                          * thread-block cluster (ksplit <= 8), reduce through distributed shared memory and the full
+                          * fused epilogue still runs once per tile */
     float* out_r;        /* optional second output [rows][ldor]: the tf32-rounded value (GEMM operand of the next
                           * layer) while `out` keeps the unrounded one (fp32 residual stream) */
     int ldor;
@@ -63,6 +66,10 @@ int mpb_tc_gemm(const mpb_tc_gemm_params* p, int BN, void* stream);
 int mpb_tc_set_producer(int mode);
 /* max CTAs per thread-block cluster sharing (TMA-multicasting) one A tile: 1 (default, off), 2 or 4. */
 int mpb_tc_set_cluster(int max_cluster);
+
+/* diagnostics: how many (cluster_x, 1, ksplit)-CTA clusters of the cluster split-K kernel (tile width BN) can be
+ * resident at once (cudaOccupancyMaxActiveClusters); < 0: -cudaError_t */
+int mpb_tc_max_clusters(int BN, int cluster_x, int ksplit);
 
 /* tapmask[m] for an (nimg,H,W) pixel grid and a kh x kw filter with atrous rate dil. */
 int mpb_build_tapmask(int nimg, int H, int W, int kh, int kw, int dil, unsigned short* out, void* stream);
@@ -186,6 +193,13 @@ typedef struct mpb_opt_chunk { long start; int len; int tensor; } mpb_opt_chunk;
 int mpb_opt_step(int nchunks, const mpb_opt_chunk* chunks, int ntensors, float* param, const float* grad,
                  float* m, float* v, float* ema, float* norm2, const float* hyper, float grad_scale,
                  float clip_norm, float beta1, float beta2, float eps, float ema_decay, void* stream);
+/* the same over a sub-range of the chunk table: `chunks` points at the first chunk of the range, whose tensors are
+ * tensor0 .. tensor0+ntensors-1 (chunk.tensor stays an absolute index into norm2).  The update is per variable, so
+ * a group of variables can be stepped as soon as its gradients are final, under the rest of the backward pass. */
+int mpb_opt_step_range(int nchunks, const mpb_opt_chunk* chunks, int tensor0, int ntensors, float* param,
+                       const float* grad, float* m, float* v, float* ema, float* norm2, const float* hyper,
+                       float grad_scale, float clip_norm, float beta1, float beta2, float eps, float ema_decay,
+                       void* stream);
 
 #ifdef __cplusplus
 }

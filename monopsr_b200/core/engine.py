@@ -15,6 +15,7 @@ reference's ``batch_size: 1`` (configs/monopsr_model_000.yaml:14-17).  The whole
 captured into a CUDA graph after the first call.
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -54,12 +55,17 @@ class Engine:
         self.s_full = torch.cuda.Stream(device=self.dev)
         self.s_wc = torch.cuda.Stream(device=self.dev)
         self.s_wf = torch.cuda.Stream(device=self.dev)
+        self.s_opt = torch.cuda.Stream(device=self.dev)
+        self.early_opt = False      # set by the single-GPU train step: head train-op under the towers' backward
         self.overlap = True
         import os
         self.fill = float(os.environ.get("MPB_TILE_FILL", "0.9"))   # min fraction of SMs a launch must fill before widening tiles
         self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
-        self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "64"))
+        self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "128"))
         self.wgrad_fill = float(os.environ.get("MPB_WGRAD_FILL", "0.5"))   # target CTAs / SMs when choosing split-K
+        self.csk = int(os.environ.get("MPB_CSK", "1"))                    # cluster split-K (DSMEM reduce) for long reductions
+        self.csk_bn = int(os.environ.get("MPB_CSK_BN", "128"))            # widest tile that may be split over a cluster
+        self.ctas_per_sm = {64: 2, 128: int(os.environ.get("MPB_CTAS128", "2")), 256: 1}   # see tc_gemm.cuh
 
     # ------------------------------------------------------------------ parameters
     def _dev_shape(self, name, shape, kind):
@@ -120,6 +126,15 @@ class Engine:
         self.opt_chunks = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.dev)
         self.n_chunks = len(chunks)
         self.norm2 = z(len(self.trainable_names))
+        # the variables outside the two towers (squash, decoder, FC stacks, heads: 45 % of the parameters) sit at
+        # the end of the arena; their gradients are final before the towers' backward pass starts, so their
+        # train-op runs on a side stream under it ("head" part; the rest is the "towers" part)
+        t_head = min(i for i, n in enumerate(self.trainable_names) if not n.startswith("FirstStage"))
+        assert all(not n.startswith("FirstStage") for n in self.trainable_names[t_head:])
+        c_head = min(i for i, c in enumerate(chunks) if c[2] >= t_head)
+        nt = len(self.trainable_names)
+        self.opt_parts = {"all": (0, len(chunks), 0, nt), "towers": (0, c_head, 0, t_head),
+                          "head": (c_head, len(chunks) - c_head, t_head, nt - t_head)}
 
     def view(self, name, arena=None):
         a, off, ds = self.layout[name]
@@ -279,13 +294,27 @@ class Engine:
             for st_ in streams:
                 self._cur().wait_stream(st_)
 
-    def _pick_bn(self, mtiles, ncols, allowed=(256, 128, 64)):
-        for bn in allowed:
-            if ncols % bn == 0 and mtiles * (ncols // bn) >= int(self.fill * self.sms):
-                return bn
-        for bn in reversed(allowed):
-            if ncols % bn == 0:
-                return bn
+    def _plan_tiles(self, mtiles, ncols, nkb):
+        """(tile width, split-K) of a FWD / DGRAD launch; rules read off tools/gemm_sweep.py on B200
+        (profiles/r1_notes.md).  Wide tiles halve the operand traffic per FLOP and make the main loop MMA-bound,
+        but a 128 x 256 tile grid of these layers covers only 36-48 SMs: long reductions are therefore split in
+        two over a 2-CTA cluster (a TPC) that reduces through DSMEM; clusters of 3-4 fragment the GPCs."""
+        tiles = {bn: mtiles * (ncols // bn) for bn in (256, 128, 64) if ncols % bn == 0}
+        lo = int(self.fill * 100)                     # CTAs below which a launch is considered too small
+        if self.csk and nkb >= 16:
+            for bn in (256, 128):
+                if bn in tiles and bn <= self.csk_bn and lo <= 2 * tiles[bn] <= self.sms * self.ctas_per_sm[bn]:
+                    return bn, 2
+        for bn in (256, 128):
+            if bn in tiles and tiles[bn] >= lo:
+                # short reductions are epilogue-bound: once the grid needs a second wave anyway, 64-wide
+                # tiles (two CTAs per SM, one's epilogue under the other's main loop) win
+                if nkb <= 8 and tiles[bn] > self.sms and 64 in tiles:
+                    break
+                return bn, 1
+        for bn in (64, 128, 256):
+            if bn in tiles:
+                return bn, 1
         raise ValueError("no tile width divides %d" % ncols)
 
     def gemm(self, op, M, H, W, k, dil, Cin, Cout, X, ldx, Wt, ldw, out, ldo, Y=None, ldy=0, tapmask=None,
@@ -301,16 +330,13 @@ class Engine:
         p.out_r, p.ldor = _ptr(out_r), ldor
         mt = (M + 127) // 128
         if bn is None:
-            # short reductions are epilogue (memory) bound: small tiles keep two CTAs per SM so one
-            # CTA's epilogue overlaps the other's main loop
             kdepth = k * k * (Cin if op == TC_FWD else Cout)
-            allowed = (64,) if (kdepth <= self.shortk and op != TC_WGRAD) else (256, 128, 64)
-            if op == TC_FWD:
-                bn = self._pick_bn(mt, Cout, allowed)
-            elif op == TC_DGRAD:
-                bn = self._pick_bn(mt, Cin, allowed)
-            else:
+            if op == TC_WGRAD:
                 bn = 128 if Cin % 128 == 0 else 64
+            else:
+                bn, ks = self._plan_tiles(mt, Cout if op == TC_FWD else Cin, kdepth // 32)
+                if ksplit == 1 and not atomic and M % (H * W) == 0:
+                    p.ksplit = ks
         if getattr(self, "_record", None) is not None:
             self._record.append((p, bn, 2.0 * M * Cin * Cout * k * k))
         self._chk(self.L.mpb_tc_gemm(ctypes.byref(p), bn, self._st()), "mpb_tc_gemm")
@@ -347,10 +373,12 @@ class Engine:
         return {"ms": ms_, "gflop": flop / 1e9, "tflops": flop / (ms_ * 1e-3) / 1e12, "launches": len(rec)}
 
     def wgrad(self, M, H, W, k, dil, Cin, Cout, X, ldx, dY, ldy, dW, tapmask=None, rowscale=None):
-        bn = 128 if (Cin % 128 == 0 and self.wgrad_bn >= 128) else 64
+        # widest tile that divides Cin, then enough K slices (RED.ADD into the zeroed gradient arena) to put
+        # about one CTA on every SM: 128 x 256 tiles at ~144 CTAs ran 1.7x faster than 64-wide ones
+        bn = next(b for b in (256, 128, 64) if Cin % b == 0 and b <= self.wgrad_bn)
         tiles = ((Cout + 127) // 128) * (k * k * Cin // bn)
         nkb = (M + 31) // 32
-        ksplit = max(1, min(int(self.wgrad_fill * self.sms + tiles - 1) // tiles, max(1, nkb // 4)))
+        ksplit = max(1, min(int(self.wgrad_fill * self.sms + tiles // 2) // tiles, max(1, nkb // 4)))
         self.gemm(TC_WGRAD, M, H, W, k, dil, Cin, Cout, X, ldx, None, k * k * Cin, dW, 0, Y=dY, ldy=ldy,
                   tapmask=tapmask, rowscale=rowscale, atomic=1, ksplit=ksplit, bn=bn)
 
@@ -383,16 +411,19 @@ class Engine:
         first = min(self.layout[n][1] for n in self.trainable_names if not n.startswith("FirstStage"))
         self.round_off, self.round_len = first, self.n_train - first
 
-    def prepare_weights(self):
+    def prepare_weights(self, part="all"):
         """fold frozen BN into the tower convs, tf32-round every GEMM weight (run after each update)."""
         L, st = self.L, self._st()
         if getattr(self, "bn_layers", None) is None:
             self._build_bn_table()
-        self._chk(L.mpb_fold_bn_multi(self.bn_rows, _ptr(self.bn_layers), _ptr(self.bn_row2layer), BN_EPS_RESNET, st),
-                  "fold_bn_multi")
-        self._chk(L.mpb_round_copy(self.round_len, _ptr(self.params[self.round_off:]), _ptr(self.prep[self.round_off:]), st),
-                  "round_copy")
-        self._prepared = True
+        if part in ("all", "towers"):
+            self._chk(L.mpb_fold_bn_multi(self.bn_rows, _ptr(self.bn_layers), _ptr(self.bn_row2layer), BN_EPS_RESNET, st),
+                      "fold_bn_multi")
+        if part in ("all", "head"):
+            self._chk(L.mpb_round_copy(self.round_len, _ptr(self.params[self.round_off:]), _ptr(self.prep[self.round_off:]),
+                                       st), "round_copy")
+        if part in ("all", "towers"):
+            self._prepared = True
 
     # ------------------------------------------------------------------ inputs
     def set_inputs(self, S):
@@ -711,6 +742,13 @@ class Engine:
                   mask=self.concat, ldm=2048, colsum=self.gview(lastc["scope"] + "/conv3/BatchNorm/beta"), round_tf32=1)
         self.gemm(TC_DGRAD, Mc, 12, 12, 1, 1, 1024, 512, self.g_squashed, 512, wsq.view(-1)[1024:], 2048,
                   self.g_fullcrop, 1024)
+        if self.early_opt:
+            # every gradient outside the towers is final (FC stacks on s_wc, decoder wgrads on s_wf, the rest here)
+            for s_ in (self._cur(), self.s_wf, self.s_wc):
+                self.s_opt.wait_stream(s_)
+            with torch.cuda.stream(self.s_opt):
+                self.optimizer_step(1.0, part="head")
+                self.prepare_weights(part="head")
         with self._side(self.s_full):
             self._chk(L.mpb_crop_pool_bwd(Tf["h"], Tf["w"], 1024, _ptr(lastf["o"]), N, _ptr(I["boxes_2d_norm"]), 24,
                                           _ptr(self.g_fullcrop), 1024, _ptr(self.d_fullfeat), self._st()), "crop_pool_bwd")
@@ -736,11 +774,13 @@ class Engine:
         self.hyper_host[0] = lr_t
         self.hyper.copy_(self.hyper_host, non_blocking=True)
 
-    def optimizer_step(self, grad_scale=1.0):
-        self._chk(self.L.mpb_opt_step(self.n_chunks, _ptr(self.opt_chunks), len(self.trainable_names), _ptr(self.params),
-                                      _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.ema),
-                                      _ptr(self.norm2), _ptr(self.hyper), grad_scale, 1.0, 0.9, 0.999, 1e-8, 0.9999,
-                                      self._st()), "opt_step")
+    def optimizer_step(self, grad_scale=1.0, part="all"):
+        c0, nc, t0, nt = self.opt_parts[part]
+        chunk_bytes = ctypes.sizeof(OptChunk)
+        self._chk(self.L.mpb_opt_step_range(nc, ctypes.c_void_p(self.opt_chunks.data_ptr() + c0 * chunk_bytes), t0, nt,
+                                            _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
+                                            _ptr(self.ema), _ptr(self.norm2), _ptr(self.hyper), grad_scale, 1.0, 0.9,
+                                            0.999, 1e-8, 0.9999, self._st()), "opt_step")
         self._prepared = False
 
     def allreduce_grads(self):
@@ -792,11 +832,21 @@ class Engine:
         self._warm()
         g = torch.cuda.CUDAGraph()
         c0 = _lib.launch_count()
+        # measured: stepping the head variables under the towers' backward pass is ~1.5 % SLOWER than one train-op
+        # at the end (the HBM-bound Adam pass slows the concurrent GEMMs more than the overlap saves): off
+        early = int(os.environ.get("MPB_EARLY_OPT", "0")) != 0
         with torch.cuda.graph(g):
             self.forward(train=True)
+            self.early_opt = early
             self.backward()
-            self.optimizer_step(1.0)
-            self.prepare_weights()
+            self.early_opt = False
+            if early:
+                self.optimizer_step(1.0, part="towers")
+                self.prepare_weights(part="towers")
+                self._join(self.s_opt)
+            else:
+                self.optimizer_step(1.0)
+                self.prepare_weights()
         self.launches_per_step = _lib.launch_count() - c0
         self._graph = g
 

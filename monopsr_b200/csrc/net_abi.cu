@@ -39,6 +39,11 @@ MPB_API int mpb_tc_set_cluster(int max_cluster) {
     return max_cluster;
 }
 
+namespace mpb { int tc_gemm_max_clusters(int BN, int cx, int ks); }
+MPB_API int mpb_tc_max_clusters(int BN, int cluster_x, int ksplit) {
+    return mpb::tc_gemm_max_clusters(BN, cluster_x, ksplit);
+}
+
 #ifdef MPB_TC_TRACE
 namespace mpb { int tc_gemm_set_trace(void* buf); }
 MPB_API int mpb_tc_set_trace(void* buf) { return mpb::tc_gemm_set_trace(buf); }

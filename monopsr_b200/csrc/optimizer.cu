@@ -95,17 +95,25 @@ opt_adam_ema_kernel(const mpb_opt_chunk* __restrict__ chunks, float* __restrict_
 
 }  // namespace mpb
 
-MPB_API int mpb_opt_step(int nchunks, const mpb_opt_chunk* chunks, int ntensors, float* param, const float* grad,
-                         float* m, float* v, float* ema, float* norm2, const float* hyper, float grad_scale,
-                         float clip_norm, float beta1, float beta2, float eps, float ema_decay, void* stream) {
+MPB_API int mpb_opt_step_range(int nchunks, const mpb_opt_chunk* chunks, int tensor0, int ntensors, float* param,
+                               const float* grad, float* m, float* v, float* ema, float* norm2, const float* hyper,
+                               float grad_scale, float clip_norm, float beta1, float beta2, float eps, float ema_decay,
+                               void* stream) {
     using namespace mpb;
-    if (nchunks <= 0 || !chunks || !param || !grad || !m || !v || !ema || !norm2 || !hyper) return -1;
+    if (nchunks <= 0 || !chunks || !param || !grad || !m || !v || !ema || !norm2 || !hyper || tensor0 < 0) return -1;
     cudaStream_t s = (cudaStream_t)stream;
-    MPB_CUDA_TRY(cudaMemsetAsync(norm2, 0, sizeof(float) * ntensors, s));
+    MPB_CUDA_TRY(cudaMemsetAsync(norm2 + tensor0, 0, sizeof(float) * ntensors, s));
     opt_sumsq_kernel<<<nchunks, kOptThreads, 0, s>>>(chunks, grad, grad_scale, norm2);
     MPB_LAUNCH_CHECK();
     opt_adam_ema_kernel<<<nchunks, kOptThreads, 0, s>>>(chunks, param, grad, m, v, ema, norm2, hyper, grad_scale,
                                                        clip_norm, beta1, beta2, eps, ema_decay);
     MPB_LAUNCH_CHECK();
     return 0;
+}
+
+MPB_API int mpb_opt_step(int nchunks, const mpb_opt_chunk* chunks, int ntensors, float* param, const float* grad,
+                         float* m, float* v, float* ema, float* norm2, const float* hyper, float grad_scale,
+                         float clip_norm, float beta1, float beta2, float eps, float ema_decay, void* stream) {
+    return mpb_opt_step_range(nchunks, chunks, 0, ntensors, param, grad, m, v, ema, norm2, hyper, grad_scale, clip_norm,
+                              beta1, beta2, eps, ema_decay, stream);
 }

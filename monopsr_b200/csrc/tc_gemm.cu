@@ -127,63 +127,131 @@ __device__ __forceinline__ int tap_delta(int tap, int kh, int kw, int dil, int W
 // warp-uniform branch per option and row, took ~7000 clk per chunk; see profiles/r1_notes.md).
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// Cluster split-K (ks > 1): the ks CTAs of a thread-block cluster hold partial accumulators of the SAME
+// output tile (disjoint K ranges).  32-column chunk c is owned by cluster rank c % ks.  Phase 1
+// (tc_epilogue_dump): every CTA copies the chunks it does not own from TMEM into its own shared memory,
+// already in the swizzled staging layout.  After a cluster barrier the owner (tc_epilogue) adds the peers'
+// partials straight out of their shared memory (DSMEM, ld.shared::cluster.v4) in the transposed domain and
+// runs the normal fused epilogue -- the partial sums never touch HBM/L2, the output needs no zero-fill and
+// no atomics, and the epilogue work of a tile is spread over the ks CTAs.
+__device__ __forceinline__ float4 ld_dsmem4(uint32_t local_saddr, uint32_t peer) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(peer));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
+
+// Staging in the (idle) pipeline stages: one 4 KB transposition scratch tile (32 rows x 128 B) per epilogue warp,
+// then, for cluster split-K, one 16 KB region (4 quads) per chunk this CTA does NOT own, packed densely:
+// dump_idx = position of chunk c among the non-owned chunks of cluster rank d.
+__device__ __forceinline__ int dump_idx(int c, int d, int ks) { return c - (c > d ? (c - d + ks - 1) / ks : 0); }
+__device__ __forceinline__ float* dump_region(float* stg_base, int nepi, int idx, int quad) {
+    return stg_base + (nepi + idx * 4 + quad) * 1024;
+}
+
 template <int BN, int OP>
-__device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem_full_bar, uint32_t tmem_acc,
-                                            int quad, int half, int nhalf, int lane, int m0, int n0,
-                                            float* stg_warp TC_TR_ARG) {
+__device__ __forceinline__ void tc_epilogue_dump(const TcGemmParams& p, uint32_t tmem_full_bar, uint32_t tmem_acc,
+                                                 int quad, int half, int nhalf, int lane, int m0,
+                                                 float* stg_base, int nepi, int ks, int rank TC_TR_ARG) {
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (quad == 0 && half == 0 && lane == 0) TC_TR(52);
-    float4* stg4 = reinterpret_cast<float4*>(stg_warp);
-    const int row0 = m0 + quad * 32;               // first accumulator row of this warp
+    if (ks == 1) return;
+    const int row0 = m0 + quad * 32;
     const int nrows = (OP == TC_WGRAD) ? p.Cout : p.M;
-    const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16);
-    const int ldo = (OP == TC_WGRAD) ? p.ldw : p.ldo;
-    const int g = lane >> 3, q = lane & 7;         // after the transpose: rows 4i+g, columns 4q..4q+3
     float rs = 1.f;
     if (p.rowscale && row0 + lane < nrows) rs = __ldg(p.rowscale + row0 + lane);
-    const bool has_res = p.res != nullptr, has_mask = p.mask != nullptr, do_round = p.round_tf32 != 0;
-    const bool has_outr = p.out_r != nullptr, is_atomic = p.atomic != 0;
-    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int nvalid = nrows - row0;               // warp-uniform; >= 32 except in the last row tile
+    const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-    for (int c0 = half * 32; c0 < BN; c0 += 32 * nhalf) {
-        const int col = n0 + c0 + q * 4;
-        // issue every global read of this chunk first (independent 16-byte loads), so their latency
-        // overlaps the TMEM read and the shared-memory transpose
-        float4 rv[8], mv[8];
-        if (has_res) {
-            const float* rp = p.res + (size_t)(row0 + g) * p.ldr + col;
-#pragma unroll
-            for (int i = 0; i < 8; i++) rv[i] = (4 * i + g < nvalid) ? ldg4(rp + (size_t)(4 * i) * p.ldr) : zero4;
-        }
-        if (has_mask) {
-            const float* mp = p.mask + (size_t)(row0 + g) * p.ldm + col;
-#pragma unroll
-            for (int i = 0; i < 8; i++) mv[i] = (4 * i + g < nvalid) ? ldg4(mp + (size_t)(4 * i) * p.ldm) : zero4;
-        }
-        const float4 sc = p.scale ? ldg4(p.scale + col) : one4;
-        const float4 sh = p.shift ? ldg4(p.shift + col) : zero4;
+    for (int c = half; c < BN / 32; c += nhalf) {
+        if (c % ks == rank) continue;
+        float4* stg4 = reinterpret_cast<float4*>(dump_region(stg_base, nepi, dump_idx(c, rank, ks), quad));
         float x[32];
-        tmem_ld32(trow + c0, x);
+        tmem_ld32(trow + c * 32, x);
 #pragma unroll
         for (int j = 0; j < 8; j++)
             stg4[lane * 8 + (j ^ (lane & 7))] =
                 make_float4(x[4 * j] * rs, x[4 * j + 1] * rs, x[4 * j + 2] * rs, x[4 * j + 3] * rs);
-        __syncwarp();
-        // after the transpose x[4i..4i+3] = columns col..col+3 of row 4i+g.  Every option below is ONE
-        // warp-uniform branch around a straight run of 32 independent operations.
+    }
+}
+
+struct EpiCtx {
+    int quad, row0, nvalid, ldo, ks, rank;
+    uint32_t trow;
+    float rs;
+    bool has_res, has_mask, do_round, has_outr, is_atomic;
+    float* stg_base;
+    float* scratch;            // this warp's 4 KB transposition tile
+    int nepi;
+    uint32_t cl_x, cl_nx;      // cluster split-K: DSMEM rank of K slice z of this tile = cl_x + cl_nx * z
+};
+
+// fused epilogue of one 32-column chunk: accumulator from TMEM (+ the cluster peers' partials)
+template <int BN, int OP>
+__device__ __forceinline__ void epi_chunk(const TcGemmParams& p, const EpiCtx& c, int cc, int lane, int n0) {
+    const int g = lane >> 3, q = lane & 7;         // after the transpose: rows 4i+g, columns 4q..4q+3
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c0 = cc * 32;
+    float4* stg4 = reinterpret_cast<float4*>(c.scratch);
+    (void)stg4;
+        const int col = n0 + c0 + q * 4;
+        // issue every global read of this chunk first (independent 16-byte loads), so their latency
+        // overlaps the TMEM read and the shared-memory transpose
+        float4 rv[8], mv[8];
+        if (c.has_res) {
+            const float* rp = p.res + (size_t)(c.row0 + g) * p.ldr + col;
+#pragma unroll
+            for (int i = 0; i < 8; i++) rv[i] = (4 * i + g < c.nvalid) ? ldg4(rp + (size_t)(4 * i) * p.ldr) : zero4;
+        }
+        if (c.has_mask) {
+            const float* mp = p.mask + (size_t)(c.row0 + g) * p.ldm + col;
+#pragma unroll
+            for (int i = 0; i < 8; i++) mv[i] = (4 * i + g < c.nvalid) ? ldg4(mp + (size_t)(4 * i) * p.ldm) : zero4;
+        }
+        const float4 sc = p.scale ? ldg4(p.scale + col) : one4;
+        const float4 sh = p.shift ? ldg4(p.shift + col) : zero4;
+        float x[32];
+        {
+            tmem_ld32(c.trow + c0, x);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                stg4[lane * 8 + (j ^ (lane & 7))] =
+                    make_float4(x[4 * j] * c.rs, x[4 * j + 1] * c.rs, x[4 * j + 2] * c.rs, x[4 * j + 3] * c.rs);
+            __syncwarp();
+            // after the transpose x[4i..4i+3] = columns col..col+3 of row 4i+g
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int rl = 4 * i + g;
+                const float4 t = stg4[rl * 8 + (q ^ (rl & 7))];
+                x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+            }
+            __syncwarp();         // the next chunk overwrites the scratch tile
+            if (c.ks > 1) {       // cluster split-K: add the peers' partials out of their shared memory
+#pragma unroll 1
+                for (int pr = 1; pr < c.ks; pr++) {
+                    const int pz = (c.rank + pr) % c.ks;
+                    const uint32_t peer = c.cl_x + c.cl_nx * (uint32_t)pz;
+                    const uint32_t sreg = smem_u32(dump_region(c.stg_base, c.nepi, dump_idx(cc, pz, c.ks), c.quad));
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int rl = 4 * i + g;
+                        const float4 t = ld_dsmem4(sreg + (uint32_t)(rl * 8 + (q ^ (rl & 7))) * 16u, peer);
+                        x[4 * i] += t.x; x[4 * i + 1] += t.y; x[4 * i + 2] += t.z; x[4 * i + 3] += t.w;
+                    }
+                }
+            }
+        }
+        // every option below is ONE warp-uniform branch around a straight run of 32 independent operations
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const int rl = 4 * i + g;
-            const float4 t = stg4[rl * 8 + (q ^ (rl & 7))];
-            x[4 * i] = fmaf(t.x, sc.x, sh.x);
-            x[4 * i + 1] = fmaf(t.y, sc.y, sh.y);
-            x[4 * i + 2] = fmaf(t.z, sc.z, sh.z);
-            x[4 * i + 3] = fmaf(t.w, sc.w, sh.w);
+            x[4 * i] = fmaf(x[4 * i], sc.x, sh.x);
+            x[4 * i + 1] = fmaf(x[4 * i + 1], sc.y, sh.y);
+            x[4 * i + 2] = fmaf(x[4 * i + 2], sc.z, sh.z);
+            x[4 * i + 3] = fmaf(x[4 * i + 3], sc.w, sh.w);
         }
-        __syncwarp();                  // the next chunk overwrites the staging tile
-        if (has_res) {
+        if (c.has_res) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 x[4 * i] += rv[i].x; x[4 * i + 1] += rv[i].y; x[4 * i + 2] += rv[i].z; x[4 * i + 3] += rv[i].w;
@@ -193,7 +261,7 @@ __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem
 #pragma unroll
             for (int e = 0; e < 32; e++) x[e] = fmaxf(x[e], 0.f);
         }
-        if (has_mask) {
+        if (c.has_mask) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 x[4 * i] = mv[i].x > 0.f ? x[4 * i] : 0.f;
@@ -209,14 +277,14 @@ __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem
                 x[4 * i] *= s2.x; x[4 * i + 1] *= s2.y; x[4 * i + 2] *= s2.z; x[4 * i + 3] *= s2.w;
             }
         }
-        if (do_round) {
+        if (c.do_round) {
 #pragma unroll
             for (int e = 0; e < 32; e++) x[e] = round_tf32(x[e]);
         }
-        float* op = p.out + (size_t)(row0 + g) * ldo + col;
-        const size_t ostep = (size_t)4 * ldo;
-        if (nvalid >= 32) {
-            if (is_atomic) {
+        float* op = p.out + (size_t)(c.row0 + g) * c.ldo + col;
+        const size_t ostep = (size_t)4 * c.ldo;
+        if (c.nvalid >= 32) {
+            if (c.is_atomic) {
 #pragma unroll
                 for (int i = 0; i < 8; i++)
                     atomicAdd(reinterpret_cast<float4*>(op + i * ostep), make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]));
@@ -228,9 +296,9 @@ __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem
         } else {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                if (4 * i + g < nvalid) {
+                if (4 * i + g < c.nvalid) {
                     const float4 o = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-                    if (is_atomic) atomicAdd(reinterpret_cast<float4*>(op + i * ostep), o);
+                    if (c.is_atomic) atomicAdd(reinterpret_cast<float4*>(op + i * ostep), o);
                     else *reinterpret_cast<float4*>(op + i * ostep) = o;
                 } else {
                     x[4 * i] = x[4 * i + 1] = x[4 * i + 2] = x[4 * i + 3] = 0.f;   // keep tail rows out of colsum
@@ -248,17 +316,48 @@ __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem
                 cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
                 cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
             }
-            if (g == 0 && nvalid > 0) atomicAdd(reinterpret_cast<float4*>(p.colsum + col), cs);
+            if (g == 0 && c.nvalid > 0) atomicAdd(reinterpret_cast<float4*>(p.colsum + col), cs);
         }
-        if (has_outr) {
-            float* orp = p.out_r + (size_t)(row0 + g) * p.ldor + col;
+        if (c.has_outr) {
+            float* orp = p.out_r + (size_t)(c.row0 + g) * p.ldor + col;
 #pragma unroll
             for (int i = 0; i < 8; i++)
-                if (4 * i + g < nvalid)
+                if (4 * i + g < c.nvalid)
                     *reinterpret_cast<float4*>(orp + (size_t)(4 * i) * p.ldor) =
                         make_float4(round_tf32(x[4 * i]), round_tf32(x[4 * i + 1]), round_tf32(x[4 * i + 2]), round_tf32(x[4 * i + 3]));
         }
-        if (quad == 0 && lane == 0 && c0 == 0) TC_TR(53);
+}
+
+// ks == 1: this CTA owns the whole accumulator; ks > 1 (cluster split-K, see tc_epilogue_dump): it finishes the
+// chunks it owns.  (A third variant -- slices meeting in a global fp32 workspace, last arriver finishes the tile --
+// was measured 1.5-2x slower than either: L2 RED.ADD throughput plus a fence per slice; profiles/r1_notes.md.)
+template <int BN, int OP>
+__device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem_acc,
+                                            int quad, int half, int nhalf, int lane, int m0, int n0,
+                                            float* stg_base, int ks, int rank, int nepi,
+                                            uint32_t cl_x, uint32_t cl_nx TC_TR_ARG) {
+    EpiCtx c;
+    c.cl_x = cl_x; c.cl_nx = cl_nx;
+    c.quad = quad;
+    c.row0 = m0 + quad * 32;                       // first accumulator row of this warp
+    const int nrows = (OP == TC_WGRAD) ? p.Cout : p.M;
+    c.nvalid = nrows - c.row0;                     // warp-uniform; >= 32 except in the last row tile
+    c.trow = tmem_acc + ((uint32_t)(quad * 32) << 16);
+    c.ldo = (OP == TC_WGRAD) ? p.ldw : p.ldo;
+    c.rs = 1.f;
+    if (p.rowscale && c.row0 + lane < nrows) c.rs = __ldg(p.rowscale + c.row0 + lane);
+    c.has_res = p.res != nullptr; c.has_mask = p.mask != nullptr; c.do_round = p.round_tf32 != 0;
+    c.has_outr = p.out_r != nullptr; c.is_atomic = p.atomic != 0;
+    c.stg_base = stg_base;
+    c.scratch = stg_base + (quad + 4 * half) * 1024;
+    c.nepi = nepi;
+    c.ks = ks;
+    c.rank = rank;
+    // owned chunks: rank, rank + ks, ...; the j-th of them goes to the warp with half == j % nhalf
+#pragma unroll 1
+    for (int cc = rank + half * ks; cc < BN / 32; cc += nhalf * ks) {
+        epi_chunk<BN, OP>(p, c, cc, lane, n0);
+        if (quad == 0 && lane == 0 && half == 0 && cc == rank) TC_TR(53);
     }
     if (quad == 0 && half == 0 && lane == 0) TC_TR(54);
     tc_fence_before();
@@ -410,8 +509,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 #ifdef MPB_TC_TRACE
         long long* trc = nullptr;
 #endif
-        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp, 0, 1, lane, m0, n0,
-                            reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * 1024 TC_TR_PASS);
+        float* stg_base = reinterpret_cast<float*>(smem_raw + (base - raw));
+        tc_epilogue_dump<BN, OP>(p, tmem_full_bar, tmem_acc, warp, 0, 1, lane, m0, stg_base, 4, 1, 0 TC_TR_PASS);
+        tc_epilogue<BN, OP>(p, tmem_acc, warp, 0, 1, lane, m0, n0, stg_base, 1, 0, 4, 0, 1 TC_TR_PASS);
     } else {
         // =========================== MMA ISSUER (warp 4) ===========================
         constexpr bool a_mn = (OP == TC_WGRAD);
@@ -461,9 +561,22 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 //   MN-major tiles  : 32x32 boxes with SWIZZLE_128B_ATOM_32B, one per 32-column group
 // Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue.
 // =====================================================================================
-// epilogue warps: 4 for 64-wide tiles (two CTAs per SM keep each other's epilogue hidden), 8 otherwise
-template <int BN> constexpr int tma_epi_warps() { return BN == 64 ? 4 : 8; }
+// epilogue warps / minimum CTAs per SM per tile width (rationale in tc_gemm.cuh)
+#ifndef MPB_EW128
+#define MPB_EW128 4
+#endif
+#ifndef MPB_EW256
+#define MPB_EW256 8
+#endif
+#ifndef MPB_MINB128
+#define MPB_MINB128 2
+#endif
+#ifndef MPB_MINB256
+#define MPB_MINB256 1
+#endif
+template <int BN> constexpr int tma_epi_warps() { return BN == 64 ? 4 : BN == 128 ? MPB_EW128 : MPB_EW256; }
 template <int BN> constexpr int tma_threads() { return 64 + 32 * tma_epi_warps<BN>(); }
+template <int BN> constexpr int tma_min_blocks() { return BN == 64 ? 2 : BN == 128 ? MPB_MINB128 : MPB_MINB256; }
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -530,8 +643,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 // tiles of the SAME 128 rows, so the A operand is identical for all of them: each CTA fetches
 // 1/CN of the A tile and the TMA multicasts it into every CTA's shared memory -- L2 -> SM traffic
 // for A drops by CN (the GEMMs of this network are bound by exactly that traffic).
-template <int BN, int OP, int CN>
-__global__ void __launch_bounds__(tma_threads<BN>(), BN == 64 ? 2 : 1)
+// CSK: cluster split-K -- the cluster spans gridDim.z (= p.ksplit CTAs, disjoint K ranges of one tile) and the
+// partial accumulators are reduced through distributed shared memory in the epilogue (see tc_epilogue_dump).
+template <int BN, int OP, int CN, bool CSK>
+__global__ void __launch_bounds__(tma_threads<BN>(), tma_min_blocks<BN>())
 tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant__ CUtensorMap mapA,
                    const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ uint8_t smem_raw[];
@@ -725,15 +840,28 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
             if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
         }
         tc_fence_before();
-    } else {
-        constexpr int EW = tma_epi_warps<BN>();
-        const int ew = warp - 2;
-        tc_epilogue<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, ew >> 2, EW / 4, lane, m0, n0,
-                            reinterpret_cast<float*>(smem_raw + (base - raw)) + ew * 1024 TC_TR_PASS);
+    }
+    constexpr int EW = tma_epi_warps<BN>();
+    float* stg_base = reinterpret_cast<float*>(smem_raw + (base - raw));
+    const int ks = CSK ? p.ksplit : 1, krank = CSK ? (int)blockIdx.z : 0;
+    // a cluster may hold the K slices of SEVERAL row tiles (clusterDim = (cx, 1, ks)): 3 slices x 2 tiles fill
+    // whole TPCs, a bare cluster of 3 wastes every fourth SM.  DSMEM rank of slice z of my tile: my_x + cx * z
+    uint32_t cl_x = 0, cl_nx = 1;
+    if (CSK) {
+        asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(cl_x));
+        asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cl_nx));
+    }
+    if (warp >= 2)
+        tc_epilogue_dump<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, (warp - 2) >> 2, EW / 4, lane, m0, stg_base,
+                                 EW, CSK ? ks : 1, krank TC_TR_PASS);
+    if (CSK) cluster_sync_all();         // every peer's partial chunks are in its shared memory
+    if (warp >= 2) {
+        tc_epilogue<BN, OP>(p, tmem_acc, warp & 3, (warp - 2) >> 2, EW / 4, lane, m0, n0, stg_base, ks,
+                            krank, EW, cl_x, cl_nx TC_TR_PASS);
     }
     __syncthreads();
     if (tid == 0) TC_TR(55);
-    if (CN > 1) cluster_sync_all();      // no CTA leaves while peers may still multicast into it / arrive on its barriers
+    if (CN > 1 || CSK) cluster_sync_all();   // no CTA leaves while peers may still multicast into it / read its smem
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN) : "memory");
@@ -805,7 +933,13 @@ static bool make_map_im2col(CUtensorMap* m, const float* ptr, int C, int W, int 
     return true;
 }
 
-template <int BN, int OP, int CN>
+// row tiles per cluster of a cluster split-K launch: make the cluster an even number of CTAs (whole TPCs)
+static int csk_cluster_x(unsigned gx, unsigned ks) {
+    if (ks % 2 == 0 || gx % 2 != 0 || ks * 2 > 8) return 1;
+    return 2;
+}
+
+template <int BN, int OP, int CN, bool CSK = false>
 static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     alignas(64) CUtensorMap mapA, mapB;
     const int taps = p.kh * p.kw;
@@ -826,11 +960,11 @@ static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     constexpr int smem = tc_smem_bytes<BN>();
     static bool attr_set = false;
     if (!attr_set) {
-        MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN, OP, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN, OP, CN, CSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    if (CN == 1) {
-        tc_gemm_tma_kernel<BN, OP, CN><<<grid, tma_threads<BN>(), smem, s>>>(p, mapA, mapB);
+    if (CN == 1 && !CSK) {
+        tc_gemm_tma_kernel<BN, OP, CN, CSK><<<grid, tma_threads<BN>(), smem, s>>>(p, mapA, mapB);
         MPB_LAUNCH_CHECK();
         return 0;
     }
@@ -841,12 +975,12 @@ static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.x = CSK ? csk_cluster_x(grid.x, grid.z) : 1;
     at[0].val.clusterDim.y = CN;
-    at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.z = CSK ? grid.z : 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    MPB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_tma_kernel<BN, OP, CN>, p, mapA, mapB));
+    MPB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_tma_kernel<BN, OP, CN, CSK>, p, mapA, mapB));
     count_launch();
     return 0;
 }
@@ -854,6 +988,7 @@ static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
 static int g_tc_cluster = -1;   // max CTAs per cluster along N (1 disables multicast)
 template <int BN, int OP>
 static int launch_tma(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
+    if (p.ksplit > 1 && !p.atomic) return launch_tma_cn<BN, OP, 1, true>(p, grid, s);   // cluster split-K
     if (g_tc_cluster < 0) {
         // Measured on B200 (profiles/r1_notes.md): multicasting A over a cluster of column tiles does
         // NOT speed these GEMMs up (21.1 vs 19.6 ms of GEMM time per step) -- they are bound by the
@@ -876,6 +1011,28 @@ int tc_gemm_mode() {
     return g_tc_mode;
 }
 void tc_gemm_set_cluster(int c) { g_tc_cluster = c < 1 ? 1 : c; }
+// how many clusters of (cx, 1, ks) CTAs of the FWD kernel with tile width BN can be resident at once
+int tc_gemm_max_clusters(int BN, int cx, int ks) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cx * 64, 1, ks);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cx; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = ks;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = -1;
+    cudaError_t e = cudaErrorInvalidValue;
+#define MPB_Q(bn)                                                                                              \
+    if (BN == bn) {                                                                                            \
+        cfg.blockDim = dim3(tma_threads<bn>()); cfg.dynamicSmemBytes = tc_smem_bytes<bn>();                    \
+        cudaFuncSetAttribute(tc_gemm_tma_kernel<bn, TC_FWD, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             tc_smem_bytes<bn>());                                                             \
+        e = cudaOccupancyMaxActiveClusters(&n, tc_gemm_tma_kernel<bn, TC_FWD, 1, true>, &cfg);                 \
+    }
+    MPB_Q(64) MPB_Q(128) MPB_Q(256)
+#undef MPB_Q
+    return e == cudaSuccess ? n : -(int)e;
+}
+
 #ifdef MPB_TC_TRACE
 int tc_gemm_set_trace(void* buf) {
     long long* b = (long long*)buf;
@@ -923,6 +1080,22 @@ int tc_gemm_launch(const TcGemmParams& p, int BN, cudaStream_t s) {
         !al16(p.scale2) || !al16(p.colsum))
         return -1;
     if ((p.res && p.ldr % 4) || (p.mask && p.ldm % 4) || (p.out_r && p.ldor % 4)) return -1;
+    // split-K: with atomic=1 the slices RED.ADD into a zeroed output (any ksplit); with atomic=0 the slices of a
+    // tile form one thread-block cluster and reduce through DSMEM (ksplit <= 8, every slice must be non-empty:
+    // a CTA that left early would hang its cluster)
+    if (p.ksplit > 1 && !p.atomic) {
+        const int nkb_ = p.op == TC_FWD ? taps * (p.Cin / kTcBK) : p.op == TC_DGRAD ? taps * (p.Cout / kTcBK)
+                                                                                    : ceil_div(p.M, kTcBK);
+        const int per_ = ceil_div(nkb_, p.ksplit);
+        if ((p.ksplit - 1) * per_ >= nkb_) return -1;
+        if (p.ksplit > 8) return -1;
+        {                        // the chunks a CTA does not own are parked in its idle pipeline stages
+            const int n = BN / 32, ew = BN == 64 ? 4 : BN == 128 ? MPB_EW128 : MPB_EW256;
+            const int st = BN == 64 ? MPB_STAGES64 : BN == 128 ? MPB_STAGES128 : MPB_STAGES256;
+            if ((n - n / p.ksplit) * 16384 + ew * 4096 > st * (kTcABytes + BN * 128)) return -1;
+        }
+        if (!(tc_gemm_mode() == 1 && (p.M % (p.H * p.W) == 0))) return -1;
+    }
     // the TMA path needs whole images in the pixel grid (im2col walk) and 16-byte aligned pitches
     const bool tma = tc_gemm_mode() == 1 && (p.M % (p.H * p.W) == 0);
 #define MPB_TC_CASE(bn)                                                       \

@@ -30,12 +30,22 @@ using TcGemmParams = mpb_tc_gemm_params;
 
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 32;          // floats per k-block = one 128B swizzle row
-// pipeline depth: cp.async round trips are long (about 2 us under load), so keep as many
-// stages in flight as shared memory allows (one CTA per SM): 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
+// Pipeline depth / residency (measured on the whole training step, profiles/r1_notes.md): a CTA spends a
+// third to a half of its life in prologue and epilogue with the tensor pipe idle, so the step is fastest when two
+// CTAs (of the same or of different, concurrently running launches) share an SM and fill each other's gaps:
+//   BN = 64 : 4 x 24 KB stages, 4 epilogue warps, 2 CTAs/SM
+//   BN = 128: 3 x 32 KB stages, 4 epilogue warps, 2 CTAs/SM   (4 stages / 8 warps / 1 CTA per SM is 6 % slower per step)
+//   BN = 256: 4 x 48 KB stages, 8 epilogue warps, 1 CTA/SM    (main loop runs at the tcgen05 tf32 rate: 512 clk/k-block)
 #ifndef MPB_STAGES64
 #define MPB_STAGES64 4
 #endif
-template <int BN> constexpr int tc_stages() { return BN == 64 ? MPB_STAGES64 : 4; }
+#ifndef MPB_STAGES128
+#define MPB_STAGES128 3
+#endif
+#ifndef MPB_STAGES256
+#define MPB_STAGES256 4
+#endif
+template <int BN> constexpr int tc_stages() { return BN == 64 ? MPB_STAGES64 : BN == 128 ? MPB_STAGES128 : MPB_STAGES256; }
 constexpr int kTcThreads = 160;    // 4 producer/epilogue warps + 1 MMA warp
 constexpr int kTcABytes = kTcBM * 128;
 

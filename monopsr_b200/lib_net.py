@@ -60,6 +60,7 @@ _SIGS = {
     "mpb_tc_gemm": [ctypes.POINTER(TcGemmParams), c_i, c_p],
     "mpb_tc_set_producer": [c_i],
     "mpb_tc_set_cluster": [c_i],
+    "mpb_tc_max_clusters": [c_i, c_i, c_i],
     "mpb_build_tapmask": [c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "mpb_fold_bn": [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
     "mpb_fold_bn_multi": [c_i, c_p, c_p, c_f, c_p],
@@ -89,6 +90,7 @@ _SIGS = {
     "mpb_heads_mid": [ctypes.POINTER(HeadsIO), c_p],
     "mpb_heads_final": [ctypes.POINTER(HeadsIO), c_i, c_p],
     "mpb_heads_bwd_mid": [ctypes.POINTER(HeadsIO), c_p],
+    "mpb_opt_step_range": [c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_f, c_p],
     "mpb_opt_step": [c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_f, c_p],
 }
 

@@ -78,6 +78,45 @@ CASES = [
 
 @pytest.mark.parametrize("nimg,H,W,k,dil,Cin,Cout,BN", CASES)
 def test_fwd(cuda, nimg, H, W, k, dil, Cin, Cout, BN):
+    _fwd(cuda, nimg, H, W, k, dil, Cin, Cout, BN, 1)
+
+
+# cluster split-K (ksplit > 1, atomic = 0): the K slices of a tile form one thread-block cluster and are reduced
+# through distributed shared memory inside the fused epilogue; output is written once, NaN-prefilled here
+CSK_CASES = [
+    # nimg, H, W, k, dil, Cin, Cout, BN, ksplit
+    (2, 12, 12, 1, 1, 256, 128, 128, 2),
+    (2, 12, 12, 3, 4, 256, 256, 256, 3),    # 8 chunks over 3 owners (3,3,2)
+    (3, 12, 12, 3, 1, 64, 64, 64, 4),       # 2 chunks, 4 CTAs: two CTAs own nothing
+    (1, 40, 152, 3, 4, 256, 128, 64, 3),
+    (1, 40, 152, 1, 1, 1024, 256, 256, 8),
+    (3, 12, 12, 1, 1, 128, 512, 128, 4),    # K = 4 k-blocks, one per CTA
+]
+
+
+@pytest.mark.parametrize("nimg,H,W,k,dil,Cin,Cout,BN,ksplit", CSK_CASES)
+def test_fwd_fused_splitk(cuda, producer, nimg, H, W, k, dil, Cin, Cout, BN, ksplit):
+    if producer != "tma":
+        pytest.skip("fused split-K exists for the TMA kernel only")
+    _fwd(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit)
+
+
+@pytest.mark.parametrize("nimg,H,W,k,dil,Cin,Cout,BN,ksplit", CSK_CASES[:5])
+def test_dgrad_fused_splitk(cuda, producer, nimg, H, W, k, dil, Cin, Cout, BN, ksplit):
+    if producer != "tma":
+        pytest.skip("fused split-K exists for the TMA kernel only")
+    _dgrad(cuda, nimg, H, W, k, dil, Cout, Cin, BN, ksplit)     # (Cin, Cout) swapped: N = Cin must divide by BN
+
+
+def test_cluster_splitk_rejects_empty_slice(cuda):
+    p = base_params(TC_FWD, 1, 8, 16, 1, 1, 64, 64)     # 2 k-blocks cannot feed 3 slices
+    x = torch.zeros(128, 64, device=cuda)
+    p.X, p.ldx, p.Wt, p.ldw, p.out, p.ldo = x.data_ptr(), 64, x.data_ptr(), 64, x.data_ptr(), 64
+    p.ksplit = 3
+    assert mlib.load().mpb_tc_gemm(ctypes.byref(p), 64, mlib.stream_ptr()) == -1
+
+
+def _fwd(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit):
     g = torch.Generator(device="cpu").manual_seed(1)
     x = tf32_round(torch.randn(nimg, H, W, Cin, generator=g)).to(cuda)
     w = tf32_round(torch.randn(Cout, k, k, Cin, generator=g) * 0.1).to(cuda)
@@ -92,6 +131,7 @@ def test_fwd(cuda, nimg, H, W, k, dil, Cin, Cout, BN):
     tm = tapmask(nimg, H, W, k, dil, cuda) if k > 1 else None
     p.tapmask = tm.data_ptr() if tm is not None else None
     p.scale, p.shift, p.res, p.ldr, p.relu = scale.data_ptr(), shift.data_ptr(), res.data_ptr(), Cout, 1
+    p.ksplit = ksplit
     run(p, BN)
     ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(0, 3, 1, 2), padding=dil * (k // 2),
                    dilation=dil).permute(0, 2, 3, 1)
@@ -103,6 +143,10 @@ def test_fwd(cuda, nimg, H, W, k, dil, Cin, Cout, BN):
 
 @pytest.mark.parametrize("nimg,H,W,k,dil,Cin,Cout,BN", CASES[:9])
 def test_dgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN):
+    _dgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN, 1)
+
+
+def _dgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit):
     g = torch.Generator(device="cpu").manual_seed(2)
     dy = tf32_round(torch.randn(nimg, H, W, Cout, generator=g)).to(cuda)
     w = tf32_round(torch.randn(Cout, k, k, Cin, generator=g) * 0.1).to(cuda)
@@ -119,6 +163,7 @@ def test_dgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN):
     p.tapmask = tm.data_ptr() if tm is not None else None
     p.res, p.ldr, p.mask, p.ldm, p.scale2 = res.data_ptr(), Cin, mask.data_ptr(), Cin, s2.data_ptr()
     p.colsum = colsum.data_ptr()
+    p.ksplit = ksplit
     run(p, BN)
     xx = torch.zeros(nimg, Cin, H, W, dtype=torch.float64, device=cuda, requires_grad=True)
     yy = F.conv2d(xx, w.double().permute(0, 3, 1, 2), padding=dil * (k // 2), dilation=dil)
@@ -136,10 +181,23 @@ def test_dgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN):
     (32, 1, 1, 1, 1, 1088, 1024, 64, 1),
 ])
 def test_wgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit):
+    _wgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit, 1)
+
+
+@pytest.mark.parametrize("nimg,H,W,k,dil,Cin,Cout,BN,ksplit", [
+    (2, 12, 12, 1, 1, 256, 128, 128, 2), (4, 12, 12, 3, 4, 256, 256, 256, 4), (1, 40, 152, 3, 4, 64, 64, 64, 8),
+])
+def test_wgrad_fused_splitk(cuda, producer, nimg, H, W, k, dil, Cin, Cout, BN, ksplit):
+    if producer != "tma":
+        pytest.skip("fused split-K exists for the TMA kernel only")
+    _wgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit, 0)
+
+
+def _wgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit, atomic):
     g = torch.Generator(device="cpu").manual_seed(3)
     x = tf32_round(torch.randn(nimg, H, W, Cin, generator=g)).to(cuda)
     dy = tf32_round(torch.randn(nimg, H, W, Cout, generator=g)).to(cuda)
-    dw = torch.zeros(Cout, k, k, Cin, device=cuda)
+    dw = torch.zeros(Cout, k, k, Cin, device=cuda) if atomic else torch.full((Cout, k, k, Cin), float("nan"), device=cuda)
     p = base_params(TC_WGRAD, nimg, H, W, k, dil, Cin, Cout)
     p.X, p.ldx = x.data_ptr(), Cin
     p.Y, p.ldy = dy.data_ptr(), Cout
@@ -147,7 +205,7 @@ def test_wgrad(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit):
     p.out = dw.data_ptr()
     tm = tapmask(nimg, H, W, k, dil, cuda) if k > 1 else None
     p.tapmask = tm.data_ptr() if tm is not None else None
-    p.atomic, p.ksplit = 1, ksplit
+    p.atomic, p.ksplit = atomic, ksplit
     run(p, BN)
     ww = torch.zeros(Cout, Cin, k, k, dtype=torch.float64, device=cuda, requires_grad=True)
     yy = F.conv2d(x.double().permute(0, 3, 1, 2), ww, padding=dil * (k // 2), dilation=dil)

@@ -1,10 +1,14 @@
-"""Per-shape timing of every tcgen05 GEMM launch of one training step (CUDA events, isolated, warm)."""
+"""Per-shape timing of every tcgen05 GEMM launch of one training step: each distinct launch configuration is
+replayed 20x as one CUDA graph (isolated, warm L2) and timed with CUDA events.  `sm_us` = time x the fraction of
+the GPU's CTA slots the launch occupies -- the part of the machine it would need under perfect packing."""
 import collections, ctypes, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 from monopsr_b200.core import model_spec as ms
 from monopsr_b200.core.engine import Engine
+import gemm_sweep_lib as gs
 
 dev = torch.device("cuda:0")
 eng = Engine(dev, params=ms.init_params(0))
@@ -16,24 +20,21 @@ rec, eng._record = eng._record, None
 torch.cuda.synchronize()
 groups = collections.OrderedDict()
 for p, bn, fl in rec:
-    key = (p.op, p.M, p.H, p.W, p.kh, p.dil, p.Cin, p.Cout, bn, p.ksplit, p.atomic)
+    key = (p.op, p.M, p.H, p.W, p.kh, p.dil, p.Cin, p.Cout, bn, p.ksplit, p.atomic, bool(p.res), bool(p.mask), bool(p.out_r))
     groups.setdefault(key, []).append((p, bn, fl))
 rows = []
 for key, items in groups.items():
     p, bn, fl = items[0]
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for _ in range(3):
-        eng.L.mpb_tc_gemm(ctypes.byref(p), bn, st)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(20):
-        eng.L.mpb_tc_gemm(ctypes.byref(p), bn, st)
-    b.record(); torch.cuda.synchronize()
-    us = a.elapsed_time(b) * 1e3 / 20
-    rows.append((us * len(items), us, len(items), fl / us / 1e6, key))
+    us = gs.time_it(p, bn)
+    ncols = {0: p.Cout, 1: p.Cin, 2: p.kh * p.kw * p.Cin}[p.op]
+    nrows = p.Cout if p.op == 2 else p.M
+    ctas = ((nrows + 127) // 128) * (ncols // bn) * p.ksplit
+    slots = 148 * (2 if bn == 64 else 1)
+    sm_us = us * min(1.0, ctas / slots)
+    rows.append((us * len(items), us, len(items), fl / us / 1e6, ctas, sm_us * len(items), key))
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
-print("total %.1f us over %d launches, %d shapes" % (tot, len(rec), len(rows)))
-print("%9s %8s %4s %8s  op M H W k dil Cin Cout BN ksplit atomic" % ("tot_us", "us", "n", "TFLOP/s"))
-for r in rows[:45]:
-    print("%9.1f %8.1f %4d %8.1f  %s" % (r[0], r[1], r[2], r[3], r[4]))
+print("total %.1f us over %d launches, %d shapes; perfectly packed: %.1f us" % (tot, len(rec), len(rows), sum(r[5] for r in rows)))
+print("%9s %8s %4s %8s %5s %9s  op M H W k dil Cin Cout BN ksplit atomic res mask out_r" % ("tot_us", "us", "n", "TFLOP/s", "ctas", "sm_us"))
+for r in rows[:60]:
+    print("%9.1f %8.1f %4d %8.1f %5d %9.1f  %s" % r)
