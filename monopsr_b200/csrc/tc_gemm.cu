@@ -188,28 +188,35 @@ struct EpiCtx {
     uint32_t cl_x, cl_nx;      // cluster split-K: DSMEM rank of K slice z of this tile = cl_x + cl_nx * z
 };
 
-// fused epilogue of one 32-column chunk: accumulator from TMEM (+ the cluster peers' partials)
+// The per-element epilogue inputs of chunk cc (residual / mask: 8 independent 16-byte loads each).  They do not
+// depend on the accumulator, so the first chunk's are issued BEFORE the wait for the main loop and every later
+// chunk's as soon as the previous chunk has consumed its copies: their latency never sits on the critical path.
+__device__ __forceinline__ void epi_load_res(const TcGemmParams& p, const EpiCtx& c, int cc, int lane, int n0, float4 (&rv)[8]) {
+    if (!c.has_res) return;
+    const float* rp = p.res + (size_t)(c.row0 + (lane >> 3)) * p.ldr + n0 + cc * 32 + (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        rv[i] = (4 * i + (lane >> 3) < c.nvalid) ? ldg4(rp + (size_t)(4 * i) * p.ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void epi_load_mask(const TcGemmParams& p, const EpiCtx& c, int cc, int lane, int n0, float4 (&mv)[8]) {
+    if (!c.has_mask) return;
+    const float* mp = p.mask + (size_t)(c.row0 + (lane >> 3)) * p.ldm + n0 + cc * 32 + (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        mv[i] = (4 * i + (lane >> 3) < c.nvalid) ? ldg4(mp + (size_t)(4 * i) * p.ldm) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// fused epilogue of one 32-column chunk: accumulator from TMEM (+ the cluster peers' partials).  rv / mv hold
+// this chunk's residual / mask values on entry and the ones of chunk cc_next (if < BN/32) on exit.
 template <int BN, int OP>
-__device__ __forceinline__ void epi_chunk(const TcGemmParams& p, const EpiCtx& c, int cc, int lane, int n0) {
+__device__ __forceinline__ void epi_chunk(const TcGemmParams& p, const EpiCtx& c, int cc, int cc_next, int lane, int n0,
+                                          float4 (&rv)[8], float4 (&mv)[8]) {
     const int g = lane >> 3, q = lane & 7;         // after the transpose: rows 4i+g, columns 4q..4q+3
     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int c0 = cc * 32;
     float4* stg4 = reinterpret_cast<float4*>(c.scratch);
     (void)stg4;
         const int col = n0 + c0 + q * 4;
-        // issue every global read of this chunk first (independent 16-byte loads), so their latency
-        // overlaps the TMEM read and the shared-memory transpose
-        float4 rv[8], mv[8];
-        if (c.has_res) {
-            const float* rp = p.res + (size_t)(c.row0 + g) * p.ldr + col;
-#pragma unroll
-            for (int i = 0; i < 8; i++) rv[i] = (4 * i + g < c.nvalid) ? ldg4(rp + (size_t)(4 * i) * p.ldr) : zero4;
-        }
-        if (c.has_mask) {
-            const float* mp = p.mask + (size_t)(c.row0 + g) * p.ldm + col;
-#pragma unroll
-            for (int i = 0; i < 8; i++) mv[i] = (4 * i + g < c.nvalid) ? ldg4(mp + (size_t)(4 * i) * p.ldm) : zero4;
-        }
         const float4 sc = p.scale ? ldg4(p.scale + col) : one4;
         const float4 sh = p.shift ? ldg4(p.shift + col) : zero4;
         float x[32];
@@ -256,6 +263,7 @@ __device__ __forceinline__ void epi_chunk(const TcGemmParams& p, const EpiCtx& c
             for (int i = 0; i < 8; i++) {
                 x[4 * i] += rv[i].x; x[4 * i + 1] += rv[i].y; x[4 * i + 2] += rv[i].z; x[4 * i + 3] += rv[i].w;
             }
+            if (cc_next < BN / 32) epi_load_res(p, c, cc_next, lane, n0, rv);
         }
         if (p.relu) {
 #pragma unroll
@@ -269,6 +277,7 @@ __device__ __forceinline__ void epi_chunk(const TcGemmParams& p, const EpiCtx& c
                 x[4 * i + 2] = mv[i].z > 0.f ? x[4 * i + 2] : 0.f;
                 x[4 * i + 3] = mv[i].w > 0.f ? x[4 * i + 3] : 0.f;
             }
+            if (cc_next < BN / 32) epi_load_mask(p, c, cc_next, lane, n0, mv);
         }
         if (p.scale2) {
             const float4 s2 = ldg4(p.scale2 + col);
@@ -331,12 +340,9 @@ __device__ __forceinline__ void epi_chunk(const TcGemmParams& p, const EpiCtx& c
 // ks == 1: this CTA owns the whole accumulator; ks > 1 (cluster split-K, see tc_epilogue_dump): it finishes the
 // chunks it owns.  (A third variant -- slices meeting in a global fp32 workspace, last arriver finishes the tile --
 // was measured 1.5-2x slower than either: L2 RED.ADD throughput plus a fence per slice; profiles/r1_notes.md.)
-template <int BN, int OP>
-__device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem_acc,
-                                            int quad, int half, int nhalf, int lane, int m0, int n0,
-                                            float* stg_base, int ks, int rank, int nepi,
-                                            uint32_t cl_x, uint32_t cl_nx TC_TR_ARG) {
-    EpiCtx c;
+template <int OP>
+__device__ __forceinline__ void epi_setup(EpiCtx& c, const TcGemmParams& p, uint32_t tmem_acc, int quad, int half, int lane,
+                                          int m0, float* stg_base, int ks, int rank, int nepi, uint32_t cl_x, uint32_t cl_nx) {
     c.cl_x = cl_x; c.cl_nx = cl_nx;
     c.quad = quad;
     c.row0 = m0 + quad * 32;                       // first accumulator row of this warp
@@ -353,13 +359,19 @@ __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, uint32_t tmem
     c.nepi = nepi;
     c.ks = ks;
     c.rank = rank;
-    // owned chunks: rank, rank + ks, ...; the j-th of them goes to the warp with half == j % nhalf
+}
+
+// owned chunks: rank, rank + ks, ...; the j-th of them goes to the warp with half == j % nhalf
+template <int BN, int OP>
+__device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, const EpiCtx& c, int half, int nhalf, int lane, int n0,
+                                            float4 (&rv)[8], float4 (&mv)[8] TC_TR_ARG) {
+    const int step = nhalf * c.ks;
 #pragma unroll 1
-    for (int cc = rank + half * ks; cc < BN / 32; cc += nhalf * ks) {
-        epi_chunk<BN, OP>(p, c, cc, lane, n0);
-        if (quad == 0 && lane == 0 && half == 0 && cc == rank) TC_TR(53);
+    for (int cc = c.rank + half * c.ks; cc < BN / 32; cc += step) {
+        epi_chunk<BN, OP>(p, c, cc, cc + step, lane, n0, rv, mv);
+        if (c.quad == 0 && lane == 0 && half == 0 && cc == c.rank) TC_TR(53);
     }
-    if (quad == 0 && half == 0 && lane == 0) TC_TR(54);
+    if (c.quad == 0 && half == 0 && lane == 0) TC_TR(54);
     tc_fence_before();
 }
 
@@ -510,8 +522,13 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         long long* trc = nullptr;
 #endif
         float* stg_base = reinterpret_cast<float*>(smem_raw + (base - raw));
+        EpiCtx ec;
+        float4 rv[8], mv[8];
+        epi_setup<OP>(ec, p, tmem_acc, warp, 0, lane, m0, stg_base, 1, 0, 4, 0, 1);
+        epi_load_res(p, ec, 0, lane, n0, rv);
+        epi_load_mask(p, ec, 0, lane, n0, mv);
         tc_epilogue_dump<BN, OP>(p, tmem_full_bar, tmem_acc, warp, 0, 1, lane, m0, stg_base, 4, 1, 0 TC_TR_PASS);
-        tc_epilogue<BN, OP>(p, tmem_acc, warp, 0, 1, lane, m0, n0, stg_base, 1, 0, 4, 0, 1 TC_TR_PASS);
+        tc_epilogue<BN, OP>(p, ec, 0, 1, lane, n0, rv, mv TC_TR_PASS);
     } else {
         // =========================== MMA ISSUER (warp 4) ===========================
         constexpr bool a_mn = (OP == TC_WGRAD);
@@ -676,6 +693,12 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     const int nk = min(nkb, kb0 + per) - kb0;
     if (nk <= 0) return;
 
+    const int m0 = blockIdx.x * kTcBM;
+    const int n0 = blockIdx.y * BN;
+    const int crank = (CN > 1) ? (int)cluster_ctarank() : 0;
+    constexpr unsigned short kMask = (unsigned short)((1u << CN) - 1u);
+    constexpr int kSlice = kTcBM / CN;      // A rows (pixels) fetched by this CTA
+
     if (tid == 0) {
         for (int s = 0; s < kTcStages; s++) {
             mbar_init(full_bar(s), 1);     // the producer's arrive.expect_tx (+ TMA byte count)
@@ -691,6 +714,107 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+
+    // =========================== TMA PRODUCER (warp 0) ===========================
+    // The whole warp walks the (warp-uniform) loop and one elected lane issues: loop state stays in uniform
+    // registers and ptxas needs no per-lane wrapper around the UTMALDG / SYNCS instructions.  No integer division
+    // inside the loop: (tap, channel block) and the pixel coordinates are carried.
+    // The first kTcStages k-blocks need no free-slot wait and no other warp: they are issued BEFORE the CTA-wide
+    // setup barrier, so the operands of the first MMAs are in flight while TMEM is being allocated (the first TMA
+    // used to leave ~2200 clk after CTA entry, now ~600).
+    int stage = 0;
+    uint32_t phase = 0;
+    constexpr uint32_t kBytes = kTcABytes + BN * 128;
+    const int dil_ = p.dil;
+    int pr_tap = 0, pr_cb = 0, pr_th = 0, pr_tw = 0, pr_bw = 0, pr_bh = 0, pr_img0 = 0, pr_ms = 0, pr_cblocks = 1;   // FWD/DGRAD
+    int pr_k0 = 0, pr_img = 0, pr_ph = 0, pr_pw = 0, pr_ci0 = 0;                                                    // WGRAD
+    if (warp == 0) {
+        const int hw = p.H * p.W;
+        if (OP == TC_FWD || OP == TC_DGRAD) {
+            const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;
+            pr_cblocks = Ck / kTcBK;
+            pr_ms = m0 + crank * kSlice;     // first pixel of this CTA's slice of the A tile: base of the im2col walk
+            pr_img0 = pr_ms / hw;
+            const int rem0 = pr_ms - pr_img0 * hw, ph0 = rem0 / p.W, pw0 = rem0 - ph0 * p.W;
+            pr_bw = pw0 - dil_ * (p.kw / 2); pr_bh = ph0 - dil_ * (p.kh / 2);
+            pr_tap = kb0 / pr_cblocks; pr_cb = kb0 - pr_tap * pr_cblocks;
+            pr_th = pr_tap / p.kw; pr_tw = pr_tap - pr_th * p.kw;
+        } else {
+            pr_tap = n0 / p.Cin; pr_ci0 = n0 - pr_tap * p.Cin;
+            pr_th = pr_tap / p.kw; pr_tw = pr_tap - pr_th * p.kw;
+            pr_k0 = kb0 * kTcBK;
+            pr_img = pr_k0 / hw; pr_ph = (pr_k0 - pr_img * hw) / p.W; pr_pw = pr_k0 - pr_img * hw - pr_ph * p.W;
+        }
+    }
+    auto produce = [&](int i, bool wait_free) {
+        if (wait_free) mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+            if (i < 16) TC_TR(4 + i);
+            const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
+            mbar_expect_tx(full_bar(stage), kBytes);
+            if (OP == TC_FWD || OP == TC_DGRAD) {
+                const uint32_t sAs = sA + crank * kSlice * 128;
+                if (taps == 1) {
+                    if (CN > 1) tma_load_2d_mc(sAs, &mapA, full_bar(stage), pr_cb * kTcBK, pr_ms, kMask);
+                    else tma_load_2d(sA, &mapA, full_bar(stage), pr_cb * kTcBK, m0);
+                } else {
+                    // dX[p] needs dY[p - off]: mirrored tap
+                    const int ow = (OP == TC_DGRAD ? p.kw - 1 - pr_tw : pr_tw) * dil_;
+                    const int oh = (OP == TC_DGRAD ? p.kh - 1 - pr_th : pr_th) * dil_;
+                    if (CN > 1) tma_load_im2col_mc(sAs, &mapA, full_bar(stage), pr_cb * kTcBK, pr_bw, pr_bh, pr_img0, ow, oh, kMask);
+                    else tma_load_im2col(sA, &mapA, full_bar(stage), pr_cb * kTcBK, pr_bw, pr_bh, pr_img0, ow, oh);
+                }
+                if (OP == TC_FWD) {
+                    tma_load_2d(sB, &mapB, full_bar(stage), (pr_tap * pr_cblocks + pr_cb) * kTcBK, n0);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < BN / 32; g++)
+                        tma_load_2d(sB + g * 4096, &mapB, full_bar(stage), pr_tap * p.Cin + n0 + 32 * g, pr_cb * kTcBK);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    if (CN > 1) {       // the 4 column groups of the dY tile are split over the cluster
+                        if (g / (4 / CN) == crank)
+                            tma_load_2d_mc(sA + g * 4096, &mapA, full_bar(stage), m0 + 32 * g, pr_k0, kMask);
+                    } else {
+                        tma_load_2d(sA + g * 4096, &mapA, full_bar(stage), m0 + 32 * g, pr_k0);
+                    }
+                }
+                if (taps == 1) {
+#pragma unroll
+                    for (int g = 0; g < BN / 32; g++)
+                        tma_load_2d(sB + g * 4096, &mapB, full_bar(stage), pr_ci0 + 32 * g, pr_k0);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < BN / 32; g++)
+                        tma_load_im2col(sB + g * 4096, &mapB, full_bar(stage), pr_ci0 + 32 * g, pr_pw - dil_ * (p.kw / 2),
+                                        pr_ph - dil_ * (p.kh / 2), pr_img, pr_tw * dil_, pr_th * dil_);
+                }
+            }
+        }
+        __syncwarp();
+        if (OP == TC_FWD || OP == TC_DGRAD) {
+            if (++pr_cb == pr_cblocks) {
+                pr_cb = 0; ++pr_tap;
+                if (++pr_tw == p.kw) { pr_tw = 0; ++pr_th; }
+            }
+        } else {
+            pr_k0 += kTcBK;
+            pr_pw += kTcBK;
+            while (pr_pw >= p.W) {
+                pr_pw -= p.W;
+                if (++pr_ph == p.H) { pr_ph = 0; ++pr_img; }
+            }
+        }
+        if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+    };
+    const int npre = (CN == 1) ? min(nk, kTcStages) : 0;   // multicast needs the peers' barriers first
+    if (warp == 0) {
+        __syncwarp();                 // lane 0's barrier initialisation is visible to the elected lane
+        for (int i = 0; i < npre; i++) produce(i, false);
+    }
+
     tc_fence_before();
     __syncthreads();
     if (CN > 1) cluster_sync_all();      // every CTA's barriers exist before any remote arrive / multicast
@@ -708,105 +832,9 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
         }
     }
 #endif
-    const int m0 = blockIdx.x * kTcBM;
-    const int n0 = blockIdx.y * BN;
-    const int crank = (CN > 1) ? (int)cluster_ctarank() : 0;
-    constexpr unsigned short kMask = (unsigned short)((1u << CN) - 1u);
-    constexpr int kSlice = kTcBM / CN;      // A rows (pixels) fetched by this CTA
 
     if (warp == 0) {
-        // =========================== TMA PRODUCER ===========================
-        // The whole warp walks the (warp-uniform) loop and one elected lane issues: loop state stays in
-        // uniform registers and ptxas needs no per-lane wrapper around the UTMALDG / SYNCS instructions.
-        // No integer division inside the loop: (tap, channel block) and the pixel coordinates are carried.
-        int stage = 0;
-        uint32_t phase = 0;
-        constexpr uint32_t kBytes = kTcABytes + BN * 128;
-        const int r = p.dil;
-        if (OP == TC_FWD || OP == TC_DGRAD) {
-            const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;
-            const int cblocks = Ck / kTcBK;
-            // first pixel of this tile in (w,h,n) -- base coordinate of the im2col walk
-            const int hw = p.H * p.W;
-            const int ms = m0 + crank * kSlice;     // first pixel of this CTA's slice of the A tile
-            const int img0 = ms / hw, rem0 = ms - img0 * hw, ph0 = rem0 / p.W, pw0 = rem0 - ph0 * p.W;
-            const int bw = pw0 - r * (p.kw / 2), bh = ph0 - r * (p.kh / 2);
-            int tap = kb0 / cblocks, cb = kb0 - tap * cblocks;
-            int th = tap / p.kw, tw = tap - th * p.kw;
-            for (int i = 0; i < nk; i++) {
-                mbar_wait(empty_bar(stage), phase ^ 1u);
-                if (elect_one()) {
-                    if (i < 16) TC_TR(4 + i);
-                    const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
-                    mbar_expect_tx(full_bar(stage), kBytes);
-                    const uint32_t sAs = sA + crank * kSlice * 128;
-                    if (taps == 1) {
-                        if (CN > 1) tma_load_2d_mc(sAs, &mapA, full_bar(stage), cb * kTcBK, ms, kMask);
-                        else tma_load_2d(sA, &mapA, full_bar(stage), cb * kTcBK, m0);
-                    } else {
-                        // dX[p] needs dY[p - off]: mirrored tap
-                        const int ow = (OP == TC_DGRAD ? p.kw - 1 - tw : tw) * r;
-                        const int oh = (OP == TC_DGRAD ? p.kh - 1 - th : th) * r;
-                        if (CN > 1) tma_load_im2col_mc(sAs, &mapA, full_bar(stage), cb * kTcBK, bw, bh, img0, ow, oh, kMask);
-                        else tma_load_im2col(sA, &mapA, full_bar(stage), cb * kTcBK, bw, bh, img0, ow, oh);
-                    }
-                    if (OP == TC_FWD) {
-                        tma_load_2d(sB, &mapB, full_bar(stage), (tap * cblocks + cb) * kTcBK, n0);
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < BN / 32; g++)
-                            tma_load_2d(sB + g * 4096, &mapB, full_bar(stage), tap * p.Cin + n0 + 32 * g, cb * kTcBK);
-                    }
-                }
-                __syncwarp();
-                if (++cb == cblocks) {
-                    cb = 0; ++tap;
-                    if (++tw == p.kw) { tw = 0; ++th; }
-                }
-                if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
-            }
-        } else {
-            const int tap = n0 / p.Cin, ci0 = n0 - tap * p.Cin;
-            const int th = tap / p.kw, tw = tap - th * p.kw;
-            const int hw = p.H * p.W;
-            int k0 = kb0 * kTcBK;
-            int img = k0 / hw, ph = (k0 - img * hw) / p.W, pw = k0 - img * hw - ph * p.W;
-            for (int i = 0; i < nk; i++) {
-                mbar_wait(empty_bar(stage), phase ^ 1u);
-                if (elect_one()) {
-                    if (i < 16) TC_TR(4 + i);
-                    const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
-                    mbar_expect_tx(full_bar(stage), kBytes);
-#pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        if (CN > 1) {       // the 4 column groups of the dY tile are split over the cluster
-                            if (g / (4 / CN) == crank)
-                                tma_load_2d_mc(sA + g * 4096, &mapA, full_bar(stage), m0 + 32 * g, k0, kMask);
-                        } else {
-                            tma_load_2d(sA + g * 4096, &mapA, full_bar(stage), m0 + 32 * g, k0);
-                        }
-                    }
-                    if (taps == 1) {
-#pragma unroll
-                        for (int g = 0; g < BN / 32; g++)
-                            tma_load_2d(sB + g * 4096, &mapB, full_bar(stage), ci0 + 32 * g, k0);
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < BN / 32; g++)
-                            tma_load_im2col(sB + g * 4096, &mapB, full_bar(stage), ci0 + 32 * g, pw - r * (p.kw / 2),
-                                            ph - r * (p.kh / 2), img, tw * r, th * r);
-                    }
-                }
-                __syncwarp();
-                k0 += kTcBK;
-                pw += kTcBK;
-                while (pw >= p.W) {
-                    pw -= p.W;
-                    if (++ph == p.H) { ph = 0; ++img; }
-                }
-                if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
-            }
-        }
+        for (int i = npre; i < nk; i++) produce(i, true);
     } else if (warp == 1) {
         // =========================== MMA ISSUER ===========================
         constexpr bool a_mn = (OP == TC_WGRAD);
@@ -851,14 +879,21 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
         asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(cl_x));
         asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cl_nx));
     }
-    if (warp >= 2)
-        tc_epilogue_dump<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, (warp - 2) >> 2, EW / 4, lane, m0, stg_base,
-                                 EW, CSK ? ks : 1, krank TC_TR_PASS);
-    if (CSK) cluster_sync_all();         // every peer's partial chunks are in its shared memory
+    EpiCtx ec;
+    float4 rv[8], mv[8];
     if (warp >= 2) {
-        tc_epilogue<BN, OP>(p, tmem_acc, warp & 3, (warp - 2) >> 2, EW / 4, lane, m0, n0, stg_base, ks,
-                            krank, EW, cl_x, cl_nx TC_TR_PASS);
+        const int half = (warp - 2) >> 2;
+        epi_setup<OP>(ec, p, tmem_acc, warp & 3, half, lane, m0, stg_base, ks, krank, EW, cl_x, cl_nx);
+        // residual / mask of this warp's first chunk: in flight while the main loop runs
+        if (krank + half * ks < BN / 32) {
+            epi_load_res(p, ec, krank + half * ks, lane, n0, rv);
+            epi_load_mask(p, ec, krank + half * ks, lane, n0, mv);
+        }
+        tc_epilogue_dump<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, half, EW / 4, lane, m0, stg_base, EW, ks, krank
+                                 TC_TR_PASS);
     }
+    if (CSK) cluster_sync_all();         // every peer's partial chunks are in its shared memory
+    if (warp >= 2) tc_epilogue<BN, OP>(p, ec, (warp - 2) >> 2, EW / 4, lane, n0, rv, mv TC_TR_PASS);
     __syncthreads();
     if (tid == 0) TC_TR(55);
     if (CN > 1 || CSK) cluster_sync_all();   // no CTA leaves while peers may still multicast into it / read its smem
