@@ -79,6 +79,17 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def ncu_traffic_per_launch():
+    """DRAM bytes per launch of the GEMM family from the committed ncu launch list (None if absent)."""
+    import re
+    try:
+        txt = open(os.path.join(ROOT, "profiles", "r1_launch_shares.txt")).read()
+        m = re.search(r"([0-9.]+) MB per launch", txt)
+        return float(m.group(1)) * 1e6 if m else None
+    except OSError:
+        return None
+
+
 def cpu_threads():
     # torch's CPU convolutions on 12x12 maps stop scaling (and then regress) beyond a few dozen
     # threads; use what helps and report the count actually used
@@ -276,8 +287,10 @@ def main():
     roof = eng.gemm_only_roofline(flush)
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0      # dense tf32 = half the bf16 rate; sustained (long step)
     roofline = {"bound": "tensor", "achieved": roof["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": roof["tflops"] / tf32_peak, "traffic": None,
-                "kernel": "tc_gemm_kernel (tcgen05 kind::tf32), %d launches/step, %.2f ms of %.2f ms/step" %
+                "frac": roof["tflops"] / tf32_peak, "traffic": ncu_traffic_per_launch(),
+                "traffic_source": "profiles/r1_launch_shares.txt: ncu dram__bytes_read+write of the 592 GEMM launches "
+                                  "of one step / 592 (bytes per launch; ncu flushes caches between launches)",
+                "kernel": "tc_gemm_tma_kernel (tcgen05 kind::tf32), %d launches/step, %.2f ms alone vs %.2f ms/step" %
                           (roof["launches"], roof["ms"], total_ms / args.steps),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (%s)" % which,
                 "algorithmic_gflop_per_step": roof["gflop"],

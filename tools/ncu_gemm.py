@@ -1,0 +1,23 @@
+"""The representative block3 GEMM launches of one training step, launched once each after a warm-up, for
+`ncu --set full -k regex:tc_gemm_tma` (profiles/*_ncu_gemm*)."""
+import ctypes, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gemm_sweep_lib import *  # noqa
+
+CASES = [
+    # name, op, nimg, H, W, k, dil, Cin, Cout, epi, BN, ksplit, atomic
+    ("fwd 3x3 256>256 full-image, BN128 cluster split-K 2", TC_FWD, 1, 40, 152, 3, 4, 256, 256, 0, 128, 2, 0),
+    ("fwd 1x1 256>1024 +res +out_r full-image, BN64", TC_FWD, 1, 40, 152, 1, 1, 256, 1024, 1, 64, 1, 0),
+    ("fwd 1x1 1024>256 full-image, BN128 cluster split-K 2", TC_FWD, 1, 40, 152, 1, 1, 1024, 256, 0, 128, 2, 0),
+    ("dgrad 3x3 crops, BN128 cluster split-K 2", TC_DGRAD, 32, 12, 12, 3, 4, 256, 256, 0, 128, 2, 0),
+    ("wgrad 3x3 full-image, BN128 split-K 4 (RED)", TC_WGRAD, 1, 40, 152, 3, 4, 256, 256, 0, 128, 4, 1),
+    ("fwd 3x3 512>256 decoder M=18432, BN256", TC_FWD, 32, 24, 24, 3, 1, 512, 256, 0, 256, 1, 0),
+]
+for name, op, nimg, H, W, k, dil, Cin, Cout, epi, bn, ks, atomic in CASES:
+    p, keep = make(op, nimg, H, W, k, dil, Cin, Cout, epi)
+    p.ksplit, p.atomic = ks, atomic
+    for _ in range(2):
+        rc = L.mpb_tc_gemm(ctypes.byref(p), bn, mlib.stream_ptr())
+    torch.cuda.synchronize()
+    print(name, rc)
