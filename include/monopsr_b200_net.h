@@ -115,7 +115,7 @@ int mpb_crop_pool_bwd(int H, int W, int C, const float* feat, int nbox, const fl
 
 /* ---- tf.image.resize_images(align_corners=True) (net_builder.py:73-75,82-84) ---- */
 int mpb_resize_ac_fwd(int nimg, int H, int W, int C, const float* x, int OH, int OW, float* y, void* stream);
-int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, int OH, int OW, float* dx, void* stream); /* zeroes dx */
+int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, int OH, int OW, float* dx, void* stream); /* overwrites dx (gather form, no atomics) */
 
 /* ---- slim.batch_norm(is_training=True) + ReLU of the map decoder (net_builder.py:77-89) ----
  * scratch: 2*C doubles.  moving_mean/var may be NULL (no UPDATE_OPS). */
@@ -127,7 +127,10 @@ int mpb_bn_train_bwd(int M, int C, const float* z, const float* mean, const floa
 /* ---- xyz head: conv3x3 128->3 + bias (monopsr_output_builder.py:95-108); w is [3][3][3][128] ---- */
 int mpb_xyzhead_fwd(int nimg, int H, int W, const float* x, const float* w, const float* bias, float* y, void* stream);
 int mpb_xyzhead_bwd(int nimg, int H, int W, const float* x, const float* w, const float* dy, float* dx, float* dw,
-                    float* db, void* stream);   /* dw, db accumulate */
+                    float* db, void* stream);
+/* the two halves of mpb_xyzhead_bwd, so that the weight gradient can run beside the data-gradient chain */
+int mpb_xyzhead_dgrad(int nimg, int H, int W, const float* w, const float* dy, float* dx, void* stream);
+int mpb_xyzhead_wgrad(int nimg, int H, int W, const float* x, const float* dy, float* dw, float* db, void* stream);   /* dw, db accumulate */
 
 /* ---- small dense heads, N<=32 outputs (monopsr_output_builder.py:283,469,580,633); w is [N][K] ---- */
 int mpb_fc_small_fwd(int B, int K, int N, const float* x, int ldx, const float* w, const float* bias, float* y, int ldy,

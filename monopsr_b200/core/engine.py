@@ -57,6 +57,7 @@ class Engine:
         self.s_wf = torch.cuda.Stream(device=self.dev)
         self.s_opt = torch.cuda.Stream(device=self.dev)
         self.early_opt = False      # set by the single-GPU train step: head train-op under the towers' backward
+        self._grads_zeroed = False
         self.overlap = True
         import os
         self.fill = float(os.environ.get("MPB_TILE_FILL", "0.9"))   # min fraction of SMs a launch must fill before widening tiles
@@ -515,6 +516,10 @@ class Engine:
             self.prepare_weights()
         L, st, N, I = self.L, self._st(), self.N, self.inputs
         Tc, Tf = self.towers[ms.ENCODERS[0]], self.towers[ms.ENCODERS[1]]
+        if train and self.overlap:
+            with self._side(self.s_wf):      # 400 MB zero-fill of the gradient arena, beside the forward pass
+                self.grads.zero_()
+            self._grads_zeroed = True
         with self._side(self.s_full):
             ff, _ = self._tower_fwd(Tf, I["full_img"])
             self._chk(L.mpb_crop_pool_fwd(Tf["h"], Tf["w"], 1024, _ptr(ff), N, _ptr(I["boxes_2d_norm"]), 24,
@@ -695,7 +700,11 @@ class Engine:
 
     def backward(self):
         L, st, N, I, h = self.L, self._st(), self.N, self.inputs, self.h
-        self.grads.zero_()
+        if self._grads_zeroed:
+            self._join(self.s_wf)            # the zero-fill of the gradient arena ran beside the forward pass
+        else:
+            self.grads.zero_()
+        self._grads_zeroed = False
         io = self.heads_io()
         P, R = self.fc["proposal"], self.fc["regression"]
         with self._side(self.s_wc):
@@ -703,9 +712,11 @@ class Engine:
         # ---- map decoder
         sx = "output/inst_xyz_map_local/inst_xyz_map_local"
         D = self.dec[3]
-        self._chk(L.mpb_xyzhead_bwd(N, 48, 48, _ptr(D["y"]), _ptr(self.view(sx + "/weights")), _ptr(self.d_xyz),
-                                    _ptr(D["dy"]), _ptr(self.gview(sx + "/weights")), _ptr(self.gview(sx + "/biases")), st),
-                  "xyzhead_bwd")
+        with self._side(self.s_wf):      # weight gradient off the decoder's data-gradient chain
+            self._chk(L.mpb_xyzhead_wgrad(N, 48, 48, _ptr(D["y"]), _ptr(self.d_xyz), _ptr(self.gview(sx + "/weights")),
+                                          _ptr(self.gview(sx + "/biases")), self._st()), "xyzhead_wgrad")
+        self._chk(L.mpb_xyzhead_dgrad(N, 48, 48, _ptr(self.view(sx + "/weights")), _ptr(self.d_xyz), _ptr(D["dy"]), st),
+                  "xyzhead_dgrad")
         for i in (3, 2, 1, 0):
             D = self.dec[i]
             side, b = D["side"], D["scope"] + "/BatchNorm/"

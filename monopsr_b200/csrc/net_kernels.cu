@@ -400,26 +400,51 @@ __global__ void resize_ac_fwd_kernel(int nimg, int H, int W, int C4, int OH, int
     y[i] = o;
 }
 
-__global__ void resize_ac_bwd_kernel(int nimg, int H, int W, int C, int OH, int OW, const float* __restrict__ dy,
-                                     float* __restrict__ dx) {
+// Backward of the bilinear align-corners resize in GATHER form: one thread per input pixel x 4 channels sums the
+// (at most 4 x 4) output pixels that interpolate from it, with the weights recomputed by the forward's own float
+// expressions.  No zero-fill, no atomics, deterministic (the scatter version spent 60 + 150 us in memset + RED.ADD
+// on the decoder's critical path).
+__device__ __forceinline__ int resize_taps(int y, int H, int OH, int* o, float* w) {
+    // output indices oh (and weights) with y0(oh) == y or y1(oh) == y
+    const float s = (float)(H - 1) / (float)(OH - 1), inv = (float)(OH - 1) / (float)(H - 1);
+    const int lo = max(0, (int)floorf((y - 1) * inv) - 1), hi = min(OH - 1, (int)ceilf((y + 1) * inv) + 1);
+    int n = 0;
+    for (int oh = lo; oh <= hi && n < 6; oh++) {
+        const float sy = oh * s;
+        const int y0 = (int)floorf(sy), y1 = min(y0 + 1, H - 1);
+        const float ly = sy - y0;
+        float wt = 0.f;
+        if (y0 == y) wt += 1.f - ly;
+        if (y1 == y) wt += ly;
+        if (y0 == y || y1 == y) { o[n] = oh; w[n] = wt; n++; }
+    }
+    return n;
+}
+
+__global__ void resize_ac_bwd_kernel(int nimg, int H, int W, int C4, int OH, int OW, const float4* __restrict__ dy,
+                                     float4* __restrict__ dx) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)nimg * OH * OW * C;
+    const long total = (long)nimg * H * W * C4;
     if (i >= total) return;
-    const int c = (int)(i % C);
-    long p = i / C;
-    const int ow = (int)(p % OW); p /= OW;
-    const int oh = (int)(p % OH);
-    const int n = (int)(p / OH);
-    const float g = dy[i];
-    if (g == 0.f) return;
-    const float sy = oh * ((float)(H - 1) / (float)(OH - 1)), sx = ow * ((float)(W - 1) / (float)(OW - 1));
-    const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
-    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-    const float ly = sy - y0, lx = sx - x0;
-    atomicAdd(&dx[(((size_t)n * H + y0) * W + x0) * C + c], g * (1.f - ly) * (1.f - lx));
-    atomicAdd(&dx[(((size_t)n * H + y0) * W + x1) * C + c], g * (1.f - ly) * lx);
-    atomicAdd(&dx[(((size_t)n * H + y1) * W + x0) * C + c], g * ly * (1.f - lx));
-    atomicAdd(&dx[(((size_t)n * H + y1) * W + x1) * C + c], g * ly * lx);
+    const int c = (int)(i % C4);
+    long p = i / C4;
+    const int x = (int)(p % W); p /= W;
+    const int y = (int)(p % H);
+    const int n = (int)(p / H);
+    int oy[6], ox[6];
+    float wy[6], wx[6];
+    const int ny = resize_taps(y, H, OH, oy, wy), nx = resize_taps(x, W, OW, ox, wx);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < ny; a++) {
+        const float4* row = dy + ((size_t)n * OH + oy[a]) * OW * C4 + c;
+        for (int b = 0; b < nx; b++) {
+            const float4 g = __ldg(row + (size_t)ox[b] * C4);
+            const float wt = wy[a] * wx[b];
+            acc.x = fmaf(g.x, wt, acc.x); acc.y = fmaf(g.y, wt, acc.y);
+            acc.z = fmaf(g.z, wt, acc.z); acc.w = fmaf(g.w, wt, acc.w);
+        }
+    }
+    dx[i] = acc;
 }
 
 // ---------------------------------------------------------------- train-mode batch norm (+beta, ReLU)
@@ -796,8 +821,9 @@ MPB_API int mpb_resize_ac_fwd(int nimg, int H, int W, int C, const float* x, int
     return 0;
 }
 MPB_API int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, int OH, int OW, float* dx, void* stream) {
-    MPB_CUDA_TRY(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)nimg * H * W * C, ST));
-    resize_ac_bwd_kernel<<<nblk((long)nimg * OH * OW * C, 256), 256, 0, ST>>>(nimg, H, W, C, OH, OW, dy, dx);
+    if (C % 4 || H < 2 || W < 2 || OH < H || OW < W || OH > 3 * H || OW > 3 * W) return -1;   // <= 6 taps per axis
+    resize_ac_bwd_kernel<<<nblk((long)nimg * H * W * (C / 4), 256), 256, 0, ST>>>(
+        nimg, H, W, C / 4, OH, OW, reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx));
     MPB_LAUNCH_CHECK();
     return 0;
 }
@@ -831,14 +857,21 @@ MPB_API int mpb_xyzhead_fwd(int nimg, int H, int W, const float* x, const float*
     MPB_LAUNCH_CHECK();
     return 0;
 }
-MPB_API int mpb_xyzhead_bwd(int nimg, int H, int W, const float* x, const float* w, const float* dy, float* dx, float* dw,
-                            float* db, void* stream) {
+MPB_API int mpb_xyzhead_dgrad(int nimg, int H, int W, const float* w, const float* dy, float* dx, void* stream) {
     xyzhead_dgrad_kernel<<<nblk((long)nimg * H * W, 8), 256, 0, ST>>>(nimg, H, W, dy, w, dx);
     MPB_LAUNCH_CHECK();
-    const int ppc = 128;
+    return 0;
+}
+MPB_API int mpb_xyzhead_wgrad(int nimg, int H, int W, const float* x, const float* dy, float* dw, float* db, void* stream) {
+    const int ppc = 64;
     xyzhead_wgrad_kernel<<<nblk((long)nimg * H * W, ppc), 128, 0, ST>>>(nimg, H, W, x, dy, dw, db, ppc);
     MPB_LAUNCH_CHECK();
     return 0;
+}
+MPB_API int mpb_xyzhead_bwd(int nimg, int H, int W, const float* x, const float* w, const float* dy, float* dx, float* dw,
+                            float* db, void* stream) {
+    const int st = mpb_xyzhead_dgrad(nimg, H, W, w, dy, dx, stream);
+    return st ? st : mpb_xyzhead_wgrad(nimg, H, W, x, dy, dw, db, stream);
 }
 MPB_API int mpb_fc_small_fwd(int B, int K, int N, const float* x, int ldx, const float* w, const float* bias, float* y,
                              int ldy, void* stream) {

@@ -80,6 +80,8 @@ _SIGS = {
     "mpb_bn_train_fwd": [c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
     "mpb_bn_train_bwd": [c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
     "mpb_xyzhead_fwd": [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "mpb_xyzhead_dgrad": [c_i, c_i, c_i, c_p, c_p, c_p, c_p],
+    "mpb_xyzhead_wgrad": [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "mpb_xyzhead_bwd": [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "mpb_fc_small_fwd": [c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_p],
     "mpb_fc_small_bwd": [c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p],
