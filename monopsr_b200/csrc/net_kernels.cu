@@ -32,9 +32,29 @@ __global__ void fold_bn_kernel(int cout, int K, const float* __restrict__ w, con
     for (int k = threadIdx.x; k < K; k += blockDim.x) wf[(size_t)co * K + k] = rtf32(w[(size_t)co * K + k] * s);
 }
 
-__global__ void round_copy_kernel(size_t n, const float* __restrict__ src, float* __restrict__ dst) {
+// 128-bit accesses, four independent loads in flight per thread (the scalar one-element-per-thread version ran
+// at 2.2 TB/s); scalar tail for n % 4 and unaligned bases
+__global__ void __launch_bounds__(256)
+round_copy_kernel(size_t n, const float* __restrict__ src, float* __restrict__ dst) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    const size_t n4 = vec ? n >> 2 : 0;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = rtf32(src[i]);
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = __ldcs(s4 + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            d4[i + u * stride] = make_float4(rtf32(v[u].x), rtf32(v[u].y), rtf32(v[u].z), rtf32(v[u].w));
+    }
+    for (; i < n4; i += stride) {
+        const float4 v = __ldcs(s4 + i);
+        d4[i] = make_float4(rtf32(v.x), rtf32(v.y), rtf32(v.z), rtf32(v.w));
+    }
+    for (size_t j = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) dst[j] = rtf32(src[j]);
 }
 
 // d(gamma), d(beta) of a frozen BN from the conv's weight gradient:
@@ -60,35 +80,72 @@ __global__ void bn_param_grad_kernel(int cout, int K, const float* __restrict__ 
 
 // ---- whole-model variants: one launch over every (layer, output channel) pair instead of
 // one launch per layer (208 frozen-BN convs in the two towers)
-__global__ void fold_bn_multi_kernel(const mpb_bn_layer* __restrict__ layers, const int* __restrict__ row2layer, float eps) {
-    const mpb_bn_layer L = layers[row2layer[blockIdx.x]];
-    const int co = blockIdx.x - L.row0;
+// One WARP per (layer, output channel) row, 8 rows per CTA, 128-bit loads with four in flight per lane (rows are
+// 64 .. 4608 floats, every row starts on a 16-byte boundary because K % 4 == 0 for the tensor-core convs; the
+// 7x7x3 stem rows, K = 147, take the scalar path).  The block-per-row scalar versions ran at 2.3-2.6 TB/s.
+__global__ void __launch_bounds__(256)
+fold_bn_multi_kernel(int total_rows, const mpb_bn_layer* __restrict__ layers, const int* __restrict__ row2layer, float eps) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= total_rows) return;
+    const mpb_bn_layer L = layers[row2layer[row]];
+    const int co = row - L.row0;
     const float s = L.gamma[co] * rsqrtf(L.var[co] + eps);
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
         L.scale[co] = s;
         L.shift[co] = L.beta[co] - L.mean[co] * s;
     }
     const float* w = L.w + (size_t)co * L.K;
     float* wf = L.wf + (size_t)co * L.K;
-    for (int k = threadIdx.x; k < L.K; k += blockDim.x) wf[k] = rtf32(w[k] * s);
+    if ((L.K & 3) == 0) {
+        const float4* w4 = reinterpret_cast<const float4*>(w);
+        float4* f4 = reinterpret_cast<float4*>(wf);
+        const int n4 = L.K >> 2;
+        int k = lane;
+        for (; k + 96 < n4; k += 128) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = __ldcs(w4 + k + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                f4[k + 32 * u] = make_float4(rtf32(v[u].x * s), rtf32(v[u].y * s), rtf32(v[u].z * s), rtf32(v[u].w * s));
+        }
+        for (; k < n4; k += 32) {
+            const float4 v = __ldcs(w4 + k);
+            f4[k] = make_float4(rtf32(v.x * s), rtf32(v.y * s), rtf32(v.z * s), rtf32(v.w * s));
+        }
+    } else {
+        for (int k = lane; k < L.K; k += 32) wf[k] = rtf32(w[k] * s);
+    }
 }
-__global__ void bn_param_grad_multi_kernel(const mpb_bn_layer* __restrict__ layers, const int* __restrict__ row2layer,
-                                           float eps) {
-    const mpb_bn_layer L = layers[row2layer[blockIdx.x]];
-    const int co = blockIdx.x - L.row0;
+__global__ void __launch_bounds__(256)
+bn_param_grad_multi_kernel(int total_rows, const mpb_bn_layer* __restrict__ layers, const int* __restrict__ row2layer,
+                           float eps) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= total_rows) return;
+    const mpb_bn_layer L = layers[row2layer[row]];
+    const int co = row - L.row0;
     const float* w = L.w + (size_t)co * L.K;
     const float* dw = L.dw + (size_t)co * L.K;
     float acc = 0.f;
-    for (int k = threadIdx.x; k < L.K; k += blockDim.x) acc = fmaf(w[k], dw[k], acc);
-    __shared__ float red[32];
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
-        L.dgamma[co] = t / L.gamma[co] - L.mean[co] * L.dbeta[co] * rsqrtf(L.var[co] + eps);
+    if ((L.K & 3) == 0) {
+        const float4* w4 = reinterpret_cast<const float4*>(w);
+        const float4* d4 = reinterpret_cast<const float4*>(dw);
+        const int n4 = L.K >> 2;
+        int k = lane;
+        for (; k + 32 < n4; k += 64) {
+            const float4 a0 = __ldcs(w4 + k), a1 = __ldcs(w4 + k + 32), b0 = __ldcs(d4 + k), b1 = __ldcs(d4 + k + 32);
+            acc = fmaf(a0.x, b0.x, acc); acc = fmaf(a0.y, b0.y, acc); acc = fmaf(a0.z, b0.z, acc); acc = fmaf(a0.w, b0.w, acc);
+            acc = fmaf(a1.x, b1.x, acc); acc = fmaf(a1.y, b1.y, acc); acc = fmaf(a1.z, b1.z, acc); acc = fmaf(a1.w, b1.w, acc);
+        }
+        for (; k < n4; k += 32) {
+            const float4 a0 = __ldcs(w4 + k), b0 = __ldcs(d4 + k);
+            acc = fmaf(a0.x, b0.x, acc); acc = fmaf(a0.y, b0.y, acc); acc = fmaf(a0.z, b0.z, acc); acc = fmaf(a0.w, b0.w, acc);
+        }
+    } else {
+        for (int k = lane; k < L.K; k += 32) acc = fmaf(w[k], dw[k], acc);
     }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) L.dgamma[co] = acc / L.gamma[co] - L.mean[co] * L.dbeta[co] * rsqrtf(L.var[co] + eps);
 }
 
 // ---------------------------------------------------------------- stem: conv 7x7/2 + BN + ReLU
@@ -451,28 +508,46 @@ __global__ void resize_ac_bwd_kernel(int nimg, int H, int W, int C4, int OH, int
 // slim.batch_norm(is_training=True) defaults (center, no scale, eps 1e-3, decay 0.999) on the
 // decoder convs (builders/net_builder.py:77-89): statistics over all M = nimg*H*W rows.
 // stats: CTA = 32 channels x 8 row-groups, fp32 partials, final combine in double.
+// thread = 4 channels (one 16-byte load) x a strided set of rows, 4 rows in flight; CTA = 32 channel quads x 8 row
+// groups; fp32 partials per thread, combined in double.  (The one-float-per-thread version reached ~1.5 TB/s.)
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(int M, int C, const float* __restrict__ z, double* __restrict__ psum, double* __restrict__ psq) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
     const int rg = threadIdx.x >> 5;
     const int rows_per = (M + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-    float s = 0.f, q = 0.f;
-    if (c < C)
-        for (int r = r0 + rg; r < r1; r += 8) {
-            const float v = z[(size_t)r * C + c];
-            s += v;
-            q = fmaf(v, v, q);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (c < C) {
+        int r = r0 + rg;
+        for (; r + 24 < r1; r += 32) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = *reinterpret_cast<const float4*>(z + (size_t)(r + 8 * u) * C + c);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+                q.x = fmaf(v[u].x, v[u].x, q.x); q.y = fmaf(v[u].y, v[u].y, q.y);
+                q.z = fmaf(v[u].z, v[u].z, q.z); q.w = fmaf(v[u].w, v[u].w, q.w);
+            }
         }
-    __shared__ float ss[8][32], sq[8][32];
+        for (; r < r1; r += 8) {
+            const float4 v = *reinterpret_cast<const float4*>(z + (size_t)r * C + c);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+        }
+    }
+    __shared__ float4 ss[8][32], sq[8][32];
     ss[rg][threadIdx.x & 31] = s;
     sq[rg][threadIdx.x & 31] = q;
     __syncthreads();
     if (rg == 0 && c < C) {
-        double a = 0, b = 0;
-        for (int k = 0; k < 8; k++) { a += ss[k][threadIdx.x]; b += sq[k][threadIdx.x]; }
-        atomicAdd(&psum[c], a);
-        atomicAdd(&psq[c], b);
+        double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 8; k++) {
+            const float4 x = ss[k][threadIdx.x], y = sq[k][threadIdx.x];
+            a[0] += x.x; a[1] += x.y; a[2] += x.z; a[3] += x.w;
+            b[0] += y.x; b[1] += y.y; b[2] += y.z; b[3] += y.w;
+        }
+        for (int j = 0; j < 4; j++) { atomicAdd(&psum[c + j], a[j]); atomicAdd(&psq[c + j], b[j]); }
     }
 }
 __global__ void bn_finalize_kernel(int M, int C, const double* __restrict__ psum, const double* __restrict__ psq,
@@ -504,48 +579,77 @@ __global__ void bn_apply_kernel(long total4, int C4, const float4* __restrict__ 
     y[i] = o;
 }
 // backward: g = dy*(y>0); s1 = sum g; s2 = sum g*xhat; dz = rstd*(g - s1/M - xhat*s2/M); dbeta = s1
+// same thread layout as bn_stats_kernel (4 channels per thread, 2 rows in flight: three tensors are read)
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(int M, int C, const float* __restrict__ z, const float* __restrict__ y,
                      const float* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ var,
                      float eps, double* __restrict__ s1, double* __restrict__ s2) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
     const int rg = threadIdx.x >> 5;
     const int rows_per = (M + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-    float a = 0.f, b = 0.f;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (c < C) {
-        const float mu = mean[c], rs = rsqrtf(var[c] + eps);
-        for (int r = r0 + rg; r < r1; r += 8) {
-            const size_t o = (size_t)r * C + c;
-            const float g = y[o] > 0.f ? dy[o] : 0.f;
-            a += g;
-            b = fmaf(g, (z[o] - mu) * rs, b);
+        const float4 mu = *reinterpret_cast<const float4*>(mean + c), vr = *reinterpret_cast<const float4*>(var + c);
+        const float4 rs = make_float4(rsqrtf(vr.x + eps), rsqrtf(vr.y + eps), rsqrtf(vr.z + eps), rsqrtf(vr.w + eps));
+        auto acc = [&](const float4& zz, const float4& yy, const float4& dd) {
+            const float gx = yy.x > 0.f ? dd.x : 0.f, gy = yy.y > 0.f ? dd.y : 0.f;
+            const float gz = yy.z > 0.f ? dd.z : 0.f, gw = yy.w > 0.f ? dd.w : 0.f;
+            a.x += gx; a.y += gy; a.z += gz; a.w += gw;
+            b.x = fmaf(gx, (zz.x - mu.x) * rs.x, b.x); b.y = fmaf(gy, (zz.y - mu.y) * rs.y, b.y);
+            b.z = fmaf(gz, (zz.z - mu.z) * rs.z, b.z); b.w = fmaf(gw, (zz.w - mu.w) * rs.w, b.w);
+        };
+        int r = r0 + rg;
+        for (; r + 8 < r1; r += 16) {
+            const size_t o0 = (size_t)r * C + c, o1 = (size_t)(r + 8) * C + c;
+            const float4 z0 = *reinterpret_cast<const float4*>(z + o0), z1 = *reinterpret_cast<const float4*>(z + o1);
+            const float4 y0 = *reinterpret_cast<const float4*>(y + o0), y1 = *reinterpret_cast<const float4*>(y + o1);
+            const float4 d0 = *reinterpret_cast<const float4*>(dy + o0), d1 = *reinterpret_cast<const float4*>(dy + o1);
+            acc(z0, y0, d0);
+            acc(z1, y1, d1);
+        }
+        for (; r < r1; r += 8) {
+            const size_t o0 = (size_t)r * C + c;
+            acc(*reinterpret_cast<const float4*>(z + o0), *reinterpret_cast<const float4*>(y + o0),
+                *reinterpret_cast<const float4*>(dy + o0));
         }
     }
-    __shared__ float sa[8][32], sb[8][32];
+    __shared__ float4 sa[8][32], sb[8][32];
     sa[rg][threadIdx.x & 31] = a;
     sb[rg][threadIdx.x & 31] = b;
     __syncthreads();
     if (rg == 0 && c < C) {
-        double p = 0, q = 0;
-        for (int k = 0; k < 8; k++) { p += sa[k][threadIdx.x]; q += sb[k][threadIdx.x]; }
-        atomicAdd(&s1[c], p);
-        atomicAdd(&s2[c], q);
+        double p[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 8; k++) {
+            const float4 x = sa[k][threadIdx.x], w = sb[k][threadIdx.x];
+            p[0] += x.x; p[1] += x.y; p[2] += x.z; p[3] += x.w;
+            q[0] += w.x; q[1] += w.y; q[2] += w.z; q[3] += w.w;
+        }
+        for (int j = 0; j < 4; j++) { atomicAdd(&s1[c + j], p[j]); atomicAdd(&s2[c + j], q[j]); }
     }
 }
-__global__ void bn_bwd_apply_kernel(long total, int M, int C, const float* __restrict__ z, const float* __restrict__ y,
-                                    const float* __restrict__ dy, const float* __restrict__ mean,
-                                    const float* __restrict__ var, float eps, const double* __restrict__ s1,
-                                    const double* __restrict__ s2, float* __restrict__ dz, float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(long total4, int M, int C, const float* __restrict__ z, const float* __restrict__ y,
+                    const float* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                    const double* __restrict__ s1, const double* __restrict__ s2, float* __restrict__ dz,
+                    float* __restrict__ dbeta) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c = (int)(i % C);
-    const float rs = rsqrtf(var[c] + eps);
-    const float xh = (z[i] - mean[c]) * rs;
-    const float g = y[i] > 0.f ? dy[i] : 0.f;
-    const float m1 = (float)(s1[c] / M), m2 = (float)(s2[c] / M);
-    dz[i] = rtf32(rs * (g - m1 - xh * m2));
-    if (i < C) dbeta[i] = (float)s1[i];
+    if (i >= total4) return;
+    const int c = (int)(i % (C / 4)) * 4;
+    const float4 zz = reinterpret_cast<const float4*>(z)[i], yy = reinterpret_cast<const float4*>(y)[i];
+    const float4 dd = reinterpret_cast<const float4*>(dy)[i];
+    float zc[4] = {zz.x, zz.y, zz.z, zz.w}, yc[4] = {yy.x, yy.y, yy.z, yy.w}, dc[4] = {dd.x, dd.y, dd.z, dd.w}, o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float rs = rsqrtf(var[c + j] + eps);
+        const float xh = (zc[j] - mean[c + j]) * rs;
+        const float g = yc[j] > 0.f ? dc[j] : 0.f;
+        const float m1 = (float)(s1[c + j] / M), m2 = (float)(s2[c + j] / M);
+        o[j] = rtf32(rs * (g - m1 - xh * m2));
+    }
+    reinterpret_cast<float4*>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (i * 4 < C)
+        for (int j = 0; j < 4; j++) dbeta[i * 4 + j] = (float)s1[i * 4 + j];
 }
 
 // ---------------------------------------------------------------- xyz head: conv3x3 128 -> 3 (+bias)
@@ -736,7 +840,7 @@ MPB_API int mpb_fold_bn(int cout, int K, const float* w, const float* gamma, con
     return 0;
 }
 MPB_API int mpb_round_copy(long n, const float* src, float* dst, void* stream) {
-    round_copy_kernel<<<nblk(n, 256), 256, 0, ST>>>((size_t)n, src, dst);
+    round_copy_kernel<<<(int)min((long)num_sms() * 16, (long)nblk(n, 1024)), 256, 0, ST>>>((size_t)n, src, dst);
     MPB_LAUNCH_CHECK();
     return 0;
 }
@@ -748,13 +852,13 @@ MPB_API int mpb_bn_param_grad(int cout, int K, const float* w, const float* dw, 
 }
 MPB_API int mpb_fold_bn_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream) {
     if (total_rows <= 0 || !layers || !row2layer) return -1;
-    fold_bn_multi_kernel<<<total_rows, 128, 0, ST>>>(layers, row2layer, eps);
+    fold_bn_multi_kernel<<<ceil_div(total_rows, 8), 256, 0, ST>>>(total_rows, layers, row2layer, eps);
     MPB_LAUNCH_CHECK();
     return 0;
 }
 MPB_API int mpb_bn_param_grad_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream) {
     if (total_rows <= 0 || !layers || !row2layer) return -1;
-    bn_param_grad_multi_kernel<<<total_rows, 128, 0, ST>>>(layers, row2layer, eps);
+    bn_param_grad_multi_kernel<<<ceil_div(total_rows, 8), 256, 0, ST>>>(total_rows, layers, row2layer, eps);
     MPB_LAUNCH_CHECK();
     return 0;
 }
@@ -831,7 +935,8 @@ MPB_API int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, fl
                              float* var, float* moving_mean, float* moving_var, float decay, double* scratch,
                              void* stream) {
     MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, ST));
-    dim3 g(ceil_div(C, 32), min(256, ceil_div(M, 64)));
+    if (C % 4) return -1;
+    dim3 g(ceil_div(C, 128), min(num_sms() * 4, ceil_div(M, 64)));
     bn_stats_kernel<<<g, 256, 0, ST>>>(M, C, z, scratch, scratch + C);
     MPB_LAUNCH_CHECK();
     bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(M, C, scratch, scratch + C, mean, var, moving_mean, moving_var, decay);
@@ -844,11 +949,12 @@ MPB_API int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, fl
 MPB_API int mpb_bn_train_bwd(int M, int C, const float* z, const float* mean, const float* var, float eps, const float* y,
                              const float* dy, float* dz, float* dbeta, double* scratch, void* stream) {
     MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, ST));
-    dim3 g(ceil_div(C, 32), min(256, ceil_div(M, 64)));
+    if (C % 4) return -1;
+    dim3 g(ceil_div(C, 128), min(num_sms() * 4, ceil_div(M, 64)));
     bn_bwd_reduce_kernel<<<g, 256, 0, ST>>>(M, C, z, y, dy, mean, var, eps, scratch, scratch + C);
     MPB_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<nblk((long)M * C, 256), 256, 0, ST>>>((long)M * C, M, C, z, y, dy, mean, var, eps, scratch,
-                                                              scratch + C, dz, dbeta);
+    bn_bwd_apply_kernel<<<nblk((long)M * C / 4, 256), 256, 0, ST>>>((long)M * C / 4, M, C, z, y, dy, mean, var, eps, scratch,
+                                                                  scratch + C, dz, dbeta);
     MPB_LAUNCH_CHECK();
     return 0;
 }
