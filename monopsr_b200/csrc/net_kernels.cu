@@ -200,31 +200,45 @@ __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(int nimg, int Hin, int Win, int Ho, int Wo, const float* __restrict__ x,
                   const float* __restrict__ g, const float* __restrict__ scale, float* __restrict__ dw,
                   int pix_per_cta) {
-    __shared__ float sg[64];
-    __shared__ float sx[kStemK];
+    // 16 pixels are staged per barrier pair (gradients and 7x7x3 patches), so a thread runs 16 x 37 FMAs between
+    // synchronisations instead of 37
+    constexpr int PT = 16;
+    __shared__ float sg[PT][64];
+    __shared__ float sx[PT][kStemK + 1];
+    __shared__ int spix[PT][3];
     const long total = (long)nimg * Ho * Wo;
-    const long p0 = (long)blockIdx.x * pix_per_cta;
+    const long p0 = (long)blockIdx.x * pix_per_cta, pend = min(total, p0 + pix_per_cta);
     const int co = threadIdx.x & 63, part = threadIdx.x >> 6;   // 4 parts over the 147 taps
     float acc[37];
 #pragma unroll
     for (int i = 0; i < 37; i++) acc[i] = 0.f;
-    for (long pix = p0; pix < min(total, p0 + pix_per_cta); pix++) {
-        const int n = (int)(pix / (Ho * Wo)), rem = (int)(pix % (Ho * Wo)), oh = rem / Wo, ow = rem % Wo;
+    for (long pix0 = p0; pix0 < pend; pix0 += PT) {
         __syncthreads();
-        if (threadIdx.x < 64) sg[threadIdx.x] = g[(size_t)pix * 64 + threadIdx.x];
-        if (threadIdx.x < kStemK) {
-            const int t = threadIdx.x / 3, ci = threadIdx.x % 3;
-            const int ih = oh * 2 - 3 + t / 7, iw = ow * 2 - 3 + t % 7;
-            sx[threadIdx.x] = (ih >= 0 && ih < Hin && iw >= 0 && iw < Win)
-                                  ? x[(((size_t)n * Hin + ih) * Win + iw) * 3 + ci] : 0.f;
+        if (threadIdx.x < PT) {
+            const long pix = pix0 + threadIdx.x;
+            const int n = (int)(pix / (Ho * Wo)), rem = (int)(pix % (Ho * Wo));
+            spix[threadIdx.x][0] = n; spix[threadIdx.x][1] = rem / Wo; spix[threadIdx.x][2] = rem % Wo;
+        }
+        for (int i = threadIdx.x; i < PT * 64; i += blockDim.x) {
+            const long pix = pix0 + (i >> 6);
+            sg[i >> 6][i & 63] = pix < pend ? g[(size_t)pix * 64 + (i & 63)] : 0.f;
         }
         __syncthreads();
-        const float gv = sg[co];
-        if (gv != 0.f) {
+        for (int i = threadIdx.x; i < PT * kStemK; i += blockDim.x) {
+            const int q = i / kStemK, k = i - q * kStemK;
+            const int t = k / 3, ci = k - t * 3;
+            const int n = spix[q][0], ih = spix[q][1] * 2 - 3 + t / 7, iw = spix[q][2] * 2 - 3 + t % 7;
+            sx[q][k] = (pix0 + q < pend && ih >= 0 && ih < Hin && iw >= 0 && iw < Win)
+                           ? x[(((size_t)n * Hin + ih) * Win + iw) * 3 + ci] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int q = 0; q < PT; q++) {
+            const float gv = sg[q][co];
 #pragma unroll
             for (int i = 0; i < 37; i++) {
                 const int k = part * 37 + i;
-                if (k < kStemK) acc[i] = fmaf(gv, sx[k], acc[i]);
+                if (k < kStemK) acc[i] = fmaf(gv, sx[q][k], acc[i]);
             }
         }
     }
