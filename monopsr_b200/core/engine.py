@@ -64,7 +64,10 @@ class Engine:
         self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
         self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "128"))
         self.wgrad_fill = float(os.environ.get("MPB_WGRAD_FILL", "0.5"))   # target CTAs / SMs when choosing split-K
-        self.csk = int(os.environ.get("MPB_CSK", "1"))                    # cluster split-K (DSMEM reduce) for long reductions
+        # cluster split-K (DSMEM reduce) for long reductions: faster per launch (profiles/r1_gemm_sweep.txt), but the
+        # step is 2.5 % faster WITHOUT it once launches are chained with programmatic dependent launch (cluster
+        # launches do not overlap their predecessor's tail): off by default, MPB_CSK=1 enables
+        self.csk = int(os.environ.get("MPB_CSK", "0"))
         self.csk_bn = int(os.environ.get("MPB_CSK_BN", "128"))            # widest tile that may be split over a cluster
         self.ctas_per_sm = {64: 2, 128: int(os.environ.get("MPB_CTAS128", "2")), 256: 1}   # see tc_gemm.cuh
 

@@ -579,6 +579,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 // Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue.
 // =====================================================================================
 // epilogue warps / minimum CTAs per SM per tile width (rationale in tc_gemm.cuh)
+#ifndef MPB_EW64
+#define MPB_EW64 4
+#endif
 #ifndef MPB_EW128
 #define MPB_EW128 4
 #endif
@@ -591,7 +594,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
 #ifndef MPB_MINB256
 #define MPB_MINB256 1
 #endif
-template <int BN> constexpr int tma_epi_warps() { return BN == 64 ? 4 : BN == 128 ? MPB_EW128 : MPB_EW256; }
+template <int BN> constexpr int tma_epi_warps() { return BN == 64 ? MPB_EW64 : BN == 128 ? MPB_EW128 : MPB_EW256; }
 template <int BN> constexpr int tma_threads() { return 64 + 32 * tma_epi_warps<BN>(); }
 template <int BN> constexpr int tma_min_blocks() { return BN == 64 ? 2 : BN == 128 ? MPB_MINB128 : MPB_MINB256; }
 
@@ -809,6 +812,9 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
         }
         if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
     };
+    // PDL: everything above touched only parameters and shared memory; from here on global memory written by the
+    // stream predecessor is read (no-op when the launch carries no programmatic dependency)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int npre = (CN == 1) ? min(nk, kTcStages) : 0;   // multicast needs the peers' barriers first
     if (warp == 0) {
         __syncwarp();                 // lane 0's barrier initialisation is visible to the elected lane
@@ -861,7 +867,12 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                     umma_tf32(tmem_acc, ad + k * ka, bd + k * kb_, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 if (CN > 1) umma_commit_mc(empty_bar(stage), kMask);   // frees this stage in every CTA
                 else umma_commit(empty_bar(stage));
-                if (i == nk - 1) umma_commit(tmem_full_bar);
+                if (i == nk - 1) {
+                    umma_commit(tmem_full_bar);
+                    // PDL: the successor may launch now -- its setup overlaps this CTA's epilogue.  (Releasing it
+                    // at CTA start was measured slower: early successors sit on SM slots other streams could use.)
+                    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                }
                 if (i < 16) TC_TR(36 + i);
             }
             __syncwarp();
@@ -968,6 +979,18 @@ static bool make_map_im2col(CUtensorMap* m, const float* ptr, int C, int W, int 
     return true;
 }
 
+// Programmatic dependent launch (default on, MPB_PDL=0 disables): every GEMM waits (griddepcontrol.wait) for its stream predecessor
+// before touching global memory and releases its successor (griddepcontrol.launch_dependents) when its
+// accumulator is complete, so the successor's launch latency and setup overlap this grid's epilogue.
+static int g_tc_pdl = -1;
+static bool tc_gemm_pdl() {
+    if (g_tc_pdl < 0) {
+        const char* e = getenv("MPB_PDL");
+        g_tc_pdl = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return g_tc_pdl == 1;
+}
+
 // row tiles per cluster of a cluster split-K launch: make the cluster an even number of CTAs (whole TPCs)
 static int csk_cluster_x(unsigned gx, unsigned ks) {
     if (ks % 2 == 0 || gx % 2 != 0 || ks * 2 > 8) return 1;
@@ -998,7 +1021,8 @@ static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
         MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN, OP, CN, CSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    if (CN == 1 && !CSK) {
+    const bool pdl = tc_gemm_pdl();
+    if (CN == 1 && !CSK && !pdl) {
         tc_gemm_tma_kernel<BN, OP, CN, CSK><<<grid, tma_threads<BN>(), smem, s>>>(p, mapA, mapB);
         MPB_LAUNCH_CHECK();
         return 0;
@@ -1008,13 +1032,22 @@ static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     cfg.blockDim = dim3(tma_threads<BN>());
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CSK ? csk_cluster_x(grid.x, grid.z) : 1;
-    at[0].val.clusterDim.y = CN;
-    at[0].val.clusterDim.z = CSK ? grid.z : 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (CN > 1 || CSK) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = CSK ? csk_cluster_x(grid.x, grid.z) : 1;
+        at[na].val.clusterDim.y = CN;
+        at[na].val.clusterDim.z = CSK ? grid.z : 1;
+        na++;
+    }
+    if (pdl) {      // programmatic dependent launch: this grid may start while its stream predecessor drains
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     MPB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_tma_kernel<BN, OP, CN, CSK>, p, mapA, mapB));
     count_launch();
     return 0;
@@ -1125,7 +1158,7 @@ int tc_gemm_launch(const TcGemmParams& p, int BN, cudaStream_t s) {
         if ((p.ksplit - 1) * per_ >= nkb_) return -1;
         if (p.ksplit > 8) return -1;
         {                        // the chunks a CTA does not own are parked in its idle pipeline stages
-            const int n = BN / 32, ew = BN == 64 ? 4 : BN == 128 ? MPB_EW128 : MPB_EW256;
+            const int n = BN / 32, ew = BN == 64 ? MPB_EW64 : BN == 128 ? MPB_EW128 : MPB_EW256;
             const int st = BN == 64 ? MPB_STAGES64 : BN == 128 ? MPB_STAGES128 : MPB_STAGES256;
             if ((n - n / p.ksplit) * 16384 + ew * 4096 > st * (kTcABytes + BN * 128)) return -1;
         }
