@@ -192,12 +192,15 @@ int mpb_heads_bwd_mid(const mpb_heads_io* io, void* stream);       /* after the 
 /* ---- fused train-op: per-variable clip_by_norm + Adam + EMA (csrc/optimizer.cu) ----
  * Replaces slim.learning.create_train_op(..., clip_gradient_norm=1.0) (core/trainer.py:76-81) with
  * AdamOptimizer + MovingAverageOptimizer (builders/optimizer_builder.py:56-82). */
+/* chunks: the variables cut into pieces of the flat arena; the chunks of one variable must be CONTIGUOUS in the
+ * table.  norm2: scratch, one float per chunk (per-chunk sums of squares, combined per variable in a fixed order
+ * so that every data-parallel replica computes the same clip factor bit for bit). */
 typedef struct mpb_opt_chunk { long start; int len; int tensor; } mpb_opt_chunk;
 int mpb_opt_step(int nchunks, const mpb_opt_chunk* chunks, int ntensors, float* param, const float* grad,
                  float* m, float* v, float* ema, float* norm2, const float* hyper, float grad_scale,
                  float clip_norm, float beta1, float beta2, float eps, float ema_decay, void* stream);
 /* the same over a sub-range of the chunk table: `chunks` points at the first chunk of the range, whose tensors are
- * tensor0 .. tensor0+ntensors-1 (chunk.tensor stays an absolute index into norm2).  The update is per variable, so
+ * tensor0 .. tensor0+ntensors-1; norm2 needs one float per chunk of the range.  The update is per variable, so
  * a group of variables can be stepped as soon as its gradients are final, under the rest of the backward pass. */
 int mpb_opt_step_range(int nchunks, const mpb_opt_chunk* chunks, int tensor0, int ntensors, float* param,
                        const float* grad, float* m, float* v, float* ema, float* norm2, const float* hyper,

@@ -23,6 +23,20 @@ def allreduce_flat(flat, group=None):
     return 1.0 / world
 
 
+def allreduce_start(flat, group=None):
+    """start summing `flat` in place without blocking the caller's stream (NCCL: on its own stream, after the
+    work already queued on the current one); returns a handle for allreduce_finish, None when not distributed"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
+def allreduce_finish(work):
+    """make the caller's stream (NCCL) / thread (gloo) wait for a bucket started with allreduce_start"""
+    if work is not None:
+        work.wait()
+
+
 def shard_samples(num_samples, rank, world):
     """weak scaling: sample indices handled by `rank` (round-robin over the global batch)"""
     return list(range(rank, num_samples, world))

@@ -129,7 +129,7 @@ class Engine:
         raw = bytes(arr)
         self.opt_chunks = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.dev)
         self.n_chunks = len(chunks)
-        self.norm2 = z(len(self.trainable_names))
+        self.norm2 = z(len(chunks))            # per-chunk sums of squares (combined per variable in a fixed order)
         # the variables outside the two towers (squash, decoder, FC stacks, heads: 45 % of the parameters) sit at
         # the end of the arena; their gradients are final before the towers' backward pass starts, so their
         # train-op runs on a side stream under it ("head" part; the rest is the "towers" part)
@@ -702,6 +702,18 @@ class Engine:
                                    _ptr(self.gview(s0 + "/weights")), st), "stem_wgrad")
 
     def backward(self):
+        """head part (FC stacks, decoder, squash: every gradient outside the towers), then the two towers"""
+        self._backward_head()
+        if self.early_opt:
+            # every gradient outside the towers is final (FC stacks on s_wc, decoder wgrads on s_wf, the rest here)
+            for s_ in (self._cur(), self.s_wf, self.s_wc):
+                self.s_opt.wait_stream(s_)
+            with torch.cuda.stream(self.s_opt):
+                self.optimizer_step(1.0, part="head")
+                self.prepare_weights(part="head")
+        self._backward_towers()
+
+    def _backward_head(self, join=False):
         L, st, N, I, h = self.L, self._st(), self.N, self.inputs, self.h
         if self._grads_zeroed:
             self._join(self.s_wf)            # the zero-fill of the gradient arena ran beside the forward pass
@@ -756,13 +768,13 @@ class Engine:
                   mask=self.concat, ldm=2048, colsum=self.gview(lastc["scope"] + "/conv3/BatchNorm/beta"), round_tf32=1)
         self.gemm(TC_DGRAD, Mc, 12, 12, 1, 1, 1024, 512, self.g_squashed, 512, wsq.view(-1)[1024:], 2048,
                   self.g_fullcrop, 1024)
-        if self.early_opt:
-            # every gradient outside the towers is final (FC stacks on s_wc, decoder wgrads on s_wf, the rest here)
-            for s_ in (self._cur(), self.s_wf, self.s_wc):
-                self.s_opt.wait_stream(s_)
-            with torch.cuda.stream(self.s_opt):
-                self.optimizer_step(1.0, part="head")
-                self.prepare_weights(part="head")
+        if join:        # the gradients of the head variables are complete on THIS stream (bucketed all-reduce)
+            self._join(self.s_wf, self.s_wc)
+
+    def _backward_towers(self):
+        L, st, N, I = self.L, self._st(), self.N, self.inputs
+        Tc, Tf = self.towers[ms.ENCODERS[0]], self.towers[ms.ENCODERS[1]]
+        lastf = Tf["units"][-1]
         with self._side(self.s_full):
             self._chk(L.mpb_crop_pool_bwd(Tf["h"], Tf["w"], 1024, _ptr(lastf["o"]), N, _ptr(I["boxes_2d_norm"]), 24,
                                           _ptr(self.g_fullcrop), 1024, _ptr(self.d_fullfeat), self._st()), "crop_pool_bwd")
@@ -793,7 +805,8 @@ class Engine:
         chunk_bytes = ctypes.sizeof(OptChunk)
         self._chk(self.L.mpb_opt_step_range(nc, ctypes.c_void_p(self.opt_chunks.data_ptr() + c0 * chunk_bytes), t0, nt,
                                             _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
-                                            _ptr(self.ema), _ptr(self.norm2), _ptr(self.hyper), grad_scale, 1.0, 0.9,
+                                            _ptr(self.ema), ctypes.c_void_p(self.norm2.data_ptr() + 4 * c0), _ptr(self.hyper),
+                                            grad_scale, 1.0, 0.9,
                                             0.999, 1e-8, 0.9999, self._st()), "opt_step")
         self._prepared = False
 
@@ -819,11 +832,15 @@ class Engine:
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if distributed:
-            # two graphs around the NCCL all-reduce (kept out of capture for portability)
+            # graphs around the NCCL all-reduces (kept out of capture for portability)
             if getattr(self, "_g_fb", None) is None:
                 self._capture_split()
+            from . import dp
             self._g_fb.replay()
-            world = self.allreduce_grads()
+            head = dp.allreduce_start(self.grads[self.round_off:])     # on NCCL's stream, beside the towers' backward
+            self._g_bt.replay()
+            dp.allreduce_finish(head)
+            dp.allreduce_flat(self.grads[:self.round_off])
             self._g_opt.replay()
         else:
             if getattr(self, "_graph", None) is None:
@@ -869,13 +886,17 @@ class Engine:
         if not self._prepared:
             self.prepare_weights()
         self._warm()
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        # three graphs around two gradient buckets: [forward + head backward] -> all-reduce of the head variables'
+        # gradients (arena tail, 45 %) UNDER [towers' backward] -> all-reduce of the tower gradients -> [train-op]
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         c0 = _lib.launch_count()
         with torch.cuda.graph(g1):
             self.forward(train=True)
-            self.backward()
+            self._backward_head(join=True)
         with torch.cuda.graph(g2):
+            self._backward_towers()
+        with torch.cuda.graph(g3):
             self.optimizer_step(1.0 / dist.get_world_size())
             self.prepare_weights()
         self.launches_per_step = _lib.launch_count() - c0
-        self._g_fb, self._g_opt = g1, g2
+        self._g_fb, self._g_bt, self._g_opt = g1, g2, g3

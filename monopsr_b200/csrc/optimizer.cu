@@ -16,7 +16,7 @@ constexpr int kOptThreads = 256;
 
 __global__ void __launch_bounds__(kOptThreads)
 opt_sumsq_kernel(const mpb_opt_chunk* __restrict__ chunks, const float* __restrict__ grad, float gscale,
-                 float* __restrict__ norm2) {
+                 float* __restrict__ partial) {
     const mpb_opt_chunk ch = chunks[blockIdx.x];
     const float* g = grad + ch.start;
     float acc = 0.f;
@@ -40,18 +40,40 @@ opt_sumsq_kernel(const mpb_opt_chunk* __restrict__ chunks, const float* __restri
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int i = 0; i < kOptThreads / 32; i++) s += red[i];
-        atomicAdd(&norm2[ch.tensor], s);
+        partial[blockIdx.x] = s;      // one slot per chunk, combined in a FIXED order by the update kernel
     }
+}
+
+// ||g||^2 of the variable that chunk `me` belongs to: the chunks of a variable are contiguous in the table, so a
+// warp scans outwards from its own chunk and adds the per-chunk partials lane-strided + shuffle tree.  The order
+// depends only on the table, so every CTA of a variable -- and every data-parallel rank -- gets the same bits
+// (an atomicAdd accumulation made the clip factor, hence the replicas' parameters, differ in the last bits).
+__device__ __forceinline__ float tensor_sumsq(const mpb_opt_chunk* __restrict__ chunks, int nchunks, int me,
+                                              const float* __restrict__ partial) {
+    const int t = chunks[me].tensor;
+    int lo = me, hi = me + 1;
+    while (lo > 0 && chunks[lo - 1].tensor == t) --lo;
+    while (hi < nchunks && chunks[hi].tensor == t) ++hi;
+    float acc = 0.f;
+    for (int i = lo + (threadIdx.x & 31); i < hi; i += 32) acc += partial[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
 }
 
 // hyper[0] = lr_t = lr * sqrt(1-b2^t)/(1-b1^t) (device resident so a captured CUDA graph can be replayed)
 __global__ void __launch_bounds__(kOptThreads)
-opt_adam_ema_kernel(const mpb_opt_chunk* __restrict__ chunks, float* __restrict__ param,
+opt_adam_ema_kernel(const mpb_opt_chunk* __restrict__ chunks, int nchunks, float* __restrict__ param,
                     const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
-                    float* __restrict__ ema, const float* __restrict__ norm2, const float* __restrict__ hyper,
+                    float* __restrict__ ema, const float* __restrict__ partial, const float* __restrict__ hyper,
                     float gscale, float clip, float b1, float b2, float eps, float ema_decay) {
     const mpb_opt_chunk ch = chunks[blockIdx.x];
-    const float nrm = sqrtf(norm2[ch.tensor]);
+    __shared__ float s_nrm2;
+    if (threadIdx.x < 32) {
+        const float t = tensor_sumsq(chunks, nchunks, blockIdx.x, partial);
+        if (threadIdx.x == 0) s_nrm2 = t;
+    }
+    __syncthreads();
+    const float nrm = sqrtf(s_nrm2);
     const float cf = gscale * clip / fmaxf(nrm, clip);
     const float lr_t = hyper[0];
     // 128-bit main loop (every tensor and chunk starts on a 16-byte boundary), scalar tail
@@ -102,10 +124,10 @@ MPB_API int mpb_opt_step_range(int nchunks, const mpb_opt_chunk* chunks, int ten
     using namespace mpb;
     if (nchunks <= 0 || !chunks || !param || !grad || !m || !v || !ema || !norm2 || !hyper || tensor0 < 0) return -1;
     cudaStream_t s = (cudaStream_t)stream;
-    MPB_CUDA_TRY(cudaMemsetAsync(norm2 + tensor0, 0, sizeof(float) * ntensors, s));
+    (void)ntensors;
     opt_sumsq_kernel<<<nchunks, kOptThreads, 0, s>>>(chunks, grad, grad_scale, norm2);
     MPB_LAUNCH_CHECK();
-    opt_adam_ema_kernel<<<nchunks, kOptThreads, 0, s>>>(chunks, param, grad, m, v, ema, norm2, hyper, grad_scale,
+    opt_adam_ema_kernel<<<nchunks, kOptThreads, 0, s>>>(chunks, nchunks, param, grad, m, v, ema, norm2, hyper, grad_scale,
                                                        clip_norm, beta1, beta2, eps, ema_decay);
     MPB_LAUNCH_CHECK();
     return 0;

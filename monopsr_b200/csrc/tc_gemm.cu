@@ -731,7 +731,12 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     const int dil_ = p.dil;
     int pr_tap = 0, pr_cb = 0, pr_th = 0, pr_tw = 0, pr_bw = 0, pr_bh = 0, pr_img0 = 0, pr_ms = 0, pr_cblocks = 1;   // FWD/DGRAD
     int pr_k0 = 0, pr_img = 0, pr_ph = 0, pr_pw = 0, pr_ci0 = 0;                                                    // WGRAD
-    if (warp == 0) {
+    // Two issuing warps: one producer iteration (free-slot wait, expect_tx, 2..9 TMA instructions with their
+    // uniform-register set-up) takes ~420 clk of ONE thread's latency, more than the MMAs of a 64- or 128-wide
+    // k-block (128 / 256 clk).  Warp 0 therefore issues the even k-blocks and the first epilogue warp (idle during
+    // the main loop) the odd ones; both walk the same coordinate sequence and skip the other's iterations.
+    constexpr bool kTwoProducers = (CN == 1);
+    if (warp == 0 || (kTwoProducers && warp == 2)) {
         const int hw = p.H * p.W;
         if (OP == TC_FWD || OP == TC_DGRAD) {
             const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;
@@ -749,9 +754,9 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
             pr_img = pr_k0 / hw; pr_ph = (pr_k0 - pr_img * hw) / p.W; pr_pw = pr_k0 - pr_img * hw - pr_ph * p.W;
         }
     }
-    auto produce = [&](int i, bool wait_free) {
-        if (wait_free) mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (elect_one()) {
+    auto produce = [&](int i, bool wait_free, bool mine) {
+        if (mine && wait_free) mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (mine && elect_one()) {
             if (i < 16) TC_TR(4 + i);
             const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
             mbar_expect_tx(full_bar(stage), kBytes);
@@ -818,7 +823,7 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     const int npre = (CN == 1) ? min(nk, kTcStages) : 0;   // multicast needs the peers' barriers first
     if (warp == 0) {
         __syncwarp();                 // lane 0's barrier initialisation is visible to the elected lane
-        for (int i = 0; i < npre; i++) produce(i, false);
+        for (int i = 0; i < npre; i++) produce(i, false, true);
     }
 
     tc_fence_before();
@@ -840,7 +845,7 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
 #endif
 
     if (warp == 0) {
-        for (int i = npre; i < nk; i++) produce(i, true);
+        for (int i = npre; i < nk; i++) produce(i, true, !kTwoProducers || (i & 1) == 0);
     } else if (warp == 1) {
         // =========================== MMA ISSUER ===========================
         constexpr bool a_mn = (OP == TC_WGRAD);
@@ -899,6 +904,10 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
         if (krank + half * ks < BN / 32) {
             epi_load_res(p, ec, krank + half * ks, lane, n0, rv);
             epi_load_mask(p, ec, krank + half * ks, lane, n0, mv);
+        }
+        if (kTwoProducers && warp == 2) {      // second issuing warp: the odd k-blocks (see above)
+            for (int i = 0; i < npre; i++) produce(i, false, false);
+            for (int i = npre; i < nk; i++) produce(i, true, (i & 1) == 1);
         }
         tc_epilogue_dump<BN, OP>(p, tmem_full_bar, tmem_acc, warp & 3, half, EW / 4, lane, m0, stg_base, EW, ks, krank
                                  TC_TR_PASS);

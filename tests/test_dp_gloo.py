@@ -18,6 +18,12 @@ def _worker(rank, world, port, out):
     mean = g * scale
     expect = torch.arange(1000, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
     ok = bool(torch.allclose(mean, expect)) and dp.shard_samples(8, rank, world) == list(range(rank, 8, world))
+    # two buckets of one arena, the first one asynchronous (the engine's head / towers split)
+    a = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    w = dp.allreduce_start(a[600:])
+    dp.allreduce_flat(a[:600])
+    dp.allreduce_finish(w)
+    ok = ok and bool(torch.allclose(a / world, expect))
     out[rank] = ok
     dist.destroy_process_group()
 
@@ -37,3 +43,5 @@ def test_single_process_is_identity():
     from monopsr_b200.core import dp
     g = torch.ones(10)
     assert dp.allreduce_flat(g) == 1.0 and float(g.sum()) == 10.0
+    assert dp.allreduce_start(g) is None
+    dp.allreduce_finish(None)

@@ -238,7 +238,7 @@ def test_optimizer_step_matches_tf_adam_semantics(cuda):
     p0, m0, v0, e0 = p.double().clone(), m.double().clone(), v.double().clone(), ema.double().clone()
     lr_t = 8e-5 * math.sqrt(1 - 0.999 ** 3) / (1 - 0.9 ** 3)
     hyper = torch.tensor([lr_t, 0, 0, 0], dtype=torch.float32, device=cuda)
-    norm2 = torch.empty(len(sizes), device=cuda)
+    norm2 = torch.empty(len(chunks), device=cuda)      # one slot per chunk
     ok(L.mpb_opt_step(len(chunks), P(dchunks), len(sizes), P(p), P(g), P(m), P(v), P(ema), P(norm2), P(hyper), 0.5, 1.0,
                       0.9, 0.999, 1e-8, 0.9999, mlib.stream_ptr()))
     off = 0
