@@ -207,6 +207,18 @@ int mpb_opt_step_range(int nchunks, const mpb_opt_chunk* chunks, int tensor0, in
                        float grad_scale, float clip_norm, float beta1, float beta2, float eps, float ema_decay,
                        void* stream);
 
+/* ---- ground-truth target synthesis (csrc/targets.cu) ----
+ * Replaces the 2 x num_boxes instance_utils.tf_instance_xyz_crop_from_depth_map sub-graphs of MonoPSRModel.build
+ * (core/models/monopsr/monopsr_model.py:165-203; datasets/kitti/instance_utils.py:395-481,
+ * datasets/kitti/depth_map_utils.py:161-236, core/transform_utils.py:36-66) with one launch.
+ * depth [H][W] fp32, masks [nbox][H][W] bytes (0 / non-0), boxes_2d [nbox][4] = y1,x1,y2,x2 px, boxes_3d [nbox][ld3]
+ * (x,y,z,l,w,h,..), view_angs [nbox], cam_p [3][4]; outputs xyz_local / xyz_global [nbox][roi][roi][3] and
+ * valid [nbox][roi][roi] (1.0 where |depth| >= 0.1).  All DEVICE pointers. */
+int mpb_gt_xyz_from_depth(int nbox, int H, int W, int roi, const float* depth, const unsigned char* masks,
+                          const float* boxes_2d, const float* boxes_3d, int ld3, const float* view_angs,
+                          const float* cam_p, int centroid_middle, int rotate_view, float* xyz_local,
+                          float* xyz_global, float* valid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

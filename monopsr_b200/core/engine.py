@@ -431,7 +431,16 @@ class Engine:
 
     # ------------------------------------------------------------------ inputs
     def set_inputs(self, S):
-        """S: dict of numpy arrays / torch tensors (model_spec.synthetic_sample keys); host->device copy."""
+        """S: dict of numpy arrays / torch tensors (model_spec.synthetic_sample keys); host->device copy.
+        A sample may carry the RAW training inputs `depth_map` (H,W) and `instance_masks` (N,H,W) instead of the three
+        ground-truth maps: they are then synthesised on the GPU (core/targets.py; monopsr_model.py:165-203)."""
+        if "depth_map" in S and "gt_inst_xyz_maps_local" not in S:
+            from . import targets
+            S = dict(S)
+            maps = targets.gt_maps_from_depth(S.pop("depth_map"), S.pop("instance_masks"), S["boxes_2d"], S["boxes_3d"],
+                                              S["est_view_angs"], S["cam_p"], self.dev, roi=ms.CROP,
+                                              centroid_type="middle", rotate_view=True)
+            S.update(maps)
         for k, v in S.items():
             t = torch.as_tensor(np.asarray(v)) if not isinstance(v, torch.Tensor) else v
             if t.dtype == torch.float64:
