@@ -219,6 +219,15 @@ int mpb_gt_xyz_from_depth(int nbox, int H, int W, int roi, const float* depth, c
                           const float* cam_p, int centroid_middle, int rotate_view, float* xyz_local,
                           float* xyz_global, float* valid, void* stream);
 
+/* network inputs from the raw camera image: ImgPreprocessor.preprocess_input (core/img_preprocessor.py:12-35: minus
+ * channel means, legacy bilinear resize to PH x PW), the RGB instance crops (tf.image.crop_and_resize with the
+ * normalised boxes, monopsr_model.py:222-226) and the down-sized full image (resize_bilinear align_corners=True,
+ * :228-233).  img [H][W][3] uint8 (img_is_u8) or fp32, DEVICE; channel_means: 3 floats on the HOST; preprocessed
+ * [PH][PW][3] is an output too; rgb_crops [nbox][crop][crop][3] and full_img [FH][FW][3] may be NULL. */
+int mpb_image_inputs(int H, int W, const void* img, int img_is_u8, const float* channel_means, int PH, int PW,
+                     float* preprocessed, int nbox, const float* boxes_norm, int crop, float* rgb_crops, int FH, int FW,
+                     float* full_img, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,3 +87,108 @@ MPB_API int mpb_gt_xyz_from_depth(int nbox, int H, int W, int roi, const float* 
     MPB_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Network inputs from the raw camera image (second half):
+//   ImgPreprocessor.preprocess_input (core/img_preprocessor.py:12-35): float(img) - channel means, then
+//       tf.image.resize_images(bilinear, align_corners=False: TF1 legacy mapping in = out * in_size/out_size)
+//   rgb crops: tf.image.crop_and_resize(img_preprocessed, boxes_2d_norm, 0, img_roi_size)   (monopsr_model.py:222-226)
+//   full image: tf.image.resize_bilinear(img_preprocessed, resized_full_img_shape, align_corners=True)   (:228-233)
+// Three launches (the 320 x 1216 preprocessed image is materialised once: 4.7 MB, both consumers read it).
+namespace mpb {
+
+__device__ __forceinline__ float lerp2(float tl, float tr, float bl, float br, float lx, float ly) {
+    const float t = tl + (tr - tl) * lx, b = bl + (br - bl) * lx;
+    return t + (b - t) * ly;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+image_preprocess_kernel(int H, int W, int OH, int OW, const TIn* __restrict__ img, float m0, float m1, float m2,
+                        float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= OH * OW) return;
+    const int ow = i % OW, oh = i / OW;
+    const float sy = oh * ((float)H / (float)OH), sx = ow * ((float)W / (float)OW);     // legacy (no half-pixel) mapping
+    const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    const float mean[3] = {m0, m1, m2};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float tl = (float)img[((size_t)y0 * W + x0) * 3 + c] - mean[c], tr = (float)img[((size_t)y0 * W + x1) * 3 + c] - mean[c];
+        const float bl = (float)img[((size_t)y1 * W + x0) * 3 + c] - mean[c], br = (float)img[((size_t)y1 * W + x1) * 3 + c] - mean[c];
+        out[(size_t)i * 3 + c] = lerp2(tl, tr, bl, br, lx, ly);
+    }
+}
+
+// tf.image.crop_and_resize, bilinear, extrapolation value 0, one source image (box_ind = 0), C = 3
+__global__ void __launch_bounds__(256)
+image_crops_kernel(int H, int W, const float* __restrict__ img, int nbox, const float* __restrict__ boxes_norm, int crop,
+                   float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbox * crop * crop) return;
+    const int cx = i % crop, cy = (i / crop) % crop, b = i / (crop * crop);
+    const float y1 = boxes_norm[b * 4], x1 = boxes_norm[b * 4 + 1], y2 = boxes_norm[b * 4 + 2], x2 = boxes_norm[b * 4 + 3];
+    // TF's expressions, op by op and without FMA contraction: whether the last row / column of a box that ends exactly at
+    // 1.0 is inside the image (in <= size-1) depends on the last bit of this sum
+    const float hs = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(y2, y1), (float)(H - 1)), (float)(crop - 1)) : 0.f;
+    const float ws = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(x2, x1), (float)(W - 1)), (float)(crop - 1)) : 0.f;
+    const float in_y = crop > 1 ? __fadd_rn(__fmul_rn(y1, (float)(H - 1)), __fmul_rn((float)cy, hs))
+                                : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1, y2)), (float)(H - 1));
+    const float in_x = crop > 1 ? __fadd_rn(__fmul_rn(x1, (float)(W - 1)), __fmul_rn((float)cx, ws))
+                                : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1, x2)), (float)(W - 1));
+    float* o = out + (size_t)i * 3;
+    if (in_y < 0 || in_y > H - 1 || in_x < 0 || in_x > W - 1) { o[0] = o[1] = o[2] = 0.f; return; }
+    const int t = (int)floorf(in_y), bo = (int)ceilf(in_y), l = (int)floorf(in_x), r = (int)ceilf(in_x);
+    const float ly = in_y - t, lx = in_x - l;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        o[c] = lerp2(img[((size_t)t * W + l) * 3 + c], img[((size_t)t * W + r) * 3 + c], img[((size_t)bo * W + l) * 3 + c],
+                     img[((size_t)bo * W + r) * 3 + c], lx, ly);
+}
+
+// tf.image.resize_bilinear(align_corners=True), C = 3
+__global__ void __launch_bounds__(256)
+image_resize_ac_kernel(int H, int W, const float* __restrict__ img, int OH, int OW, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= OH * OW) return;
+    const int ow = i % OW, oh = i / OW;
+    const float sy = OH > 1 ? oh * ((float)(H - 1) / (float)(OH - 1)) : 0.f, sx = OW > 1 ? ow * ((float)(W - 1) / (float)(OW - 1)) : 0.f;
+    const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        out[(size_t)i * 3 + c] = lerp2(img[((size_t)y0 * W + x0) * 3 + c], img[((size_t)y0 * W + x1) * 3 + c],
+                                       img[((size_t)y1 * W + x0) * 3 + c], img[((size_t)y1 * W + x1) * 3 + c], lx, ly);
+}
+
+}  // namespace mpb
+
+MPB_API int mpb_image_inputs(int H, int W, const void* img, int img_is_u8, const float* channel_means, int PH, int PW,
+                             float* preprocessed, int nbox, const float* boxes_norm, int crop, float* rgb_crops, int FH,
+                             int FW, float* full_img, void* stream) {
+    if (H < 2 || W < 2 || PH < 1 || PW < 1 || !img || !channel_means || !preprocessed) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const float m0 = channel_means[0], m1 = channel_means[1], m2 = channel_means[2];   // HOST pointer: 3 constants
+    if (img_is_u8)
+        mpb::image_preprocess_kernel<unsigned char><<<mpb::ceil_div(PH * PW, 256), 256, 0, s>>>(
+            H, W, PH, PW, (const unsigned char*)img, m0, m1, m2, preprocessed);
+    else
+        mpb::image_preprocess_kernel<float><<<mpb::ceil_div(PH * PW, 256), 256, 0, s>>>(H, W, PH, PW, (const float*)img, m0,
+                                                                                       m1, m2, preprocessed);
+    MPB_LAUNCH_CHECK();
+    if (rgb_crops) {
+        if (nbox <= 0 || crop <= 0 || !boxes_norm) return -1;
+        mpb::image_crops_kernel<<<mpb::ceil_div(nbox * crop * crop, 256), 256, 0, s>>>(PH, PW, preprocessed, nbox, boxes_norm,
+                                                                                     crop, rgb_crops);
+        MPB_LAUNCH_CHECK();
+    }
+    if (full_img) {
+        if (FH <= 0 || FW <= 0) return -1;
+        mpb::image_resize_ac_kernel<<<mpb::ceil_div(FH * FW, 256), 256, 0, s>>>(PH, PW, preprocessed, FH, FW, full_img);
+        MPB_LAUNCH_CHECK();
+    }
+    return 0;
+}

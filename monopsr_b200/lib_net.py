@@ -93,6 +93,7 @@ _SIGS = {
     "mpb_heads_final": [ctypes.POINTER(HeadsIO), c_i, c_p],
     "mpb_heads_bwd_mid": [ctypes.POINTER(HeadsIO), c_p],
     "mpb_gt_xyz_from_depth": [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p],
+    "mpb_image_inputs": [c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p],
     "mpb_opt_step_range": [c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_f, c_p],
     "mpb_opt_step": [c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_f, c_p],
 }

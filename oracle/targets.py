@@ -104,3 +104,66 @@ def gt_maps(boxes_2d, boxes_3d, instance_masks, depth_map, viewing_angles, cam_p
                                                 viewing_angles, cam_p, False, centroid_type, rotate_view)
         loc.append(a); glo.append(g); val.append(v)
     return np.stack(loc), np.stack(glo), np.stack(val)
+
+
+# ------------------------------------------------------------------------------------------------ image inputs
+# ImgPreprocessor.preprocess_input (core/img_preprocessor.py:12-35) + the two consumers in MonoPSRModel.build
+# (monopsr_model.py:222-233).  TF image-op semantics restated (UNPINNED against TF itself; the crop_and_resize
+# restatement is the one oracle/network.py uses for the feature-map crops).
+KITTI_CHANNEL_MEANS = np.array([92.8403, 97.7996, 93.5843], F)
+
+
+def _bilinear(img, sy, sx):
+    """img (H,W,C); sy (oh,), sx (ow,) source coordinates -> (oh, ow, C); lerp order as TF: x first, then y"""
+    H, W, _ = img.shape
+    y0 = np.floor(sy).astype(np.int64); x0 = np.floor(sx).astype(np.int64)
+    y1 = np.minimum(y0 + 1, H - 1); x1 = np.minimum(x0 + 1, W - 1)
+    ly = (sy - y0).astype(F)[:, None, None]; lx = (sx - x0).astype(F)[None, :, None]
+    tl, tr = img[np.ix_(y0, x0)], img[np.ix_(y0, x1)]
+    bl, br = img[np.ix_(y1, x0)], img[np.ix_(y1, x1)]
+    t = tl + (tr - tl) * lx
+    b = bl + (br - bl) * lx
+    return (t + (b - t) * ly).astype(F)
+
+
+def preprocess_input(rgb_image, out_hw, means=KITTI_CHANNEL_MEANS):
+    """float(img) - means, then tf.image.resize_images (bilinear, align_corners=False, TF1 legacy mapping)"""
+    img = rgb_image.astype(F) - means.astype(F)
+    H, W, _ = img.shape
+    oh, ow = out_hw
+    sy = np.arange(oh, dtype=F) * (F(H) / F(oh))
+    sx = np.arange(ow, dtype=F) * (F(W) / F(ow))
+    return _bilinear(img, sy, sx)
+
+
+def crop_and_resize(img, boxes_norm, crop):
+    """tf.image.crop_and_resize (bilinear, extrapolation 0), one image (H,W,C) -> (N,crop,crop,C)"""
+    H, W, C = img.shape
+    out = np.zeros((len(boxes_norm), crop, crop, C), F)
+    for n, (y1, x1, y2, x2) in enumerate(boxes_norm.astype(F)):
+        hs, ws = (y2 - y1) * F(H - 1) / F(crop - 1), (x2 - x1) * F(W - 1) / F(crop - 1)
+        in_y = y1 * F(H - 1) + np.arange(crop, dtype=F) * hs
+        in_x = x1 * F(W - 1) + np.arange(crop, dtype=F) * ws
+        vy, vx = (in_y >= 0) & (in_y <= H - 1), (in_x >= 0) & (in_x <= W - 1)
+        t = np.clip(np.floor(in_y), 0, H - 1).astype(np.int64); b = np.clip(np.ceil(in_y), 0, H - 1).astype(np.int64)
+        l = np.clip(np.floor(in_x), 0, W - 1).astype(np.int64); r = np.clip(np.ceil(in_x), 0, W - 1).astype(np.int64)
+        ly = (in_y - np.floor(in_y)).astype(F)[:, None, None]; lx = (in_x - np.floor(in_x)).astype(F)[None, :, None]
+        tt = img[np.ix_(t, l)] + (img[np.ix_(t, r)] - img[np.ix_(t, l)]) * lx
+        bb = img[np.ix_(b, l)] + (img[np.ix_(b, r)] - img[np.ix_(b, l)]) * lx
+        o = tt + (bb - tt) * ly
+        out[n] = np.where((vy[:, None] & vx[None, :])[..., None], o, 0).astype(F)
+    return out
+
+
+def resize_bilinear_ac(img, out_hw):
+    """tf.image.resize_bilinear(align_corners=True), (H,W,C) -> (oh,ow,C)"""
+    H, W, _ = img.shape
+    oh, ow = out_hw
+    sy = np.arange(oh, dtype=F) * (F(H - 1) / F(oh - 1))
+    sx = np.arange(ow, dtype=F) * (F(W - 1) / F(ow - 1))
+    return _bilinear(img.astype(F), sy, sx)
+
+
+def image_inputs(rgb_image, boxes_norm, image_input_shape=(320, 1216), roi=48, full_shape=(160, 608)):
+    pre = preprocess_input(rgb_image, image_input_shape)
+    return crop_and_resize(pre, boxes_norm, roi), resize_bilinear_ac(pre, full_shape)[None], pre

@@ -90,3 +90,32 @@ def test_engine_accepts_raw_depth_inputs(cuda):
     eng.backward()
     torch.cuda.synchronize()
     assert np.isfinite(eng.losses()["total_loss"])
+
+
+@pytest.mark.parametrize("as_u8", [True, False])
+def test_image_inputs_match_oracle(cuda, as_u8):
+    rng = np.random.RandomState(11)
+    H, W, n = 375, 1242, 32
+    img = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    src = img if as_u8 else img.astype(np.float32) + rng.rand(H, W, 3).astype(np.float32)
+    boxes = np.stack([rng.uniform(0, 0.5, n), rng.uniform(0, 0.7, n), rng.uniform(0.55, 1.0, n), rng.uniform(0.75, 1.0, n)],
+                     1).astype(np.float32)
+    boxes[0] = [0, 0, 1, 1]
+    boxes[1] = [-0.05, 0.2, 0.5, 1.1]                      # partly outside the image: extrapolation value 0
+    out = mt.image_inputs(src, boxes, "cuda:0")
+    torch.cuda.synchronize()
+    ecrops, efull, epre = T.image_inputs(src, boxes)
+    # fp32 lerps of 0..255 pixel values; the kernel contracts a + (b - a) * l into FMAs, numpy does not: a few ulps of
+    # 255 per stage, two stages
+    np.testing.assert_allclose(out["img_preprocessed"].cpu().numpy(), epre, rtol=1e-5, atol=5e-4)
+    np.testing.assert_allclose(out["rgb_crops"].cpu().numpy(), ecrops, rtol=1e-5, atol=2e-3)
+    np.testing.assert_allclose(out["full_img"].cpu().numpy(), efull, rtol=1e-5, atol=2e-3)
+    assert out["rgb_crops"].shape == (n, 48, 48, 3) and out["full_img"].shape == (1, 160, 608, 3)
+    assert (out["rgb_crops"][1, 0] == 0).all()
+
+
+def test_image_inputs_reject_bad_arguments(cuda):
+    with pytest.raises(ValueError):
+        mt.image_inputs(np.zeros((10, 10, 4), np.uint8), np.zeros((1, 4), np.float32), "cuda:0")
+    with pytest.raises(ValueError):
+        mt.image_inputs(np.zeros((10, 10, 3), np.uint8), np.zeros((1, 4), np.float32), "cuda:0", mean_sub_type="none")

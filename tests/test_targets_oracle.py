@@ -77,3 +77,31 @@ def test_gt_maps_structure():
     dy = (loc - loc_b)[..., 1]
     for b in range(5):
         np.testing.assert_allclose(dy[b][~inv[b]], b3[b, 5] / 2, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ image inputs
+def test_image_oracle_against_independent_implementations():
+    """align-corners resize against torch's interpolate, crop_and_resize against the torch restatement used for the
+    feature-map crops (oracle/network.py), legacy resize against hand-computed values"""
+    import torch
+    import torch.nn.functional as TF
+    from oracle import network as onet
+    rng = np.random.RandomState(1)
+    img = rng.uniform(-100, 150, (37, 53, 3)).astype(np.float32)
+    ac = T.resize_bilinear_ac(img, (20, 31))
+    ref = TF.interpolate(torch.from_numpy(img).permute(2, 0, 1)[None].double(), size=(20, 31), mode="bilinear",
+                         align_corners=True)[0].permute(1, 2, 0).numpy()
+    np.testing.assert_allclose(ac, ref, rtol=1e-5, atol=1e-3)      # fp32 lerps of +-150 values vs an fp64 reference
+    # (a box ending exactly at 1.0 is avoided here: whether its last row is "inside" depends on the last fp32 bit of
+    # y1*(H-1) + i*scale, which the fp32 oracle reproduces as TF computes it and an fp64 reference does not)
+    boxes = np.array([[0.1, 0.2, 0.6, 0.9], [0.0, 0.0, 0.98, 0.97], [-0.1, 0.5, 0.4, 1.23]], np.float32)   # last one leaves the image
+    cr = T.crop_and_resize(img, boxes, 8)
+    ref = onet.crop_and_resize(torch.from_numpy(img)[None].double(), torch.from_numpy(boxes).double(), 8, 8).numpy()
+    np.testing.assert_allclose(cr, ref, rtol=1e-5, atol=1e-3)
+    assert (cr[2][0] == 0).all()                                   # rows above the image: extrapolation value 0
+    # legacy (align_corners=False, no half-pixel) bilinear: 4 -> 2 samples source pixels 0 and 2 exactly
+    u8 = np.arange(4 * 4 * 3, dtype=np.uint8).reshape(4, 4, 3)
+    pre = T.preprocess_input(u8, (2, 2), means=np.zeros(3, np.float32))
+    assert np.array_equal(pre, u8[::2, ::2].astype(np.float32))
+    same = T.preprocess_input(u8, (4, 4))
+    np.testing.assert_allclose(same, u8.astype(np.float32) - T.KITTI_CHANNEL_MEANS, rtol=0, atol=1e-5)
