@@ -193,6 +193,24 @@ def tfops_micro(dev):
                                                     mlib.stream_ptr()))
     out["matchcostgrad_us"] = t(lambda: L.mpb_matchcostgrad(b, n, n, x.data_ptr(), y.data_ptr(), mt.data_ptr(),
                                                             g1.data_ptr(), g2.data_ptr(), mlib.stream_ptr()))
+    # SURVEY 8f rank 2 (the step before the path): targets from a 375 x 1242 depth map + 32 masks, inputs from the image
+    from monopsr_b200.core import model_spec as ms, targets as mtg
+    import time
+    S = ms.synthetic_sample(0)
+    rng = np.random.RandomState(0)
+    H, W = 375, 1242
+    depth = torch.from_numpy(rng.uniform(3, 60, (H, W)).astype(np.float32)).to(dev)
+    masks_h = rng.rand(ms.NUM_BOXES, H, W) < 0.6
+    masks = torch.from_numpy(masks_h).to(dev)
+    args = [torch.from_numpy(S[k]).to(dev) for k in ("boxes_2d", "boxes_3d", "est_view_angs", "cam_p")]
+    out["gt_targets_us"] = t(lambda: mtg.gt_maps_from_depth(depth, masks, *args, dev))
+    img = torch.from_numpy(rng.randint(0, 256, (H, W, 3)).astype(np.uint8)).to(dev)
+    bn = torch.from_numpy(S["boxes_2d_norm"]).to(dev)
+    out["image_inputs_us"] = t(lambda: mtg.image_inputs(img, bn, dev))
+    from oracle import targets as otg          # the CPU restatement, timed once beside it (a reported baseline)
+    t0 = time.perf_counter()
+    otg.gt_maps(S["boxes_2d"], S["boxes_3d"], masks_h, depth.cpu().numpy(), S["est_view_angs"], S["cam_p"])
+    out["gt_targets_cpu_oracle_us"] = (time.perf_counter() - t0) * 1e6
     return out
 
 
