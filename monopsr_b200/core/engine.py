@@ -68,6 +68,7 @@ class Engine:
         # step is 2.5 % faster WITHOUT it once launches are chained with programmatic dependent launch (cluster
         # launches do not overlap their predecessor's tail): off by default, MPB_CSK=1 enables
         self.csk = int(os.environ.get("MPB_CSK", "0"))
+        self.csk_fwd = int(os.environ.get("MPB_CSK_FWD", str(self.csk)))   # the forward pass alone (only 2 streams there)
         self.csk_bn = int(os.environ.get("MPB_CSK_BN", "128"))            # widest tile that may be split over a cluster
         self.ctas_per_sm = {64: 2, 128: int(os.environ.get("MPB_CTAS128", "2")), 256: 1}   # see tc_gemm.cuh
 
@@ -298,14 +299,14 @@ class Engine:
             for st_ in streams:
                 self._cur().wait_stream(st_)
 
-    def _plan_tiles(self, mtiles, ncols, nkb):
+    def _plan_tiles(self, mtiles, ncols, nkb, csk=None):
         """(tile width, split-K) of a FWD / DGRAD launch; rules read off tools/gemm_sweep.py on B200
         (profiles/r1_notes.md).  Wide tiles halve the operand traffic per FLOP and make the main loop MMA-bound,
         but a 128 x 256 tile grid of these layers covers only 36-48 SMs: long reductions are therefore split in
         two over a 2-CTA cluster (a TPC) that reduces through DSMEM; clusters of 3-4 fragment the GPCs."""
         tiles = {bn: mtiles * (ncols // bn) for bn in (256, 128, 64) if ncols % bn == 0}
         lo = int(self.fill * 100)                     # CTAs below which a launch is considered too small
-        if self.csk and nkb >= 16:
+        if (self.csk if csk is None else csk) and nkb >= 16:
             for bn in (256, 128):
                 if bn in tiles and bn <= self.csk_bn and lo <= 2 * tiles[bn] <= self.sms * self.ctas_per_sm[bn]:
                     return bn, 2
@@ -338,7 +339,8 @@ class Engine:
             if op == TC_WGRAD:
                 bn = 128 if Cin % 128 == 0 else 64
             else:
-                bn, ks = self._plan_tiles(mt, Cout if op == TC_FWD else Cin, kdepth // 32)
+                bn, ks = self._plan_tiles(mt, Cout if op == TC_FWD else Cin, kdepth // 32,
+                                          csk=self.csk_fwd if op == TC_FWD else self.csk)
                 if ksplit == 1 and not atomic and M % (H * W) == 0:
                     p.ksplit = ks
         if getattr(self, "_record", None) is not None:
