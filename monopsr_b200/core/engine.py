@@ -52,14 +52,21 @@ class Engine:
         # side streams: the two towers are independent until the concat, and weight gradients are
         # off the critical path of the data-gradient chain -> they run concurrently (also inside
         # the captured CUDA graph, where the fork/join become graph edges)
-        self.s_full = torch.cuda.Stream(device=self.dev)
+        # Priorities (recorded per kernel node at capture): the block scheduler dispatches queued grids in
+        # submission order, so a short kernel of a latency-critical chain can wait tens of microseconds behind the
+        # CTAs of a bulk launch from another stream.  The dependent chains (main, full-image tower, FC stacks) run
+        # at high priority; weight gradients, zero-fills and the side train-op are filler at default priority.
+        # Measured: 9.09 vs 8.55 ms/step -- the starved weight-gradient streams finish late -- so OFF by default.
+        hi = -1 if int(os.environ.get("MPB_STREAM_PRIO", "0")) else 0
+        self.s_main = torch.cuda.Stream(device=self.dev, priority=hi)     # capture stream of the step
+        self.s_full = torch.cuda.Stream(device=self.dev, priority=hi)
+        self.s_fc = torch.cuda.Stream(device=self.dev, priority=hi)
         self.s_wc = torch.cuda.Stream(device=self.dev)
         self.s_wf = torch.cuda.Stream(device=self.dev)
         self.s_opt = torch.cuda.Stream(device=self.dev)
         self.early_opt = False      # set by the single-GPU train step: head train-op under the towers' backward
         self._grads_zeroed = False
         self.overlap = True
-        import os
         self.fill = float(os.environ.get("MPB_TILE_FILL", "0.9"))   # min fraction of SMs a launch must fill before widening tiles
         self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
         self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "128"))
@@ -544,7 +551,7 @@ class Engine:
         self.gemm(TC_FWD, Mc, 12, 12, 1, 1, 2048, 512, self.concat, 2048, self.pview("squash/1x1_conv/weights"), 2048,
                   self.squashed, 512, shift=self.view("squash/1x1_conv/biases"), relu=1, round_tf32=1)
         self._chk(L.mpb_maxpool2_fwd(N, 12, 12, 512, _ptr(self.squashed), 512, _ptr(self.pooled), 512, st), "pool")
-        with self._side(self.s_wc):
+        with self._side(self.s_fc):
             self._fc_forward()
         self._chk(L.mpb_resize_ac_fwd(N, 12, 12, 512, _ptr(self.squashed), 24, 24, _ptr(self.r1), st), "resize1")
         x = self.r1
@@ -566,7 +573,7 @@ class Engine:
         sx = "output/inst_xyz_map_local/inst_xyz_map_local"
         self._chk(L.mpb_xyzhead_fwd(N, 48, 48, _ptr(x), _ptr(self.view(sx + "/weights")), _ptr(self.view(sx + "/biases")),
                                     _ptr(self.xyz), st), "xyzhead_fwd")
-        self._join(self.s_wc)            # the FC stacks ran beside the decoder
+        self._join(self.s_fc)            # the FC stacks ran beside the decoder
         io = self.heads_io()
         self._chk(L.mpb_heads_final(ctypes.byref(io), 1 if train else 0, st), "heads_final")
 
@@ -716,8 +723,8 @@ class Engine:
         """head part (FC stacks, decoder, squash: every gradient outside the towers), then the two towers"""
         self._backward_head()
         if self.early_opt:
-            # every gradient outside the towers is final (FC stacks on s_wc, decoder wgrads on s_wf, the rest here)
-            for s_ in (self._cur(), self.s_wf, self.s_wc):
+            # every gradient outside the towers is final (FC stacks on s_fc, decoder wgrads on s_wf, the rest here)
+            for s_ in (self._cur(), self.s_wf, self.s_fc):
                 self.s_opt.wait_stream(s_)
             with torch.cuda.stream(self.s_opt):
                 self.optimizer_step(1.0, part="head")
@@ -733,7 +740,7 @@ class Engine:
         self._grads_zeroed = False
         io = self.heads_io()
         P, R = self.fc["proposal"], self.fc["regression"]
-        with self._side(self.s_wc):
+        with self._side(self.s_fc):
             self._fc_backward()
         # ---- map decoder
         sx = "output/inst_xyz_map_local/inst_xyz_map_local"
@@ -764,7 +771,7 @@ class Engine:
             if i == 2:
                 self._chk(L.mpb_resize_ac_bwd(N, 24, 24, 256, _ptr(self.d_r2), 48, 48, _ptr(self.dec[1]["dy"]), st), "resize2_bwd")
         self._chk(L.mpb_resize_ac_bwd(N, 12, 12, 512, _ptr(self.d_r1), 24, 24, _ptr(self.d_squashed), st), "resize1_bwd")
-        self._join(self.s_wc)            # d(pooled) from the FC stacks
+        self._join(self.s_fc)            # d(pooled) from the FC stacks
         self._chk(L.mpb_maxpool2_bwd(N, 12, 12, 512, _ptr(self.squashed), 512, _ptr(self.d_flat), 512, _ptr(self.d_squashed),
                                      512, 1, st), "pool_bwd")
         # ---- squash
@@ -780,7 +787,7 @@ class Engine:
         self.gemm(TC_DGRAD, Mc, 12, 12, 1, 1, 1024, 512, self.g_squashed, 512, wsq.view(-1)[1024:], 2048,
                   self.g_fullcrop, 1024)
         if join:        # the gradients of the head variables are complete on THIS stream (bucketed all-reduce)
-            self._join(self.s_wf, self.s_wc)
+            self._join(self.s_wf, self.s_fc)
 
     def _backward_towers(self):
         L, st, N, I = self.L, self._st(), self.N, self.inputs
@@ -877,7 +884,7 @@ class Engine:
         # measured: stepping the head variables under the towers' backward pass is ~1.5 % SLOWER than one train-op
         # at the end (the HBM-bound Adam pass slows the concurrent GEMMs more than the overlap saves): off
         early = int(os.environ.get("MPB_EARLY_OPT", "0")) != 0
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=self.s_main):
             self.forward(train=True)
             self.early_opt = early
             self.backward()
@@ -901,12 +908,12 @@ class Engine:
         # gradients (arena tail, 45 %) UNDER [towers' backward] -> all-reduce of the tower gradients -> [train-op]
         g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         c0 = _lib.launch_count()
-        with torch.cuda.graph(g1):
+        with torch.cuda.graph(g1, stream=self.s_main):
             self.forward(train=True)
             self._backward_head(join=True)
-        with torch.cuda.graph(g2):
+        with torch.cuda.graph(g2, stream=self.s_main):
             self._backward_towers()
-        with torch.cuda.graph(g3):
+        with torch.cuda.graph(g3, stream=self.s_main):
             self.optimizer_step(1.0 / dist.get_world_size())
             self.prepare_weights()
         self.launches_per_step = _lib.launch_count() - c0
