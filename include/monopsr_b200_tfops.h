@@ -70,6 +70,10 @@ int mpb_matchcostgrad(int b, int n, int m, const float* xyz1, const float* xyz2,
  * used by bench.py to report "gpu_launches". */
 unsigned long long mpb_launch_count(void);
 
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the per-tensor checksum of TensorFlow
+ * checkpoints (monopsr_b200/core/tf_checkpoint.py). */
+unsigned mpb_crc32c(const void* data, unsigned long long n, unsigned crc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,6 +194,31 @@ class Engine:
     def export_grads(self):
         return self.export_params(self.grads)
 
+    def load_checkpoint(self, prefix, kind="monopsr", use_ema=False):
+        """Restore variables from a TensorFlow checkpoint `prefix` (core/tf_checkpoint.py): kind 'monopsr' = a MonoPSR
+        training checkpoint (use_ema: the MovingAverageOptimizer shadows, as evaluation does), 'detection' = the
+        pre-trained object-detection-API ResNet-101 for both encoders (core/checkpoint_utils.py:64-117).  Variables
+        absent from the checkpoint (or of another shape) keep their current values; returns the mapping report."""
+        from . import tf_checkpoint
+        table = [(n, s, k) for n, (s, k) in self.ptable.items()]
+        loaded, report = tf_checkpoint.load_checkpoint(prefix, table, kind=kind, use_ema=use_ema)
+        P = self.export_params()
+        P.update(loaded)
+        self.load_params(P)
+        return report
+
+    def save_checkpoint(self, prefix, global_step=None):
+        """Write the variables (TF names and layouts) and their EMA shadows as a TensorFlow tensor bundle."""
+        from . import tf_checkpoint
+        T = self.export_params()
+        trainable = set(self.trainable_names)
+        for n, v in self.export_params(self.ema).items():
+            if n in trainable:
+                T[n + tf_checkpoint.EMA_SUFFIX] = v
+        if global_step is not None:
+            T["global_step"] = np.array(int(global_step), np.int64)
+        tf_checkpoint.write_bundle(prefix, T, with_data_crc=True)
+
     # ------------------------------------------------------------------ activations
     def _alloc_activations(self):
         N = self.N

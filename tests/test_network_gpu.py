@@ -100,3 +100,4 @@ def test_graph_replay_equals_eager_and_trains(cuda):
         losses.append(e2.losses()["total_loss"])
     assert all(np.isfinite(losses))
     assert e2.launches_per_step > 500
+

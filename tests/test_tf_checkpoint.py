@@ -1,0 +1,136 @@
+"""TensorFlow tensor-bundle reader / writer without TensorFlow (monopsr_b200/core/tf_checkpoint.py) and the variable
+mapping of the reference's two restore paths.  No TF-written checkpoint exists in the reference checkout, so the format
+is checked by round trips through the writer, known CRC-32C / varint / snappy vectors and hand-assembled bytes."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from monopsr_b200.core import model_spec as ms
+from monopsr_b200.core import tf_checkpoint as C
+
+
+def test_primitives_known_answers():
+    assert C.crc32c(b"123456789") == 0xE3069283                     # the standard CRC-32C check value
+    assert C.crc32c(b"") == 0 and C.crc32c(b"\x00" * 32) == 0x8A9136AA          # RFC 3720 B.4 test vector
+    assert C.unmask_crc(C.mask_crc(0xDEADBEEF)) == 0xDEADBEEF
+    assert C._put_varint(300) == b"\xac\x02" and C._varint(b"\xac\x02", 0) == (300, 2)
+    # snappy: literal "abcd" + copy(offset 4, length 8) -> "abcdabcdabcd"
+    assert C.snappy_decompress(bytes([12, (4 - 1) << 2]) + b"abcd" + bytes([((8 - 4) << 2) | 1, 4])) == b"abcdabcdabcd"
+    with pytest.raises(ValueError):
+        C.snappy_decompress(bytes([4, 1 | (0 << 2), 9]))            # copy before any output
+
+
+def _tensors(seed=0, n_small=150):
+    rng = np.random.RandomState(seed)
+    T = {"a/weights": rng.randn(3, 3, 4, 8).astype(np.float32), "a/BatchNorm/gamma": rng.randn(8).astype(np.float32),
+         "global_step": np.array(123, np.int64), "dbl": rng.randn(5, 7), "flags": rng.rand(9) < 0.5,
+         "half": rng.randn(6).astype(np.float16), "empty": np.zeros((0, 3), np.float32)}
+    for i in range(n_small):                                         # several index blocks
+        T["layer_%03d/biases" % i] = rng.randn(i % 7 + 1).astype(np.float32)
+    return T
+
+
+def test_roundtrip_and_checksums(tmp_path):
+    T = _tensors()
+    prefix = str(tmp_path / "model.ckpt-5")
+    C.write_bundle(prefix, T, block_entries=16)
+    R = C.read_bundle(prefix, verify_data=True)
+    assert set(R) == set(T)
+    for k in T:
+        assert R[k].dtype == T[k].dtype and R[k].shape == T[k].shape and np.array_equal(R[k], T[k]), k
+    sub = C.read_bundle(prefix, names={"a/weights", "global_step"})
+    assert set(sub) == {"a/weights", "global_step"} and int(sub["global_step"]) == 123
+    # footer: magic in the last 8 bytes; a flipped byte in an index block or in the data file is detected
+    raw = bytearray(open(prefix + ".index", "rb").read())
+    assert struct.unpack("<Q", raw[-8:])[0] == C.MAGIC
+    raw[10] ^= 0xFF
+    open(prefix + ".index", "wb").write(bytes(raw))
+    with pytest.raises(ValueError):
+        C.read_bundle(prefix)
+    C.write_bundle(prefix, T)
+    data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    data[5] ^= 0x01
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    with pytest.raises(ValueError):
+        C.read_bundle(prefix, verify_data=True)
+    with pytest.raises(ValueError):
+        open(prefix + ".index", "wb").write(b"not a table" * 10)
+        C.read_bundle(prefix)
+
+
+def test_reads_prefix_compressed_and_snappy_blocks(tmp_path):
+    """a block as LevelDB's BlockBuilder writes it (shared key prefixes between restart points), once uncompressed
+    and once as a snappy literal, assembled by hand"""
+    a = np.arange(6, dtype=np.float32).reshape(2, 3)
+    b = np.arange(4, dtype=np.float32)
+    raw = a.tobytes() + b.tobytes()
+    e1 = C._entry_proto(a, 0, C.crc32c(a.tobytes()))
+    e2 = C._entry_proto(b, a.nbytes, C.crc32c(b.tobytes()))
+    header = b"\x08\x01\x10\x00"
+    k1, k2 = b"scope/conv/biases", b"scope/conv/weights"
+    shared = len(os.path.commonprefix([k1, k2]))
+    body = (b"\x00\x00" + C._put_varint(len(header)) + header +
+            b"\x00" + C._put_varint(len(k1)) + C._put_varint(len(e2)) + k1 + e2 +
+            C._put_varint(shared) + C._put_varint(len(k2) - shared) + C._put_varint(len(e1)) + k2[shared:] + e1 +
+            struct.pack("<II", 0, 1))
+    for compressed in (False, True):
+        if compressed:                     # one snappy literal holding the whole block
+            n = len(body) - 1
+            stored = C._put_varint(len(body)) + bytes([61 << 2]) + struct.pack("<H", n) + body
+            ctype = b"\x01"
+        else:
+            stored, ctype = body, b"\x00"
+        blk = stored + ctype + struct.pack("<I", C.mask_crc(C.crc32c(ctype, C.crc32c(stored))))
+        meta_body, meta_tr = C._block([])
+        idx_body, idx_tr = C._block([(k2, C._put_varint(0) + C._put_varint(len(stored)))], restart_interval=1)
+        out = blk + meta_body + meta_tr
+        mh = C._put_varint(len(blk)) + C._put_varint(len(meta_body))
+        ih = C._put_varint(len(out)) + C._put_varint(len(idx_body))
+        out += idx_body + idx_tr
+        out += mh + ih + b"\x00" * (40 - len(mh) - len(ih)) + struct.pack("<Q", C.MAGIC)
+        prefix = str(tmp_path / ("hand%d" % compressed))
+        open(prefix + ".index", "wb").write(out)
+        open(prefix + ".data-00000-of-00001", "wb").write(raw)
+        R = C.read_bundle(prefix, verify_data=True)
+        assert np.array_equal(R["scope/conv/weights"], a) and np.array_equal(R["scope/conv/biases"], b)
+
+
+def test_monopsr_checkpoint_mapping(tmp_path):
+    table = ms.param_table()[:40] + [t for t in ms.param_table() if t[0].startswith("squash")]
+    rng = np.random.RandomState(1)
+    ck = {n: rng.randn(*s).astype(np.float32) for n, s, _ in table}
+    ck.update({n + C.EMA_SUFFIX: v * 0.5 for n, v in list(ck.items())[:10]})
+    ck["global_step"] = np.array(7, np.int64)
+    wrong = table[3][0]
+    ck[wrong] = np.zeros((1, 2, 3), np.float32)                      # same name, different shape: skipped
+    del ck[table[5][0]]                                              # absent: reported missing
+    prefix = str(tmp_path / "model.ckpt-7")
+    C.write_bundle(prefix, ck)
+    params, rep = C.load_checkpoint(prefix, table, kind="monopsr")
+    assert wrong in rep["shape_mismatch"] and table[5][0] in rep["missing"]
+    assert set(rep["loaded"]) == set(params) and len(params) == len(table) - 2
+    assert np.array_equal(params[table[0][0]], ck[table[0][0]])
+    ema, _ = C.load_checkpoint(prefix, table, kind="monopsr", use_ema=True)
+    assert np.array_equal(ema[table[0][0]], ck[table[0][0] + C.EMA_SUFFIX])          # shadow wins where present
+    assert np.array_equal(ema[table[20][0]], ck[table[20][0]])
+    with pytest.raises(ValueError):
+        C.load_checkpoint(prefix, table, kind="bogus")
+
+
+def test_detection_checkpoint_feeds_both_encoders(tmp_path):
+    """'FirstStageFeatureExtractor/x' -> '..._crop/x' and '..._full/x' (core/checkpoint_utils.py:64-117)"""
+    table = ms.param_table()
+    crop = [t for t in table if t[0].startswith(ms.ENCODERS[0] + "/")][:12]
+    full = [t for t in table if t[0].startswith(ms.ENCODERS[1] + "/")][:12]
+    rng = np.random.RandomState(2)
+    ck = {"FirstStageFeatureExtractor/" + n[len(ms.ENCODERS[0]) + 1:]: rng.randn(*s).astype(np.float32) for n, s, _ in crop}
+    ck["SecondStageBoxPredictor/weights"] = np.zeros((4, 4), np.float32)
+    prefix = str(tmp_path / "model.ckpt")
+    C.write_bundle(prefix, ck)
+    params, rep = C.load_checkpoint(prefix, crop + full, kind="detection")
+    assert len(params) == 24 and not rep["missing"] and not rep["shape_mismatch"]
+    for (nc, _, _), (nf, _, _) in zip(crop, full):
+        assert np.array_equal(params[nc], params[nf])
+        assert np.array_equal(params[nc], ck["FirstStageFeatureExtractor/" + nc[len(ms.ENCODERS[0]) + 1:]])
