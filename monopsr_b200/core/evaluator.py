@@ -1,0 +1,54 @@
+"""Inference / evaluation driver -- host-side mirror of the per-checkpoint loop of src/monopsr/core/evaluator.py
+(run_checkpoint_once, :136-385) for the B200 engine: restore a checkpoint (EMA shadows, as the reference's
+MovingAverageOptimizer swapping saver does), run every sample forward, format and save the predictions
+(monopsr_model.py:960-1102 via core/predictions.py) and, in 'val' mode, collect the losses.  The KITTI native AP
+evaluator the reference shells out to afterwards (evaluator_utils.py) is not part of this."""
+import os
+import time
+
+import numpy as np
+
+from . import predictions as P
+
+
+class Evaluator(object):
+    def __init__(self, engine, output_types, output_dirs, train_val_test="val", centroid_type="middle",
+                 post_process_cen_x=True, num_alpha_bins=12, log=print):
+        if train_val_test not in ("val", "test"):
+            raise ValueError("Invalid run mode", train_val_test)
+        self.engine, self.output_types, self.output_dirs = engine, list(output_types), dict(output_dirs)
+        self.mode, self.centroid_type, self.post_process_cen_x = train_val_test, centroid_type, post_process_cen_x
+        self.num_alpha_bins, self.log = num_alpha_bins, log
+        for d in self.output_dirs.values():
+            os.makedirs(d, exist_ok=True)
+
+    def predict(self, sample, sample_dict):
+        """one sample: engine inputs `sample` (Engine.set_inputs keys) + the reference's sample_dict (constants.SAMPLE_*)
+        -> formatted prediction dict"""
+        eng = self.engine
+        eng.set_inputs(sample)
+        eng.forward(train=False)
+        out = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v))
+               for k, v in eng.outputs().items() if v is not None}
+        if P.KEY_VALID_MASK_MAPS not in out:          # test mode: tf.ones mask (monopsr_model.py:218)
+            out[P.KEY_VALID_MASK_MAPS] = np.ones(out[P.KEY_INST_XYZ_MAP_LOCAL].shape[:3] + (1,), np.float32)
+        out[P.SAMPLE_LABEL_CLASS_INDICES] = np.asarray(sample["class_indices"])
+        return P.format_predictions(out, sample_dict, output_types=self.output_types, train_val_test=self.mode,
+                                    num_boxes=out[P.KEY_VALID_MASK_MAPS].shape[0], num_alpha_bins=self.num_alpha_bins,
+                                    centroid_type=self.centroid_type, post_process_cen_x=self.post_process_cen_x)
+
+    def run_checkpoint_once(self, checkpoint_prefix, samples, use_ema=True):
+        """samples: iterable of (sample, sample_dict).  Returns {'num_samples', 'mean_losses' (val), 'seconds'}"""
+        if checkpoint_prefix is not None:
+            self.engine.load_checkpoint(checkpoint_prefix, use_ema=use_ema)
+        t0, n, sums = time.time(), 0, {}
+        for sample, sample_dict in samples:
+            pred = self.predict(sample, sample_dict)
+            P.save_predictions(sample_dict[P.SAMPLE_NAME], pred, self.output_dirs, self.output_types)
+            if self.mode == "val":
+                for k, v in self.engine.losses().items():
+                    sums[k] = sums.get(k, 0.0) + float(v)
+            n += 1
+            self.log("Step {}: {} / {}, Inference on sample {}".format(
+                os.path.basename(str(checkpoint_prefix)), n, "?", sample_dict[P.SAMPLE_NAME]))
+        return {"num_samples": n, "mean_losses": {k: v / max(n, 1) for k, v in sums.items()}, "seconds": time.time() - t0}

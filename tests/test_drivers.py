@@ -1,0 +1,105 @@
+"""Training / evaluation drivers (core/trainer.py, core/evaluator.py) with a stub engine: control flow, checkpoint
+naming / resume / pruning and the prediction files -- the reference's trainer.py:122-209 and evaluator loop."""
+import os
+
+import numpy as np
+import pytest
+
+from monopsr_b200.core import evaluator as E
+from monopsr_b200.core import predictions as P
+from monopsr_b200.core import trainer as T
+from monopsr_b200.core.config_utils import config_dict_to_object
+
+
+class StubEngine(object):
+    """records calls; save_checkpoint writes an empty '<prefix>.index' like a tensor bundle would"""
+
+    def __init__(self):
+        self.calls, self.step_count, self.loaded = [], 0, []
+        self.N = 32
+
+    def train_step(self, sample):
+        self.calls.append(("train", self.step_count))
+        self.step_count += 1
+
+    def losses(self):
+        return {"total_loss": 10.0 / (1 + self.step_count), "lwh_offs": 1.0}
+
+    def save_checkpoint(self, prefix, global_step=None):
+        for ext in (".index", ".data-00000-of-00001"):
+            open(prefix + ext, "wb").close()
+        self.calls.append(("save", global_step))
+
+    def load_checkpoint(self, prefix, kind="monopsr", use_ema=False):
+        self.loaded.append((os.path.basename(prefix), kind, use_ema))
+        return {"loaded": [], "missing": []}
+
+    # inference side
+    def set_inputs(self, sample):
+        self.sample = sample
+
+    def forward(self, train=True):
+        self.calls.append(("forward", train))
+
+    def outputs(self):
+        rng = np.random.RandomState(0)
+        n = self.N
+        b3 = self.sample["boxes_3d"]
+        return {"inst_xyz_map_local": rng.randn(n, 48, 48, 3).astype(np.float32), "valid_mask_maps": None,
+                "lwh": b3[:, 3:6], "alpha_bins": rng.randn(n, 12).astype(np.float32),
+                "alpha_regs": rng.randn(n, 12).astype(np.float32) * 0.1, "view_ang": self.sample["est_view_angs"][:, None],
+                "centroids": b3[:, :3].copy()}
+
+
+def _config(tmp_path, overwrite=False, max_it=25):
+    return config_dict_to_object({
+        "config_name": "stub_cfg", "model_config": {"model_type": "monopsr_model"},
+        "train_config": {"max_iterations": max_it, "summary_interval": 10, "checkpoint_interval": 10,
+                         "max_checkpoints_to_keep": 2, "overwrite_checkpoints": overwrite,
+                         "paths_config": {"checkpoint_dir": str(tmp_path / "ckpt"), "logdir": str(tmp_path / "log")}}})
+
+
+def test_train_loop_checkpoints_and_resume(tmp_path):
+    eng, lines = StubEngine(), []
+    cfg = _config(tmp_path)
+    loss = T.train(eng, cfg, lambda: {"x": 1}, log=lambda *a: lines.append(" ".join(map(str, a))))
+    trains = [c for c in eng.calls if c[0] == "train"]
+    assert len(trains) == 26 and [c[1] for c in eng.calls if c[0] == "save"] == [0, 10, 20]      # steps 0..25 inclusive
+    assert eng.calls.index(("save", 10)) < eng.calls.index(("train", 10))                        # saved BEFORE the step
+    ck = sorted(f for f in os.listdir(tmp_path / "ckpt") if f.endswith(".index"))
+    assert ck == ["monopsr_model-00000010.index", "monopsr_model-00000020.index"]                # max_to_keep = 2
+    assert any("Step 20: Total Loss" in l for l in lines) and any("Starting from step 0 / 25" in l for l in lines)
+    assert loss == pytest.approx(10.0 / 22)
+    # resume: newest checkpoint, step from its name
+    eng2 = StubEngine()
+    T.train(eng2, _config(tmp_path, max_it=30), lambda: {}, log=lambda *a: None)
+    assert eng2.loaded == [("monopsr_model-00000020", "monopsr", False)]
+    assert [c[1] for c in eng2.calls if c[0] == "train"] == list(range(20, 31))
+    # overwrite_checkpoints: start from scratch, pre-trained detection weights if given
+    eng3 = StubEngine()
+    T.train(eng3, _config(tmp_path, overwrite=True, max_it=3), lambda: {}, pretrained_checkpoint="/x/model.ckpt",
+            log=lambda *a: None)
+    assert eng3.loaded == [("model.ckpt", "detection", False)] and eng3.calls[0] == ("save", 0)
+    assert T.latest_checkpoint(str(tmp_path / "nope"), "m") == (None, 0)
+
+
+def test_evaluator_writes_predictions(tmp_path):
+    from monopsr_b200.core import model_spec as ms
+    S = ms.synthetic_sample(0)
+    eng = StubEngine()
+    types = [P.KEY_INST_XYZ_MAP_LOCAL, P.KEY_VALID_MASK_MAPS, P.KEY_CENTROIDS, P.KEY_LWH, P.KEY_VIEW_ANG, P.KEY_ALPHA]
+    dirs = {P.OUT_DIR_XYZ_MAP_LOCAL: str(tmp_path / "xyz"), P.OUT_DIR_BOX_2D: str(tmp_path / "b2"),
+            P.OUT_DIR_BOX_3D: str(tmp_path / "b3")}
+    ev = E.Evaluator(eng, types, dirs, train_val_test="test", log=lambda *a: None)
+    sd = {P.SAMPLE_NAME: "000007", P.SAMPLE_IMAGE_INPUT: np.zeros((375, 1242, 3), np.uint8), P.SAMPLE_NUM_OBJS: 4,
+          P.SAMPLE_CAM_P: S["cam_p"], P.SAMPLE_LABEL_SCORES: np.linspace(0.3, 0.9, 32).astype(np.float32),
+          P.SAMPLE_LABEL_BOXES_2D: S["boxes_2d"]}
+    res = ev.run_checkpoint_once("/ckpts/monopsr_model-00120000", [(S, sd)])
+    assert res["num_samples"] == 1 and eng.loaded == [("monopsr_model-00120000", "monopsr", True)]
+    assert ("forward", False) in eng.calls
+    b3 = np.loadtxt(os.path.join(dirs[P.OUT_DIR_BOX_3D], "000007.txt"))
+    b2 = np.loadtxt(os.path.join(dirs[P.OUT_DIR_BOX_2D], "000007.txt"))
+    assert b3.shape == (4, 9) and b2.shape == (4, 7)
+    assert np.load(os.path.join(dirs[P.OUT_DIR_XYZ_MAP_LOCAL], "000007.npy")).shape == (4, 48, 48, 3)
+    with pytest.raises(ValueError):
+        E.Evaluator(eng, types, dirs, train_val_test="train")
