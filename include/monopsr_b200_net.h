@@ -121,6 +121,9 @@ int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, int OH, in
  * scratch: 2*C doubles.  moving_mean/var may be NULL (no UPDATE_OPS). */
 int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, float eps, float* y, float* mean, float* var,
                      float* moving_mean, float* moving_var, float decay, double* scratch, void* stream);
+/* inference-mode counterpart (is_training=False: moving statistics, no update) */
+int mpb_bn_infer_fwd(int M, int C, const float* z, const float* beta, const float* moving_mean, const float* moving_var,
+                     float eps, float* y, void* stream);
 int mpb_bn_train_bwd(int M, int C, const float* z, const float* mean, const float* var, float eps, const float* y,
                      const float* dy, float* dz, float* dbeta, double* scratch, void* stream);
 

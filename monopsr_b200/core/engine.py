@@ -588,11 +588,15 @@ class Engine:
             self.gemm(TC_FWD, D["M"], side, side, 3, 1, D["cin"], D["cout"], x, D["cin"], self.pview(D["scope"] + "/weights"),
                       9 * D["cin"], D["z"], D["cout"], tapmask=self.tm24 if side == 24 else self.tm48)
             b = D["scope"] + "/BatchNorm/"
-            mm = self.view(b + "moving_mean") if train else None
-            mv = self.view(b + "moving_variance") if train else None
-            self._chk(L.mpb_bn_train_fwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")), BN_EPS_DECODER,
-                                         _ptr(D["y"]), _ptr(D["mean"]), _ptr(D["var"]), _ptr(mm), _ptr(mv),
-                                         BN_DECAY_DECODER, _ptr(self.bn_scratch), st), "bn_train_fwd")
+            if train:      # batch statistics + moving-average update (UPDATE_OPS)
+                self._chk(L.mpb_bn_train_fwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")), BN_EPS_DECODER,
+                                             _ptr(D["y"]), _ptr(D["mean"]), _ptr(D["var"]),
+                                             _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
+                                             BN_DECAY_DECODER, _ptr(self.bn_scratch), st), "bn_train_fwd")
+            else:          # validation / inference graphs are built with is_training=False: moving statistics
+                self._chk(L.mpb_bn_infer_fwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")),
+                                             _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
+                                             BN_EPS_DECODER, _ptr(D["y"]), st), "bn_infer_fwd")
             D["x"] = x
             x = D["y"]
         sx = "output/inst_xyz_map_local/inst_xyz_map_local"

@@ -960,6 +960,16 @@ MPB_API int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, fl
     MPB_LAUNCH_CHECK();
     return 0;
 }
+// slim.batch_norm(is_training=False): the moving statistics instead of the batch's (validation / inference graphs:
+// MonoPSRModel is built with is_training = (train_val_test == 'train'), monopsr_model.py:139, net_builder.py:39,79,87)
+MPB_API int mpb_bn_infer_fwd(int M, int C, const float* z, const float* beta, const float* moving_mean,
+                             const float* moving_var, float eps, float* y, void* stream) {
+    if (M <= 0 || C <= 0 || C % 4 || !z || !beta || !moving_mean || !moving_var || !y) return -1;
+    bn_apply_kernel<<<nblk((long)M * C / 4, 256), 256, 0, ST>>>((long)M * C / 4, C / 4, (const float4*)z, moving_mean,
+                                                              moving_var, beta, eps, (float4*)y);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
 MPB_API int mpb_bn_train_bwd(int M, int C, const float* z, const float* mean, const float* var, float eps, const float* y,
                              const float* dy, float* dz, float* dbeta, double* scratch, void* stream) {
     MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, ST));

@@ -194,6 +194,12 @@ def train_bn_relu(x, P, scope):
     return Q(torch.relu((x - mean) / torch.sqrt(var + BN_EPS_DECODER) + P[scope + "/beta"])), mean, var
 
 
+def infer_bn_relu(x, P, scope):
+    """slim.batch_norm defaults, is_training=False: moving statistics (validation / inference graphs)."""
+    y = (x - P[scope + "/moving_mean"]) / torch.sqrt(P[scope + "/moving_variance"] + BN_EPS_DECODER) + P[scope + "/beta"]
+    return Q(torch.relu(y)), P[scope + "/moving_mean"], P[scope + "/moving_variance"]
+
+
 def fc(x, P, scope, relu=True):
     """slim.fully_connected; the 1024-wide ReLU layers run on the tensor cores in the product
     (weights and outputs tf32-rounded), the small linear heads run in plain fp32."""
@@ -243,14 +249,15 @@ def forward(P, S, train=True):
     pooled = max_pool_2x2(squashed)
     x = Q(resize_bilinear_ac(squashed, 24, 24))
     bn_stats = {}
+    bn_relu = train_bn_relu if train else infer_bn_relu      # is_training = (train_val_test == 'train'), monopsr_model.py:139
     for i in (1, 2):
         sc = "map_decoder/conv2/conv2_%d" % i
-        x, m, v = train_bn_relu(conv_hwio(x, Q(P[sc + "/weights"])), P, sc + "/BatchNorm")
+        x, m, v = bn_relu(conv_hwio(x, Q(P[sc + "/weights"])), P, sc + "/BatchNorm")
         bn_stats[sc] = (m, v)
     x = Q(resize_bilinear_ac(x, 48, 48))
     for i in (1, 2):
         sc = "map_decoder/conv3/conv3_%d" % i
-        x, m, v = train_bn_relu(conv_hwio(x, Q(P[sc + "/weights"])), P, sc + "/BatchNorm")
+        x, m, v = bn_relu(conv_hwio(x, Q(P[sc + "/weights"])), P, sc + "/BatchNorm")
         bn_stats[sc] = (m, v)
     map_features = x
 

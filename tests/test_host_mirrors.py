@@ -145,3 +145,22 @@ def test_geometry_restatement_vs_numpy_twins():
     gx = np.cos(ang) * pts[0] + np.sin(ang) * pts[2] + cen[0]
     gz = -np.sin(ang) * pts[0] + np.cos(ang) * pts[2] + cen[2]
     assert np.allclose(glob[0], gx) and np.allclose(glob[2], gz)
+
+
+def test_oracle_inference_mode_batch_norm():
+    """is_training=False (validation / inference graphs, monopsr_model.py:139): moving statistics, eps 1e-3, beta only"""
+    import torch
+    from oracle import network as onet
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4, 6, 6, 8, generator=g, dtype=torch.float64) * 3 + 1
+    P = {"s/moving_mean": torch.randn(8, generator=g, dtype=torch.float64),
+         "s/moving_variance": torch.rand(8, generator=g, dtype=torch.float64) + 0.5,
+         "s/beta": torch.randn(8, generator=g, dtype=torch.float64)}
+    y, m, v = onet.infer_bn_relu(x, P, "s")
+    ref = torch.relu((x - P["s/moving_mean"]) / torch.sqrt(P["s/moving_variance"] + 1e-3) + P["s/beta"])
+    assert torch.allclose(y, ref, rtol=1e-12, atol=1e-12) and m is P["s/moving_mean"]
+    # with the batch's own statistics as "moving" statistics the two modes coincide
+    P["s/moving_mean"], P["s/moving_variance"] = x.mean((0, 1, 2)), x.var((0, 1, 2), unbiased=False)
+    yt, _, _ = onet.train_bn_relu(x, P, "s")
+    yi, _, _ = onet.infer_bn_relu(x, P, "s")
+    assert torch.allclose(yt, yi, rtol=1e-10, atol=1e-10)

@@ -1,0 +1,43 @@
+"""GPU tests of code added after the round-1 GPU budget was spent: they have never run on a B200, so they are marked
+xfail(strict=False) -- they report XPASS / XFAIL without being able to break the suite.  Drop the marker once they
+have been seen to pass."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="added after the GPU budget of round 1 was spent; "
+                                                                      "not yet run on a B200")]
+
+from monopsr_b200.core import model_spec as ms  # noqa: E402
+from monopsr_b200.core.engine import Engine  # noqa: E402
+from oracle import network as onet  # noqa: E402
+
+
+def test_inference_mode_forward_matches_oracle(cuda):
+    """forward(train=False): decoder batch norm with the MOVING statistics (is_training=False graphs)"""
+    P, S = ms.init_params(0, randomize_bn=True), ms.synthetic_sample(0)
+    eng = Engine(cuda, params=P)
+    eng.set_inputs(S)
+    eng.forward(train=False)
+    o = eng.outputs()
+    out, _ = onet.forward(onet.to_torch(P, torch.float64, cuda), onet.to_torch(S, torch.float64, cuda), train=False)
+    for k in ("centroids", "lwh", "inst_xyz_map_local"):
+        a, b = o[k].double().reshape(-1), out[k].reshape(-1)
+        assert float((a - b).norm() / b.norm()) < 2e-2, k
+    eng.forward(train=True)                       # and the two modes really differ on the decoder output
+    assert not torch.allclose(eng.outputs()["inst_xyz_map_local"], o["inst_xyz_map_local"].clone())
+
+
+def test_checkpoint_roundtrip_through_tf_bundle(cuda, tmp_path):
+    """Engine.save_checkpoint -> TensorFlow tensor bundle -> Engine.load_checkpoint restores variables and EMA shadows"""
+    a = Engine(cuda, params=ms.init_params(3))
+    a.ema.mul_(0.5)                                         # make the shadows differ from the variables
+    prefix = str(tmp_path / "model.ckpt-11")
+    a.save_checkpoint(prefix, global_step=11)
+    b = Engine(cuda, params=ms.init_params(4))
+    rep = b.load_checkpoint(prefix)
+    assert not rep["missing"] and not rep["shape_mismatch"]
+    assert torch.equal(a.params, b.params) and torch.equal(a.state, b.state)
+    c = Engine(cuda, params=ms.init_params(4))
+    c.load_checkpoint(prefix, use_ema=True)
+    assert torch.equal(c.params, a.ema)
