@@ -557,7 +557,12 @@ class Engine:
         self._chk(self.L.mpb_bias_relu(N, 1024, _ptr(acc), 1024, _ptr(self.view(wname + "/biases")), 1, 1, _ptr(out), ldo,
                                        self._st()), "bias_relu")
 
-    def forward(self, train=True):
+    def forward(self, train=True, compute_losses=None):
+        """train: the reference's is_training (decoder batch norm with batch statistics + moving-average update, and
+        the gradient arena is zeroed for a backward pass); compute_losses (default = train): evaluate the losses in
+        the heads kernel -- validation runs an is_training=False graph but still reports losses."""
+        if compute_losses is None:
+            compute_losses = train
         if not self._prepared:
             self.prepare_weights()
         L, st, N, I = self.L, self._st(), self.N, self.inputs
@@ -604,7 +609,7 @@ class Engine:
                                     _ptr(self.xyz), st), "xyzhead_fwd")
         self._join(self.s_fc)            # the FC stacks ran beside the decoder
         io = self.heads_io()
-        self._chk(L.mpb_heads_final(ctypes.byref(io), 1 if train else 0, st), "heads_final")
+        self._chk(L.mpb_heads_final(ctypes.byref(io), 1 if compute_losses else 0, st), "heads_final")
 
     def _fc_forward(self):
         """heads_static, proposal stack, lwh/alpha heads, heads_mid, regression stack, cen_y/cen_z heads"""

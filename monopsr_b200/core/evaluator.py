@@ -27,7 +27,7 @@ class Evaluator(object):
         -> formatted prediction dict"""
         eng = self.engine
         eng.set_inputs(sample)
-        eng.forward(train=False)
+        eng.forward(train=False, compute_losses=self.mode == "val")
         out = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v))
                for k, v in eng.outputs().items() if v is not None}
         if P.KEY_VALID_MASK_MAPS not in out:          # test mode: tf.ones mask (monopsr_model.py:218)

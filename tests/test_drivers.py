@@ -38,7 +38,7 @@ class StubEngine(object):
     def set_inputs(self, sample):
         self.sample = sample
 
-    def forward(self, train=True):
+    def forward(self, train=True, compute_losses=None):
         self.calls.append(("forward", train))
 
     def outputs(self):
