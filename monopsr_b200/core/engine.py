@@ -467,7 +467,16 @@ class Engine:
     def set_inputs(self, S):
         """S: dict of numpy arrays / torch tensors (model_spec.synthetic_sample keys); host->device copy.
         A sample may carry the RAW training inputs `depth_map` (H,W) and `instance_masks` (N,H,W) instead of the three
-        ground-truth maps: they are then synthesised on the GPU (core/targets.py; monopsr_model.py:165-203)."""
+        ground-truth maps: they are then synthesised on the GPU (core/targets.py; monopsr_model.py:165-203).  Likewise
+        the RAW camera image `rgb_image` (H,W,3) instead of `rgb_crops` + `full_img` (monopsr_model.py:128-133,222-233)
+        -- the form datasets/kitti_loader.engine_sample produces."""
+        if "rgb_image" in S and "rgb_crops" not in S:
+            from . import targets
+            S = dict(S)
+            im = targets.image_inputs(S.pop("rgb_image"), S["boxes_2d_norm"], self.dev,
+                                      image_input_shape=(ms.FULL_H * 2, ms.FULL_W * 2), img_roi_size=ms.CROP,
+                                      resized_full_img_shape=(ms.FULL_H, ms.FULL_W), mean_sub_type="kitti")
+            S["rgb_crops"], S["full_img"] = im["rgb_crops"], im["full_img"]
         if "depth_map" in S and "gt_inst_xyz_maps_local" not in S:
             from . import targets
             S = dict(S)

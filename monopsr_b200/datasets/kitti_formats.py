@@ -1,5 +1,6 @@
-"""KITTI label / calibration formats and the label-derived part of a training sample (SURVEY.md section 8f rank 4,
-partial: the data formats on the input side of the path; the loader, oversampling and augmentation are not built).
+"""KITTI label / calibration / depth / instance formats, object filters and the label-derived part of a training sample
+(the data formats on the input side of the path; the loader itself, oversampling and
+augmentation are in datasets/kitti_loader.py and datasets/augment.py).
 
 Host-side numpy mirrors of
   ObjectLabel, read_labels, filter_labels_by_class      src/monopsr/datasets/kitti/obj_utils.py:85-206
@@ -10,7 +11,13 @@ Host-side numpy mirrors of
   get_mean_lwh_and_std_dev, class_str_to_index          src/monopsr/datasets/kitti/obj_utils.py:986-1127
   get_prop_cen_z_offset                                 src/monopsr/datasets/kitti/instance_utils.py:972-985
 and of the label-derived fields of KittiDataset's sample dict (datasets/kitti/kitti_dataset.py:345-395,450-487),
-returned under the key names Engine.set_inputs / model_spec.synthetic_sample use.
+returned under the key names Engine.set_inputs / model_spec.synthetic_sample use, plus
+  Difficulty, ObjectFilter, filter_labels*, apply_obj_filter   src/monopsr/datasets/kitti/obj_utils.py:12-15,25-82,193-368
+  two_d_iou                                             src/monopsr/core/evaluation.py:23-61 and
+                                                        src/monopsr/datasets/kitti/evaluation.py:6-44 (rounded)
+  merge_kitti_and_mscnn_obj_labels                      src/monopsr/datasets/kitti/obj_utils.py:1037-1089
+  read_depth_map / read_instance_image / get_instance_mask_list
+                                                        depth_map_utils.py:9-17, instance_utils.py:10-44
 Golden vectors from the reference's own functions on its KITTI test fixture: tests/golden/kitti_formats_golden.npz.
 """
 import csv
@@ -192,3 +199,175 @@ def label_fields(obj_labels, cam_p, image_shape, classes=("Car",), num_alpha_bin
         "gt_alpha_valid_bins": pad([b[2] for b in bins], (num_alpha_bins,)),
         "label_scores": pad([o.score for o in labels], ()),
     }
+
+
+# ---------------------------------------------------------------------------------------------- object filters
+class Difficulty(object):
+    EASY, MODERATE, HARD, ALL = 0, 1, 2, 3
+    _NAMES = ("easy", "moderate", "hard", "all")
+
+    @staticmethod
+    def to_string(difficulty):
+        return Difficulty._NAMES[difficulty]
+
+    @staticmethod
+    def from_string(difficulty_str):
+        if difficulty_str not in Difficulty._NAMES:
+            raise KeyError(difficulty_str)
+        return Difficulty._NAMES.index(difficulty_str)
+
+
+# KITTI difficulty thresholds, indexed by Difficulty (easy, moderate, hard)
+_MIN_HEIGHT, _MAX_OCCLUSION, _MAX_TRUNCATION = (40, 25, 25), (0, 1, 2), (0.15, 0.3, 0.5)
+
+
+class ObjectFilter(object):
+    """classes / difficulty / min 2-D box height / max truncation / max occlusion / depth range; None = not applied"""
+
+    def __init__(self, config):
+        self.classes = config.classes
+        self.difficulty = Difficulty.from_string(config.difficulty_str)
+        self.box_2d_height = config.box_2d_height
+        self.truncation = config.truncation
+        self.occlusion = config.occlusion
+        self.depth_range = config.depth_range
+
+    @staticmethod
+    def create_obj_filter(classes, difficulty, occlusion, truncation, box_2d_height, depth_range):
+        import types
+        return ObjectFilter(types.SimpleNamespace(
+            classes=classes, difficulty_str=Difficulty.to_string(difficulty), occlusion=occlusion, truncation=truncation,
+            box_2d_height=box_2d_height, depth_range=depth_range))
+
+
+def _as_label_array(obj_labels):
+    a = np.empty(len(obj_labels), dtype=object)
+    for i, o in enumerate(obj_labels):
+        a[i] = o
+    return a
+
+
+def filter_labels(obj_labels, classes=None, difficulty=None, box_2d_height=None, occlusion=None, truncation=None,
+                  depth_range=None):
+    """-> (kept labels as an object array, boolean keep mask); the comparisons are the reference's: difficulty uses
+    <= / >= on the KITTI thresholds, the explicit limits are strict (height >, truncation <, occlusion <, depth open)."""
+    keep = np.full(len(obj_labels), True)
+    for i, o in enumerate(obj_labels):
+        ok = True
+        if classes is not None:
+            ok &= o.type in classes
+        if difficulty is not None and difficulty != Difficulty.ALL:
+            ok &= bool(o.occlusion <= _MAX_OCCLUSION[difficulty] and o.truncation <= _MAX_TRUNCATION[difficulty]
+                       and (o.y2 - o.y1) >= _MIN_HEIGHT[difficulty])
+        if box_2d_height is not None:
+            ok &= bool((o.y2 - o.y1) > box_2d_height)
+        if occlusion is not None:
+            ok &= bool(o.occlusion < occlusion)
+        if truncation is not None:
+            ok &= bool(o.truncation < truncation)
+        if depth_range is not None:
+            ok &= bool(depth_range[0] < o.t[2] < depth_range[1])
+        keep[i] = ok
+    return _as_label_array(obj_labels)[keep], keep
+
+
+def apply_obj_filter(obj_labels, obj_filter):
+    return filter_labels(obj_labels, classes=obj_filter.classes, difficulty=obj_filter.difficulty,
+                         box_2d_height=obj_filter.box_2d_height, occlusion=obj_filter.occlusion,
+                         truncation=obj_filter.truncation, depth_range=obj_filter.depth_range)
+
+
+def boxes_2d_from_obj_labels(obj_labels):
+    return np.asarray([object_label_to_box_2d(o) for o in obj_labels], np.float32)
+
+
+def boxes_3d_from_obj_labels(obj_labels):
+    return np.asarray([object_label_to_box_3d(o) for o in obj_labels], np.float32)
+
+
+def two_d_iou(box, boxes, decimals=None):
+    """IoU of one box against (N,4) boxes, any consistent corner order.  The reference has two copies of this function:
+    core/evaluation.py:23-61 returns the quotient as is (used by the box jitter's acceptance test), while
+    datasets/kitti/evaluation.py:6-44 rounds it to 3 decimals (used when matching MS-CNN detections): decimals=3."""
+    boxes = np.asarray(boxes)
+    lo = np.maximum(box[:2], boxes[:, :2])
+    hi = np.minimum(box[2:4], boxes[:, 2:4])
+    wh = hi - lo
+    hit = (wh[:, 0] > 0) & (wh[:, 1] > 0)
+    iou = np.zeros(len(boxes), np.float64)
+    if hit.any():
+        inter = wh[hit, 0] * wh[hit, 1]
+        area = (box[2] - box[0]) * (box[3] - box[1])
+        areas = (boxes[hit, 2] - boxes[hit, 0]) * (boxes[hit, 3] - boxes[hit, 1])
+        iou[hit] = inter / (area + areas - inter)
+    return iou if decimals is None else iou.round(decimals)
+
+
+def merge_kitti_and_mscnn_obj_labels(kitti_obj_labels, mscnn_obj_labels, min_iou, default_score_type="distance"):
+    """KITTI labels whose 2-D box and score are replaced by the best-overlapping MS-CNN detection (IoU >= min_iou);
+    labels left without a score get one from their depth ('distance'), 1 ('max') or 0 ('min')."""
+    import copy
+    merged = copy.deepcopy(kitti_obj_labels)
+    kitti_boxes = boxes_2d_from_obj_labels(kitti_obj_labels)
+    for det in mscnn_obj_labels:
+        det_box = object_label_to_box_2d(det)
+        ious = two_d_iou(det_box, kitti_boxes, decimals=3)
+        best = int(np.argmax(ious))
+        if ious[best] >= min_iou:
+            m = merged[best]
+            m.y1, m.x1, m.y2, m.x2 = det_box
+            m.score = det.score
+    for m in merged:
+        if m.score == 0:
+            if default_score_type == "distance":
+                m.score = np.clip(1.0 - (m.t[2] / 45.0), 0.1, 1.0)
+            elif default_score_type in ("max", "min"):
+                m.score = 1.0 if default_score_type == "max" else 0.0
+            else:
+                raise ValueError("Invalid default score type", default_score_type)
+    return merged
+
+
+# ---------------------------------------------------------------------------------------------- image-like inputs
+def _imread(path, flag):
+    import cv2
+    img = cv2.imread(path, flag)
+    if img is None:
+        raise FileNotFoundError("Image could not be read:", path)
+    return img
+
+
+def read_rgb_image(path):
+    """uint8 (H,W,3) RGB (cv2 decodes BGR; kitti_dataset.py:252-253)"""
+    import cv2
+    return _imread(path, cv2.IMREAD_COLOR)[..., ::-1]
+
+
+def read_depth_map(depth_map_path):
+    """uint16 png, metres x 256 -> float32 metres; depths under 10 cm are 'no depth' (0)"""
+    import cv2
+    depth = _imread(depth_map_path, cv2.IMREAD_ANYDEPTH) / 256.0
+    depth[depth < 0.1] = 0.0
+    return depth.astype(np.float32)
+
+
+def write_depth_map(depth_map_path, depth_map, png_compression=3):
+    import cv2
+    cv2.imwrite(depth_map_path, (np.asarray(depth_map) * 256.0).astype(np.uint16),
+                [cv2.IMWRITE_PNG_COMPRESSION, png_compression])
+
+
+def read_instance_image(instance_image_path):
+    """uint8 (H,W): pixel = index of the object label it belongs to, 255 = none"""
+    import cv2
+    return _imread(instance_image_path, cv2.IMREAD_GRAYSCALE)
+
+
+def get_instance_mask_list(instance_img, num_instances=None):
+    """(k,H,W) boolean masks, one per label index; without `num_instances`, k = highest index present + 1"""
+    if num_instances is None:
+        present = instance_img[instance_img != 255]
+        if len(present) == 0:
+            return []
+        num_instances = int(np.max(present)) + 1
+    return np.asarray([instance_img == i for i in range(num_instances)])

@@ -41,3 +41,29 @@ def test_checkpoint_roundtrip_through_tf_bundle(cuda, tmp_path):
     c = Engine(cuda, params=ms.init_params(4))
     c.load_checkpoint(prefix, use_ema=True)
     assert torch.equal(c.params, a.ema)
+
+
+def test_kitti_loader_feeds_the_engine(cuda, tmp_path):
+    """synthetic KITTI tree -> KittiDataset -> PrefetchLoader -> Engine.train_step: the raw image / depth map /
+    instance masks of the sample are turned into crops, the resized image and the ground-truth maps on the GPU"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kitti_tree
+    from monopsr_b200.core import targets
+    from monopsr_b200.datasets import kitti_loader as KL
+    dataset_dir, data_dir = kitti_tree.make_tree(str(tmp_path))
+    cfg = kitti_tree.apply_overrides(KL.DatasetBuilder.get_config_obj(KL.DatasetBuilder.KITTI_TRAIN), dataset_dir, {})
+    ds = KL.KittiDataset(cfg, "train", data_dir=data_dir, rng=np.random.RandomState(0))
+    eng = Engine(cuda, params=ms.init_params(0))
+    with KL.PrefetchLoader(ds, max_samples=3) as loader:
+        losses = []
+        for sample, sample_dict in loader:
+            eng.train_step(sample)
+            losses.append(eng.losses()["total_loss"])
+            want = targets.image_inputs(sample["rgb_image"], sample["boxes_2d_norm"], cuda)
+            assert torch.equal(eng.inputs["rgb_crops"], want["rgb_crops"])
+            assert torch.equal(eng.inputs["full_img"], want["full_img"])
+            assert eng.inputs["gt_valid_mask_maps"].shape == (32, 48, 48, 1)
+            assert 0 < float(eng.inputs["gt_valid_mask_maps"].mean()) < 1
+    assert len(losses) == 3 and all(np.isfinite(losses))
