@@ -61,6 +61,15 @@ typedef struct mpb_tc_gemm_params {
 /* BN: tile width in output columns (64, 128 or 256). */
 int mpb_tc_gemm(const mpb_tc_gemm_params* p, int BN, void* stream);
 
+/* 3xTF32 forward variant of mpb_tc_gemm (op must be MPB_TC_FWD, BN 64 or 128, split-K only with atomic=1): the
+ * operands are read as stored -- UNROUNDED fp32 -- split on chip into tf32 hi + lo parts and contracted with three
+ * MMAs per k-step, for fp32-level accuracy (the reference's convolutions / matmuls are fp32: net_builder.py:44-89,
+ * monopsr_output_builder.py:166-283) at the memory traffic of the single-pass kernel.  Same epilogue options. */
+int mpb_tc_gemm_x3(const mpb_tc_gemm_params* p, int BN, void* stream);
+/* 1 (default): the elementwise / weight-preparation kernels round every GEMM operand they produce to tf32;
+ * 0: they leave it as computed (what mpb_tc_gemm_x3 wants).  Synchronous; set it outside graph capture. */
+int mpb_set_operand_rounding(int on);
+
 /* operand staging of the GEMM core: 1 = TMA (cp.async.bulk.tensor, default), 0 = cp.async (LSU) producers.
  * Returns the mode in effect (TMA falls back to 0 when the driver lacks cuTensorMapEncode*). */
 int mpb_tc_set_producer(int mode);

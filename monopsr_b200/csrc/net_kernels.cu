@@ -8,10 +8,14 @@
 
 namespace mpb {
 
+// Operand rounding: every GEMM operand produced here is rounded to tf32 (round-to-nearest; the tensor core itself
+// truncates).  The 3xTF32 forward path (tc_gemm_x3_kernel) wants the operands UNROUNDED instead: one switch for all
+// producers of this file, 1 by default, flipped by mpb_set_operand_rounding().
+__constant__ int c_round_operands = 1;
 __device__ __forceinline__ float rtf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return c_round_operands ? __uint_as_float(u) : x;
 }
 
 // ---------------------------------------------------------------- weight preparation
@@ -958,6 +962,11 @@ MPB_API int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, fl
     bn_apply_kernel<<<nblk((long)M * C / 4, 256), 256, 0, ST>>>((long)M * C / 4, C / 4, (const float4*)z, mean, var, beta, eps,
                                                               (float4*)y);
     MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_set_operand_rounding(int on) {
+    const int v = on ? 1 : 0;
+    MPB_CUDA_TRY(cudaMemcpyToSymbol(mpb::c_round_operands, &v, sizeof(v)));
     return 0;
 }
 // slim.batch_norm(is_training=False): the moving statistics instead of the batch's (validation / inference graphs:

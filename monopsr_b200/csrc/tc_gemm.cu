@@ -930,6 +930,198 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     }
 }
 
+// =====================================================================================
+// 3xTF32 forward variant ("x3", opt-in: mpb_tc_gemm_x3 / MPB_PRECISION=x3 in the engine).
+//
+// kind::tf32 reads the top 19 bits of each fp32 operand (TRUNCATION, measured: profiles/r1_notes.md), so one
+// pass carries ~3e-4 relative error per GEMM, which the decoder's train-mode batch norm amplifies past the 1e-3
+// parity bar (tools/precision_study.py).  Here the operands stay UNROUNDED fp32 in HBM and every k-block is
+// split on chip:  x = hi + lo,  hi = x & 0xFFFFE000 (exactly what the tensor core reads when handed x itself,
+// so it needs no copy),  lo = x - hi (exact in fp32, <= 13 significant bits).  Three MMAs per k-step,
+//     acc += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo          (the dropped lo*lo term is ~2^-22 relative)
+// give fp32-level accuracy (3.6e-7 on a K=2304 contraction, numpy emulation in tests/test_x3_split.py) for the
+// HBM / L2 traffic of the single-pass kernel: the TMA brings each tile in once and the four epilogue warps,
+// idle during the main loop, write the lo tiles (same swizzled layout, so the hi descriptors + a constant
+// offset address them).
+//   stage = [A | B | A_lo | B_lo];  barriers: full (TMA landed) -> split (lo written, 128 arrivals) -> MMA ->
+//   empty (tcgen05.commit).  Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = splitters, then
+//   the same fused epilogue as the single-pass kernel.  FWD only, no multicast / cluster split-K.
+// NOT YET RUN ON A B200 (written after the round-1 GPU budget was spent); nothing calls it by default.
+// =====================================================================================
+constexpr int kX3Stages = 3;
+template <int BN> constexpr uint32_t x3_half_bytes() { return kTcABytes + BN * 128; }      // [A | B]
+template <int BN> constexpr int x3_smem_bytes() { return kX3Stages * 2 * (int)x3_half_bytes<BN>() + 1024 + 256; }
+constexpr int kX3Threads = 192;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float tf32_lo(float x) {      // x - (what kind::tf32 reads of x)
+    return __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kX3Threads, 1)
+tc_gemm_x3_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant__ CUtensorMap mapA,
+                  const __grid_constant__ CUtensorMap mapB) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    constexpr uint32_t kHalf = x3_half_bytes<BN>();
+    constexpr uint32_t kStage = 2 * kHalf;
+    const uint32_t bar_base = base + kX3Stages * kStage;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto split_bar = [&](int s) { return bar_base + 8u * (kX3Stages + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kX3Stages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (3 * kX3Stages);
+    const uint32_t tmem_slot = tmem_full_bar + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef MPB_TC_TRACE
+    long long* trc = nullptr;
+#endif
+    const int taps = p.kh * p.kw;
+    const int cblocks = p.Cin / kTcBK;
+    const int nkb = taps * cblocks;
+    const int per = (nkb + p.ksplit - 1) / p.ksplit;
+    const int kb0 = blockIdx.z * per;
+    const int nk = min(nkb, kb0 + per) - kb0;
+    if (nk <= 0) return;
+    const int m0 = blockIdx.x * kTcBM;
+    const int n0 = blockIdx.y * BN;
+
+    if (tid == 0) {
+        for (int s = 0; s < kX3Stages; s++) {
+            mbar_init(full_bar(s), 1);       // the producer's arrive.expect_tx (+ TMA byte count)
+            mbar_init(split_bar(s), 128);    // every splitter thread, after its own cross-proxy fence
+            mbar_init(empty_bar(s), 1);      // one tcgen05.commit
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+
+    // ---- TMA producer state (warp 0; warp-uniform, one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    int pr_tap = 0, pr_cb = 0, pr_th = 0, pr_tw = 0, pr_bw = 0, pr_bh = 0, pr_img0 = 0;
+    if (warp == 0) {
+        const int hw = p.H * p.W;
+        pr_img0 = m0 / hw;
+        const int rem0 = m0 - pr_img0 * hw, ph0 = rem0 / p.W, pw0 = rem0 - ph0 * p.W;
+        pr_bw = pw0 - p.dil * (p.kw / 2); pr_bh = ph0 - p.dil * (p.kh / 2);
+        pr_tap = kb0 / cblocks; pr_cb = kb0 - pr_tap * cblocks;
+        pr_th = pr_tap / p.kw; pr_tw = pr_tap - pr_th * p.kw;
+    }
+    auto produce = [&](bool wait_free) {
+        if (wait_free) mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+            const uint32_t sA = base + stage * kStage, sB = sA + kTcABytes;
+            mbar_expect_tx(full_bar(stage), kHalf);
+            if (taps == 1) tma_load_2d(sA, &mapA, full_bar(stage), pr_cb * kTcBK, m0);
+            else tma_load_im2col(sA, &mapA, full_bar(stage), pr_cb * kTcBK, pr_bw, pr_bh, pr_img0, pr_tw * p.dil, pr_th * p.dil);
+            tma_load_2d(sB, &mapB, full_bar(stage), (pr_tap * cblocks + pr_cb) * kTcBK, n0);
+        }
+        __syncwarp();
+        if (++pr_cb == cblocks) {
+            pr_cb = 0; ++pr_tap;
+            if (++pr_tw == p.kw) { pr_tw = 0; ++pr_th; }
+        }
+        if (++stage == kX3Stages) { stage = 0; phase ^= 1u; }
+    };
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: global memory of the stream predecessor from here on
+    const int npre = min(nk, kX3Stages);
+    if (warp == 0) {
+        __syncwarp();
+        for (int i = 0; i < npre; i++) produce(false);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot_ptr;
+
+    float* stg_base = reinterpret_cast<float*>(smem_raw + (base - raw));
+    EpiCtx ec;
+    float4 rv[8], mv[8];
+    if (warp == 0) {
+        for (int i = npre; i < nk; i++) produce(true);
+    } else if (warp == 1) {
+        // =========================== MMA ISSUER ===========================
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(kTcBM >> 4) << 24);
+        const uint64_t ad0 = desc_kmajor(base), bd0 = desc_kmajor(base + kTcABytes);
+        constexpr uint64_t lo_off = kHalf >> 4;
+        int st = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < nk; i++) {
+            mbar_wait(split_bar(st), ph);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the lo tiles came through the generic proxy
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t ad = ad0 + (uint64_t)((st * kStage) >> 4);
+                const uint64_t bd = bd0 + (uint64_t)((st * kStage) >> 4);
+#pragma unroll
+                for (int k = 0; k < kTcBK / 8; k++) {
+                    umma_tf32(tmem_acc, ad + lo_off + k * 2, bd + k * 2, idesc, (i > 0 || k > 0) ? 1u : 0u);   // A_lo * B_hi
+                    umma_tf32(tmem_acc, ad + k * 2, bd + lo_off + k * 2, idesc, 1u);                            // A_hi * B_lo
+                    umma_tf32(tmem_acc, ad + k * 2, bd + k * 2, idesc, 1u);                                     // A_hi * B_hi
+                }
+                umma_commit(empty_bar(st));
+                if (i == nk - 1) {
+                    umma_commit(tmem_full_bar);
+                    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                }
+            }
+            __syncwarp();
+            if (++st == kX3Stages) { st = 0; ph ^= 1u; }
+        }
+        tc_fence_before();
+    } else {
+        // =========================== SPLITTERS, then EPILOGUE (warps 2..5) ===========================
+        epi_setup<TC_FWD>(ec, p, tmem_acc, warp & 3, 0, lane, m0, stg_base, 1, 0, 4, 0, 1);
+        epi_load_res(p, ec, 0, lane, n0, rv);
+        epi_load_mask(p, ec, 0, lane, n0, mv);
+        const int t = tid - 64;
+        constexpr int n4 = (int)(kHalf / 16);          // float4s of [A | B]; a multiple of 128
+        int st = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < nk; i++) {
+            mbar_wait(full_bar(st), ph);
+            const uint32_t hi = base + st * kStage + (uint32_t)t * 16u, lo = hi + kHalf;
+#pragma unroll 4
+            for (int j = 0; j < n4 / 128; j++) {
+                const float4 v = lds4(hi + (uint32_t)j * 2048u);
+                sts4(lo + (uint32_t)j * 2048u, make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+            mbar_arrive(split_bar(st));
+            if (++st == kX3Stages) { st = 0; ph ^= 1u; }
+        }
+        tc_epilogue_dump<BN, TC_FWD>(p, tmem_full_bar, tmem_acc, warp & 3, 0, 1, lane, m0, stg_base, 4, 1, 0 TC_TR_PASS);
+        tc_epilogue<BN, TC_FWD>(p, ec, 0, 1, lane, n0, rv, mv TC_TR_PASS);
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1076,6 +1268,62 @@ static int launch_tma(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     if (g_tc_cluster >= 4 && grid.y % 4 == 0) return launch_tma_cn<BN, OP, 4>(p, grid, s);
     if (g_tc_cluster >= 2 && grid.y % 2 == 0) return launch_tma_cn<BN, OP, 2>(p, grid, s);
     return launch_tma_cn<BN, OP, 1>(p, grid, s);
+}
+
+template <int BN>
+static int launch_x3(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
+    alignas(64) CUtensorMap mapA, mapB;
+    const int taps = p.kh * p.kw;
+    const int nimg = p.M / (p.H * p.W);
+    bool ok = true;
+    if (taps == 1) ok &= make_map_2d(&mapA, p.X, p.Cin, p.M, p.ldx, kTcBM, false);
+    else ok &= make_map_im2col(&mapA, p.X, p.Cin, p.W, p.H, nimg, p.ldx, p.kh, p.kw, p.dil, kTcBM, false);
+    ok &= make_map_2d(&mapB, p.Wt, (long)taps * p.Cin, p.Cout, p.ldw, BN, false);
+    if (!ok) return -2;
+    constexpr int smem = x3_smem_bytes<BN>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kX3Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    int na = 0;
+    if (tc_gemm_pdl()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = na;
+    MPB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_x3_kernel<BN>, p, mapA, mapB));
+    count_launch();
+    return 0;
+}
+
+// 3xTF32 forward GEMM (see tc_gemm_x3_kernel): FWD only, BN 64 or 128, whole images in the pixel grid, split-K only
+// in its atomic (RED.ADD into a zeroed output) form.  Operands are read as stored -- hand it UNROUNDED fp32.
+int tc_gemm_x3_launch(const TcGemmParams& p, int BN, cudaStream_t s) {
+    if (p.op != TC_FWD || p.M <= 0 || p.Cin <= 0 || p.Cout <= 0 || p.ksplit < 1) return -1;
+    if (BN != 64 && BN != 128) return -1;
+    if (p.Cin % kTcBK || p.Cout % BN || p.ldo % 4 || p.ldx % 4 || p.ldw % 4) return -1;
+    if (p.ksplit > 1 && !p.atomic) return -1;
+    if (p.M % (p.H * p.W) != 0 || !tma_api_ready()) return -1;
+    if (p.tapmask) { /* the im2col TMA zero-fills padding taps itself; the mask is only used by the cp.async path */ }
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    if (!al16(p.out) || !al16(p.out_r) || !al16(p.res) || !al16(p.mask) || !al16(p.scale) || !al16(p.shift) ||
+        !al16(p.scale2) || !al16(p.colsum))
+        return -1;
+    if ((p.res && p.ldr % 4) || (p.mask && p.ldm % 4) || (p.out_r && p.ldor % 4)) return -1;
+    const int taps = p.kh * p.kw;
+    if (p.ksplit > 1 && (p.ksplit - 1) * ceil_div(taps * (p.Cin / kTcBK), p.ksplit) >= taps * (p.Cin / kTcBK)) return -1;
+    dim3 grid(ceil_div(p.M, kTcBM), p.Cout / BN, p.ksplit);
+    if (grid.y > 65535 || grid.z > 65535) return -1;
+    return BN == 64 ? launch_x3<64>(p, grid, s) : launch_x3<128>(p, grid, s);
 }
 
 static int g_tc_mode = -1;   // 0 = cp.async producers, 1 = TMA producers

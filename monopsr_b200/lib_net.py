@@ -78,6 +78,8 @@ _SIGS = {
     "mpb_resize_ac_fwd": [c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
     "mpb_resize_ac_bwd": [c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
     "mpb_bn_train_fwd": [c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
+    "mpb_tc_gemm_x3": [c_p, c_i, c_p],
+    "mpb_set_operand_rounding": [c_i],
     "mpb_bn_infer_fwd": [c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
     "mpb_bn_train_bwd": [c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
     "mpb_xyzhead_fwd": [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],

@@ -29,19 +29,21 @@ spin_up()
 _side = torch.cuda.Stream(device=dev)
 
 
-def time_it(p, bn, n=20):
+def time_it(p, bn, n=20, x3=False):
     """n back-to-back launches replayed as ONE CUDA graph (the ctypes + tensor-map-encode launch path costs
-    ~10 us of CPU per call, more than the shorter kernels run), timed with CUDA events; us per launch"""
+    ~10 us of CPU per call, more than the shorter kernels run), timed with CUDA events; us per launch.
+    x3: the 3xTF32 forward variant (mpb_tc_gemm_x3) instead of the single-pass kernel"""
     st = ctypes.c_void_p(_side.cuda_stream)
+    launch = L.mpb_tc_gemm_x3 if x3 else L.mpb_tc_gemm
     with torch.cuda.stream(_side):
         for _ in range(2):
-            if L.mpb_tc_gemm(ctypes.byref(p), bn, st) != 0:
+            if launch(ctypes.byref(p), bn, st) != 0:
                 return None
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=_side):
             for _ in range(n):
-                L.mpb_tc_gemm(ctypes.byref(p), bn, st)
+                launch(ctypes.byref(p), bn, st)
         g.replay()
         torch.cuda.synchronize()
         best = 1e30

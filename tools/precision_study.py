@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from monopsr_b200.core import model_spec as ms
 from oracle import network as onet
-dev = torch.device("cuda:0")
+dev = torch.device(os.environ.get("MPB_STUDY_DEV", "cuda:0"))
 P, S = ms.init_params(0, randomize_bn=True), ms.synthetic_sample(0)
 Pt, St = onet.to_torch(P, torch.float64, dev), onet.to_torch(S, torch.float64, dev)
 def run():
