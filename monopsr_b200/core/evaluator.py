@@ -1,13 +1,15 @@
 """Inference / evaluation driver -- host-side mirror of the per-checkpoint loop of src/monopsr/core/evaluator.py
 (run_checkpoint_once, :136-385) for the B200 engine: restore a checkpoint (EMA shadows, as the reference's
 MovingAverageOptimizer swapping saver does), run every sample forward, format and save the predictions
-(monopsr_model.py:960-1102 via core/predictions.py) and, in 'val' mode, collect the losses.  The KITTI native AP
-evaluator the reference shells out to afterwards (evaluator_utils.py) is not part of this."""
+(monopsr_model.py:960-1102 via core/predictions.py) and, in 'val' mode, collect the losses; then
+(`convert_and_evaluate`, evaluator.py:336-372) convert the prediction files to KITTI result files and run the AP
+evaluation (core/evaluator_utils.py, core/kitti_eval.py -- in process instead of the reference's compiled binary)."""
 import os
 import time
 
 import numpy as np
 
+from . import evaluator_utils
 from . import predictions as P
 
 
@@ -52,3 +54,41 @@ class Evaluator(object):
             self.log("Step {}: {} / {}, Inference on sample {}".format(
                 os.path.basename(str(checkpoint_prefix)), n, "?", sample_dict[P.SAMPLE_NAME]))
         return {"num_samples": n, "mean_losses": {k: v / max(n, 1) for k, v in sums.items()}, "seconds": time.time() - t0}
+
+    def convert_and_evaluate(self, dataset, predictions_base_dir, global_step, kitti_score_threshold=0.1,
+                             results_root=None, checkpoint_name="model", label_dir=None, already_evaluated_path=None):
+        """After the epoch (evaluator.py:336-372): 'val' converts the 2-D detections (if box_2d is an output type) and
+        the 3-D detections (if centroids is) and evaluates each conversion; 'test' does the 3-D part when the split
+        has labels.  -> list of core.kitti_eval.evaluate results, in that order.  The reference appends the step to
+        its list of evaluated checkpoints (already_evaluated_path) in 'val' mode."""
+        label_dir = label_dir if label_dir is not None else getattr(dataset, "kitti_label_dir", None)
+        results_root = results_root if results_root is not None else os.path.join(predictions_base_dir, "offline_eval")
+        out = []
+
+        def native():
+            out.append(evaluator_utils.run_kitti_native_eval(
+                checkpoint_name, dataset.data_split, kitti_score_threshold, global_step, label_dir, predictions_base_dir,
+                results_root, log=self.log))
+
+        quiet = None
+        if self.mode == "val":
+            if P.KEY_BOX_2D in self.output_types:
+                evaluator_utils.save_predictions_box_2d_in_kitti_format(
+                    kitti_score_threshold, dataset, predictions_base_dir, self.output_dirs[P.OUT_DIR_BOX_2D], global_step,
+                    log=quiet)
+                native()
+            if P.KEY_CENTROIDS in self.output_types:
+                evaluator_utils.save_predictions_box_3d_in_kitti_format(
+                    kitti_score_threshold, dataset, predictions_base_dir, self.output_dirs[P.OUT_DIR_BOX_3D],
+                    self.output_dirs[P.OUT_DIR_BOX_2D], global_step, log=quiet)
+                native()
+            if already_evaluated_path is not None:
+                with open(already_evaluated_path, "ba") as f:
+                    np.savetxt(f, [global_step], fmt="%d")
+        elif dataset.has_kitti_labels:
+            evaluator_utils.save_predictions_box_3d_in_kitti_format(
+                kitti_score_threshold, dataset, predictions_base_dir, self.output_dirs[P.OUT_DIR_BOX_3D],
+                self.output_dirs[P.OUT_DIR_BOX_2D], global_step, log=quiet)
+            native()
+        self.log("\nStep {}: Finished evaluation".format(global_step))
+        return out

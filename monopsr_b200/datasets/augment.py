@@ -20,84 +20,92 @@ AUG_FLIPPING = "flipping"
 AUG_PCA_JITTER = "pca_jitter"
 
 
+def _negated(array, index):
+    """copy of `array` with array[index] negated"""
+    out = np.array(array, copy=True)
+    out[index] = -np.asarray(array)[index]
+    return out
+
+
 def flip_image(image):
-    return np.fliplr(image)
+    return image[:, ::-1]
 
 
 def flip_points(points):
     """(N,3) points mirrored in x"""
-    out = np.copy(points)
-    out[:, 0] = -points[:, 0]
-    return out
+    return _negated(points, (slice(None), 0))
 
 
 def flip_point_cloud(point_cloud):
     """(3,N) point cloud mirrored in x"""
-    out = np.copy(point_cloud)
-    out[0] = -point_cloud[0]
-    return out
+    return _negated(point_cloud, 0)
 
 
-def _flip_ry(ry):
-    return np.pi - ry if ry >= 0 else -np.pi - ry
+def flip_ground_plane(ground_plane):
+    """plane a x + b y + c z + d = 0 mirrored in x"""
+    return _negated(ground_plane, 0)
+
+
+def _mirror_heading(ry):
+    """heading of the mirrored object: pi - ry, kept in (-pi, pi] (-pi - ry for negative headings)"""
+    ry = np.asarray(ry, dtype=np.float64)
+    return np.where(ry >= 0, np.pi, -np.pi) - ry
 
 
 def flip_label_in_3d_only(obj_label):
     """mirrored copy of a label: ry and t.x only (the 2-D box is left as is, as in the reference)"""
     out = copy.deepcopy(obj_label)
-    out.ry = _flip_ry(obj_label.ry)
+    out.ry = float(_mirror_heading(obj_label.ry))
     out.t = (-out.t[0], out.t[1], out.t[2])
     return out
 
 
 def flip_boxes_3d(boxes_3d, flip_ry=True):
-    out = np.copy(boxes_3d)
+    out = _negated(boxes_3d, (slice(None), 0))
     if flip_ry:
-        ry = boxes_3d[:, 6]
-        out[:, 6] = np.where(ry >= 0, np.pi - ry, -np.pi - ry)
-    out[:, 0] = -boxes_3d[:, 0]
-    return out
-
-
-def flip_ground_plane(ground_plane):
-    out = np.copy(ground_plane)
-    out[0] = -ground_plane[0]
+        out[:, 6] = _mirror_heading(np.asarray(boxes_3d)[:, 6])
     return out
 
 
 def flip_stereo_calib_p2(calib_p2, image_shape):
     """P2 of the mirrored image: principal point reflected about the image width, baseline term negated"""
-    out = np.copy(calib_p2)
+    out = _negated(calib_p2, (0, 3))
     out[0, 2] = image_shape[1] - calib_p2[0, 2]
-    out[0, 3] = -calib_p2[0, 3]
     return out
 
 
 def apply_image_noise(image_rgb, rng=np.random):
     """One of: G/B channel swap (p 0.1), per-pixel gaussian (sigma 10), per-channel gaussian (sigma 8), brightness
     (sigma 15), uniform noise of random amplitude < 10 (p 0.4 each).  As in the reference every effect is applied to
-    the ORIGINAL image, so when several fire only the last one survives."""
-    image_rgb = np.asarray(image_rgb, dtype=np.uint8)
-    out = image_rgb
-    fire = rng.rand(5)
+    the ORIGINAL image, so when several fire only the last one survives; the draws are made in the reference's order
+    (five gate values first, then the parameters of each effect that fires)."""
+    src = np.asarray(image_rgb, dtype=np.uint8)
+    shape = src.shape
+    gates = rng.rand(5)
 
-    def clipped(noise):
-        return np.uint8(np.clip(image_rgb + noise, 0.0, 255.0))
+    def swap_gb():
+        # (sic) the reference assigns two VIEWS of the same array to each other: channel 1 receives channel 2 and
+        # channel 2 then receives the already overwritten channel 1, so both end up holding the old channel 2
+        img = src.copy()
+        img[:, :, 1] = img[:, :, 2]
+        return img
 
-    if fire[0] < 0.10:
-        out = np.copy(image_rgb)
-        # (sic) the reference's tuple assignment of two VIEWS copies channel 2 into 1 and then 1 (already
-        # overwritten) back into 2: both end up holding the old channel 2
-        out[:, :, 1], out[:, :, 2] = out[:, :, 2], out[:, :, 1]
-    if fire[1] < 0.40:
-        out = clipped(rng.randn(*image_rgb.shape) * 10.0)
-    if fire[2] < 0.40:
-        out = clipped(rng.randn(3) * 8.0)
-    if fire[3] < 0.40:
-        out = clipped(rng.randn(1) * 15.0)
-    if fire[4] < 0.40:
-        amount = rng.uniform(0, 10)
-        out = clipped(rng.uniform(-amount, amount, image_rgb.shape))
+    def additive(draw):
+        return lambda: np.uint8(np.clip(src + draw(), 0.0, 255.0))
+
+    def uniform_noise():
+        amplitude = rng.uniform(0, 10)
+        return rng.uniform(-amplitude, amplitude, shape)
+
+    effects = ((0.10, swap_gb),
+               (0.40, additive(lambda: rng.randn(*shape) * 10.0)),
+               (0.40, additive(lambda: rng.randn(3) * 8.0)),
+               (0.40, additive(lambda: rng.randn(1) * 15.0)),
+               (0.40, additive(uniform_noise)))
+    out = src
+    for gate, (p, effect) in zip(gates, effects):
+        if gate < p:
+            out = effect()
     return out
 
 

@@ -1,0 +1,3 @@
+// oracle/boost_shim -- see boost/geometry.hpp
+#pragma once
+#include <boost/geometry.hpp>

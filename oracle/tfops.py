@@ -34,7 +34,8 @@ def build(force=False):
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "libtfops_oracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir(os.environ.get("MONOPSR_REFERENCE", "/root/reference")):
-        if force or not os.path.exists(os.path.join(_HERE, "_ref", "libtfops_ref_cpu.so")):
+        if force or not all(os.path.exists(os.path.join(_HERE, "_ref", f))
+                            for f in ("libtfops_ref_cpu.so", "evaluate_object_3d_offline")):
             subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 

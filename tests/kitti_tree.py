@@ -144,3 +144,29 @@ def summarize(sample_dict):
         else:
             out[k] = a
     return out
+
+
+def write_predictions(root, sample_names, seed=11):
+    """'%0.5f' prediction files as core/predictions.save_predictions writes them, for the evaluator_utils converters:
+    <root>/box_3d (x y z l w h ry score class), <root>/box_2d (y1 x1 y2 x2 alpha score class), <root>/box_2d_only
+    (y1 x1 y2 x2 score class).  One sample gets no file, one an empty file, one only low scores."""
+    rng = np.random.RandomState(seed)
+    d3, d2, d2o = (os.path.join(root, d) for d in ("box_3d", "box_2d", "box_2d_only"))
+    for d in (d3, d2, d2o):
+        os.makedirs(d, exist_ok=True)
+    for i, name in enumerate(sample_names):
+        if i == 1 and len(sample_names) > 3:
+            continue                                  # no prediction file at all
+        n = 0 if i == 2 else int(rng.randint(1, 7))
+        x = rng.uniform(-25, 25, n)
+        z = rng.uniform(4, 60, n)
+        b3 = np.column_stack([x, rng.uniform(1.2, 2.0, n), z, rng.uniform(3, 5, n), rng.uniform(1.4, 2, n),
+                              rng.uniform(1.3, 1.8, n), rng.uniform(-3.1, 3.1, n),
+                              rng.uniform(0.0, 0.09, n) if i == 0 else rng.uniform(0, 1, n), np.zeros(n)])
+        y1, x1 = rng.uniform(100, 250, n), rng.uniform(0, 1000, n)
+        b2 = np.column_stack([y1, x1, y1 + rng.uniform(20, 120, n), x1 + rng.uniform(20, 200, n),
+                              rng.uniform(-3.1, 3.1, n), b3[:, 7], np.zeros(n)])
+        np.savetxt(os.path.join(d3, name + ".txt"), b3, fmt="%0.5f")
+        np.savetxt(os.path.join(d2, name + ".txt"), b2, fmt="%0.5f")
+        np.savetxt(os.path.join(d2o, name + ".txt"), b2[:, [0, 1, 2, 3, 5, 6]], fmt="%0.5f")
+    return d3, d2, d2o

@@ -103,3 +103,41 @@ def test_evaluator_writes_predictions(tmp_path):
     assert np.load(os.path.join(dirs[P.OUT_DIR_XYZ_MAP_LOCAL], "000007.npy")).shape == (4, 48, 48, 3)
     with pytest.raises(ValueError):
         E.Evaluator(eng, types, dirs, train_val_test="train")
+
+
+def test_loader_to_ap_numbers_with_a_stub_engine(tmp_path):
+    """val split of the synthetic KITTI tree -> PrefetchLoader(epochs=1) -> Evaluator (the stub engine answers with the
+    ground-truth boxes) -> prediction files -> KITTI result files -> AP lines and the results file"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kitti_tree
+    from monopsr_b200.datasets import kitti_loader as KL
+    dataset_dir, data_dir = kitti_tree.make_tree(str(tmp_path / "tree"))
+    cfg = kitti_tree.apply_overrides(KL.DatasetBuilder.get_config_obj(KL.DatasetBuilder.KITTI_TRAIN), dataset_dir,
+                                     {"data_split": "val", "use_mscnn_detections": False})
+    ds = KL.KittiDataset(cfg, "val", data_dir=data_dir, rng=np.random.RandomState(0))
+    eng = StubEngine()
+    types = [P.KEY_CENTROIDS, P.KEY_LWH, P.KEY_VIEW_ANG, P.KEY_ALPHA]
+    base = str(tmp_path / "predictions")
+    dirs = {P.OUT_DIR_BOX_2D: base + "/box_2d", P.OUT_DIR_BOX_3D: base + "/box_3d"}
+    lines = []
+    ev = E.Evaluator(eng, types, dirs, train_val_test="val", log=lambda *a: lines.append(" ".join(map(str, a))))
+    with KL.PrefetchLoader(ds, epochs=1) as loader:
+        res = ev.run_checkpoint_once(None, loader)
+    assert res["num_samples"] == 3 and set(res["mean_losses"]) == {"total_loss", "lwh_offs"}
+    assert sorted(os.listdir(dirs[P.OUT_DIR_BOX_3D])) == ["000008.txt", "000108.txt"]
+    done = str(tmp_path / "already_evaluated.txt")
+    # (box scores of unscored ground-truth labels are tiny: score_boxes multiplies by the label score)
+    out = ev.convert_and_evaluate(ds, base, 1200, kitti_score_threshold=0.001, checkpoint_name="stub_cfg",
+                                  already_evaluated_path=done)
+    assert len(out) == 1 and open(done).read().split() == ["1200"]
+    ap = out[0]["ap"]
+    assert {"car_detection", "car_detection_BEV", "car_detection_3D", "car_heading_3D"} <= set(ap)
+    c = out[0]["curves"]["car_detection"]
+    assert c[2][0] == 1.0                                   # the labelled 2-D boxes come back: precision 1
+    assert out[0]["curves"]["car_detection_3D"].shape == (3, 41)      # (the stub's 3-D boxes are not meant to match)
+    results = open(os.path.join(base, "offline_eval", "results", "val", "stub_cfg_results_0.001.txt")).read().splitlines()
+    assert results[0] == "1200" and results[1:] == out[0]["lines"]
+    assert any(l.startswith("car_detection_3D AP:") for l in lines) and "Finished evaluation" in lines[-1]
+    kitti_files = sorted(os.listdir(os.path.join(base, "kitti_predictions_3d", "val", "0.001", "1200", "data")))
+    assert kitti_files == ["000008.txt", "000076.txt", "000108.txt"]       # a sample without detections: empty file
