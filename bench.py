@@ -320,6 +320,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
         "config": {"workload": "cfg2: 32 crops 48x48x3 + 160x608 full image per GPU, monopsr_model_000 "
                                "fwd+bwd+train-op (clip+Adam+EMA)", "crops_per_gpu": CROPS_PER_SAMPLE,
+                   "precision": "3xTF32 forward (MPB_PRECISION=x3), single-pass tf32 backward" if getattr(eng, "x3", False)
+                                else "single-pass tf32",
                    "points_per_instance": 2304, "parallelism": "dp%d" % world, "l2": "flushed between timed steps",
                    "weights": "random-init, seed 0"},
         "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -391,7 +391,10 @@ class Engine:
             p.round_tf32, p.out_r, p.ldor = 0, None, 0
             if not atomic:
                 p.ksplit = 1
-            self._chk(self.L.mpb_tc_gemm_x3(ctypes.byref(p), 128 if Cout % 128 == 0 else 64, self._st()), "mpb_tc_gemm_x3")
+            bn3 = 128 if Cout % 128 == 0 else 64
+            if getattr(self, "_record", None) is not None:
+                self._record.append((p, -bn3, 2.0 * M * Cin * Cout * k * k))      # negative tile width = x3 launch
+            self._chk(self.L.mpb_tc_gemm_x3(ctypes.byref(p), bn3, self._st()), "mpb_tc_gemm_x3")
             return
         if getattr(self, "_record", None) is not None:
             self._record.append((p, bn, 2.0 * M * Cin * Cout * k * k))
@@ -410,7 +413,10 @@ class Engine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
                 for p, bn, _ in rec:
-                    self._chk(self.L.mpb_tc_gemm(ctypes.byref(p), bn, self._st()), "mpb_tc_gemm")
+                    if bn < 0:
+                        self._chk(self.L.mpb_tc_gemm_x3(ctypes.byref(p), -bn, self._st()), "mpb_tc_gemm_x3")
+                    else:
+                        self._chk(self.L.mpb_tc_gemm(ctypes.byref(p), bn, self._st()), "mpb_tc_gemm")
         torch.cuda.synchronize(self.dev)
         g.replay()
         torch.cuda.synchronize(self.dev)

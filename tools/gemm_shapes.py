@@ -25,7 +25,8 @@ for p, bn, fl in rec:
 rows = []
 for key, items in groups.items():
     p, bn, fl = items[0]
-    us = gs.time_it(p, bn)
+    us = gs.time_it(p, abs(bn), x3=bn < 0)          # negative tile width: a 3xTF32 forward launch (MPB_PRECISION=x3)
+    bn = abs(bn)
     ncols = {0: p.Cout, 1: p.Cin, 2: p.kh * p.kw * p.Cin}[p.op]
     nrows = p.Cout if p.op == 2 else p.M
     ctas = ((nrows + 127) // 128) * (ncols // bn) * p.ksplit
