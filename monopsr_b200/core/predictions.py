@@ -28,7 +28,7 @@ SAMPLE_NAME, SAMPLE_IMAGE_INPUT, SAMPLE_NUM_OBJS = "sample_name", "sample_image_
 SAMPLE_CAM_P, SAMPLE_LABEL_SCORES = "sample_cam_p", "sample_label_scores"
 SAMPLE_LABEL_BOXES_2D, SAMPLE_LABEL_BOXES_3D = "sample_label_boxes_2d", "sample_label_boxes_3d"
 SAMPLE_VIEWING_ANGLES_3D, SAMPLE_LABEL_CLASS_INDICES = "sample_viewing_angles_3d", "sample_label_class_indices"
-OUT_DIR_XYZ_MAP_LOCAL, OUT_DIR_BOX_2D, OUT_DIR_BOX_3D = "out_dir_xyz_map_local", "out_dir_box_2d", "out_dir_box_3d"
+OUT_DIR_XYZ_MAP_LOCAL, OUT_DIR_BOX_2D, OUT_DIR_BOX_3D = "output_xyz_map_dir", "output_box_2d_dir", "output_box_3d_dir"
 
 
 def np_angle_bin_to_orientation(angle_bin, residual, num_bins):

@@ -44,7 +44,9 @@ class StubEngine(object):
     def outputs(self):
         rng = np.random.RandomState(0)
         n = self.N
-        b3 = self.sample["boxes_3d"]
+        b3 = self.sample.get("boxes_3d")          # absent in 'test' mode samples
+        if b3 is None:
+            b3 = np.tile(np.asarray([0.0, 1.5, 20.0, 3.9, 1.6, 1.5, 0.0], np.float32), (n, 1))
         return {"inst_xyz_map_local": rng.randn(n, 48, 48, 3).astype(np.float32), "valid_mask_maps": None,
                 "lwh": b3[:, 3:6], "alpha_bins": rng.randn(n, 12).astype(np.float32),
                 "alpha_regs": rng.randn(n, 12).astype(np.float32) * 0.1, "view_ang": self.sample["est_view_angs"][:, None],
