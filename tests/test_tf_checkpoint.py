@@ -134,3 +134,38 @@ def test_detection_checkpoint_feeds_both_encoders(tmp_path):
     for (nc, _, _), (nf, _, _) in zip(crop, full):
         assert np.array_equal(params[nc], params[nf])
         assert np.array_equal(params[nc], ck["FirstStageFeatureExtractor/" + nc[len(ms.ENCODERS[0]) + 1:]])
+
+
+def test_primitives_against_the_tensorflow_ecosystem_code_in_tensorboard():
+    """tensorboard ships TensorFlow's record checksum (CRC-32C + the rotate-and-add mask) and the generated protobuf
+    classes of tensor_shape.proto / types.proto / versions.proto: an independent implementation, written by the
+    TensorFlow authors, of three pieces the bundle format is made of."""
+    pw = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    shape_pb2 = pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    types_pb2 = pytest.importorskip("tensorboard.compat.proto.types_pb2")
+    rs = np.random.RandomState(0)
+    for n in (0, 1, 7, 8, 9, 63, 64, 65, 1000, 4097):
+        data = rs.randint(0, 256, n).astype(np.uint8).tobytes()
+        assert C.crc32c(data) == pw.crc32c(data)
+        assert C.mask_crc(C.crc32c(data)) == pw.masked_crc32c(data)
+    # the enum values the reader / writer use for dtypes
+    for np_dtype, name in ((np.float32, "DT_FLOAT"), (np.float64, "DT_DOUBLE"), (np.int32, "DT_INT32"),
+                           (np.int64, "DT_INT64"), (np.uint8, "DT_UINT8"), (np.float16, "DT_HALF"), (np.bool_, "DT_BOOL")):
+        if np.dtype(np_dtype) in C.DTYPE_ENUM:
+            assert C.DTYPE_ENUM[np.dtype(np_dtype)] == getattr(types_pb2, name), name
+            assert np.dtype(C.DTYPES[getattr(types_pb2, name)]) == np.dtype(np_dtype)
+    assert C.DTYPE_ENUM[np.dtype(np.float32)] == types_pb2.DT_FLOAT and C.DTYPE_ENUM[np.dtype(np.int64)] == types_pb2.DT_INT64
+    # BundleEntryProto.shape (field 2) as written here parses with the generated TensorShapeProto class, and a shape
+    # serialised BY that class parses with the reader
+    for shape in ((), (7,), (3, 3, 64, 256), (1, 0, 5), (18432, 1024)):
+        arr = np.zeros(shape, np.float32) if int(np.prod(shape, dtype=np.int64)) < 10 ** 6 else np.lib.stride_tricks.as_strided(
+            np.zeros(1, np.float32), shape=shape, strides=(0,) * len(shape))
+        msg = C._entry_proto(arr, 12, 0xABCDEF)
+        fields = {f: v for f, _, v in C._proto_fields(msg)}
+        assert fields[1] == types_pb2.DT_FLOAT and fields[4] == 12 and fields[5] == arr.size * 4
+        parsed = shape_pb2.TensorShapeProto.FromString(bytes(fields.get(2, b"")))
+        assert tuple(d.size for d in parsed.dim) == tuple(shape)
+        theirs = shape_pb2.TensorShapeProto(dim=[shape_pb2.TensorShapeProto.Dim(size=s) for s in shape]).SerializeToString()
+        assert C._parse_shape(theirs) == tuple(shape)
+    with pytest.raises(ValueError):
+        C._parse_shape(shape_pb2.TensorShapeProto(unknown_rank=True).SerializeToString())
