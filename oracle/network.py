@@ -229,6 +229,67 @@ def to_torch(P, dtype=torch.float64, device="cpu"):
             for k, v in P.items()}
 
 
+def prop_cen_y_from_box(boxes_2d, cam_p, prop_cen_z):
+    """tf_est_y_from_box_2d_and_depth (instance_utils.py:907-953; numpy twin :841-904), 'middle' centroids of cars with
+    the KITTI trend offset: the box centre row back-projected at depth z, minus 0.0648"""
+    N = boxes_2d.shape[0]
+    box_cv = ((boxes_2d[:, 2] + boxes_2d[:, 0]) / 2.0 - cam_p[1, 2]).reshape(N, 1)
+    return box_cv * (prop_cen_z / cam_p[0, 0]) - 0.0648
+
+
+def train_projections(xyz_local, valid, boxes_2d, cam_p, est_view, gt_view, cen_y, cen_z):
+    """The train / val-only geometry of the graph: local map -> camera frame -> image, expected pixel-centre grid,
+    normalised projection error, global depth map.  Numpy twins in the reference (pinned in
+    tests/test_oracle_geometry.py): inst_points_local_to_global (instance_utils.py:552-564), project_pc_to_image
+    (calib_utils.py:245-260), get_exp_proj_uv_map(use_pixel_centres=True) (instance_utils.py:684-735)."""
+    N = xyz_local.shape[0]
+    dt, dev = xyz_local.dtype, xyz_local.device
+    f, centre_u = cam_p[0, 0], cam_p[0, 2]
+    x_offset = -cam_p[0, 3] / cam_p[0, 0]
+    # xyz projection (monopsr_model.py:416-448; output_builder :663-746)
+    proj_cen = torch.cat([cen_z * torch.tan(gt_view) + x_offset, cen_y, cen_z], dim=1)
+    c, s = torch.cos(gt_view)[:, :, None], torch.sin(gt_view)[:, :, None]      # (N,1,1)
+    lx, ly, lz = xyz_local[..., 0], xyz_local[..., 1], xyz_local[..., 2]      # (N,48,48)
+    gx = c * lx + s * lz + proj_cen[:, 0, None, None]
+    gy = ly + proj_cen[:, 1, None, None]
+    gz = -s * lx + c * lz + proj_cen[:, 2, None, None]
+    pu = cam_p[0, 0] * gx + cam_p[0, 1] * gy + cam_p[0, 2] * gz + cam_p[0, 3]
+    pv = cam_p[1, 0] * gx + cam_p[1, 1] * gy + cam_p[1, 2] * gz + cam_p[1, 3]
+    pw = cam_p[2, 0] * gx + cam_p[2, 1] * gy + cam_p[2, 2] * gz + cam_p[2, 3]
+    proj_u, proj_v = pu / pw, pv / pw
+    # expected uv at pixel centres (instance_utils.py:738-788): linspace(start+half, stop-half, 48)
+    lin = torch.arange(48, dtype=dt, device=dev) / 47.0
+    v1, u1, v2, u2 = [boxes_2d[:, i] for i in range(4)]
+    hu, hv = (u2 - u1) / 48 / 2.0, (v2 - v1) / 48 / 2.0
+    grid_u = (u1 + hu)[:, None] + ((u2 - hu) - (u1 + hu))[:, None] * lin[None, :]
+    grid_v = (v1 + hv)[:, None] + ((v2 - hv) - (v1 + hv))[:, None] * lin[None, :]
+    exp_u = grid_u[:, None, :].expand(N, 48, 48)
+    exp_v = grid_v[:, :, None].expand(N, 48, 48)
+    bw, bh = (u2 - u1)[:, None, None], (v2 - v1)[:, None, None]
+    vm = valid[..., 0]
+    eu = torch.clamp((exp_u - proj_u) / bw * vm, -2.0, 2.0)
+    ev = torch.clamp((exp_v - proj_v) / bh * vm, -2.0, 2.0)
+    nvalid = vm.sum((1, 2))
+    nvalid = torch.where(nvalid < 1.0, torch.ones_like(nvalid), nvalid)
+    proj_err_norm = (eu.sum((1, 2)) + ev.sum((1, 2))) / nvalid
+
+    # global depth map (instance_utils.py:607-681, rotate_view=True, quirk Q6)
+    x1b, x2b = boxes_2d[:, 1], boxes_2d[:, 3]
+    sp = (x2b - x1b) / 48 / 2.0
+    va_l = torch.atan2((x1b + sp - centre_u) / f, torch.ones_like(x1b)).reshape(N, 1)
+    va_r = torch.atan2((x2b - sp - centre_u) / f, torch.ones_like(x1b)).reshape(N, 1)
+    inst_xz = cen_z / torch.cos(est_view)
+    l_o = inst_xz / torch.cos(va_l - est_view)
+    r_o = inst_xz / torch.cos(va_r - est_view)
+    off_l = (l_o * torch.sin(va_l - est_view) * torch.sin(est_view)).reshape(N)
+    off_r = (r_o * torch.sin(va_r - est_view) * torch.sin(est_view)).reshape(N)
+    off = (-off_l)[:, None] + ((-off_r) - (-off_l))[:, None] * lin[None, :]       # (N,48), along ROWS
+    depth_global = xyz_local[..., 2:3] + cen_z.reshape(N, 1, 1, 1) + off.reshape(N, 48, 1, 1)
+    return {"global_xyz": torch.stack([gx, gy, gz], dim=-1), "proj_uv": torch.stack([proj_u, proj_v], dim=-1),
+            "exp_uv": torch.stack([exp_u, exp_v], dim=-1), "proj_err_norm": proj_err_norm,
+            "inst_depth_map_global": depth_global}
+
+
 def forward(P, S, train=True):
     """P: dict of torch tensors (see to_torch); S: dict of torch tensors (the synthetic feed_dict).
     Returns (output_dict, aux) -- output_dict keys follow core/constants.py KEY_*."""
@@ -295,8 +356,7 @@ def forward(P, S, train=True):
     # centroid proposals :407-438 ; instance_utils.py:907-953
     f = cam_p[0, 0]
     prop_cen_z = (f * lwh[:, 2] / (boxes_2d[:, 2] - boxes_2d[:, 0]) + S["prop_cen_z_offset"]).reshape(N, 1)
-    box_cv = ((boxes_2d[:, 2] + boxes_2d[:, 0]) / 2.0 - centre_v).reshape(N, 1)
-    prop_cen_y = box_cv * (prop_cen_z / f) - 0.0648
+    prop_cen_y = prop_cen_y_from_box(boxes_2d, cam_p, prop_cen_z)
     out["prop_cen_z"] = prop_cen_z
 
     # regression fc :200-274
@@ -319,47 +379,9 @@ def forward(P, S, train=True):
     if not train:
         return out, aux
 
-    # xyz projection (monopsr_model.py:416-448; output_builder :663-746)
-    gt_view = S["gt_view_angs"].reshape(N, 1)
-    proj_cen = torch.cat([cen_z * torch.tan(gt_view) + x_offset, cen_y, cen_z], dim=1)
-    c, s = torch.cos(gt_view)[:, :, None], torch.sin(gt_view)[:, :, None]      # (N,1,1)
-    lx, ly, lz = xyz_local[..., 0], xyz_local[..., 1], xyz_local[..., 2]      # (N,48,48)
-    gx = c * lx + s * lz + proj_cen[:, 0, None, None]
-    gy = ly + proj_cen[:, 1, None, None]
-    gz = -s * lx + c * lz + proj_cen[:, 2, None, None]
-    pu = cam_p[0, 0] * gx + cam_p[0, 1] * gy + cam_p[0, 2] * gz + cam_p[0, 3]
-    pv = cam_p[1, 0] * gx + cam_p[1, 1] * gy + cam_p[1, 2] * gz + cam_p[1, 3]
-    pw = cam_p[2, 0] * gx + cam_p[2, 1] * gy + cam_p[2, 2] * gz + cam_p[2, 3]
-    proj_u, proj_v = pu / pw, pv / pw
-    # expected uv at pixel centres (instance_utils.py:738-788): linspace(start+half, stop-half, 48)
-    lin = torch.arange(48, dtype=dt, device=dev) / 47.0
-    v1, u1, v2, u2 = [boxes_2d[:, i] for i in range(4)]
-    hu, hv = (u2 - u1) / 48 / 2.0, (v2 - v1) / 48 / 2.0
-    grid_u = (u1 + hu)[:, None] + ((u2 - hu) - (u1 + hu))[:, None] * lin[None, :]
-    grid_v = (v1 + hv)[:, None] + ((v2 - hv) - (v1 + hv))[:, None] * lin[None, :]
-    exp_u = grid_u[:, None, :].expand(N, 48, 48)
-    exp_v = grid_v[:, :, None].expand(N, 48, 48)
-    bw, bh = (u2 - u1)[:, None, None], (v2 - v1)[:, None, None]
-    vm = valid[..., 0]
-    eu = torch.clamp((exp_u - proj_u) / bw * vm, -2.0, 2.0)
-    ev = torch.clamp((exp_v - proj_v) / bh * vm, -2.0, 2.0)
-    nvalid = vm.sum((1, 2))
-    nvalid = torch.where(nvalid < 1.0, torch.ones_like(nvalid), nvalid)
-    out["proj_err_norm"] = (eu.sum((1, 2)) + ev.sum((1, 2))) / nvalid
-
-    # global depth map (instance_utils.py:607-681, rotate_view=True, quirk Q6)
-    x1b, x2b = boxes_2d[:, 1], boxes_2d[:, 3]
-    sp = (x2b - x1b) / 48 / 2.0
-    va_l = torch.atan2((x1b + sp - centre_u) / f, torch.ones_like(x1b)).reshape(N, 1)
-    va_r = torch.atan2((x2b - sp - centre_u) / f, torch.ones_like(x1b)).reshape(N, 1)
-    inst_xz = cen_z / torch.cos(est_view)
-    l_o = inst_xz / torch.cos(va_l - est_view)
-    r_o = inst_xz / torch.cos(va_r - est_view)
-    off_l = (l_o * torch.sin(va_l - est_view) * torch.sin(est_view)).reshape(N)
-    off_r = (r_o * torch.sin(va_r - est_view) * torch.sin(est_view)).reshape(N)
-    off = (-off_l)[:, None] + ((-off_r) - (-off_l))[:, None] * lin[None, :]       # (N,48), along ROWS
-    depth_global = xyz_local[..., 2:3] + cen_z.reshape(N, 1, 1, 1) + off.reshape(N, 48, 1, 1)
-    out["inst_depth_map_global"] = depth_global
+    g = train_projections(xyz_local, valid, boxes_2d, cam_p, est_view, S["gt_view_angs"].reshape(N, 1), cen_y, cen_z)
+    out["proj_err_norm"] = g["proj_err_norm"]
+    out["inst_depth_map_global"] = g["inst_depth_map_global"]
     return out, aux
 
 
