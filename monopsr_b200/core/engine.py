@@ -590,10 +590,13 @@ class Engine:
         self._chk(self.L.mpb_bias_relu(N, 1024, _ptr(acc), 1024, _ptr(self.view(wname + "/biases")), 1, 1, _ptr(out), ldo,
                                        self._st()), "bias_relu")
 
-    def forward(self, train=True, compute_losses=None):
+    def forward(self, train=True, compute_losses=None, features_only=False):
         """train: the reference's is_training (decoder batch norm with batch statistics + moving-average update, and
         the gradient arena is zeroed for a backward pass); compute_losses (default = train): evaluate the losses in
-        the heads kernel -- validation runs an is_training=False graph but still reports losses."""
+        the heads kernel -- validation runs an is_training=False graph but still reports losses.
+        features_only: stop after the feature extractor (net_builder.extract_features, net_builder.py:17-96) and
+        return {'features_for_map': (N,48,48,128), 'features_for_box_3d': (N,6,6,512)}; needs only the inputs
+        rgb_crops, full_img and boxes_2d_norm."""
         if compute_losses is None:
             compute_losses = train
         if not self._prepared:
@@ -614,8 +617,9 @@ class Engine:
         self.gemm(TC_FWD, Mc, 12, 12, 1, 1, 2048, 512, self.concat, 2048, self.pview("squash/1x1_conv/weights"), 2048,
                   self.squashed, 512, shift=self.view("squash/1x1_conv/biases"), relu=1, round_tf32=1)
         self._chk(L.mpb_maxpool2_fwd(N, 12, 12, 512, _ptr(self.squashed), 512, _ptr(self.pooled), 512, st), "pool")
-        with self._side(self.s_fc):
-            self._fc_forward()
+        if not features_only:
+            with self._side(self.s_fc):
+                self._fc_forward()
         self._chk(L.mpb_resize_ac_fwd(N, 12, 12, 512, _ptr(self.squashed), 24, 24, _ptr(self.r1), st), "resize1")
         x = self.r1
         for i, D in enumerate(self.dec):
@@ -637,6 +641,8 @@ class Engine:
                                              BN_EPS_DECODER, _ptr(D["y"]), st), "bn_infer_fwd")
             D["x"] = x
             x = D["y"]
+        if features_only:
+            return {"features_for_map": x.view(N, 48, 48, 128), "features_for_box_3d": self.pooled.view(N, 6, 6, 512)}
         sx = "output/inst_xyz_map_local/inst_xyz_map_local"
         self._chk(L.mpb_xyzhead_fwd(N, 48, 48, _ptr(x), _ptr(self.view(sx + "/weights")), _ptr(self.view(sx + "/biases")),
                                     _ptr(self.xyz), st), "xyzhead_fwd")

@@ -164,3 +164,29 @@ def test_oracle_inference_mode_batch_norm():
     yt, _, _ = onet.train_bn_relu(x, P, "s")
     yi, _, _ = onet.infer_bn_relu(x, P, "s")
     assert torch.allclose(yt, yi, rtol=1e-10, atol=1e-10)
+
+
+def test_net_builder_plugin_boundary():
+    """extract_features: only resnet101_4x_squash, inputs by the reference's keys, the two feature maps back"""
+    import types
+    from monopsr_b200.builders import net_builder as NB
+
+    class Eng(object):
+        def set_inputs(self, S):
+            self.S = S
+
+        def forward(self, train=True, compute_losses=None, features_only=False):
+            self.args = (train, features_only)
+            return {"features_for_map": "MAP", "features_for_box_3d": "BOX"}
+    eng = Eng()
+    model = types.SimpleNamespace(engine=eng, boxes_2d_norm="B")
+    out = NB.extract_features(model, "resnet101_4x_squash", None, {NB.NET_IN_RGB_CROP: "C", NB.NET_IN_FULL_IMG: "F"}, False)
+    assert out == {NB.FEATURES_FOR_MAP: "MAP", NB.FEATURES_FOR_BOX_3D: "BOX"}
+    assert eng.S == {"rgb_crops": "C", "full_img": "F", "boxes_2d_norm": "B"} and eng.args == (False, True)
+    NB.extract_features(eng, "resnet101_4x_squash", None, {NB.NET_IN_RGB_CROP: "C", NB.NET_IN_FULL_IMG: "F"}, True)
+    assert eng.args == (True, True) and "boxes_2d_norm" not in eng.S
+    with pytest.raises(ValueError):
+        NB.extract_features(model, "vgg16", None, {}, True)
+    cfg = types.SimpleNamespace(net_type="resnet101_4x_squash",
+                                net_config=types.SimpleNamespace(resnet101_4x_squash="EXTRACTOR"))
+    assert NB.get_net_config(cfg) == "EXTRACTOR"
