@@ -111,7 +111,10 @@ def apply_image_noise(image_rgb, rng=np.random):
 
 def jitter_obj_boxes_2d(obj_labels, iou_threshold_min, image_shape, rng=np.random):
     """Copies of the labels with randomly shifted / rescaled 2-D boxes: rejection sampling until the new box (clamped to
-    the image) overlaps the original with IoU >= iou_threshold_min; boxes under 10 px in either side are left alone."""
+    the image) overlaps the original with IoU >= iou_threshold_min; boxes under 10 px in either side are left alone.
+    The acceptance test is core/evaluation.two_d_iou of the reference (unrounded) for one box against one box, written
+    out on scalars -- the loop runs ~100 times per sample -- with the same operand types: the candidate in double
+    precision, the original box and its area in the precision the label carries (float32 when read from a file)."""
     img_h, img_w = image_shape[0], image_shape[1]
     out = np.empty(len(obj_labels), dtype=object)
     for i, o in enumerate(obj_labels):
@@ -122,12 +125,19 @@ def jitter_obj_boxes_2d(obj_labels, iou_threshold_min, image_shape, rng=np.rando
             continue
         cx, cy = (o.x2 + o.x1) / 2, (o.y2 + o.y1) / 2
         original = np.asarray([[o.x1, o.y1, o.x2, o.y2]])
-        iou = 0
+        ox1, oy1, ox2, oy2 = (float(v) for v in original[0])
+        o_area = float((original[0, 2] - original[0, 0]) * (original[0, 3] - original[0, 1]))     # in the label's precision
+        iou = 0.0
         while iou < iou_threshold_min:
             ncx, ncy = rng.normal(cx, half_w / 3), rng.normal(cy, half_h / 3)
             nhw, nhh = rng.normal(half_w, half_w / 6), rng.normal(half_h, half_h / 6)
-            x1, x2 = np.maximum(0, ncx - nhw), np.minimum(img_w - 1, ncx + nhw)
-            y1, y2 = np.maximum(0, ncy - nhh), np.minimum(img_h - 1, ncy + nhh)
-            iou = K.two_d_iou(np.asarray([x1, y1, x2, y2]), original)
-        new.x1, new.y1, new.x2, new.y2 = x1, y1, x2, y2
+            x1, x2 = max(0.0, ncx - nhw), min(float(img_w - 1), ncx + nhw)
+            y1, y2 = max(0.0, ncy - nhh), min(float(img_h - 1), ncy + nhh)
+            w, h = min(x2, ox2) - max(x1, ox1), min(y2, oy2) - max(y1, oy1)
+            if w > 0 and h > 0:
+                inter = w * h
+                iou = inter / ((x2 - x1) * (y2 - y1) + o_area - inter)
+            else:
+                iou = 0.0
+        new.x1, new.y1, new.x2, new.y2 = np.float64(x1), np.float64(y1), np.float64(x2), np.float64(y2)
     return out

@@ -10,7 +10,8 @@
                       (monopsr_model.py:494-503); at 8.5 ms per step the PNG decode + label work (tens of ms) would
                       dominate, so samples are produced by a background thread into a bounded queue while the GPU runs.
                       One producer thread => the dataset's random stream is consumed in the same order as a
-                      synchronous loop, so seeded runs stay reproducible.
+                      synchronous loop, so seeded runs stay reproducible; with workers > 0 the PNG decoding (the bulk
+                      of the time, no randomness) of the next samples runs on extra threads (ReadAhead).
 """
 import fnmatch
 import os
@@ -159,13 +160,31 @@ class KittiDataset(object):
             return np.asarray(f.read().splitlines())
 
     # ------------------------------------------------------------------ one sample
+    _READERS = {"rgb": K.read_rgb_image, "depth": K.read_depth_map, "instance": K.read_instance_image}
+
+    def sample_files(self, sample_name):
+        """(kind, path) of the image-like files one sample may read"""
+        files = [("rgb", self.get_rgb_image_path(sample_name))]
+        if self.train_val_test in ("train", "val"):
+            files += [("instance", self.instance_dir + "/{}.png".format(sample_name)),
+                      ("depth", self.depth_dir + "/{}.png".format(sample_name))]
+        return files
+
+    def _read(self, kind, path):
+        ahead = getattr(self, "_read_ahead", None)       # set by PrefetchLoader(workers > 0)
+        if ahead is not None:
+            hit = ahead.take(kind, path)
+            if hit is not None:
+                return hit
+        return self._READERS[kind](path)
+
     def _oversample_indices(self, num_objs):
         extra = self.rng.choice(num_objs, self.num_boxes - num_objs, replace=True)
         return np.hstack([np.arange(0, num_objs), extra])
 
     def _load_one(self, sample):
         name = sample.name
-        rgb_image = K.read_rgb_image(self.get_rgb_image_path(name))
+        rgb_image = self._read("rgb", self.get_rgb_image_path(name))
         image_shape = rgb_image.shape[0:2]
         image_input = rgb_image
         cam_p = K.read_frame_calib(self.calib_dir + "/{}.txt".format(name)).p2
@@ -191,7 +210,7 @@ class KittiDataset(object):
                 kitti_labels, _ = K.apply_obj_filter(kitti_labels, self.obj_filter)
                 if len(kitti_labels) < 1:
                     return None
-            masks = K.get_instance_mask_list(K.read_instance_image(self.instance_dir + "/{}.png".format(name)), num_all)
+            masks = K.get_instance_mask_list(self._read("instance", self.instance_dir + "/{}.png".format(name)), num_all)
             masks = masks[keep]
             if self.oversample:
                 idx = self._oversample_indices(num_objs)
@@ -225,7 +244,7 @@ class KittiDataset(object):
                 SAMPLE_VIEWING_ANGLES_3D: np.asarray([K.get_viewing_angle_box_3d(b, cam_p) for b in boxes_3d],
                                                      dtype=np.float32),
                 SAMPLE_INSTANCE_MASKS: masks,
-                SAMPLE_DEPTH_MAP: K.read_depth_map(self.depth_dir + "/{}.png".format(name)),
+                SAMPLE_DEPTH_MAP: self._read("depth", self.depth_dir + "/{}.png".format(name)),
             }
         elif mode == "test":
             labels = K.read_labels(self.mscnn_label_dir, name)
@@ -333,6 +352,14 @@ class DatasetBuilder(object):
         return KittiDataset(dataset_config, train_val_test, **kw)
 
 
+def _as_uint8(masks):
+    """boolean (N,H,W) masks as uint8 without copying 15 MB when they are already contiguous"""
+    m = np.asarray(masks)
+    if m.dtype == np.bool_ and m.flags["C_CONTIGUOUS"]:
+        return m.view(np.uint8)
+    return np.ascontiguousarray(m, dtype=np.uint8)
+
+
 def engine_sample(sample_dict, train_val_test="train"):
     """sample_dict -> the dict Engine.set_inputs takes: the placeholders of monopsr_model.py:494-552 under the engine's
     key names, fp32 / int32, with the RAW image, depth map and instance masks -- the crops, the resized full image and
@@ -358,11 +385,48 @@ def engine_sample(sample_dict, train_val_test="train"):
             "gt_alpha_valid_bins": f32(SAMPLE_ALPHA_VALID_BINS),
             "gt_view_angs": f32(SAMPLE_VIEWING_ANGLES_3D),
             "depth_map": f32(SAMPLE_DEPTH_MAP),
-            "instance_masks": np.ascontiguousarray(s[SAMPLE_INSTANCE_MASKS], dtype=np.uint8),
+            "instance_masks": _as_uint8(s[SAMPLE_INSTANCE_MASKS]),
         })
     elif train_val_test != "test":
         raise ValueError("Invalid run mode", train_val_test)
     return out
+
+
+class ReadAhead(object):
+    """Decodes the PNGs of the next `lookahead` samples of the split on `workers` threads (cv2 releases the GIL) while
+    the single producer thread does the ordered, random-stream-consuming part of the work.  Purely a cache keyed by
+    (kind, path): a miss falls back to a direct read, a failed read re-raises where the direct read would have."""
+
+    def __init__(self, dataset, workers=4, lookahead=8):
+        from concurrent.futures import ThreadPoolExecutor
+        self.dataset, self.lookahead = dataset, max(1, lookahead)
+        self.pool = ThreadPoolExecutor(max_workers=max(1, workers), thread_name_prefix="kitti-decode")
+        self.pending = {}            # (kind, path) -> Future, insertion-ordered
+        self.hits = self.misses = 0
+
+    def schedule(self):
+        ds = self.dataset
+        start = ds._index_in_epoch
+        for sample in ds.sample_list[start:start + self.lookahead]:
+            for key in ds.sample_files(sample.name):
+                if key not in self.pending:
+                    self.pending[key] = self.pool.submit(ds._READERS[key[0]], key[1])
+        while len(self.pending) > 6 * self.lookahead:           # reshuffled away or never used: forget the oldest
+            self.pending.pop(next(iter(self.pending))).cancel()
+
+    def take(self, kind, path):
+        f = self.pending.pop((kind, path), None)
+        if f is None:
+            self.misses += 1
+            return None
+        self.hits += 1
+        return f.result()
+
+    def close(self):
+        for f in self.pending.values():
+            f.cancel()
+        self.pending.clear()
+        self.pool.shutdown(wait=True)
 
 
 class PrefetchLoader(object):
@@ -376,8 +440,11 @@ class PrefetchLoader(object):
 
     _END = object()
 
-    def __init__(self, dataset, shuffle=None, depth=4, max_samples=None, epochs=None, convert=engine_sample):
+    def __init__(self, dataset, shuffle=None, depth=4, max_samples=None, epochs=None, convert=engine_sample, workers=0):
+        """workers > 0: decode the image files of upcoming samples on that many extra threads (ReadAhead)"""
         self.dataset = dataset
+        self.read_ahead = ReadAhead(dataset, workers, lookahead=2 * workers + depth) if workers > 0 else None
+        dataset._read_ahead = self.read_ahead
         self.shuffle = (dataset.train_val_test == "train") if shuffle is None else shuffle
         self.max_samples, self.epochs = max_samples, epochs
         self.convert = convert
@@ -403,6 +470,8 @@ class PrefetchLoader(object):
                     (last_epoch is None or ds.epochs_completed < last_epoch):
                 sample_dict = None
                 while sample_dict is None and not self._stop.is_set():
+                    if self.read_ahead is not None:
+                        self.read_ahead.schedule()
                     sample_dict = ds.next_batch(batch_size=1, shuffle=self.shuffle)[0]
                 if sample_dict is None or not self._put((self.convert(sample_dict, ds.train_val_test), sample_dict)):
                     return
@@ -436,6 +505,9 @@ class PrefetchLoader(object):
             except queue.Empty:
                 break
         self._thread.join(timeout=5.0)
+        if self.read_ahead is not None:
+            self.dataset._read_ahead = None
+            self.read_ahead.close()
 
     def __enter__(self):
         return self

@@ -306,3 +306,33 @@ def test_prefetch_loader_order_bound_errors_and_shutdown(tree):
             next(loader)
         with pytest.raises(OSError):
             next(loader)
+
+
+def test_read_ahead_changes_nothing_but_the_speed(tree):
+    """workers > 0: same samples, same order, same values as the single-thread loader; the decoded files come from
+    the read-ahead cache; a missing file fails where the direct read would"""
+    runs = []
+    for workers in (0, 3):
+        np.random.seed(21)
+        ds, _ = _dataset(tree, "train_all_noise")
+        with KL.PrefetchLoader(ds, depth=2, max_samples=10, workers=workers) as loader:
+            runs.append([(s[KL.SAMPLE_NAME], e["boxes_2d"], e["rgb_image"], e["depth_map"], e["instance_masks"])
+                         for e, s in loader])
+            if workers:
+                assert loader.read_ahead.hits >= 10 and ds._read_ahead is loader.read_ahead
+        assert ds._read_ahead is None
+    assert len(runs[0]) == len(runs[1]) == 10
+    for a, b in zip(*runs):
+        assert a[0] == b[0]
+        for x, y in zip(a[1:], b[1:]):
+            assert np.array_equal(x, y)
+    ds, _ = _dataset(tree, "val_kitti")
+    os.rename(ds.depth_dir + "/000108.png", ds.depth_dir + "/000108.png.away")
+    try:
+        with KL.PrefetchLoader(ds, epochs=1, workers=2) as loader:
+            e, s = next(loader)
+            assert s[KL.SAMPLE_NAME] == "000008"
+            with pytest.raises(FileNotFoundError):
+                next(loader)
+    finally:
+        os.rename(ds.depth_dir + "/000108.png.away", ds.depth_dir + "/000108.png")
