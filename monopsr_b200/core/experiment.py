@@ -17,6 +17,9 @@ from . import trainer as trainer_mod
 from ..datasets.kitti_loader import DatasetBuilder, KittiDataset, PrefetchLoader
 
 
+LOADER_WORKERS = max(1, min(4, (os.cpu_count() or 2) // 2))      # PNG decode threads beside the ordered producer
+
+
 def output_types_list(output_config):
     """MonoPSROutputBuilder.get_output_types_list (monopsr_output_builder.py:76-81)"""
     return sorted(k for k in output_config.__dict__.keys() if not k.startswith("__"))
@@ -81,7 +84,7 @@ class ExperimentEvaluator(object):
                                      train_val_test=self.eval_mode, centroid_type=d.centroid_type,
                                      post_process_cen_x=getattr(self.model_config, "post_process_cen_x", True),
                                      num_alpha_bins=d.num_alpha_bins, log=self.log)
-        with PrefetchLoader(self.dataset, shuffle=False, epochs=1) as samples:
+        with PrefetchLoader(self.dataset, shuffle=False, epochs=1, workers=LOADER_WORKERS) as samples:
             res = ev.run_checkpoint_once(checkpoint_to_restore, samples)
         res["global_step"] = global_step
         if self.eval_mode == "val" and not self.do_kitti_native_eval:
@@ -144,7 +147,7 @@ def train(config, device="cuda:0", engine_factory=_default_engine, data_dir=None
     config_utils.validate_for_engine(config)
     dataset = KittiDataset(config.dataset_config, "train", data_dir=data_dir)
     engine = engine_factory(device)
-    with PrefetchLoader(dataset, shuffle=True) as loader:
+    with PrefetchLoader(dataset, shuffle=True, workers=LOADER_WORKERS) as loader:
         return trainer_mod.train(engine, config, loader.sample_fn, pretrained_checkpoint=pretrained_checkpoint, log=log)
 
 
