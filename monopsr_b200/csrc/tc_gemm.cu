@@ -977,6 +977,10 @@ tc_gemm_x3_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant_
     const uint32_t base = (raw + 1023u) & ~1023u;
     constexpr uint32_t kHalf = x3_half_bytes<BN>();
     constexpr uint32_t kStage = 2 * kHalf;
+    static_assert(kHalf % 1024 == 0 && kTcABytes % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
+    static_assert((kHalf / 16) % 128 == 0, "the splitter threads share the float4s of a stage evenly");
+    static_assert(x3_smem_bytes<BN>() <= 227 * 1024, "shared memory per CTA");
+    static_assert(((kX3Stages * kStage + 2048) >> 4) < (1u << 14), "descriptor address field: no carry");
     const uint32_t bar_base = base + kX3Stages * kStage;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto split_bar = [&](int s) { return bar_base + 8u * (kX3Stages + s); };
