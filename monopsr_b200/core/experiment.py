@@ -142,13 +142,35 @@ class ExperimentEvaluator(object):
 
 
 # ---------------------------------------------------------------------------------------------- entry points
-def train(config, device="cuda:0", engine_factory=_default_engine, data_dir=None, pretrained_checkpoint=None, log=print):
-    """run_training.train: dataset in 'train' mode, prefetching loader, trainer.train"""
+def data_parallel_setup(device="cuda:0"):
+    """(rank, world, device).  Under torchrun (WORLD_SIZE > 1): one process per GPU, NCCL process group, this rank's
+    device = cuda:LOCAL_RANK -- Engine.train_step then all-reduces the gradients (samples are
+    independent, one per GPU and step, no other exchange).  Otherwise (0, 1, device)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, device
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+    return dist.get_rank(), world, "cuda:%d" % local
+
+
+def train(config, device="cuda:0", engine_factory=_default_engine, data_dir=None, pretrained_checkpoint=None, log=print,
+          seed=None):
+    """run_training.train: dataset in 'train' mode, prefetching loader, trainer.train.  Data parallel under torchrun:
+    every rank walks its OWN shuffled order of the split (generator seeded with seed + rank; with seed=None rank 0 uses
+    numpy's global generator as the reference does), rank 0 writes the checkpoints."""
     config_utils.validate_for_engine(config)
-    dataset = KittiDataset(config.dataset_config, "train", data_dir=data_dir)
+    rank, world, device = data_parallel_setup(device)
+    rng = np.random if (seed is None and rank == 0) else np.random.RandomState((seed or 0) + rank)
+    dataset = KittiDataset(config.dataset_config, "train", data_dir=data_dir, rng=rng)
     engine = engine_factory(device)
     with PrefetchLoader(dataset, shuffle=True, workers=LOADER_WORKERS) as loader:
-        return trainer_mod.train(engine, config, loader.sample_fn, pretrained_checkpoint=pretrained_checkpoint, log=log)
+        return trainer_mod.train(engine, config, loader.sample_fn, pretrained_checkpoint=pretrained_checkpoint, log=log,
+                                 chief=rank == 0)
 
 
 def evaluate(config, device="cuda:0", engine_factory=_default_engine, data_dir=None, max_polls=None, log=print):

@@ -35,10 +35,14 @@ def prune_checkpoints(checkpoint_dir, model_type, keep):
             os.remove(f)
 
 
-def train(engine, config, sample_fn, pretrained_checkpoint=None, log=print):
+def train(engine, config, sample_fn, pretrained_checkpoint=None, log=print, chief=True):
     """trainer.train(model, config).  config: parse_yaml_config result (config_name, model_config.model_type,
     train_config.{max_iterations, summary_interval, checkpoint_interval, max_checkpoints_to_keep,
-    overwrite_checkpoints, paths_config.checkpoint_dir}).  Returns the last total loss that was read back."""
+    overwrite_checkpoints, paths_config.checkpoint_dir}).  Returns the last total loss that was read back.
+    chief=False (data-parallel ranks other than 0; the replicas are bit-identical): same steps, same restore, but no
+    checkpoint files and no console output."""
+    if not chief:
+        log = lambda *a, **k: None
     tc = config.train_config
     model_type = config.model_config.model_type
     ckpt_dir = tc.paths_config.checkpoint_dir
@@ -59,7 +63,7 @@ def train(engine, config, sample_fn, pretrained_checkpoint=None, log=print):
     log("Starting from step {} / {}".format(start, tc.max_iterations))
     last_time, last_loss = time.time(), None
     for step in range(start, tc.max_iterations + 1):
-        if step % tc.checkpoint_interval == 0:
+        if step % tc.checkpoint_interval == 0 and chief:
             engine.save_checkpoint("{}-{:08d}".format(prefix, step), global_step=step)
             prune_checkpoints(ckpt_dir, model_type, tc.max_checkpoints_to_keep)
             log("{}: Step {} / {}: Checkpoint saved to {}-{:08d}".format(config.config_name, step, tc.max_iterations,

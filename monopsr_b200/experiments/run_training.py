@@ -1,5 +1,6 @@
 """python -m monopsr_b200.experiments.run_training --config_path configs/monopsr_model_000.yaml --data_split train
---device 0            (same flags as src/monopsr/experiments/run_training.py:19-44; the config copy / backup in the
+--device 0            (data parallel: torchrun --nproc-per-node N -m monopsr_b200.experiments.run_training ...;
+same flags as src/monopsr/experiments/run_training.py:19-44; the config copy / backup in the
 experiment's output folder is :49-66)"""
 import argparse
 import datetime
@@ -37,7 +38,8 @@ def keep_config_copy(config_path, config, log=print):
 
 def main(argv=None, **kw):
     args = parse_args(argv)
-    os.environ["CUDA_VISIBLE_DEVICES"] = args.device
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:          # under torchrun every rank takes cuda:LOCAL_RANK instead
+        os.environ["CUDA_VISIBLE_DEVICES"] = args.device
     config = config_utils.parse_yaml_config(args.config_path, data_dir=args.data_dir)
     keep_config_copy(args.config_path, config)
     config.dataset_config.data_split = args.data_split

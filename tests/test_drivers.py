@@ -143,3 +143,12 @@ def test_loader_to_ap_numbers_with_a_stub_engine(tmp_path):
     assert any(l.startswith("car_detection_3D AP:") for l in lines) and "Finished evaluation" in lines[-1]
     kitti_files = sorted(os.listdir(os.path.join(base, "kitti_predictions_3d", "val", "0.001", "1200", "data")))
     assert kitti_files == ["000008.txt", "000076.txt", "000108.txt"]       # a sample without detections: empty file
+
+
+def test_non_chief_rank_trains_without_writing(tmp_path):
+    eng, lines = StubEngine(), []
+    T.train(eng, _config(tmp_path, max_it=12), lambda: {}, log=lines.append, chief=False)
+    assert len([c for c in eng.calls if c[0] == "train"]) == 13 and not [c for c in eng.calls if c[0] == "save"]
+    assert lines == [] and not [f for f in os.listdir(tmp_path / "ckpt")]
+    from monopsr_b200.core import experiment as X
+    assert X.data_parallel_setup("cuda:3") == (0, 1, "cuda:3")
