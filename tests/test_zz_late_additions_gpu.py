@@ -69,6 +69,24 @@ def test_kitti_loader_feeds_the_engine(cuda, tmp_path):
     assert len(losses) == 3 and all(np.isfinite(losses))
 
 
+def test_feature_extractor_plugin(cuda):
+    """net_builder.extract_features returns the same feature maps a full forward pass produces"""
+    from monopsr_b200.builders import net_builder as NB
+    S = ms.synthetic_sample(0)
+    eng = Engine(cuda, params=ms.init_params(0))
+    eng.set_inputs(S)
+    eng.forward(train=True)
+    want_map, want_box = eng.dec[-1]["y"].clone().view(32, 48, 48, 128), eng.pooled.clone().view(32, 6, 6, 512)
+    eng2 = Engine(cuda, params=ms.init_params(0))
+    model = type("M", (), {"engine": eng2, "boxes_2d_norm": S["boxes_2d_norm"]})()
+    f = NB.extract_features(model, "resnet101_4x_squash", None,
+                            {NB.NET_IN_RGB_CROP: S["rgb_crops"], NB.NET_IN_FULL_IMG: S["full_img"]}, True)
+    torch.cuda.synchronize()
+    assert f[NB.FEATURES_FOR_MAP].shape == (32, 48, 48, 128) and f[NB.FEATURES_FOR_BOX_3D].shape == (32, 6, 6, 512)
+    assert torch.equal(f[NB.FEATURES_FOR_BOX_3D], want_box)
+    assert torch.allclose(f[NB.FEATURES_FOR_MAP], want_map, rtol=1e-4, atol=1e-5)      # (split-K RED order may differ)
+
+
 # ------------------------------------------------------------------------------------------------ 3xTF32 forward
 X3_CASES = [
     # nimg, H, W, k, dil, Cin, Cout, BN, ksplit
@@ -152,21 +170,3 @@ def test_x3_engine_forward_meets_the_parity_bar(cuda, monkeypatch):
     finally:
         mlib.check(mlib.load().mpb_set_operand_rounding(1), "mpb_set_operand_rounding")
         Engine._rounding_touched = True
-
-
-def test_feature_extractor_plugin(cuda):
-    """net_builder.extract_features returns the same feature maps a full forward pass produces"""
-    from monopsr_b200.builders import net_builder as NB
-    S = ms.synthetic_sample(0)
-    eng = Engine(cuda, params=ms.init_params(0))
-    eng.set_inputs(S)
-    eng.forward(train=True)
-    want_map, want_box = eng.dec[-1]["y"].clone().view(32, 48, 48, 128), eng.pooled.clone().view(32, 6, 6, 512)
-    eng2 = Engine(cuda, params=ms.init_params(0))
-    model = type("M", (), {"engine": eng2, "boxes_2d_norm": S["boxes_2d_norm"]})()
-    f = NB.extract_features(model, "resnet101_4x_squash", None,
-                            {NB.NET_IN_RGB_CROP: S["rgb_crops"], NB.NET_IN_FULL_IMG: S["full_img"]}, True)
-    torch.cuda.synchronize()
-    assert f[NB.FEATURES_FOR_MAP].shape == (32, 48, 48, 128) and f[NB.FEATURES_FOR_BOX_3D].shape == (32, 6, 6, 512)
-    assert torch.equal(f[NB.FEATURES_FOR_BOX_3D], want_box)
-    assert torch.allclose(f[NB.FEATURES_FOR_MAP], want_map, rtol=1e-4, atol=1e-5)      # (split-K RED order may differ)
