@@ -6,7 +6,7 @@
 OUT=gpurun_out/r2_first
 mkdir -p $OUT
 echo "== late GPU tests (xfail-marked: look for XPASS)" | tee $OUT/summary.txt
-timeout 600 python -m pytest tests/test_zz_late_additions_gpu.py -q -rxX -p no:cacheprovider > $OUT/late_tests.log 2>&1
+timeout 1200 python -m pytest tests/test_zz_late_additions_gpu.py -q -rxX -s -p no:cacheprovider > $OUT/late_tests.log 2>&1
 tail -25 $OUT/late_tests.log | tee -a $OUT/summary.txt
 echo "== 3xTF32 vs single-pass per shape (us, error vs fp64)" | tee -a $OUT/summary.txt
 timeout 300 python tools/x3_sweep.py > $OUT/x3_sweep.txt 2>&1
