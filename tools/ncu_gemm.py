@@ -1,5 +1,6 @@
 """The representative block3 GEMM launches of one training step, launched once each after a warm-up, for
-`ncu --set full -k regex:tc_gemm_tma` (profiles/*_ncu_gemm*)."""
+`ncu --set full -k regex:tc_gemm_tma` (profiles/*_ncu_gemm*).  With --x3: the forward cases through the 3xTF32 kernel
+(`ncu --set full -k regex:tc_gemm_x3 ... python tools/ncu_gemm.py --x3`)."""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -14,10 +15,16 @@ CASES = [
     ("wgrad 3x3 full-image, BN128 split-K 4 (RED)", TC_WGRAD, 1, 40, 152, 3, 4, 256, 256, 0, 128, 4, 1),
     ("fwd 3x3 512>256 decoder M=18432, BN256", TC_FWD, 32, 24, 24, 3, 1, 512, 256, 0, 256, 1, 0),
 ]
+X3 = "--x3" in sys.argv
 for name, op, nimg, H, W, k, dil, Cin, Cout, epi, bn, ks, atomic in CASES:
+    if X3 and op != TC_FWD:
+        continue
     p, keep = make(op, nimg, H, W, k, dil, Cin, Cout, epi)
-    p.ksplit, p.atomic = ks, atomic
+    p.ksplit, p.atomic = (1, 0) if X3 else (ks, atomic)
     for _ in range(2):
-        rc = L.mpb_tc_gemm(ctypes.byref(p), bn, mlib.stream_ptr())
+        if X3:
+            rc = L.mpb_tc_gemm_x3(ctypes.byref(p), min(bn, 128), mlib.stream_ptr())
+        else:
+            rc = L.mpb_tc_gemm(ctypes.byref(p), bn, mlib.stream_ptr())
     torch.cuda.synchronize()
     print(name, rc)
