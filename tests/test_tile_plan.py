@@ -45,3 +45,44 @@ def test_plan_is_launchable(mt, ncols, nkb):
     assert ncols % bn == 0 and ks in (1, 2)
     per = -(-nkb // ks)
     assert (ks - 1) * per < nkb
+
+
+def test_x3_mode_dispatch_of_forward_gemms():
+    """MPB_PRECISION=x3: forward launches go to mpb_tc_gemm_x3 with no rounding, no rounded second output, no
+    cluster split-K and a 128- or 64-wide tile; backward launches keep the single-pass kernel (host logic only)"""
+    import torch
+    from monopsr_b200.lib_net import TC_DGRAD, TC_FWD
+
+    class Lib(object):
+        def __init__(self):
+            self.calls = []
+
+        def mpb_tc_gemm(self, p, bn, st):
+            q = p._obj
+            self.calls.append(("tf32", bn, q.round_tf32, q.out_r, q.ksplit, q.atomic))
+            return 0
+
+        def mpb_tc_gemm_x3(self, p, bn, st):
+            q = p._obj
+            self.calls.append(("x3", bn, q.round_tf32, q.out_r, q.ksplit, q.atomic))
+            return 0
+
+    e = planner(csk=1)
+    e.csk_fwd, e.x3, e.L, e._record, e._launch_checks = 1, True, Lib(), [], True
+    e._st = lambda: None
+    e._chk = lambda status, what: None
+    x = torch.zeros(6080, 256)
+    w, o, o2 = torch.zeros(256, 2304), torch.zeros(6080, 256), torch.zeros(6080, 256)
+    e.gemm(TC_FWD, 6080, 40, 152, 3, 2, 256, 256, x, 256, w, 2304, o, 256, relu=1, round_tf32=1, out_r=o2, ldor=256)
+    e.gemm(TC_FWD, 6080, 40, 152, 1, 1, 256, 64, x, 256, w, 256, o, 64)
+    e.gemm(TC_FWD, 32, 1, 1, 1, 1, 256, 1024, x, 256, w, 256, o, 1024, atomic=1, ksplit=4, bn=64)
+    e.gemm(TC_DGRAD, 6080, 40, 152, 3, 2, 256, 256, x, 256, w, 2304, o, 256, round_tf32=1)
+    kinds = [c[0] for c in e.L.calls]
+    assert kinds == ["x3", "x3", "x3", "tf32"]
+    assert e.L.calls[0][1:] == (128, 0, None, 1, 0)          # planner would have asked for a 2-CTA cluster: dropped
+    assert e.L.calls[1][1] == 64 and e.L.calls[2][1:] == (128, 0, None, 4, 1)      # atomic split-K is kept
+    assert e.L.calls[3][2] == 1 and e.L.calls[3][4] == 2     # the backward launch is planned as before
+    assert [r[1] for r in e._record] == [-128, -64, -128, 128]
+    e.x3 = False
+    e.gemm(TC_FWD, 6080, 40, 152, 3, 2, 256, 256, x, 256, w, 2304, o, 256, relu=1, round_tf32=1, out_r=o2, ldor=256)
+    assert e.L.calls[-1][0] == "tf32" and e.L.calls[-1][2] == 1 and e.L.calls[-1][3] == o2.data_ptr()
