@@ -10,6 +10,7 @@ import time
 import numpy as np
 
 from . import evaluator_utils
+from . import metrics as M
 from . import predictions as P
 
 
@@ -35,25 +36,45 @@ class Evaluator(object):
         if P.KEY_VALID_MASK_MAPS not in out:          # test mode: tf.ones mask (monopsr_model.py:218)
             out[P.KEY_VALID_MASK_MAPS] = np.ones(out[P.KEY_INST_XYZ_MAP_LOCAL].shape[:3] + (1,), np.float32)
         out[P.SAMPLE_LABEL_CLASS_INDICES] = np.asarray(sample["class_indices"])
+        self.last_metrics = None
+        if self.mode == "val" and "boxes_3d" in sample:
+            self.last_metrics = M.evaluate_predictions(out, sample, sample_dict[P.SAMPLE_NUM_OBJS], self.output_types,
+                                                       self.centroid_type, point_set=self._point_set_metrics(sample_dict))
         return P.format_predictions(out, sample_dict, output_types=self.output_types, train_val_test=self.mode,
                                     num_boxes=out[P.KEY_VALID_MASK_MAPS].shape[0], num_alpha_bins=self.num_alpha_bins,
                                     centroid_type=self.centroid_type, post_process_cen_x=self.post_process_cen_x)
 
+    def _point_set_metrics(self, sample_dict):
+        """metric_emd / metric_chamfer on the device tensors of the engine (None when the engine has none, e.g. a stub)"""
+        eng = self.engine
+        inputs = getattr(eng, "inputs", None)
+        if P.KEY_INST_XYZ_MAP_LOCAL not in self.output_types or not inputs or "gt_inst_xyz_maps_local" not in inputs:
+            return None
+        from . import losses_custom
+        r = losses_custom.point_set_metrics(eng.outputs()[P.KEY_INST_XYZ_MAP_LOCAL], inputs["gt_inst_xyz_maps_local"],
+                                            inputs["gt_valid_mask_maps"], int(sample_dict[P.SAMPLE_NUM_OBJS]))
+        return {k: v.detach().cpu().numpy() for k, v in r.items()}
+
     def run_checkpoint_once(self, checkpoint_prefix, samples, use_ema=True):
-        """samples: iterable of (sample, sample_dict).  Returns {'num_samples', 'mean_losses' (val), 'seconds'}"""
+        """samples: iterable of (sample, sample_dict).  Returns {'num_samples', 'mean_losses' (val), 'metrics' (val:
+        name -> list of per-object values, for evaluator_utils.save_metrics), 'seconds'}"""
         if checkpoint_prefix is not None:
             self.engine.load_checkpoint(checkpoint_prefix, use_ema=use_ema)
         t0, n, sums = time.time(), 0, {}
+        metrics_lists = {}
         for sample, sample_dict in samples:
             pred = self.predict(sample, sample_dict)
             P.save_predictions(sample_dict[P.SAMPLE_NAME], pred, self.output_dirs, self.output_types)
             if self.mode == "val":
                 for k, v in self.engine.losses().items():
                     sums[k] = sums.get(k, 0.0) + float(v)
+                if self.last_metrics:
+                    M.accumulate(metrics_lists, self.last_metrics)
             n += 1
             self.log("Step {}: {} / {}, Inference on sample {}".format(
                 os.path.basename(str(checkpoint_prefix)), n, "?", sample_dict[P.SAMPLE_NAME]))
-        return {"num_samples": n, "mean_losses": {k: v / max(n, 1) for k, v in sums.items()}, "seconds": time.time() - t0}
+        return {"num_samples": n, "mean_losses": {k: v / max(n, 1) for k, v in sums.items()}, "metrics": metrics_lists,
+                "seconds": time.time() - t0}
 
     def convert_and_evaluate(self, dataset, predictions_base_dir, global_step, kitti_score_threshold=0.1,
                              results_root=None, checkpoint_name="model", label_dir=None, already_evaluated_path=None):

@@ -12,6 +12,7 @@ import numpy as np
 
 from . import config_utils
 from . import evaluator as evaluator_mod
+from . import evaluator_utils
 from . import predictions as P
 from . import trainer as trainer_mod
 from ..datasets.kitti_loader import DatasetBuilder, KittiDataset, PrefetchLoader
@@ -87,6 +88,12 @@ class ExperimentEvaluator(object):
         with PrefetchLoader(self.dataset, shuffle=False, epochs=1, workers=LOADER_WORKERS) as samples:
             res = ev.run_checkpoint_once(checkpoint_to_restore, samples)
         res["global_step"] = global_step
+        if self.eval_mode == "val" and res.get("metrics"):
+            evaluator_utils.save_metrics(
+                os.path.join(self.predictions_base_dir, "offline_eval", "metrics", self.config.config_name,
+                             self.dataset_config.data_split),
+                self.dataset_config.data_split, global_step, res["metrics"],
+                metrics_to_show=getattr(self.model_config, "metrics_to_show", ()) or ())
         if self.eval_mode == "val" and not self.do_kitti_native_eval:
             with open(self.already_evaluated_path, "ba") as f:
                 np.savetxt(f, [global_step], fmt="%d")

@@ -50,7 +50,7 @@ class StubEngine(object):
         return {"inst_xyz_map_local": rng.randn(n, 48, 48, 3).astype(np.float32), "valid_mask_maps": None,
                 "lwh": b3[:, 3:6], "alpha_bins": rng.randn(n, 12).astype(np.float32),
                 "alpha_regs": rng.randn(n, 12).astype(np.float32) * 0.1, "view_ang": self.sample["est_view_angs"][:, None],
-                "centroids": b3[:, :3].copy()}
+                "centroids": b3[:, :3].copy(), "prop_cen_z": b3[:, 2:3] + 0.5, "lwh_offs": np.zeros((n, 3), np.float32)}
 
 
 def _config(tmp_path, overwrite=False, max_it=25):
@@ -152,3 +152,33 @@ def test_non_chief_rank_trains_without_writing(tmp_path):
     assert lines == [] and not [f for f in os.listdir(tmp_path / "ckpt")]
     from monopsr_b200.core import experiment as X
     assert X.data_parallel_setup("cuda:3") == (0, 1, "cuda:3")
+
+
+def test_validation_metrics():
+    """core/metrics.py: the error metrics of MonoPSRModel.evaluate_predictions on the first num_objs rows"""
+    from monopsr_b200.core import metrics as M
+    rs = np.random.RandomState(0)
+    n = 8
+    b3 = rs.rand(n, 7).astype(np.float32) * [10, 2, 40, 4, 2, 2, 3]
+    out = {"prop_cen_z": rs.rand(n, 1).astype(np.float32) * 40, "centroids": rs.rand(n, 3).astype(np.float32) * 10,
+           "lwh": rs.rand(n, 3).astype(np.float32) * 4, "lwh_offs": rs.rand(n, 3).astype(np.float32),
+           "view_ang": rs.rand(n, 1).astype(np.float32)}
+    sample = {"boxes_3d": b3, "gt_view_angs": rs.rand(n).astype(np.float32)}
+    types = [P.KEY_CENTROIDS, P.KEY_LWH, P.KEY_VIEW_ANG, P.KEY_INST_XYZ_MAP_LOCAL]
+    m = M.evaluate_predictions(out, sample, 3, types, "middle",
+                               point_set={"metric_emd": np.arange(8.0), "metric_chamfer": np.arange(8.0) * 2})
+    cen = np.column_stack([b3[:, 0], b3[:, 1] - b3[:, 5] / 2, b3[:, 2]])
+    assert m[M.METRIC_EMD].tolist() == [0, 1, 2] and m[M.METRIC_CHAMFER].tolist() == [0, 2, 4]
+    np.testing.assert_allclose(m[M.METRIC_PROP_CEN_Z_ERR], cen[:3, 2:3] - out["prop_cen_z"][:3], rtol=1e-6)
+    np.testing.assert_allclose(m[M.METRIC_CEN_Y_ERR], cen[:3, 1] - out["centroids"][:3, 1], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m[M.METRIC_DIM_ERR], (b3[:3, 3:6] - out["lwh"][:3]) - out["lwh_offs"][:3], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m[M.METRIC_VIEW_ANG_ERR], sample["gt_view_angs"][:3, None] - out["view_ang"][:3], rtol=1e-6)
+    assert m[M.METRIC_DIM_ERR].shape == (3, 3) and m[M.METRIC_CEN_X_ERR].shape == (3,)
+    bottom = M.evaluate_predictions(out, sample, 3, [P.KEY_CENTROIDS], "bottom")
+    np.testing.assert_allclose(bottom[M.METRIC_CEN_Y_ERR], b3[:3, 1] - out["centroids"][:3, 1], rtol=1e-5, atol=1e-6)
+    assert set(bottom) == {M.METRIC_PROP_CEN_Z_ERR, M.METRIC_CEN_X_ERR, M.METRIC_CEN_Y_ERR, M.METRIC_CEN_Z_ERR}
+    with pytest.raises(ValueError):
+        M.gt_centroids(b3, "top")
+    lists = M.accumulate({}, m)
+    lists = M.accumulate(lists, {M.METRIC_EMD: np.array([np.nan, 1.0]), M.METRIC_CHAMFER: np.array([5.0])})
+    assert lists[M.METRIC_EMD] == [0, 1, 2] and lists[M.METRIC_CHAMFER] == [0, 2, 4, 5] and len(lists[M.METRIC_DIM_ERR]) == 9

@@ -79,6 +79,10 @@ def test_evaluation_entry_point(exp):
     results = os.path.join(pred, "offline_eval", "results", "val", "monopsr_model_000_results_0.1.txt")
     assert open(results).read().splitlines()[0] == "0"
     assert any(l.startswith("All checkpoints evaluated") for l in lines)
+    mdir = os.path.join(pred, "offline_eval", "metrics", "monopsr_model_000", "val")          # metrics csv per step
+    rows = open(os.path.join(mdir, "metrics_avg_abs_val.csv")).read().splitlines()
+    assert len(rows) == 4 and rows[0].split(",")[0].strip() == "step" and "cen_z_err" in rows[0]
+    assert [r.split(",")[0].strip() for r in rows[1:]] == ["0", "2", "4"]
     # a second run finds everything evaluated already
     again = run_evaluation.main(["--config_path", path, "--data_dir", data_dir, "--max_polls", "1"],
                                 engine_factory=lambda d: StubEngine(), log=lambda *a: None)
