@@ -87,6 +87,36 @@ def test_feature_extractor_plugin(cuda):
     assert torch.allclose(f[NB.FEATURES_FOR_MAP], want_map, rtol=1e-4, atol=1e-5)      # (split-K RED order may differ)
 
 
+def test_validation_pass_on_the_engine(cuda, tmp_path):
+    """val split of the synthetic KITTI tree through the real engine: predictions, losses, per-object EMD / Chamfer
+    metrics from the point-set ops, KITTI result files and the AP lines"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kitti_tree
+    from monopsr_b200.core import evaluator as E
+    from monopsr_b200.core import metrics as M
+    from monopsr_b200.core import predictions as P
+    from monopsr_b200.datasets import kitti_loader as KL
+    dataset_dir, data_dir = kitti_tree.make_tree(str(tmp_path / "tree"))
+    cfg = kitti_tree.apply_overrides(KL.DatasetBuilder.get_config_obj(KL.DatasetBuilder.KITTI_TRAIN), dataset_dir,
+                                     {"data_split": "val"})
+    ds = KL.KittiDataset(cfg, "val", data_dir=data_dir, rng=np.random.RandomState(0))
+    eng = Engine(cuda, params=ms.init_params(0))
+    base = str(tmp_path / "predictions")
+    dirs = {P.OUT_DIR_BOX_2D: base + "/b2", P.OUT_DIR_BOX_3D: base + "/b3", P.OUT_DIR_XYZ_MAP_LOCAL: base + "/xyz"}
+    types = [P.KEY_INST_XYZ_MAP_LOCAL, P.KEY_CENTROIDS, P.KEY_LWH, P.KEY_VIEW_ANG, P.KEY_ALPHA]
+    ev = E.Evaluator(eng, types, dirs, train_val_test="val", log=lambda *a: None)
+    with KL.PrefetchLoader(ds, epochs=1, workers=2) as loader:
+        res = ev.run_checkpoint_once(None, loader)
+    assert res["num_samples"] >= 2 and np.isfinite(res["mean_losses"]["total_loss"])
+    for k in (M.METRIC_EMD, M.METRIC_CHAMFER, M.METRIC_CEN_Z_ERR, M.METRIC_DIM_ERR):
+        assert len(res["metrics"][k]) > 0 and np.all(np.isfinite(res["metrics"][k])), k
+    assert min(res["metrics"][M.METRIC_EMD]) >= 0 and min(res["metrics"][M.METRIC_CHAMFER]) >= 0
+    out = ev.convert_and_evaluate(ds, base, 0, kitti_score_threshold=0.0)
+    assert out and any(l.startswith("car_detection AP:") for l in out[0]["lines"])
+
+
 def test_x3_suite_in_a_child_process():
     """The 3xTF32 kernel has never run on a B200: its tests (tests/x3_gpu_cases.py) run in a CHILD process, so that a
     trap or a crash of the untried kernel cannot take this process' CUDA context -- and with it the exit status of
