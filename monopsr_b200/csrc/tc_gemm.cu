@@ -948,7 +948,13 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
 //   the same fused epilogue as the single-pass kernel.  FWD only, no multicast / cluster split-K.
 // NOT YET RUN ON A B200 (written after the round-1 GPU budget was spent); nothing calls it by default.
 // =====================================================================================
-constexpr int kX3Stages = 3;
+#ifndef MPB_X3_STAGES
+#define MPB_X3_STAGES 3          // sweepable: MPB_NVCC_EXTRA="-DMPB_X3_STAGES=2 -DMPB_X3_MINB=2" puts two 64-wide CTAs on an SM
+#endif
+#ifndef MPB_X3_MINB
+#define MPB_X3_MINB 1
+#endif
+constexpr int kX3Stages = MPB_X3_STAGES;
 template <int BN> constexpr uint32_t x3_half_bytes() { return kTcABytes + BN * 128; }      // [A | B]
 template <int BN> constexpr int x3_smem_bytes() { return kX3Stages * 2 * (int)x3_half_bytes<BN>() + 1024 + 256; }
 constexpr int kX3Threads = 192;
@@ -969,7 +975,7 @@ __device__ __forceinline__ float tf32_lo(float x) {      // x - (what kind::tf32
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kX3Threads, 1)
+__global__ void __launch_bounds__(kX3Threads, MPB_X3_MINB)
 tc_gemm_x3_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant__ CUtensorMap mapA,
                   const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ uint8_t smem_raw[];
