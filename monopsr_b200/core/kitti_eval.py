@@ -166,3 +166,22 @@ def evaluate(gt_dir, result_dir, low_iou=False, write_stats=False, log=None):
         for ln in lines:
             log(ln)
     return {"ap": ap, "curves": curves, "lines": lines}
+
+
+def main(argv=None):
+    """python -m monopsr_b200.core.kitti_eval [--low_iou] gt_dir result_dir   (the reference binary's command line,
+    evaluate_object_3d_offline.cpp:971-1004: prints the result folder's name, then the AP lines)"""
+    import sys
+    args = list(sys.argv[1:] if argv is None else argv)
+    low = "--low_iou" in args
+    args = [a for a in args if a != "--low_iou"]
+    if len(args) != 2:
+        print("Usage: python -m monopsr_b200.core.kitti_eval [--low_iou] gt_dir result_dir")
+        return 1
+    print(os.path.basename(os.path.normpath(args[1])))
+    evaluate(args[0], args[1], low_iou=low, write_stats=True, log=print)
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -126,3 +126,13 @@ def test_parsing_and_argument_checks(tmp_path):
     empty = E.eval_class([], [], 0, 0, 0, 0.7)
     assert empty["n_gt"] == 0 and not empty["precision"].any()
     assert E.average_precision(np.ones(41)) == 100.0
+
+
+def test_command_line(tmp_path, capsys):
+    gt_dir, res_dir = kitti_eval_cases.make_case(str(tmp_path), "sparse")
+    assert E.main([gt_dir, res_dir]) == 0
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "results" and out[1:] == GOLD["sparse"]["lines"]
+    assert E.main(["--low_iou", gt_dir, res_dir]) == 0
+    assert capsys.readouterr().out.splitlines()[1:] == GOLD["sparse/low_iou"]["lines"]
+    assert E.main([gt_dir]) == 1
