@@ -42,6 +42,13 @@ class ObjectLabel(object):
         return isinstance(other, ObjectLabel) and all(
             np.array_equal(v, other.__dict__[k]) for k, v in self.__dict__.items())
 
+    def __deepcopy__(self, memo):
+        # every field is an immutable scalar / string except the position `t` (the box jitter copies ~30 labels per sample)
+        new = ObjectLabel.__new__(ObjectLabel)
+        new.__dict__.update(self.__dict__)
+        new.t = np.array(self.t, copy=True) if isinstance(self.t, np.ndarray) else tuple(self.t)
+        return new
+
 
 def read_labels(label_dir, sample_name):
     """list of ObjectLabel from <label_dir>/<sample_name>.txt (15 columns, 16 for detection results)"""

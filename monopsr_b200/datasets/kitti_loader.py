@@ -210,8 +210,10 @@ class KittiDataset(object):
                 kitti_labels, _ = K.apply_obj_filter(kitti_labels, self.obj_filter)
                 if len(kitti_labels) < 1:
                     return None
-            masks = K.get_instance_mask_list(self._read("instance", self.instance_dir + "/{}.png".format(name)), num_all)
-            masks = masks[keep]
+            instance_image = self._read("instance", self.instance_dir + "/{}.png".format(name))
+            # one mask per KEPT label (pixel value = the label's index in the file); the reference expands all labels
+            # first and filters afterwards -- same masks
+            masks = np.asarray([instance_image == i for i in np.flatnonzero(keep)])
             if self.oversample:
                 idx = self._oversample_indices(num_objs)
                 labels, masks = labels[idx], masks[idx]
