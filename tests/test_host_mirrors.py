@@ -190,3 +190,23 @@ def test_net_builder_plugin_boundary():
     cfg = types.SimpleNamespace(net_type="resnet101_4x_squash",
                                 net_config=types.SimpleNamespace(resnet101_4x_squash="EXTRACTOR"))
     assert NB.get_net_config(cfg) == "EXTRACTOR"
+
+
+def test_oracle_crop_and_resize_against_grid_sample():
+    """an independent implementation of the same sampling rule: for boxes inside the image, tf.image.crop_and_resize
+    is bilinear sampling at x = x1 (W-1) + i (x2-x1)(W-1)/(cw-1), i.e. torch's grid_sample(align_corners=True)"""
+    import torch.nn.functional as F
+    from oracle import network as onet
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(1, 40, 152, 5, generator=g, dtype=torch.float64)
+    lo = torch.rand(9, 2, generator=g, dtype=torch.float64) * 0.6
+    boxes = torch.cat([lo, lo + 0.05 + torch.rand(9, 2, generator=g, dtype=torch.float64) * 0.35], dim=1)   # y1 x1 y2 x2 in [0,1]
+    ch, cw = 24, 24
+    got = onet.crop_and_resize(img, boxes, ch, cw)
+    iy = torch.arange(ch, dtype=torch.float64) / (ch - 1)
+    ix = torch.arange(cw, dtype=torch.float64) / (cw - 1)
+    gy = (boxes[:, 0:1] + iy[None, :] * (boxes[:, 2:3] - boxes[:, 0:1])) * 2 - 1           # (N,ch) in [-1,1]
+    gx = (boxes[:, 1:2] + ix[None, :] * (boxes[:, 3:4] - boxes[:, 1:2])) * 2 - 1
+    grid = torch.stack([gx[:, None, :].expand(-1, ch, -1), gy[:, :, None].expand(-1, -1, cw)], dim=-1)
+    want = F.grid_sample(img.permute(0, 3, 1, 2).expand(9, -1, -1, -1), grid, mode="bilinear", align_corners=True)
+    assert torch.allclose(got, want.permute(0, 2, 3, 1), rtol=1e-10, atol=1e-12)
