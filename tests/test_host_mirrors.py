@@ -210,3 +210,86 @@ def test_oracle_crop_and_resize_against_grid_sample():
     grid = torch.stack([gx[:, None, :].expand(-1, ch, -1), gy[:, :, None].expand(-1, -1, cw)], dim=-1)
     want = F.grid_sample(img.permute(0, 3, 1, 2).expand(9, -1, -1, -1), grid, mode="bilinear", align_corners=True)
     assert torch.allclose(got, want.permute(0, 2, 3, 1), rtol=1e-10, atol=1e-12)
+
+
+def test_oracle_bottleneck_and_stem_against_torchvision():
+    """an independent implementation of the standard blocks: torchvision's Bottleneck (eval-mode batch norm = the frozen
+    affine of the towers, eps 1e-5; 3x3 conv dilated by the atrous rate) and its 7x7/2 stem with padding 3, which is
+    what conv2d_same pads explicitly (resnet_utils.py:111-122) -- fed with the same random weights as the oracle"""
+    tv = pytest.importorskip("torchvision.models.resnet")
+    from oracle import network as onet
+    g = torch.Generator().manual_seed(11)
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+
+    def bn_params(P, scope, c):
+        P[scope + "/gamma"], P[scope + "/beta"] = rnd(c) * 0.3 + 1, rnd(c) * 0.2
+        P[scope + "/moving_mean"], P[scope + "/moving_variance"] = rnd(c) * 0.1, torch.rand(c, generator=g, dtype=torch.float64) + 0.5
+
+    def load_bn(bn, P, scope):
+        bn.weight.data, bn.bias.data = P[scope + "/gamma"].clone(), P[scope + "/beta"].clone()
+        bn.running_mean.data, bn.running_var.data = P[scope + "/moving_mean"].clone(), P[scope + "/moving_variance"].clone()
+
+    for cin, base, rate, proj in ((256, 64, 1, False), (256, 128, 2, True), (1024, 256, 4, False)):
+        cout = base * 4
+        P, s = {}, "enc/resnet_v1_101/blockX/unit_1"
+        b = s + "/bottleneck_v1"
+        shapes = {"conv1": (1, 1, cin, base), "conv2": (3, 3, base, base), "conv3": (1, 1, base, cout)}
+        if proj:
+            shapes["shortcut"] = (1, 1, cin, cout)
+        for name, shp in shapes.items():
+            P["%s/%s/weights" % (b, name)] = rnd(*shp) / (shp[0] * shp[1] * shp[2]) ** 0.5          # HWIO
+            bn_params(P, "%s/%s/BatchNorm" % (b, name), shp[3])
+        down = None
+        if proj:
+            down = torch.nn.Sequential(torch.nn.Conv2d(cin, cout, 1, bias=False), torch.nn.BatchNorm2d(cout))
+        m = tv.Bottleneck(cin, base, stride=1, downsample=down, dilation=rate).double().eval()
+        for conv, bn, name in ((m.conv1, m.bn1, "conv1"), (m.conv2, m.bn2, "conv2"), (m.conv3, m.bn3, "conv3")):
+            conv.weight.data = P["%s/%s/weights" % (b, name)].permute(3, 2, 0, 1).clone()           # HWIO -> OIHW
+            load_bn(bn, P, "%s/%s/BatchNorm" % (b, name))
+        if proj:
+            down[0].weight.data = P[b + "/shortcut/weights"].permute(3, 2, 0, 1).clone()
+            load_bn(down[1], P, b + "/shortcut/BatchNorm")
+        x = torch.relu(rnd(2, 12, 12, cin))
+        with torch.no_grad():
+            want = m(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+            got = onet.bottleneck(x, P, s, cout, base, rate)
+        assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-9, atol=1e-9), (cin, base, rate)
+
+    # stem: 7x7 stride 2 with explicit padding 3, frozen BN, ReLU (the pooling that follows differs: SAME vs padding 1)
+    P = {"enc/resnet_v1_101/conv1/weights": rnd(7, 7, 3, 64) / 12.0}
+    bn_params(P, "enc/resnet_v1_101/conv1/BatchNorm", 64)
+    net = tv.ResNet(tv.Bottleneck, [1, 1, 1, 1]).double().eval()
+    net.conv1.weight.data = P["enc/resnet_v1_101/conv1/weights"].permute(3, 2, 0, 1).clone()
+    load_bn(net.bn1, P, "enc/resnet_v1_101/conv1/BatchNorm")
+    x = rnd(2, 48, 48, 3) * 50
+    with torch.no_grad():
+        want = net.relu(net.bn1(net.conv1(x.permute(0, 3, 1, 2)))).permute(0, 2, 3, 1)
+        got = torch.relu(onet.conv_bn(x, P, "enc/resnet_v1_101/conv1", 2))
+    assert torch.allclose(got, want, rtol=1e-9, atol=1e-9)
+    # SAME 3x3/2 max pooling on an even grid = windows starting at 0, 2, 4, ... clipped at the far edge
+    pooled = onet.max_pool_same_3x3_s2(got)
+    want_pool = torch.nn.functional.max_pool2d(got.permute(0, 3, 1, 2), 3, 2, ceil_mode=True).permute(0, 2, 3, 1)
+    assert pooled.shape == (2, 12, 12, 64) and torch.equal(pooled, want_pool)
+
+
+def test_oracle_batch_norm_and_huber_against_torch_functional():
+    """slim.batch_norm defaults (no gamma, eps 1e-3, biased batch variance / moving statistics) and the Huber loss
+    (delta 1) against torch's own functional implementations"""
+    import torch.nn.functional as F
+    from oracle import network as onet
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 6, 6, 16, generator=g, dtype=torch.float64) * 2 + 0.5
+    P = {"bn/beta": torch.randn(16, generator=g, dtype=torch.float64),
+         "bn/moving_mean": torch.randn(16, generator=g, dtype=torch.float64) * 0.3,
+         "bn/moving_variance": torch.rand(16, generator=g, dtype=torch.float64) + 0.5}
+    y, mean, var = onet.train_bn_relu(x, P, "bn")
+    want = F.relu(F.batch_norm(x.permute(0, 3, 1, 2), None, None, None, P["bn/beta"], True, 0.0, 1e-3)).permute(0, 2, 3, 1)
+    assert torch.allclose(y, want, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(mean, x.mean((0, 1, 2))) and torch.allclose(var, x.var((0, 1, 2), unbiased=False))
+    y, _, _ = onet.infer_bn_relu(x, P, "bn")
+    want = F.relu(F.batch_norm(x.permute(0, 3, 1, 2), P["bn/moving_mean"], P["bn/moving_variance"], None, P["bn/beta"],
+                               False, 0.0, 1e-3)).permute(0, 2, 3, 1)
+    assert torch.allclose(y, want, rtol=1e-10, atol=1e-12)
+    d = torch.randn(1000, generator=g, dtype=torch.float64) * 2
+    assert torch.allclose(onet.huber(d), F.smooth_l1_loss(d, torch.zeros_like(d), reduction="none", beta=1.0))
+    assert torch.allclose(onet.huber(d), F.huber_loss(d, torch.zeros_like(d), reduction="none", delta=1.0))
