@@ -80,6 +80,10 @@ def validate_for_engine(cfg):
     need(list(d.classes) == ["Car"], "classes must be ['Car']")
     need(d.centroid_type == "middle", "centroid_type must be 'middle'")
     need(bool(m.rotate_view), "rotate_view must be True")
+    for stack in ("proposal_fc_layers", "regression_fc_layers"):
+        fc = getattr(m, stack, None)
+        need(fc is not None and list(fc.layer_sizes) == [1024, 1024], "%s.layer_sizes must be [1024, 1024]" % stack)
+        need(fc is not None and float(fc.dropout_keep_prob) == 1.0, "%s.dropout_keep_prob must be 1.0 (no dropout kernel)" % stack)
     oc = m.output_config
     expect = dict(inst_xyz_map_local="map", lwh="offset", alpha="dc", view_ang="est", cen_x="from_view_ang_and_z",
                   cen_y="offset", cen_z="offset", centroids="xyz", inst_xyz_map_global="projection",

@@ -237,6 +237,61 @@ def prop_cen_y_from_box(boxes_2d, cam_p, prop_cen_z):
     return box_cv * (prop_cen_z / cam_p[0, 0]) - 0.0648
 
 
+def box_heads(P, S, pooled):
+    """The FC stacks and box heads on the pooled (N,6,6,512) features (monopsr_output_builder.py:126-302, 407-488,
+    551-623): layer names, widths and the order of the concatenated inputs are pinned to the record of the reference's
+    own builder code (tests/test_arch_golden.py)."""
+    dt, dev = pooled.dtype, pooled.device
+    N = pooled.shape[0]
+    boxes_2d, cam_p = S["boxes_2d"], S["cam_p"]
+    # proposal fc :126-194
+    flat = pooled.reshape(N, -1)
+    est_view = S["est_view_angs"].reshape(N, 1)
+    centre_u, centre_v = cam_p[0, 2], cam_p[1, 2]
+    box_ij = boxes_2d - torch.stack([centre_v, centre_u, centre_v, centre_u])
+    box_h = (boxes_2d[:, 2] - boxes_2d[:, 0]).reshape(N, 1)
+    img_h, img_w = 320.0, 1216.0                      # model_config.image_input_shape
+    box_h_norm = box_h / img_h
+    box_ij_norm = box_ij / torch.tensor([img_h / 2, img_w / 2, img_h / 2, img_w / 2], dtype=dt, device=dev)
+    # tf.one_hot(squeeze(class_indices), num_classes=1): 1.0 only for index 0 (quirk Q7)
+    one_hot = (S["class_indices"].reshape(N, 1) == 0).to(dt)
+    cam_norm = cam_p.reshape(1, 12) / torch.tensor(
+        [1000.0, 1.0, 1000.0, 100.0, 1.0, 1000.0, 1000.0, 1.0, 1.0, 1.0, 1.0, 1.0], dtype=dt, device=dev)
+    p = "output/proposal_fc/proposal_fc"
+    img_fc = fc(flat, P, p + "/img_fc")
+    feat = torch.cat([img_fc, box_ij_norm, box_h_norm, est_view, one_hot, cam_norm.expand(N, 12)], dim=1)
+    feat = fc(fc(feat, P, p + "/fc0"), P, p + "/fc1")
+    lwh_offs = fc(feat, P, "output/lwh/lwh", relu=False)
+    lwh = S["mean_lwh"] + lwh_offs
+    alpha = fc(feat, P, "output/alpha", relu=False)
+    alpha_bins, alpha_regs = alpha[:, :12], alpha[:, 12:24]
+    out = {"lwh": lwh, "lwh_offs": lwh_offs, "alpha_bins": alpha_bins, "alpha_regs": alpha_regs,
+           "view_ang": est_view, "_est_view": est_view}
+
+    # centroid proposals :407-438 ; instance_utils.py:907-953
+    f = cam_p[0, 0]
+    prop_cen_z = (f * lwh[:, 2] / (boxes_2d[:, 2] - boxes_2d[:, 0]) + S["prop_cen_z_offset"]).reshape(N, 1)
+    prop_cen_y = prop_cen_y_from_box(boxes_2d, cam_p, prop_cen_z)
+    out["prop_cen_z"] = prop_cen_z
+
+    # regression fc :200-274
+    p = "output/regression_fc/regression_fc"
+    img_fc2 = fc(flat, P, p + "/img_fc")
+    feat2 = torch.cat([img_fc2, box_ij_norm, box_h_norm, est_view, one_hot, lwh_offs, alpha_bins, alpha_regs,
+                       prop_cen_y / 1.666754, prop_cen_z / MAX_DEPTH], dim=1)
+    feat2 = fc(fc(feat2, P, p + "/fc0"), P, p + "/fc1")
+    cen_y_offs = fc(feat2, P, "output/cen_y/cen_y", relu=False)
+    cen_z_offs = fc(feat2, P, "output/cen_z_offs/cen_z", relu=False)
+    cen_y = prop_cen_y + cen_y_offs
+    cen_z = prop_cen_z + cen_z_offs
+    x_offset = -cam_p[0, 3] / cam_p[0, 0]
+    cen_x = cen_z * torch.tan(est_view) + x_offset
+    out.update({"cen_y": cen_y, "cen_y_offs": cen_y_offs, "cen_z": cen_z, "cen_z_offs": cen_z_offs,
+                "cen_x": cen_x, "centroids": torch.cat([cen_x, cen_y, cen_z], dim=1)})
+
+    return out
+
+
 def train_projections(xyz_local, valid, boxes_2d, cam_p, est_view, gt_view, cen_y, cen_z):
     """The train / val-only geometry of the graph: local map -> camera frame -> image, expected pixel-centre grid,
     normalised projection error, global depth map.  Numpy twins in the reference (pinned in
@@ -329,50 +384,9 @@ def forward(P, S, train=True):
     valid = S["gt_valid_mask_maps"]
     out["valid_mask_maps"] = valid
 
-    # proposal fc :126-194
-    flat = pooled.reshape(N, -1)
-    est_view = S["est_view_angs"].reshape(N, 1)
-    centre_u, centre_v = cam_p[0, 2], cam_p[1, 2]
-    box_ij = boxes_2d - torch.stack([centre_v, centre_u, centre_v, centre_u])
-    box_h = (boxes_2d[:, 2] - boxes_2d[:, 0]).reshape(N, 1)
-    img_h, img_w = 320.0, 1216.0                      # model_config.image_input_shape
-    box_h_norm = box_h / img_h
-    box_ij_norm = box_ij / torch.tensor([img_h / 2, img_w / 2, img_h / 2, img_w / 2], dtype=dt, device=dev)
-    # tf.one_hot(squeeze(class_indices), num_classes=1): 1.0 only for index 0 (quirk Q7)
-    one_hot = (S["class_indices"].reshape(N, 1) == 0).to(dt)
-    cam_norm = cam_p.reshape(1, 12) / torch.tensor(
-        [1000.0, 1.0, 1000.0, 100.0, 1.0, 1000.0, 1000.0, 1.0, 1.0, 1.0, 1.0, 1.0], dtype=dt, device=dev)
-    p = "output/proposal_fc/proposal_fc"
-    img_fc = fc(flat, P, p + "/img_fc")
-    feat = torch.cat([img_fc, box_ij_norm, box_h_norm, est_view, one_hot, cam_norm.expand(N, 12)], dim=1)
-    feat = fc(fc(feat, P, p + "/fc0"), P, p + "/fc1")
-    lwh_offs = fc(feat, P, "output/lwh/lwh", relu=False)
-    lwh = S["mean_lwh"] + lwh_offs
-    alpha = fc(feat, P, "output/alpha", relu=False)
-    alpha_bins, alpha_regs = alpha[:, :12], alpha[:, 12:24]
-    out.update({"lwh": lwh, "lwh_offs": lwh_offs, "alpha_bins": alpha_bins, "alpha_regs": alpha_regs,
-                "view_ang": est_view})
-
-    # centroid proposals :407-438 ; instance_utils.py:907-953
-    f = cam_p[0, 0]
-    prop_cen_z = (f * lwh[:, 2] / (boxes_2d[:, 2] - boxes_2d[:, 0]) + S["prop_cen_z_offset"]).reshape(N, 1)
-    prop_cen_y = prop_cen_y_from_box(boxes_2d, cam_p, prop_cen_z)
-    out["prop_cen_z"] = prop_cen_z
-
-    # regression fc :200-274
-    p = "output/regression_fc/regression_fc"
-    img_fc2 = fc(flat, P, p + "/img_fc")
-    feat2 = torch.cat([img_fc2, box_ij_norm, box_h_norm, est_view, one_hot, lwh_offs, alpha_bins, alpha_regs,
-                       prop_cen_y / 1.666754, prop_cen_z / MAX_DEPTH], dim=1)
-    feat2 = fc(fc(feat2, P, p + "/fc0"), P, p + "/fc1")
-    cen_y_offs = fc(feat2, P, "output/cen_y/cen_y", relu=False)
-    cen_z_offs = fc(feat2, P, "output/cen_z_offs/cen_z", relu=False)
-    cen_y = prop_cen_y + cen_y_offs
-    cen_z = prop_cen_z + cen_z_offs
-    x_offset = -cam_p[0, 3] / cam_p[0, 0]
-    cen_x = cen_z * torch.tan(est_view) + x_offset
-    out.update({"cen_y": cen_y, "cen_y_offs": cen_y_offs, "cen_z": cen_z, "cen_z_offs": cen_z_offs,
-                "cen_x": cen_x, "centroids": torch.cat([cen_x, cen_y, cen_z], dim=1)})
+    heads = box_heads(P, S, pooled)
+    out.update(heads)
+    est_view, cen_y, cen_z = out.pop("_est_view"), out["cen_y"], out["cen_z"]
 
     aux = {"map_features": map_features, "features_pooled": pooled, "features_squashed": squashed,
            "crop_feat": crop_feat, "full_feat": full_feat, "bn_stats": bn_stats, "concat": concat}
