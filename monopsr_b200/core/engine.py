@@ -28,6 +28,12 @@ from . import model_spec as ms
 BN_EPS_RESNET = 1e-5
 BN_EPS_DECODER = 1e-3
 BN_DECAY_DECODER = 0.999
+# train-op constants (optimizer_builder.py:23-118 with monopsr_model_000.yaml:141-152; trainer.py:76-81).  Pinned to
+# the calls the reference's own optimizer_builder makes: tests/test_arch_golden.py::test_train_op_constants
+LR_INITIAL, LR_DECAY_STEPS, LR_DECAY_FACTOR = 0.00008, 10000, 0.8          # exponential_decay, staircase
+ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON = 0.9, 0.999, 1e-8                   # tf.train.AdamOptimizer defaults
+EMA_DECAY = 0.9999                                                        # MovingAverageOptimizer(average_decay)
+CLIP_GRADIENT_NORM = 1.0                                                  # per variable (slim.learning.create_train_op)
 KPAD = 1088          # 1043 / 1060 concat widths padded to a multiple of 64
 
 
@@ -882,11 +888,11 @@ class Engine:
 
     # ------------------------------------------------------------------ train-op
     def learning_rate(self, step):
-        return 0.00008 * (0.8 ** (step // 10000))        # exponential_decay, staircase (yaml:145-150)
+        return LR_INITIAL * (LR_DECAY_FACTOR ** (step // LR_DECAY_STEPS))        # exponential_decay, staircase (yaml:145-150)
 
     def set_hyper(self, step):
         t = step + 1
-        lr_t = self.learning_rate(step) * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        lr_t = self.learning_rate(step) * math.sqrt(1.0 - ADAM_BETA2 ** t) / (1.0 - ADAM_BETA1 ** t)
         self.hyper_host = getattr(self, "hyper_host", torch.zeros(4, pin_memory=True))
         self.hyper_host[0] = lr_t
         self.hyper.copy_(self.hyper_host, non_blocking=True)
@@ -897,8 +903,8 @@ class Engine:
         self._chk(self.L.mpb_opt_step_range(nc, ctypes.c_void_p(self.opt_chunks.data_ptr() + c0 * chunk_bytes), t0, nt,
                                             _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
                                             _ptr(self.ema), ctypes.c_void_p(self.norm2.data_ptr() + 4 * c0), _ptr(self.hyper),
-                                            grad_scale, 1.0, 0.9,
-                                            0.999, 1e-8, 0.9999, self._st()), "opt_step")
+                                            grad_scale, CLIP_GRADIENT_NORM, ADAM_BETA1,
+                                            ADAM_BETA2, ADAM_EPSILON, EMA_DECAY, self._st()), "opt_step")
         self._prepared = False
 
     def allreduce_grads(self):

@@ -328,6 +328,33 @@ def install():
     tf.Assert = lambda cond, data: cond
     tf.control_dependencies = lambda deps: contextlib.nullcontext()
     tf.logging = types.SimpleNamespace(set_verbosity=lambda *a: None, ERROR=0)
+
+    # optimizer construction (optimizer_builder.py): every call is recorded with the arguments the reference passes;
+    # what it does NOT pass stays at the TensorFlow default, noted here from the TF 1.x signatures
+    def optimizer(kind, defaults):
+        def make(learning_rate, **kwargs):
+            cfg = dict(defaults)
+            cfg.update(kwargs)
+            RECORD.append({"op": kind, "learning_rate": learning_rate, "passed": sorted(kwargs), "config": cfg})
+            return {"optimizer": kind, "learning_rate": learning_rate, "config": cfg}
+        return make
+
+    def exponential_decay(learning_rate, global_step, decay_steps, decay_rate, staircase=False, name=None):
+        r = {"op": "exponential_decay", "learning_rate": learning_rate, "decay_steps": decay_steps, "decay_rate": decay_rate,
+             "staircase": staircase}
+        RECORD.append(r)
+        return r
+
+    def moving_average_optimizer(opt, average_decay=0.9999, num_updates=None, sequential_update=True):
+        RECORD.append({"op": "MovingAverageOptimizer", "average_decay": average_decay, "num_updates": num_updates,
+                       "wraps": opt["optimizer"]})
+        return {"optimizer": "MovingAverageOptimizer", "inner": opt}
+    tf.train = types.SimpleNamespace(
+        AdamOptimizer=optimizer("AdamOptimizer", {"beta1": 0.9, "beta2": 0.999, "epsilon": 1e-08}),
+        RMSPropOptimizer=optimizer("RMSPropOptimizer", {}), MomentumOptimizer=optimizer("MomentumOptimizer", {}),
+        GradientDescentOptimizer=optimizer("GradientDescentOptimizer", {}), exponential_decay=exponential_decay)
+    contrib.opt = types.SimpleNamespace(MovingAverageOptimizer=moving_average_optimizer)
+    tf.summary = types.SimpleNamespace(scalar=lambda name, tensor, **k: name)
     sys.modules["tensorflow"], sys.modules["tensorflow.contrib"], sys.modules["tensorflow.contrib.slim"] = tf, contrib, slim
     sys.modules.setdefault("png", types.ModuleType("png"))           # pypng: imported by depth_map_utils, never called here
     return tf

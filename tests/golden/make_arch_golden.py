@@ -67,7 +67,22 @@ def main():
         ob.add_cen_y_output(output_key=constants.KEY_CEN_Y, features_in=f2, prop_cen_y=prop_y, gt_cen_y=T([n, 1]))
         ob.add_cen_z_output(output_key=constants.KEY_CEN_Z, features_in=f2, prop_cen_z=prop_z, gt_cen_z=T([n, 1]))
 
-    out = {"net_type": mc["net_type"], "record": fake_tf.RECORD, "n_feature_ops": n_feature_ops,
+    n_layer_ops = len(fake_tf.RECORD)
+
+    # ---- the train-op (row a18): the optimizer the reference's optimizer_builder constructs from the yaml, and the
+    # gradient clipping its trainer asks slim.learning.create_train_op for (a literal in core/trainer.py, read with ast)
+    import ast
+    from monopsr.builders import optimizer_builder
+    optimizer_builder.build(obj(cfg["train_config"]["optimizer"]), set(), fake_tf.Tensor([], tag="global_step"))
+    clip = None
+    for node in ast.walk(ast.parse(open("/root/reference/src/monopsr/core/trainer.py").read())):
+        if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "create_train_op":
+            clip = {k.arg: ast.literal_eval(k.value) for k in node.keywords if k.arg == "clip_gradient_norm"}
+    train_op = {"record": fake_tf.RECORD[n_layer_ops:], "create_train_op": clip,
+                "max_iterations": cfg["train_config"]["max_iterations"]}
+    del fake_tf.RECORD[n_layer_ops:]
+
+    out = {"net_type": mc["net_type"], "record": fake_tf.RECORD, "n_feature_ops": n_feature_ops, "train_op": train_op,
            "features": {k: v.get_shape().as_list() for k, v in feats.items()},
            "extractor_config": mc["net_config"][mc["net_type"]]}
     path = os.path.join(HERE, "arch_golden.json")
@@ -77,6 +92,7 @@ def main():
     convs = [r for r in fake_tf.RECORD[:n_feature_ops] if r["op"] == "conv2d"]
     print("wrote", path, os.path.getsize(path), "bytes;", len(fake_tf.RECORD), "ops,", len(convs), "convolutions")
     print({k: v for k, v in out["features"].items()})
+    print(train_op)
     for r in convs[:4] + convs[-5:]:
         print(r["scope"], r["kernel"], "s%d r%d" % (r["stride"], r["rate"]), r["padding"], r["cin"], "->", r["cout"], r["activation"],
               "bn" if r["batch_norm"] else "bias" if r["bias"] else "-", r["out_shape"])

@@ -197,3 +197,23 @@ def test_oracle_concat_order_matches_the_record():
     assert {1024, 1025, 1026, 1027} <= pa and 1029 not in pa
     pa, ra = moved("cam_p", 0.001)
     assert set(range(1031, 1043)) & pa and not (pa & {1029, 1030})
+
+
+def test_train_op_constants():
+    """the optimizer the reference's optimizer_builder constructs from monopsr_model_000.yaml (recorded calls) and the
+    clipping its trainer requests, against the constants of the engine's train-op"""
+    from monopsr_b200.core import engine as E
+    t = G["train_op"]
+    by = {r["op"]: r for r in t["record"]}
+    lr = by["exponential_decay"]
+    assert (lr["learning_rate"], lr["decay_steps"], lr["decay_rate"], lr["staircase"]) == \
+        (E.LR_INITIAL, E.LR_DECAY_STEPS, E.LR_DECAY_FACTOR, True)
+    adam = by["AdamOptimizer"]
+    assert adam["passed"] == [] and adam["learning_rate"] == lr            # only the schedule is passed: TF defaults
+    assert adam["config"] == {"beta1": E.ADAM_BETA1, "beta2": E.ADAM_BETA2, "epsilon": E.ADAM_EPSILON}
+    ema = by["MovingAverageOptimizer"]
+    assert ema["average_decay"] == E.EMA_DECAY and ema["num_updates"] is None and ema["wraps"] == "AdamOptimizer"
+    assert t["create_train_op"] == {"clip_gradient_norm": E.CLIP_GRADIENT_NORM}
+    e = E.Engine.__new__(E.Engine)
+    for step in (0, 1, 9999, 10000, 25000, t["max_iterations"]):
+        assert e.learning_rate(step) == lr["learning_rate"] * lr["decay_rate"] ** (step // lr["decay_steps"])
