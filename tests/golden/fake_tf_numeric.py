@@ -14,8 +14,23 @@ import numpy as np
 
 
 class T(np.ndarray):
+    """tensors are immutable: `a += b` on a TF tensor REBINDS a -- it must not write through to an array another
+    name (or a slice of another tensor) still refers to, as numpy's in-place operators would"""
+
     def get_shape(self):
         return _Shape(self.shape)
+
+    def __iadd__(self, other):
+        return np.add(self, other).view(T)
+
+    def __isub__(self, other):
+        return np.subtract(self, other).view(T)
+
+    def __imul__(self, other):
+        return np.multiply(self, other).view(T)
+
+    def __itruediv__(self, other):
+        return np.true_divide(self, other).view(T)
 
 
 class _Shape(list):
@@ -85,12 +100,47 @@ def install():
     tf.squeeze = lambda x, axis=None, **k: t(np.squeeze(np.asarray(x), axis=axis))
     tf.reshape = lambda x, shape, **k: t(np.reshape(np.asarray(x), shape))
     tf.shape = lambda x, **k: list(np.shape(x))
-    tf.reduce_sum = lambda x, axis=None, **k: t(np.sum(np.asarray(x, np.float64), axis=tuple(axis) if isinstance(axis, list) else axis))
     tf.to_float = lambda x, **k: t(np.asarray(x, np.float64))
     tf.divide = lambda a, b, **k: t(np.asarray(a, np.float64) / b)
     tf.where = lambda c, a, b: t(np.where(c, a, b))
     tf.is_nan = lambda x: np.isnan(np.asarray(x, np.float64))
     tf.one_hot = one_hot
+    # geometry ops (instance_utils.py:567-681,738-788,907-953; transform_utils.py:69-173; calib_utils.py:263-280;
+    # monopsr_output_builder.py:407-438,551-571,663-746)
+    f64 = lambda x: np.asarray(x, np.float64)
+    tf.stack = lambda values, axis=0, **k: t(np.stack([f64(v) for v in values], axis=axis))
+    tf.concat = lambda values, axis, **k: t(np.concatenate([f64(v) for v in values], axis=axis))
+    tf.sin, tf.cos, tf.tan = (lambda x, **k: t(np.sin(f64(x)))), (lambda x, **k: t(np.cos(f64(x)))), (lambda x, **k: t(np.tan(f64(x))))
+    tf.atan = lambda x, **k: t(np.arctan(f64(x)))
+    tf.atan2 = lambda y, x, **k: t(np.arctan2(f64(y), f64(x)))
+    tf.matmul = lambda a, b, **k: t(np.matmul(f64(a), f64(b)))
+    tf.linspace = lambda start, stop, num, **k: t(np.linspace(float(start), float(stop), int(num)))
+    tf.transpose = lambda x, perm=None, **k: t(np.transpose(f64(x), perm))
+    tf.tile = lambda x, multiples, **k: t(np.tile(f64(x), multiples))
+    tf.zeros = lambda shape, dtype=np.float32, **k: t(np.zeros(shape, np.float64))
+    tf.less = lambda a, b, **k: f64(a) < b
+    tf.round = lambda x, **k: t(np.round(f64(x)))          # both round half to even
+    tf.pad = lambda x, paddings, mode="CONSTANT", constant_values=0, **k: t(np.pad(f64(x), paddings, constant_values=constant_values))
+    tf.meshgrid = lambda *a, **k: [t(m) for m in np.meshgrid(*[f64(v) for v in a], indexing=k.get("indexing", "xy"))]
+    tf.clip_by_value = lambda x, lo, hi, **k: t(np.clip(f64(x), lo, hi))
+    tf.abs = lambda x, **k: t(np.abs(f64(x)))
+    tf.maximum = lambda a, b, **k: t(np.maximum(f64(a), f64(b)))
+
+    def reduce_sum(x, axis=None, reduction_indices=None, keep_dims=False, keepdims=False, **k):
+        ax = axis if axis is not None else reduction_indices
+        return t(np.sum(f64(x), axis=tuple(ax) if isinstance(ax, (list, tuple)) else ax, keepdims=keep_dims or keepdims))
+    tf.reduce_sum = reduce_sum
+
+    def map_fn(fn, elems, dtype=None, **k):
+        if isinstance(elems, (list, tuple)):
+            n = len(elems[0])
+            results = [fn(tuple(t(e[i]) for e in elems)) for i in range(n)]
+        else:
+            results = [fn(t(e)) for e in elems]
+        if isinstance(results[0], (list, tuple)):
+            return type(results[0])(t(np.stack([f64(r[j]) for r in results])) for j in range(len(results[0])))
+        return t(np.stack([f64(r) for r in results]))
+    tf.map_fn = map_fn
     tf.summary = _Any("tensorflow.summary")
     tf.summary.scalar = lambda *a, **k: None
     tf.nn = _Any("tensorflow.nn")
