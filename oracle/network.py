@@ -2,9 +2,14 @@
 
 fp64 (or fp32, for the CPU timing baseline) RESTATEMENT in plain torch of the MonoPSR
 per-instance network of ``monopsr_model_000`` -- NOT TensorFlow, which is an un-vendored,
-un-installable dependency of the reference (requirements.txt:13).  Parity of the network
-is therefore UNPINNED against the real TF1 graph (the reference has no test at this
-boundary); this file follows, line by line:
+un-installable dependency of the reference (requirements.txt:13).  Parity against the real
+TF1 graph is UNPINNED for the arithmetic of TensorFlow's own kernels (convolution, batch
+norm, resize, crop_and_resize: cross-checked against torchvision / torch.nn.functional in
+tests/test_host_mirrors.py).  Everything that lives in the reference's Python IS pinned to
+that code, executed rather than read: the architecture to the record of its graph builders
+(tests/test_arch_golden.py), the geometry to its TF functions and numpy twins run on arrays
+(tests/test_geometry_tf_golden.py, tests/test_oracle_geometry.py), the loss to its
+MonoPSRModel.loss (tests/test_loss_golden.py).  This file follows, line by line:
 
   nets/resnet_v1.py:78-139,142-254,310-330   bottleneck, resnet_v1, resnet_v1_101
   nets/resnet_utils.py:59-122,125-219,222-272 subsample, conv2d_same, stack_blocks_dense, arg_scope
