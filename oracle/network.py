@@ -404,6 +404,23 @@ def forward(P, S, train=True):
     return out, aux
 
 
+def regression_targets(out, S):
+    """gt_dict entries of the offset heads as the output builder creates them (monopsr_output_builder.py:441-488,
+    573-609, 625-661; gt centroid: monopsr_model.py:262-277, centroid_type 'middle').  Pinned to those methods
+    executed on arrays: tests/test_loss_golden.py::test_regression_targets."""
+    b3 = S["boxes_3d"]
+    gt_cen_y = b3[:, 1:2] - b3[:, 5:6] / 2.0          # centroid_type 'middle' (yaml:20)
+    gt_cen_z = b3[:, 2:3]
+    prop_cen_y = out["cen_y"] - out["cen_y_offs"]
+    return {
+        # gt_lwh - pred_lwh: a graph tensor that depends on the prediction; TF differentiates through it
+        # (reference quirk Q9, kept as is)
+        "lwh_offs": b3[:, 3:6] - out["lwh"],
+        "cen_z_offs": gt_cen_z - out["prop_cen_z"],
+        "cen_y_offs": gt_cen_y - prop_cen_y,
+    }
+
+
 def loss(out, S):
     """monopsr_model.py:554-958 with the weights of monopsr_model_000.yaml:102-118."""
     N = NUM_BOXES
@@ -411,23 +428,16 @@ def loss(out, S):
     L = {}
     L["inst_xyz_map_local"] = 100.0 * smooth_l1_nonzero(out["inst_xyz_map_local"],
                                                         S["gt_inst_xyz_maps_local"], valid) / N
-    b3 = S["boxes_3d"]
-    gt_lwh = b3[:, 3:6]
-    # gt_dict['lwh_offs'] = gt_lwh - pred_lwh (output_builder.py:655-660): a graph tensor that
-    # depends on the prediction; TF differentiates through it (reference quirk Q9, kept as is).
-    gt_lwh_offs = gt_lwh - out["lwh"]
-    L["lwh_offs"] = 1.0 * huber(out["lwh_offs"] - gt_lwh_offs).sum() / N
+    T = regression_targets(out, S)
+    L["lwh_offs"] = 1.0 * huber(out["lwh_offs"] - T["lwh_offs"]).sum() / N
     eps = 0.001
     onehot = torch.full((N, 12), eps / 12, dtype=out["alpha_bins"].dtype, device=out["alpha_bins"].device)
     onehot[torch.arange(N, device=onehot.device), S["gt_alpha_bins"].long()] = 1.0 - eps
     logp = torch.log_softmax(out["alpha_bins"], dim=1)
     L["alpha_bins"] = 0.3 * (-(onehot * logp).sum(1)).sum() / N
     L["alpha_regs"] = 1.0 * (huber(out["alpha_regs"] - S["gt_alpha_regs"]) * S["gt_alpha_valid_bins"]).sum() / N
-    gt_cen_y = b3[:, 1:2] - b3[:, 5:6] / 2.0          # centroid_type 'middle' (yaml:20)
-    gt_cen_z = b3[:, 2:3]
-    prop_cen_y = out["cen_y"] - out["cen_y_offs"]
-    L["cen_z_offs"] = 0.1 * huber(out["cen_z_offs"] - (gt_cen_z - out["prop_cen_z"])).sum() / N
-    L["cen_y_offs"] = 0.1 * huber(out["cen_y_offs"] - (gt_cen_y - prop_cen_y)).sum() / N
+    L["cen_z_offs"] = 0.1 * huber(out["cen_z_offs"] - T["cen_z_offs"]).sum() / N
+    L["cen_y_offs"] = 0.1 * huber(out["cen_y_offs"] - T["cen_y_offs"]).sum() / N
     L["proj_err"] = 0.1 * huber(out["proj_err_norm"]).sum() / N        # SUM_BY_NONZERO over 32 ones
     L["inst_depth_map_global"] = 10.0 * smooth_l1_nonzero(out["inst_depth_map_global"],
                                                           S["gt_inst_xyz_maps_global"][..., 2:3], valid) / N

@@ -47,7 +47,31 @@ def main():
         dataset=types.SimpleNamespace(num_alpha_bins=nb), pl_gt_alpha_valid_bins=valid_bins, map_roi_size=mc["map_roi_size"])
     losses, total = MonoPSRModel.loss(me, {k: fake_tf_numeric.t(v) for k, v in out.items()},
                                       {k: fake_tf_numeric.t(v) for k, v in gt.items()})
-    save = {"out/" + k: v for k, v in out.items()}
+    # ---- the regression targets (gt_dict of the offset heads): the output builder's own add_*_output methods, with
+    # slim.fully_connected answering with given offsets
+    from monopsr.core import constants
+    preds = {"lwh": rs.randn(n, 3) * 0.3, "cen_y": rs.randn(n, 1) * 0.2, "cen_z": rs.randn(n, 1)}
+    import monopsr.core.models.monopsr.monopsr_output_builder as mob
+    mob.slim.fully_connected = lambda x, num_outputs, activation_fn=None, scope=None, **k: fake_tf_numeric.t(preds[scope])
+    ob = MonoPSROutputBuilder(model_config.output_config, model_config, obj(cfg["dataset_config"]),
+                              {constants.FEATURES_FOR_MAP: None, constants.FEATURES_FOR_BOX_3D: None}, n, mc["map_roi_size"],
+                              None, "train")
+    tg = {"mean_lwh": np.tile([3.892, 1.619, 1.530], (n, 1)), "boxes_3d": rs.rand(n, 7) * [20, 2, 40, 2, 1, 1, 3] + [-10, 1, 5, 3, 1.2, 1.2, -1.5],
+          "prop_cen_y": rs.randn(n, 1) * 0.5 + 1.2, "prop_cen_z": rs.rand(n, 1) * 40 + 5}
+    b3 = tg["boxes_3d"]
+    gt_cen_y = b3[:, 1:2] - b3[:, 5:6] / 2                   # monopsr_model.py:266-270, centroid_type 'middle'
+    T = fake_tf_numeric.t
+    ob.add_lwh_output(features_to_use=None, est_lwh=T(tg["mean_lwh"]), gt_lwh=T(b3[:, 3:6]))
+    ob.add_cen_y_output(output_key=constants.KEY_CEN_Y, features_in=None, prop_cen_y=T(tg["prop_cen_y"]), gt_cen_y=T(gt_cen_y))
+    ob.add_cen_z_output(output_key=constants.KEY_CEN_Z, features_in=None, prop_cen_z=T(tg["prop_cen_z"]), gt_cen_z=T(b3[:, 2:3]))
+    targets = {"in/" + k: v for k, v in tg.items()}
+    targets.update({"pred/" + k: v for k, v in preds.items()})
+    for k in ("lwh", "lwh_offs", "cen_y", "cen_y_offs", "cen_z", "cen_z_offs"):
+        targets["out/" + k] = np.asarray(ob._output_dict[k], np.float64)
+        targets["gt/" + k] = np.asarray(ob._gt_dict[k], np.float64)
+
+    save = {"targets/" + k: v for k, v in targets.items()}
+    save.update({"out/" + k: v for k, v in out.items()})
     save.update({"gt/" + k: v for k, v in gt.items()})
     save["gt/alpha_valid_bins"] = valid_bins
     save.update({"loss/" + k: np.asarray(v, np.float64) for k, v in losses.items()})

@@ -57,3 +57,18 @@ def test_terms_react_to_their_own_inputs_only():
         L2, _ = onet.loss(o2, S)
         changed = {k for k in base if abs(float(L2[k]) - float(base[k])) > 1e-12}
         assert changed == {term}, (key, changed)
+
+
+def test_regression_targets():
+    """gt_dict of the offset heads as MonoPSROutputBuilder.add_lwh_output / add_cen_y_output / add_cen_z_output create it
+    (executed on arrays, fully_connected answering with given offsets) against oracle.regression_targets -- including
+    the quirk that the 'ground-truth' dimension offsets are measured from the PREDICTED dimensions"""
+    t = lambda a: torch.as_tensor(np.asarray(a, np.float64))
+    g = {k[len("targets/"):]: G[k] for k in G.files if k.startswith("targets/")}
+    np.testing.assert_allclose(g["out/lwh"], g["in/mean_lwh"] + g["pred/lwh"])             # sanity of the recording
+    out = {"lwh": t(g["out/lwh"]), "lwh_offs": t(g["out/lwh_offs"]), "cen_y": t(g["out/cen_y"]),
+           "cen_y_offs": t(g["out/cen_y_offs"]), "prop_cen_z": t(g["in/prop_cen_z"])}
+    T = onet.regression_targets(out, {"boxes_3d": t(g["in/boxes_3d"])})
+    for k in ("lwh_offs", "cen_y_offs", "cen_z_offs"):
+        np.testing.assert_allclose(T[k].numpy(), g["gt/" + k], rtol=1e-12, atol=1e-13, err_msg=k)
+    assert np.allclose(g["gt/lwh_offs"], g["in/boxes_3d"][:, 3:6] - g["out/lwh"])          # gt_lwh - PREDICTED lwh
