@@ -169,3 +169,40 @@ def test_primitives_against_the_tensorflow_ecosystem_code_in_tensorboard():
         assert C._parse_shape(theirs) == tuple(shape)
     with pytest.raises(ValueError):
         C._parse_shape(shape_pb2.TensorShapeProto(unknown_rank=True).SerializeToString())
+
+
+def test_detection_checkpoint_mapping_equals_the_reference_restore_logic():
+    """which model variable is fed from which checkpoint variable: map_detection_checkpoint against the record of the
+    reference's own restore code (checkpoint_utils.restore_obj_detection_api_weights + get_variable_restore_map +
+    variables_helper.get_variables_available_in_checkpoint, executed: tests/golden/make_restore_golden.py) on the same
+    synthetic detection checkpoint -- both towers from 'FirstStageFeatureExtractor/', block4 and the RPN / predictor
+    variables untouched, a variable with a foreign shape skipped"""
+    import importlib.util
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_restore_golden", os.path.join(here, "golden", "make_restore_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = json.load(open(os.path.join(here, "golden", "restore_golden.json")))["restored"]
+    mv = gen.model_variables()
+    ck_shapes = gen.detection_checkpoint(mv)
+    ck = {n: np.zeros(s, np.float32) for n, s in ck_shapes.items()}
+    from monopsr_b200.core import model_spec as ms
+    loaded, report = C.map_detection_checkpoint(ck, ms.param_table())
+    want = {}
+    for saver in gold:                                      # checkpoint name -> model variable, per tower
+        assert saver["other"] == {}                         # nothing but '<first stage>/x' -> '<tower>/x' pairs
+        for suffix in saver["suffixes"]:
+            want[saver["model_prefix"] + suffix] = saver["ckpt_prefix"] + suffix
+    assert sorted(s["model_prefix"] for s in gold) == sorted(e + "/" for e in ms.ENCODERS)
+    table = {n for n, _, _ in ms.param_table()}
+    # the reference also "restores" block4 of nothing (not in the first-stage scope) -- and this engine has no block4
+    want_here = {m: c for m, c in want.items() if m in table}
+    assert set(loaded) == set(want_here)
+    assert all(c == "FirstStageFeatureExtractor/" + m.split("/", 1)[1] for m, c in want_here.items())
+    assert not [m for m in want if "/block4/" in m]                     # block4 lives in the SECOND stage of the checkpoint
+    assert len(gold[0]["suffixes"]) == len(gold[1]["suffixes"]) == 469
+    for enc in ms.ENCODERS:
+        assert enc + "/resnet_v1_101/conv1/weights" not in loaded       # foreign shape: skipped by both
+        assert enc + "/resnet_v1_101/conv1/BatchNorm/gamma" in loaded
+    assert not any(n.startswith(("squash/", "map_decoder/", "output/")) for n in loaded)
