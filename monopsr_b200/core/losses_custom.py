@@ -48,15 +48,18 @@ class ChamferDistance(Loss):
         return (dist1.sum() + dist2.sum()) / float(b)
 
 
-def point_set_metrics(pred_xyz_maps, gt_xyz_maps, valid_mask_maps, num_objs):
+def point_set_metrics(pred_xyz_maps, gt_xyz_maps, valid_mask_maps, num_objs, ops=None):
     """metric_emd / metric_chamfer of monopsr_model.py:1112-1170: per-object distances divided by
-    the object's number of valid pixels -> two (num_objs,) tensors."""
+    the object's number of valid pixels -> two (num_objs,) tensors.  `ops` = (approx_match, match_cost, nn_distance)
+    replaces the sm_100a ops (the assembly around them is tested on the CPU with stand-ins)."""
+    approx_match, match_cost, nn_distance = ops or (tf_approxmatch.approx_match, tf_approxmatch.match_cost,
+                                                     tf_nndistance.nn_distance)
     n = pred_xyz_maps.shape[0]
     p = (pred_xyz_maps * valid_mask_maps).reshape(n, -1, 3).contiguous()
     t = (gt_xyz_maps * valid_mask_maps).reshape(n, -1, 3).contiguous()
     nvalid = valid_mask_maps[:num_objs].sum(dim=(1, 2, 3))
-    match = tf_approxmatch.approx_match(p, t)
-    emd = tf_approxmatch.match_cost(p, t, match)[:num_objs] / nvalid
-    d1, _, d2, _ = tf_nndistance.nn_distance(p, t)
+    match = approx_match(p, t)
+    emd = match_cost(p, t, match)[:num_objs] / nvalid
+    d1, _, d2, _ = nn_distance(p, t)
     chamfer = (d1.sum(1) + d2.sum(1))[:num_objs] / nvalid
     return {"metric_emd": emd, "metric_chamfer": chamfer}

@@ -182,3 +182,43 @@ def test_validation_metrics():
     lists = M.accumulate({}, m)
     lists = M.accumulate(lists, {M.METRIC_EMD: np.array([np.nan, 1.0]), M.METRIC_CHAMFER: np.array([5.0])})
     assert lists[M.METRIC_EMD] == [0, 1, 2] and lists[M.METRIC_CHAMFER] == [0, 2, 4, 5] and len(lists[M.METRIC_DIM_ERR]) == 9
+
+
+def test_metrics_equal_the_reference_evaluate_predictions():
+    """core/metrics.py + losses_custom.point_set_metrics against MonoPSRModel.evaluate_predictions executed on arrays
+    (tests/golden/make_metrics_golden.py); the two custom ops are answered by the same plain stand-ins on both sides"""
+    import torch
+    from monopsr_b200.core import losses_custom
+    from monopsr_b200.core import metrics as M
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_golden.npz"))
+    pred = {k[5:]: G[k] for k in G.files if k.startswith("pred/")}
+    gt = {k[3:]: G[k] for k in G.files if k.startswith("gt/")}
+    n_obj = int(G["num_objs"])
+
+    def nn_distance(a, b):
+        d = ((a[:, :, None, :] - b[:, None, :, :]) ** 2).sum(-1)
+        return d.min(2).values, d.argmin(2), d.min(1).values, d.argmin(1)
+
+    def approx_match(a, b):
+        return torch.eye(a.shape[1], dtype=a.dtype).expand(a.shape[0], -1, -1)
+
+    def match_cost(a, b, match):
+        return (torch.sqrt(((b[:, :, None, :] - a[:, None, :, :]) ** 2).sum(-1)) * match).sum((1, 2))
+    t = lambda a: torch.as_tensor(np.asarray(a, np.float64))
+    ps = losses_custom.point_set_metrics(t(pred["inst_xyz_map_local"]), t(gt["inst_xyz_map_local"]), t(gt["valid_mask_maps"]),
+                                         n_obj, ops=(approx_match, match_cost, nn_distance))
+    # a sample whose derived ground truth is the golden gt_dict: pred lwh = 0 so that gt offsets = box dimensions
+    b3 = np.zeros((32, 7), np.float32)
+    b3[:, 3:6] = gt["lwh_offs"]
+    b3[:, 0], b3[:, 2] = gt["centroids"][:, 0], gt["centroids"][:, 2]
+    b3[:, 1] = gt["centroids"][:, 1] + b3[:, 5] / 2
+    outputs = {"prop_cen_z": pred["prop_cen_z"], "centroids": pred["centroids"], "lwh": np.zeros((32, 3)),
+               "lwh_offs": pred["lwh_offs"], "view_ang": pred["view_ang"]}
+    sample = {"boxes_3d": b3, "gt_view_angs": gt["view_ang"][:, 0]}
+    types_ = [P.KEY_INST_XYZ_MAP_LOCAL, P.KEY_CENTROIDS, P.KEY_LWH, P.KEY_VIEW_ANG]
+    m = M.evaluate_predictions(outputs, sample, n_obj, types_, "middle", point_set={k: v.numpy() for k, v in ps.items()})
+    want = {k[7:]: G[k] for k in G.files if k.startswith("metric/")}
+    assert sorted(m) == sorted(want)
+    for k, v in want.items():
+        assert np.asarray(m[k]).shape == v.shape, (k, np.asarray(m[k]).shape, v.shape)
+        np.testing.assert_allclose(m[k], v, rtol=2e-6, atol=2e-6, err_msg=k)          # (boxes_3d round-trips through float32)
