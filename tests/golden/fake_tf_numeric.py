@@ -101,6 +101,7 @@ def install():
     tf.reshape = lambda x, shape, **k: t(np.reshape(np.asarray(x), shape))
     tf.shape = lambda x, **k: list(np.shape(x))
     tf.to_float = lambda x, **k: t(np.asarray(x, np.float64))
+    tf.cast = lambda x, dtype, **k: t(np.asarray(x, np.float64 if dtype in (np.float32, np.float64) else dtype))
     tf.divide = lambda a, b, **k: t(np.asarray(a, np.float64) / b)
     tf.where = lambda c, a, b: t(np.where(c, a, b))
     tf.is_nan = lambda x: np.isnan(np.asarray(x, np.float64))

@@ -60,6 +60,14 @@ def main():
     save.update({"gt/" + k: v for k, v in gt.items()})
     save.update({"metric/" + k: np.asarray(v, np.float64) for k, v in metrics.items()})
     save["num_objs"] = np.asarray(num_objs)
+    # the two point-set LOSS classes (losses_custom.py:135-198) on the same arrays, same stand-in ops
+    import monopsr.core.losses_custom as lc
+    lc.tf_nndistance.nn_distance = nn_distance
+    lc.tf_approxmatch.approx_match, lc.tf_approxmatch.match_cost = approx_match, match_cost
+    save["loss/chamfer_dist"] = np.asarray(lc.ChamferDistance()(F.t(pred["inst_xyz_map_local"]), F.t(gt["inst_xyz_map_local"]),
+                                                                weights=F.t(valid)), np.float64)
+    save["loss/emd"] = np.asarray(lc.EarthMoversDistance()(F.t(pred["inst_xyz_map_local"]), F.t(gt["inst_xyz_map_local"]),
+                                                           weights=F.t(valid)), np.float64)
     path = os.path.join(HERE, "metrics_golden.npz")
     np.savez_compressed(path, **save)
     print({k: np.asarray(v).shape for k, v in metrics.items()})

@@ -222,3 +222,10 @@ def test_metrics_equal_the_reference_evaluate_predictions():
     for k, v in want.items():
         assert np.asarray(m[k]).shape == v.shape, (k, np.asarray(m[k]).shape, v.shape)
         np.testing.assert_allclose(m[k], v, rtol=2e-6, atol=2e-6, err_msg=k)          # (boxes_3d round-trips through float32)
+    # the two point-set loss classes: mask both clouds, flatten to (B, h*w, 3), op, sum / B
+    cd = losses_custom.ChamferDistance(ops=(nn_distance,))(t(pred["inst_xyz_map_local"]), t(gt["inst_xyz_map_local"]),
+                                                            weights=t(gt["valid_mask_maps"]))
+    emd = losses_custom.EarthMoversDistance(ops=(approx_match, match_cost))(
+        t(pred["inst_xyz_map_local"]), t(gt["inst_xyz_map_local"]), weights=t(gt["valid_mask_maps"]))
+    np.testing.assert_allclose(float(cd), float(G["loss/chamfer_dist"]), rtol=1e-12)
+    np.testing.assert_allclose(float(emd), float(G["loss/emd"]), rtol=1e-12)
