@@ -142,6 +142,30 @@ def install():
             return type(results[0])(t(np.stack([f64(r[j]) for r in results])) for j in range(len(results[0])))
         return t(np.stack([f64(r) for r in results]))
     tf.map_fn = map_fn
+    # ground-truth target synthesis (instance_utils.py:395-481, depth_map_utils.py:161-236)
+    tf.to_int32 = lambda x, **k: t(np.asarray(x).astype(np.int32))
+    tf.greater_equal = lambda a, b, **k: f64(a) >= b
+    tf.reduce_max = lambda x, axis=None, keepdims=False, keep_dims=False, **k: t(np.max(f64(x), axis=axis, keepdims=keepdims or keep_dims))
+    tf.stop_gradient = lambda x, **k: x
+
+    def resize_nearest_neighbor(images, size, align_corners=False, **k):
+        """TF 1.8 ResizeNearestNeighbor: in = min(round_half_away(out * scale), in_size - 1) with
+        scale = (in - 1) / (out - 1) when align_corners (else floor(out * in / out))"""
+        x = f64(images)
+        n, ih, iw, c = x.shape
+        oh, ow = int(size[0]), int(size[1])
+
+        def index(o, i):
+            j = np.arange(o, dtype=np.float32)
+            if align_corners and o > 1:
+                r = j * np.float32((i - 1) / (o - 1))
+                r = np.where(r >= 0, np.floor(r + np.float32(0.5)), np.ceil(r - np.float32(0.5)))
+            else:
+                r = np.floor(j * np.float32(i / o))
+            return np.minimum(r.astype(np.int64), i - 1)
+        return t(x[:, index(oh, ih)][:, :, index(ow, iw)])
+    tf.image = _Any("tensorflow.image")
+    tf.image.resize_nearest_neighbor = resize_nearest_neighbor
     tf.summary = _Any("tensorflow.summary")
     tf.summary.scalar = lambda *a, **k: None
     tf.nn = _Any("tensorflow.nn")

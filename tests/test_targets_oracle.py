@@ -105,3 +105,26 @@ def test_image_oracle_against_independent_implementations():
     assert np.array_equal(pre, u8[::2, ::2].astype(np.float32))
     same = T.preprocess_input(u8, (4, 4))
     np.testing.assert_allclose(same, u8.astype(np.float32) - T.KITTI_CHANNEL_MEANS, rtol=0, atol=1e-5)
+
+
+def test_against_the_reference_tf_functions_executed_on_arrays():
+    """oracle.targets.instance_xyz_crop_from_depth_map against the reference's TENSORFLOW version of the same function,
+    unmodified, executed through the numpy-backed TF stand-in (tests/golden/make_targets_tf_golden.py): box rounding,
+    mask, crop, nearest-neighbour resize, back-projection at pixel centres, centroid adjustment, view normalisation,
+    valid-pixel threshold.  The stand-in computes in float64, the oracle in float32 (as TF would): tolerance 1e-4 on
+    values of order 10, exact on the validity masks."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_targets_tf_golden", os.path.join(here, "golden", "make_targets_tf_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    depth, masks, b2, b3, view, cam_p = gen.inputs()
+    G = np.load(os.path.join(here, "golden", "targets_tf_golden.npz"))
+    for name, view_norm, ctype, rot in (("local", True, "middle", True), ("global", False, "middle", True),
+                                        ("local_bottom_norot", True, "bottom", False)):
+        for i in range(4):
+            xyz, valid = T.instance_xyz_crop_from_depth_map(i, b2, b3, masks, depth, (48, 48), view, cam_p, view_norm,
+                                                            centroid_type=ctype, rotate_view=rot)
+            assert np.array_equal(valid, G["valid_" + name][i]), (name, i)
+            np.testing.assert_allclose(xyz, G["xyz_" + name][i], rtol=0, atol=2e-4, err_msg="%s %d" % (name, i))
+    assert 0.3 < G["valid_local"].mean() < 0.9
