@@ -6,7 +6,9 @@ un-installable dependency of the reference (requirements.txt:13).  Parity agains
 TF1 graph is UNPINNED for the arithmetic of TensorFlow's own kernels (convolution, batch
 norm, resize, crop_and_resize: cross-checked against torchvision / torch.nn.functional in
 tests/test_host_mirrors.py).  Everything that lives in the reference's Python IS pinned to
-that code, executed rather than read: the architecture to the record of its graph builders
+that code, executed rather than read -- end to end by running its whole MonoPSRModel
+__init__ / build / loss on arrays and comparing all outputs and loss terms
+(tests/test_graph_golden.py), and piecewise: the architecture to the record of its graph builders
 (tests/test_arch_golden.py), the geometry to its TF functions and numpy twins run on arrays
 (tests/test_geometry_tf_golden.py, tests/test_oracle_geometry.py), the loss to its
 MonoPSRModel.loss (tests/test_loss_golden.py).  This file follows, line by line:
