@@ -352,9 +352,14 @@ def train_projections(xyz_local, valid, boxes_2d, cam_p, est_view, gt_view, cen_
             "inst_depth_map_global": depth_global}
 
 
-def forward(P, S, train=True):
+def forward(P, S, train=True, projections=None):
     """P: dict of torch tensors (see to_torch); S: dict of torch tensors (the synthetic feed_dict).
-    Returns (output_dict, aux) -- output_dict keys follow core/constants.py KEY_*."""
+    Returns (output_dict, aux) -- output_dict keys follow core/constants.py KEY_*.
+    train: the reference's is_training (train_val_test == 'train': batch statistics in the decoder's batch norm);
+    projections (default = train): the train-or-val part of the graph (projection error, global depth map) -- the
+    'val' graph is forward(train=False, projections=True)."""
+    if projections is None:
+        projections = train
     dt = S["rgb_crops"].dtype
     dev = S["rgb_crops"].device
     N = S["rgb_crops"].shape[0]
@@ -397,7 +402,7 @@ def forward(P, S, train=True):
 
     aux = {"map_features": map_features, "features_pooled": pooled, "features_squashed": squashed,
            "crop_feat": crop_feat, "full_feat": full_feat, "bn_stats": bn_stats, "concat": concat}
-    if not train:
+    if not projections:
         return out, aux
 
     g = train_projections(xyz_local, valid, boxes_2d, cam_p, est_view, S["gt_view_angs"].reshape(N, 1), cen_y, cen_z)

@@ -83,23 +83,26 @@ def main():
     dcfg = obj(cfg["dataset_config"])
     dataset = types.SimpleNamespace(num_boxes=dcfg.num_boxes, num_alpha_bins=dcfg.num_alpha_bins, centroid_type=dcfg.centroid_type,
                                     dataset_config=dcfg, classes_name="Car", classes=["Car"])
-    model = mm.MonoPSRModel(obj(cfg["model_config"]), "train", dataset)
-    out, gt, _ = model.build()
-    losses, total = model.loss(out, gt)
-    out = out.dict if hasattr(out, "dict") else out
     save = {}
-    for k, v in out.items():
-        a = np.asarray(v)
-        if a.dtype.kind == "f":
-            save["out/" + k] = a[:, ::6, ::6] if a.ndim == 4 else a
-    for k, v in losses.items():
-        save["loss/" + k] = np.asarray(v, np.float64)
-    save["total"] = np.asarray(total, np.float64)
+    for mode, prefix in (("train", ""), ("val", "val/")):          # 'val': is_training=False graph, still with losses
+        FT.FEEDS.clear()
+        FT.FEEDS.update({k: list(v) for k, v in feeds.items()})
+        model = mm.MonoPSRModel(obj(cfg["model_config"]), mode, dataset)
+        out, gt, _ = model.build()
+        losses, total = model.loss(out, gt)
+        out = out.dict if hasattr(out, "dict") else out
+        for k, v in out.items():
+            a = np.asarray(v)
+            if a.dtype.kind == "f":
+                save[prefix + "out/" + k] = a[:, ::6, ::6] if a.ndim == 4 else a
+        for k, v in losses.items():
+            save[prefix + "loss/" + k] = np.asarray(v, np.float64)
+        save[prefix + "total"] = np.asarray(total, np.float64)
     save["created"] = np.asarray(sorted(set(FT.CREATED)))
     path = os.path.join(HERE, "graph_golden.npz")
     np.savez_compressed(path, **save)
     print({k: v.shape for k, v in save.items() if k.startswith("out/")})
-    print({k[5:]: float(v) for k, v in save.items() if k.startswith("loss/")}, float(total))
+    print({k[5:]: float(v) for k, v in save.items() if k.startswith("loss/")}, float(save["total"]), "val total", float(save["val/total"]))
     print("wrote", path, os.path.getsize(path), "bytes")
 
 

@@ -26,7 +26,13 @@ def _raw_sample():
     return gen.raw_sample()
 
 
-def test_whole_graph():
+import pytest
+
+
+@pytest.mark.parametrize("mode", ["train", "val"])
+def test_whole_graph(mode):
+    """'val': the is_training=False graph (decoder batch norm on its moving statistics) with projections and losses"""
+    prefix = "" if mode == "train" else "val/"
     R = _raw_sample()
     f32 = lambda a: np.asarray(a, np.float32)
     crops, full, _ = T.image_inputs(f32(R["rgb_image"]), f32(R["boxes_2d_norm"]))
@@ -41,9 +47,10 @@ def test_whole_graph():
          "gt_inst_xyz_maps_local": t(loc), "gt_inst_xyz_maps_global": t(glo), "gt_valid_mask_maps": t(val)}
     P = onet.to_torch(ms.init_params(0, randomize_bn=True), torch.float64)
     with torch.no_grad():
-        out, _ = onet.forward(P, S, train=True)
+        out, _ = onet.forward(P, S, train=(mode == "train"), projections=True)
         L, total = onet.loss(out, S)
-    want = {k[4:]: G[k] for k in G.files if k.startswith("out/")}
+    want = {k[len(prefix) + 4:]: G[k] for k in G.files if k.startswith(prefix + "out/")}
+    assert len(want) == 16
     assert set(want) <= set(out) | {"valid_mask_maps"}
     for k, v in want.items():
         a = out[k].numpy()
@@ -53,9 +60,14 @@ def test_whole_graph():
             continue
         err = np.linalg.norm(a - v) / max(np.linalg.norm(v), 1e-30)
         assert err < 2e-4, (k, err)
-    for k in (k for k in G.files if k.startswith("loss/")):
-        assert abs(float(L[k[5:]]) - float(G[k])) <= 2e-4 * max(1.0, abs(float(G[k]))), (k, float(L[k[5:]]), float(G[k]))
-    assert abs(float(total) - float(G["total"])) <= 2e-4 * float(G["total"])
+    terms = [k for k in G.files if k.startswith(prefix + "loss/")]
+    assert len(terms) == 8
+    for k in terms:
+        name = k[len(prefix) + 5:]
+        assert abs(float(L[name]) - float(G[k])) <= 2e-4 * max(1.0, abs(float(G[k]))), (k, float(L[name]), float(G[k]))
+    assert abs(float(total) - float(G[prefix + "total"])) <= 2e-4 * float(G[prefix + "total"])
+    if mode == "val":
+        assert abs(float(G["val/total"]) - float(G["total"])) > 1e-3        # the two graphs really differ
     # every variable the reference's graph created is in the parameter table -- except block4, which it builds and
     # never uses
     created = set(G["created"].tolist())
