@@ -42,23 +42,26 @@ def _ptr(t):
 
 
 class Engine:
-    _rounding_touched = False
+    _rounding_now = {}          # device index -> operand-rounding state of the library (starts at 1)
 
-    def __init__(self, device, params=None, num_boxes=ms.NUM_BOXES, seed=0, sms=148):
+    def __init__(self, device, params=None, num_boxes=ms.NUM_BOXES, seed=0, sms=148, precision=None):
         self.dev = torch.device(device)
         self.N = num_boxes
         self.L = _lib.load()
         self.sms = sms
         self._launch_checks = True
-        # MPB_PRECISION=x3: forward GEMMs as 3xTF32 (csrc/tc_gemm.cu::tc_gemm_x3_kernel) on UNROUNDED operands --
-        # fp32-level forward accuracy (the 1e-3 parity bar on the decoder maps) for ~3x the
-        # forward MMA work.  Default "tf32": single pass on operands rounded to nearest at their producers.
-        # The rounding switch is process-wide (a __constant__ of the library): engines of both kinds cannot coexist.
-        self.x3 = os.environ.get("MPB_PRECISION", "tf32").lower() == "x3"
-        if self.x3 or Engine._rounding_touched:      # the default path never calls it: the library starts at 1
-            with torch.cuda.device(self.dev):
-                _lib.check(self.L.mpb_set_operand_rounding(0 if self.x3 else 1), "mpb_set_operand_rounding")
-            Engine._rounding_touched = True
+        # Forward precision.  "x3" (default): forward GEMMs as 3xTF32 on UNROUNDED operands
+        # (csrc/tc_gemm.cu::tc_gemm_x3_kernel) -- every forward output within 1e-3 of the fp32 reference (measured
+        # <= 1e-4, profiles/r2_notes.md) for ~3x the forward MMA work.  "tf32": single pass on operands rounded to
+        # nearest at their producers -- the documented FAST mode, misses the 1e-3 bar on the decoder maps (2.6e-3).
+        # The operand-rounding switch is a __constant__ of the library: _enter() re-asserts it whenever engines of
+        # different precision alternate inside one process (they may not run concurrently).
+        self.precision = (precision or os.environ.get("MPB_PRECISION", "x3")).lower()
+        if self.precision not in ("x3", "tf32"):
+            raise ValueError("precision must be 'x3' or 'tf32' (got %r)" % self.precision)
+        self.x3 = self.precision == "x3"
+        self.rounding = 0 if self.x3 else 1
+        self._enter()
         with torch.cuda.device(self.dev):
             self._build_param_layout()
             self._alloc_state()
@@ -336,6 +339,15 @@ class Engine:
     def _cur(self):
         return torch.cuda.current_stream(self.dev)
 
+    def _enter(self):
+        """make the library's operand-rounding switch match this engine (no-op in the common single-engine case)"""
+        key = self.dev.index or 0
+        if Engine._rounding_now.get(key, 1) != self.rounding:
+            with torch.cuda.device(self.dev):
+                torch.cuda.synchronize(self.dev)
+                _lib.check(self.L.mpb_set_operand_rounding(self.rounding), "mpb_set_operand_rounding")
+            Engine._rounding_now[key] = self.rounding
+
     def _side(self, stream):
         """context: run on `stream` after everything issued so far on the current stream"""
         if not self.overlap:
@@ -417,7 +429,7 @@ class Engine:
         s = torch.cuda.Stream(device=self.dev)
         with torch.cuda.stream(s):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=s):
+            with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
                 for p, bn, _ in rec:
                     if bn < 0:
                         self._chk(self.L.mpb_tc_gemm_x3(ctypes.byref(p), -bn, self._st()), "mpb_tc_gemm_x3")
@@ -481,6 +493,7 @@ class Engine:
 
     def prepare_weights(self, part="all"):
         """fold frozen BN into the tower convs, tf32-round every GEMM weight (run after each update)."""
+        self._enter()
         L, st = self.L, self._st()
         if getattr(self, "bn_layers", None) is None:
             self._build_bn_table()
@@ -605,6 +618,7 @@ class Engine:
         rgb_crops, full_img and boxes_2d_norm."""
         if compute_losses is None:
             compute_losses = train
+        self._enter()
         if not self._prepared:
             self.prepare_weights()
         L, st, N, I = self.L, self._st(), self.N, self.inputs
@@ -923,6 +937,7 @@ class Engine:
     def train_step(self, S=None):
         """One training step on sample S (host arrays are copied in).  The kernel sequence is captured
         into a CUDA graph on first use and replayed afterwards."""
+        self._enter()
         if S is not None:
             self.set_inputs(S)
         self.set_hyper(self.step_count)
@@ -963,7 +978,7 @@ class Engine:
         # measured: stepping the head variables under the towers' backward pass is ~1.5 % SLOWER than one train-op
         # at the end (the HBM-bound Adam pass slows the concurrent GEMMs more than the overlap saves): off
         early = int(os.environ.get("MPB_EARLY_OPT", "0")) != 0
-        with torch.cuda.graph(g, stream=self.s_main):
+        with torch.cuda.graph(g, stream=self.s_main, capture_error_mode="thread_local"):
             self.forward(train=True)
             self.early_opt = early
             self.backward()
@@ -987,12 +1002,12 @@ class Engine:
         # gradients (arena tail, 45 %) UNDER [towers' backward] -> all-reduce of the tower gradients -> [train-op]
         g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         c0 = _lib.launch_count()
-        with torch.cuda.graph(g1, stream=self.s_main):
+        with torch.cuda.graph(g1, stream=self.s_main, capture_error_mode="thread_local"):
             self.forward(train=True)
             self._backward_head(join=True)
-        with torch.cuda.graph(g2, stream=self.s_main):
+        with torch.cuda.graph(g2, stream=self.s_main, capture_error_mode="thread_local"):
             self._backward_towers()
-        with torch.cuda.graph(g3, stream=self.s_main):
+        with torch.cuda.graph(g3, stream=self.s_main, capture_error_mode="thread_local"):
             self.optimizer_step(1.0 / dist.get_world_size())
             self.prepare_weights()
         self.launches_per_step = _lib.launch_count() - c0

@@ -1,9 +1,10 @@
 """GPU end-to-end tests of the network engine against the fp64 restatement (oracle/network.py).
 
-Tolerances are the measured tf32 envelope (DESIGN.md "numerics"): tcgen05 kind::tf32 keeps 10
-mantissa bits of every GEMM operand, which after ~100 layers gives ~1e-3 relative error on the
-box outputs and a few 1e-3 on the decoder maps; gradients agree to ~1e-2 (late layers) .. 1e-1
-(the stems, 100 layers of backward).  A wiring error shows up as O(1).
+Forward bar = the north star's: EVERY forward output within 1e-3 relative (l2) of the fp32 reference graph, in the
+engine's DEFAULT precision (measured on a B200: <= 1e-4, profiles/r2_notes.md).  The single-pass tf32 FAST mode
+(precision="tf32") is checked against its documented envelope only -- it misses the bar on the decoder maps.
+Gradients come from a single-pass tf32 backward: ~1e-2 (late layers) .. 1e-1 (the stems, 100 layers of
+backward); a wiring error shows up as O(1).
 """
 import numpy as np
 import pytest
@@ -39,21 +40,40 @@ def setup(cuda):
     return eng, P, S, Pt, out, aux, L, tot
 
 
-def test_forward_outputs_within_tf32_envelope(setup):
+FORWARD_KEYS = ("centroids", "lwh", "cen_x", "cen_y", "cen_z", "prop_cen_z", "inst_depth_map_global", "proj_err_norm",
+                "alpha_bins", "alpha_regs", "lwh_offs", "cen_y_offs", "cen_z_offs", "inst_xyz_map_local")
+PARITY_TOL = 1e-3          # BASELINE.json north_star: "within 1e-3 relative fp32"
+
+
+def test_forward_outputs_meet_the_parity_bar(setup):
     eng, P, S, Pt, out, aux, L, tot = setup
+    assert eng.precision != "tf32"       # the default precision is a parity-conforming one
     o = eng.outputs()
-    tol = {"centroids": 1.5e-3, "lwh": 1.5e-3, "cen_x": 1.5e-3, "cen_y": 1.5e-3, "cen_z": 1.5e-3, "prop_cen_z": 1.5e-3,
-           "inst_depth_map_global": 2e-3, "proj_err_norm": 4e-3, "alpha_bins": 5e-3, "alpha_regs": 5e-3,
-           "lwh_offs": 4e-3, "cen_y_offs": 8e-3, "cen_z_offs": 8e-3, "inst_xyz_map_local": 1.2e-2}
+    for k in FORWARD_KEYS:
+        e = l2rel(o[k], out[k].detach())
+        assert e < PARITY_TOL, (k, e)
+    assert l2rel(eng.concat[:, :1024], aux["crop_feat"].detach()) < PARITY_TOL
+    assert l2rel(eng.squashed, aux["features_squashed"].detach()) < PARITY_TOL
+    assert l2rel(eng.dec[-1]["y"], aux["map_features"].detach()) < PARITY_TOL
+    el = eng.losses()
+    for k, v in L.items():
+        assert abs(el[k] - float(v)) < 1e-3 * max(1.0, abs(float(v))), (k, el[k], float(v))
+    assert abs(el["total_loss"] - float(tot)) < 1e-3 * float(tot)
+
+
+def test_fast_mode_stays_inside_its_documented_envelope(cuda, setup):
+    """precision="tf32" (single pass): box outputs ~1e-3, decoder maps a few 1e-3 -- NOT parity-conforming"""
+    _, P, S, Pt, out, aux, L, tot = setup
+    eng = Engine(cuda, params=P, precision="tf32")
+    eng.set_inputs(S)
+    eng.forward(train=True)
+    torch.cuda.synchronize()
+    o = eng.outputs()
+    tol = {"centroids": 1.5e-3, "lwh": 1.5e-3, "cen_z": 1.5e-3, "inst_depth_map_global": 2e-3, "proj_err_norm": 4e-3,
+           "alpha_bins": 5e-3, "alpha_regs": 5e-3, "cen_z_offs": 8e-3, "inst_xyz_map_local": 1.2e-2}
     for k, t in tol.items():
         e = l2rel(o[k], out[k].detach())
         assert e < t, (k, e)
-    assert l2rel(eng.concat[:, :1024], aux["crop_feat"].detach()) < 4e-3
-    assert l2rel(eng.squashed, aux["features_squashed"].detach()) < 4e-3
-    el = eng.losses()
-    for k, v in L.items():
-        assert abs(el[k] - float(v)) < 2e-3 * max(1.0, abs(float(v))), (k, el[k], float(v))
-    assert abs(el["total_loss"] - float(tot)) < 1e-3 * float(tot)
 
 
 def test_gradients_all_parameters(setup):

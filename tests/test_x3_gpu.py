@@ -1,7 +1,6 @@
-"""GPU cases of the 3xTF32 forward path (csrc/tc_gemm.cu::tc_gemm_x3_kernel, MPB_PRECISION=x3).  NOT collected by the
-default run (the file name does not match test_*.py): tests/test_zz_late_additions_gpu.py runs this file in a child
-process, because the kernel was written after the round-1 GPU budget was spent and has never executed.
-    python -m pytest tests/x3_gpu_cases.py -q"""
+"""GPU cases of the 3xTF32 forward path (csrc/tc_gemm.cu::tc_gemm_x3_kernel), the engine's default precision.
+First run on a B200 in round 2 (profiles/r2_first_call_summary.txt): all cases pass; the error against fp64 grows
+linearly with the reduction length (~1.4e-8 * K: the tensor core's fp32 accumulator truncates), 5e-6 at K = 2304."""
 import numpy as np
 import pytest
 import torch
@@ -51,7 +50,7 @@ def test_x3_gemm_matches_fp64(cuda, nimg, H, W, k, dil, Cin, Cout, BN, ksplit):
     if not atomic:
         ref = torch.relu(ref + shift.double() + res.double())
     err = float((out.double() - ref).norm() / ref.norm())
-    assert err < 3e-6, err          # single-pass tf32 on these operands: ~4e-4
+    assert err < 2e-5, err          # measured 2e-6 (K = 256) .. 5e-6 (K = 2304); single-pass tf32 on these operands: ~4e-4
 
 
 def test_x3_rejects_what_it_does_not_implement(cuda):
@@ -70,27 +69,40 @@ def test_x3_rejects_what_it_does_not_implement(cuda):
     assert L.mpb_tc_gemm_x3(ctypes.byref(p), 64, mlib.stream_ptr()) == -1        # forward only
 
 
-def test_x3_engine_forward_meets_the_parity_bar(cuda, monkeypatch):
-    """MPB_PRECISION=x3: every output of the forward pass within 1e-3 (in fact ~1e-5) of the fp64 restatement --
+def test_x3_engine_forward_meets_the_parity_bar(cuda):
+    """precision="x3": every output of the forward pass within 1e-3 (measured: < 1e-4) of the fp64 restatement --
     including the decoder's local xyz maps, which single-pass tf32 misses by 2.6x -- and a finite training step"""
-    from monopsr_b200 import lib as mlib
-    monkeypatch.setenv("MPB_PRECISION", "x3")
-    try:
-        P, S = ms.init_params(0, randomize_bn=True), ms.synthetic_sample(0)
-        eng = Engine(cuda, params=P)
-        assert eng.x3
-        eng.set_inputs(S)
-        eng.forward(train=True)
-        o = eng.outputs()
-        out, _ = onet.forward(onet.to_torch(P, torch.float64, cuda), onet.to_torch(S, torch.float64, cuda), train=True)
-        for k in ("inst_xyz_map_local", "centroids", "lwh", "alpha_bins", "alpha_regs", "cen_z_offs", "cen_y_offs",
-                  "proj_err_norm", "inst_depth_map_global"):
-            a, b = o[k].double().reshape(-1), out[k].reshape(-1)
-            assert float((a - b).norm() / b.norm()) < 1e-3, k
-        eng.backward()
-        eng.optimizer_step()
-        torch.cuda.synchronize()
-        assert np.isfinite(eng.losses()["total_loss"])
-    finally:
-        mlib.check(mlib.load().mpb_set_operand_rounding(1), "mpb_set_operand_rounding")
-        Engine._rounding_touched = True
+    P, S = ms.init_params(0, randomize_bn=True), ms.synthetic_sample(0)
+    eng = Engine(cuda, params=P, precision="x3")
+    assert eng.x3
+    eng.set_inputs(S)
+    eng.forward(train=True)
+    o = eng.outputs()
+    out, _ = onet.forward(onet.to_torch(P, torch.float64, cuda), onet.to_torch(S, torch.float64, cuda), train=True)
+    for k in ("inst_xyz_map_local", "centroids", "lwh", "alpha_bins", "alpha_regs", "cen_z_offs", "cen_y_offs",
+              "proj_err_norm", "inst_depth_map_global"):
+        a, b = o[k].double().reshape(-1), out[k].reshape(-1)
+        assert float((a - b).norm() / b.norm()) < 1e-3, k
+    eng.backward()
+    eng.optimizer_step()
+    torch.cuda.synchronize()
+    assert np.isfinite(eng.losses()["total_loss"])
+
+
+def test_engines_of_both_precisions_alternate_in_one_process(cuda):
+    """the operand-rounding switch of the library is re-asserted per engine: a tf32 engine and an x3 engine used in turn
+    give the same results as each alone"""
+    P, S = ms.init_params(2), ms.synthetic_sample(2)
+    a, b = Engine(cuda, params=P, precision="tf32"), Engine(cuda, params=P, precision="x3")
+    outs = {}
+    for rep in range(2):
+        for name, e in (("tf32", a), ("x3", b)):
+            e.set_inputs(S)
+            e.forward(train=True)
+            torch.cuda.synchronize()
+            x = e.outputs()["inst_xyz_map_local"].clone()
+            if rep == 0:
+                outs[name] = x
+            else:
+                assert torch.equal(outs[name], x), name
+    assert not torch.equal(outs["tf32"], outs["x3"])

@@ -1,12 +1,11 @@
-"""GPU tests of code added after the round-1 GPU budget was spent: they have never run on a B200, so they are marked
-xfail(strict=False) -- they report XPASS / XFAIL without being able to break the suite.  Drop the marker once they
-have been seen to pass."""
+"""GPU tests of the rows either side of the path (inference-mode forward, checkpoint round trip, loader -> engine,
+feature-extractor plugin, validation pass).  Written at the end of round 1, first run on a B200 in round 2
+(profiles/r2_first_call_summary.txt); plain tests now -- no xfail markers."""
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="added after the GPU budget of round 1 was spent; "
-                                                                      "not yet run on a B200")]
+pytestmark = pytest.mark.gpu
 
 from monopsr_b200.core import model_spec as ms  # noqa: E402
 from monopsr_b200.core.engine import Engine  # noqa: E402
@@ -19,13 +18,13 @@ def test_inference_mode_forward_matches_oracle(cuda):
     eng = Engine(cuda, params=P)
     eng.set_inputs(S)
     eng.forward(train=False)
-    o = eng.outputs()
+    o = {k: v.clone() for k, v in eng.outputs().items()}      # outputs() are views of the engine's buffers
     out, _ = onet.forward(onet.to_torch(P, torch.float64, cuda), onet.to_torch(S, torch.float64, cuda), train=False)
     for k in ("centroids", "lwh", "inst_xyz_map_local"):
         a, b = o[k].double().reshape(-1), out[k].reshape(-1)
-        assert float((a - b).norm() / b.norm()) < 2e-2, k
+        assert float((a - b).norm() / b.norm()) < 1e-3, k
     eng.forward(train=True)                       # and the two modes really differ on the decoder output
-    assert not torch.allclose(eng.outputs()["inst_xyz_map_local"], o["inst_xyz_map_local"].clone())
+    assert not torch.allclose(eng.outputs()["inst_xyz_map_local"], o["inst_xyz_map_local"])
 
 
 def test_checkpoint_roundtrip_through_tf_bundle(cuda, tmp_path):
@@ -115,18 +114,3 @@ def test_validation_pass_on_the_engine(cuda, tmp_path):
     assert min(res["metrics"][M.METRIC_EMD]) >= 0 and min(res["metrics"][M.METRIC_CHAMFER]) >= 0
     out = ev.convert_and_evaluate(ds, base, 0, kitti_score_threshold=0.0)
     assert out and any(l.startswith("car_detection AP:") for l in out[0]["lines"])
-
-
-def test_x3_suite_in_a_child_process():
-    """The 3xTF32 kernel has never run on a B200: its tests (tests/x3_gpu_cases.py) run in a CHILD process, so that a
-    trap or a crash of the untried kernel cannot take this process' CUDA context -- and with it the exit status of
-    the whole GPU suite -- down.  The child's report is printed for the log."""
-    import os
-    import subprocess
-    import sys
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "x3_gpu_cases.py"), "-q", "-x",
-                        "-p", "no:cacheprovider"], cwd=os.path.dirname(here), stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, universal_newlines=True, timeout=900)
-    print(r.stdout[-3000:])
-    assert r.returncode == 0, r.stdout[-1500:]

@@ -5,9 +5,12 @@
 # in the (never run) 3xTF32 kernel cannot eat the call; its mbarrier waits are bounded and trap instead of spinning.
 OUT=gpurun_out/r2_first
 mkdir -p $OUT
-echo "== late GPU tests (xfail-marked: look for XPASS)" | tee $OUT/summary.txt
-timeout 1200 python -m pytest tests/test_zz_late_additions_gpu.py -q -rxX -s -p no:cacheprovider > $OUT/late_tests.log 2>&1
-tail -25 $OUT/late_tests.log | tee -a $OUT/summary.txt
+echo "== x3 cases directly" | tee $OUT/summary.txt
+timeout 600 python -m pytest tests/x3_gpu_cases.py -q -p no:cacheprovider > $OUT/x3_cases.log 2>&1
+tail -60 $OUT/x3_cases.log | tee -a $OUT/summary.txt
+echo "== late GPU tests (xfail-marked: look for XPASS)" | tee -a $OUT/summary.txt
+timeout 1200 python -m pytest tests/test_zz_late_additions_gpu.py -q -rxX -s --runxfail -p no:cacheprovider > $OUT/late_tests.log 2>&1
+tail -120 $OUT/late_tests.log | tee -a $OUT/summary.txt
 echo "== 3xTF32 vs single-pass per shape (us, error vs fp64)" | tee -a $OUT/summary.txt
 timeout 300 python tools/x3_sweep.py > $OUT/x3_sweep.txt 2>&1
 cat $OUT/x3_sweep.txt | tee -a $OUT/summary.txt
