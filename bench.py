@@ -83,7 +83,8 @@ def ncu_traffic_per_launch():
     """DRAM bytes per launch of the GEMM family from the committed ncu launch list (None if absent)."""
     import re
     try:
-        txt = open(os.path.join(ROOT, "profiles", "r1_launch_shares.txt")).read()
+        name = "r2_launch_shares.txt" if os.path.exists(os.path.join(ROOT, "profiles", "r2_launch_shares.txt")) else "r1_launch_shares.txt"
+        txt = open(os.path.join(ROOT, "profiles", name)).read()
         m = re.search(r"([0-9.]+) MB per launch", txt)
         return float(m.group(1)) * 1e6 if m else None
     except OSError:
@@ -142,15 +143,35 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def tfops_micro(dev):
-    """nn_distance / approxmatch us per batch (BASELINE configs 3 and 4), CUDA events, L2 flushed."""
-    from monopsr_b200 import lib as mlib
-    L = mlib.load()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12        # nominal: 148 SMs x 128 FMA lanes x 2 x max SM clock = 74.4
+MUFU_PEAK_TOPS = 148 * 16 * 1.965e9 / 1e12               # nominal: 16 ex2 / clk / SM = 4.65 T ex2/s
 
-    def t(fn, it=10, wu=3):
+
+def _stats(ts):
+    ts = sorted(ts)
+    return {"med": ts[len(ts) // 2], "p10": ts[len(ts) // 10], "p90": ts[(len(ts) * 9) // 10]}
+
+
+def tfops_micro(dev, iters=100, warmup=20):
+    """BASELINE configs 3 and 4 (+ the batch-256 and in-model sizes) and config 1, per SURVEY.md 8(d): CUDA events,
+    L2 read-flushed between iterations, >= 20 warm-up + >= 100 timed launches (median / p10 / p90 in us); next to
+    each op the reference's OWN kernel recompiled for sm_100a (`ref_gpu_us`, oracle/_ref/libtfops_ref_gpu.so: the
+    kernel to beat), the reference's OWN single-threaded CPU function (`cpu_baseline`, oracle/_ref/libtfops_ref_cpu.so)
+    and the roofline that bounds the op (FP32 pipe for nn_distance, MUFU for approxmatch, HBM for cost / grad)."""
+    import ctypes
+    from monopsr_b200 import lib as mlib
+    from oracle import refgpu, tfops
+    L = mlib.load()
+    peaks, which = read_peaks()
+    hbm = peaks["hbm_gbs"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sp = mlib.stream_ptr
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def t(fn, it=iters, wu=warmup):
         for _ in range(wu):
             fn()
+        torch.cuda.synchronize()
         ts = []
         for _ in range(it):
             flush.sum()      # READ-flush of L2: a write-flush leaves 126 MB of dirty lines whose write-back
@@ -161,41 +182,136 @@ def tfops_micro(dev):
             e.record()
             torch.cuda.synchronize()
             ts.append(s.elapsed_time(e) * 1e3)
-        return float(np.median(ts))
+        return _stats(ts)
 
-    out = {}
-    g = torch.Generator(device="cpu").manual_seed(100)
-    for b in (32, 256):
-        n = 2048
-        x, y = torch.randn(b, n, 3, generator=g).to(dev), torch.randn(b, n, 3, generator=g).to(dev)
+    def cpu_time(fn):
+        t0 = time.perf_counter()
+        fn()
+        return (time.perf_counter() - t0) * 1e6
+
+    have_ref_gpu, have_ref_cpu = refgpu.available(), tfops.ref_available()
+    out = {"protocol": {"iters": iters, "warmup": warmup, "l2": "read-flushed before every timed launch",
+                        "hbm_peak_gbs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json (%s)" % which,
+                        "fp32_peak_tflops": FP32_PEAK_TFLOPS, "mufu_peak_tex2s": MUFU_PEAK_TOPS,
+                        "fp32_mufu_peak_source": "nominal (SM count x lanes x max SM clock)",
+                        "ref_gpu": "reference .cu recompiled -arch=sm_100a" if have_ref_gpu else "unavailable",
+                        "cpu_baseline": "reference CPU functions, 1 thread" if have_ref_cpu else "oracle port, 1 thread"}}
+
+    # ---------------- nn_distance: cfg3 (32 x 2048^2), the north star's batch 256, the in-model 32 x 2304^2
+    for tag, b, n in (("cfg3_nn_distance_b32_n2048", 32, 2048), ("nn_distance_b256_n2048", 256, 2048),
+                      ("nn_distance_b32_n2304_inmodel", 32, 2304)):
+        g = torch.Generator(device="cpu").manual_seed(100)
+        x, y = torch.randn(b, n, 3, generator=g), torch.randn(b, n, 3, generator=g)
+        xd, yd = x.to(dev), y.to(dev)
         d1, d2 = torch.empty(b, n, device=dev), torch.empty(b, n, device=dev)
         i1 = torch.empty(b, n, device=dev, dtype=torch.int32)
         i2 = torch.empty(b, n, device=dev, dtype=torch.int32)
         g1, g2 = torch.empty(b, n, 3, device=dev), torch.empty(b, n, 3, device=dev)
         one = torch.ones(b, n, device=dev)
-        fw = lambda: L.mpb_nn_distance(b, n, x.data_ptr(), n, y.data_ptr(), d1.data_ptr(), i1.data_ptr(), d2.data_ptr(),
-                                       i2.data_ptr(), mlib.stream_ptr())
-        out["nn_distance_fwd_us_b%d" % b] = t(fw)
-        bw = lambda: L.mpb_nn_distance_grad(b, n, x.data_ptr(), n, y.data_ptr(), one.data_ptr(), i1.data_ptr(),
-                                            one.data_ptr(), i2.data_ptr(), g1.data_ptr(), g2.data_ptr(), mlib.stream_ptr())
-        out["nn_distance_grad_us_b%d" % b] = t(bw)
-        # algorithmic HBM bytes: b*(n+m)*(12+8) fwd
-        out["nn_distance_fwd_hbm_gbs_b%d" % b] = b * 2 * n * 20 / (out["nn_distance_fwd_us_b%d" % b] * 1e-6) / 1e9
-    g = torch.Generator(device="cpu").manual_seed(200)
-    b, n = 32, 1024
-    x, y = torch.randn(b, n, 3, generator=g).to(dev), torch.randn(b, n, 3, generator=g).to(dev)
-    mt = torch.empty(b, n, n, device=dev)
-    cost = torch.empty(b, device=dev)
-    g1, g2 = torch.empty(b, n, 3, device=dev), torch.empty(b, n, 3, device=dev)
-    out["approxmatch_us"] = t(lambda: L.mpb_approxmatch(b, n, n, x.data_ptr(), y.data_ptr(), mt.data_ptr(), None,
-                                                        mlib.stream_ptr()), it=5, wu=2)
-    out["matchcost_us"] = t(lambda: L.mpb_matchcost(b, n, n, x.data_ptr(), y.data_ptr(), mt.data_ptr(), cost.data_ptr(),
-                                                    mlib.stream_ptr()))
-    out["matchcostgrad_us"] = t(lambda: L.mpb_matchcostgrad(b, n, n, x.data_ptr(), y.data_ptr(), mt.data_ptr(),
-                                                            g1.data_ptr(), g2.data_ptr(), mlib.stream_ptr()))
-    # SURVEY 8f rank 2 (the step before the path): targets from a 375 x 1242 depth map + 32 masks, inputs from the image
+        fw = lambda: L.mpb_nn_distance(b, n, xd.data_ptr(), n, yd.data_ptr(), d1.data_ptr(), i1.data_ptr(), d2.data_ptr(),
+                                       i2.data_ptr(), sp())
+        bw = lambda: L.mpb_nn_distance_grad(b, n, xd.data_ptr(), n, yd.data_ptr(), one.data_ptr(), i1.data_ptr(),
+                                            one.data_ptr(), i2.data_ptr(), g1.data_ptr(), g2.data_ptr(), sp())
+        r = {"fwd_us": t(fw), "grad_us": t(bw)}
+        flop = 2.0 * b * n * n * 8                      # 2 directions x 8 FP32 ops per pair
+        bytes_fwd = b * 2 * n * 20                      # b(n+m)(12 in + 8 out)
+        us = r["fwd_us"]["med"]
+        r["roofline"] = {"bound": "fp32", "achieved": flop / (us * 1e-6) / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": flop / (us * 1e-6) / 1e12 / FP32_PEAK_TFLOPS,
+                         "note": "FP32-issue bound by construction (820 FLOP/B); the north star's 70%-of-HBM target "
+                                 "is unreachable with algorithmic bytes"}
+        r["hbm"] = {"algorithmic_bytes": bytes_fwd, "achieved_gbs": bytes_fwd / (us * 1e-6) / 1e9,
+                    "frac": bytes_fwd / (us * 1e-6) / 1e9 / hbm}
+        if have_ref_gpu:
+            r["ref_gpu_us"] = {"fwd": t(lambda: refgpu.nn_distance_launch(xd, yd, d1, i1, d2, i2), it=20, wu=3),
+                               "grad": t(lambda: getattr(refgpu.lib(), refgpu._NNG)(b, n, P(xd), n, P(yd), P(one), P(i1), P(one),
+                                                                                  P(i2), P(g1), P(g2)), it=20, wu=3)}
+            fw()
+        if b == 32:                                      # reference CPU nnsearch + gradient loops, one thread, full batch
+            xn, yn = x.numpy(), y.numpy()
+            order = "ref" if have_ref_cpu else "cpu"
+            res = {}
+            cf = cpu_time(lambda: res.update(o=tfops.nn_distance(xn, yn, order)))
+            o = res["o"]
+            ones = np.ones((b, n), np.float32)
+            cg = cpu_time(lambda: tfops.nn_distance_grad(xn, yn, ones, o[1], ones, o[3]))
+            r["cpu_baseline"] = {"fwd_us": cf, "grad_us": cg, "cores": 1, "kind": "reference" if have_ref_cpu else "port",
+                                 "sample": "the whole batch, once"}
+        out[tag] = r
+
+    # ---------------- approxmatch + match_cost + match_cost_grad: cfg4 (32 x 1024^2) and the in-model 32 x 2304^2
+    for tag, b, n in (("cfg4_approxmatch_b32_n1024", 32, 1024), ("approxmatch_b32_n2304_inmodel", 32, 2304)):
+        g = torch.Generator(device="cpu").manual_seed(200)
+        x, y = torch.randn(b, n, 3, generator=g), torch.randn(b, n, 3, generator=g)
+        xd, yd = x.to(dev), y.to(dev)
+        mt = torch.empty(b, n, n, device=dev)
+        cost = torch.empty(b, device=dev)
+        g1, g2 = torch.empty(b, n, 3, device=dev), torch.empty(b, n, 3, device=dev)
+        am = lambda: L.mpb_approxmatch(b, n, n, xd.data_ptr(), yd.data_ptr(), mt.data_ptr(), None, sp())
+        mc = lambda: L.mpb_matchcost(b, n, n, xd.data_ptr(), yd.data_ptr(), mt.data_ptr(), cost.data_ptr(), sp())
+        mg = lambda: L.mpb_matchcostgrad(b, n, n, xd.data_ptr(), yd.data_ptr(), mt.data_ptr(), g1.data_ptr(), g2.data_ptr(), sp())
+        big = n > 1024
+        r = {"match_us": t(am, it=20 if big else iters, wu=3 if big else warmup), "cost_us": t(mc), "grad_us": t(mg)}
+        mbytes = 4.0 * b * n * n
+        nexp = 30.0 * b * n * n                           # 10 levels x 3 sweeps
+        r["roofline_match"] = {"bound": "mufu", "achieved": nexp / (r["match_us"]["med"] * 1e-6) / 1e12, "peak": MUFU_PEAK_TOPS,
+                               "unit": "T ex2/s", "frac": nexp / (r["match_us"]["med"] * 1e-6) / 1e12 / MUFU_PEAK_TOPS,
+                               "hbm_gbs_on_the_single_match_write": mbytes / (r["match_us"]["med"] * 1e-6) / 1e9}
+        for k in ("cost", "grad"):
+            gbs = mbytes / (r[k + "_us"]["med"] * 1e-6) / 1e9
+            r["roofline_" + k] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                  "algorithmic_bytes": mbytes}
+        if have_ref_gpu and not big:
+            rl = refgpu.lib()
+            temp = torch.empty(32 * 4 * n, device=dev)
+            r["ref_gpu_us"] = {
+                "match": t(lambda: getattr(rl, refgpu._AM)(b, n, n, P(xd), P(yd), P(mt), P(temp)), it=5, wu=1),
+                "cost": t(lambda: getattr(rl, refgpu._MC)(b, n, n, P(xd), P(yd), P(mt), P(cost)), it=10, wu=2),
+                "grad": t(lambda: getattr(rl, refgpu._MCG)(b, n, n, P(xd), P(yd), P(mt), P(g1), P(g2)), it=10, wu=2)}
+            am()
+        if not big:                                       # reference CPU functions, one thread, bounded sample
+            bs = 2
+            xn, yn = x.numpy()[:bs], y.numpy()[:bs]
+            order = "ref" if have_ref_cpu else "cpu"
+            res = {}
+            c_m = cpu_time(lambda: res.update(m=tfops.approx_match(xn, yn, order))) * (b / bs)
+            c_c = cpu_time(lambda: tfops.match_cost(xn, yn, res["m"], order)) * (b / bs)
+            c_g = cpu_time(lambda: tfops.match_cost_grad(xn, yn, res["m"], order)) * (b / bs)
+            r["cpu_baseline"] = {"match_us": c_m, "cost_us": c_c, "grad_us": c_g, "cores": 1,
+                                 "kind": "reference" if have_ref_cpu else "port",
+                                 "sample": "%d of %d batch elements, scaled by %d" % (bs, b, b // bs)}
+        out[tag] = r
+
+    # ---------------- cfg1: ONE crop -> ResNet-101 block3 features -> centroid-z head (plumbing check; CPU = the restated graph)
+    try:
+        from monopsr_b200.core import model_spec as ms
+        from monopsr_b200.core.engine import Engine
+        from oracle import network as onet
+        P1, S1 = ms.init_params(0), ms.synthetic_sample(0)
+        eng = Engine(dev, params=P1)
+        eng.set_inputs(S1)
+        Tc = eng.towers[ms.ENCODERS[0]]
+
+        def crop_tower():
+            eng._tower_fwd(Tc, eng.inputs["rgb_crops"])
+        eng.forward(train=False)
+        out["cfg1_one_crop_features"] = {
+            "gpu_crop_tower_us_per_32_crops": t(crop_tower, it=20, wu=3),
+            "note": "the crop encoder alone on the 32 crops of one sample (the engine's granularity); per crop = / 32"}
+        torch.set_num_threads(cpu_threads())
+        Pt = onet.to_torch(P1, torch.float32)
+        x1 = torch.from_numpy(np.asarray(S1["rgb_crops"])[:1]).float()
+        with torch.no_grad():
+            onet.resnet101_block3(x1, Pt, ms.ENCODERS[0])
+            c1 = cpu_time(lambda: onet.resnet101_block3(x1, Pt, ms.ENCODERS[0]))
+        out["cfg1_one_crop_features"]["cpu_baseline"] = {"us_per_crop": c1, "cores": cpu_threads(), "kind": "port",
+                                                         "sample": "1 crop, crop encoder (restated TF1 graph, torch-CPU fp32)"}
+        del eng
+    except Exception as ex:      # the plumbing configuration must not cost the headline line
+        out["cfg1_one_crop_features"] = {"error": repr(ex)[:200]}
+
+    # ---------------- SURVEY 8f rank 2 (the step before the path): targets from a 375 x 1242 depth map + 32 masks
     from monopsr_b200.core import model_spec as ms, targets as mtg
-    import time
     S = ms.synthetic_sample(0)
     rng = np.random.RandomState(0)
     H, W = 375, 1242
@@ -203,14 +319,13 @@ def tfops_micro(dev):
     masks_h = rng.rand(ms.NUM_BOXES, H, W) < 0.6
     masks = torch.from_numpy(masks_h).to(dev)
     args = [torch.from_numpy(S[k]).to(dev) for k in ("boxes_2d", "boxes_3d", "est_view_angs", "cam_p")]
-    out["gt_targets_us"] = t(lambda: mtg.gt_maps_from_depth(depth, masks, *args, dev))
     img = torch.from_numpy(rng.randint(0, 256, (H, W, 3)).astype(np.uint8)).to(dev)
     bn = torch.from_numpy(S["boxes_2d_norm"]).to(dev)
-    out["image_inputs_us"] = t(lambda: mtg.image_inputs(img, bn, dev))
     from oracle import targets as otg          # the CPU restatement, timed once beside it (a reported baseline)
-    t0 = time.perf_counter()
-    otg.gt_maps(S["boxes_2d"], S["boxes_3d"], masks_h, depth.cpu().numpy(), S["est_view_angs"], S["cam_p"])
-    out["gt_targets_cpu_oracle_us"] = (time.perf_counter() - t0) * 1e6
+    out["gt_targets"] = {"us": t(lambda: mtg.gt_maps_from_depth(depth, masks, *args, dev), it=20, wu=3),
+                         "image_inputs_us": t(lambda: mtg.image_inputs(img, bn, dev), it=20, wu=3),
+                         "cpu_oracle_us": cpu_time(lambda: otg.gt_maps(S["boxes_2d"], S["boxes_3d"], masks_h, depth.cpu().numpy(),
+                                                                       S["est_view_angs"], S["cam_p"]))}
     return out
 
 
@@ -299,29 +414,49 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM), measured live:
-    # replay ONLY the tc_gemm launches of one step (same arguments) as a CUDA graph and time it.
+    # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM):
+    #   frac      = WHOLE-STEP fraction: the algorithmic 2*M*N*K of one step (full-tap convention; the extra
+    #               products of the h3 / x3 forward are NOT counted) / ms_per_step / dense-tf32 peak
+    #   alone     = the same launches (same arguments) replayed back to back as one CUDA graph, timed live with CUDA
+    #               events: a diagnostic only -- inside the step launches overlap (2 CTAs/SM, 2-4 streams), so the step
+    #               is shorter than that sum
+    #   tensor_busy_frac = issued MMA work / peak: forward k-blocks cost 1.5x (h3: six kind::f16 MMAs = 1.5 tf32 k-blocks)
+    #               or 3x (x3) the single pass -- how busy the tensor pipe is, as opposed to how much useful work it did
     peaks, which = read_peaks()
     roof = eng.gemm_only_roofline(flush)
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0      # dense tf32 = half the bf16 rate; sustained (long step)
-    roofline = {"bound": "tensor", "achieved": roof["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": roof["tflops"] / tf32_peak, "traffic": ncu_traffic_per_launch(),
-                "traffic_source": "profiles/r1_launch_shares.txt: ncu dram__bytes_read+write of the 592 GEMM launches "
-                                  "of one step / 592 (bytes per launch; ncu flushes caches between launches)",
-                "kernel": "tc_gemm_tma_kernel (tcgen05 kind::tf32), %d launches/step, %.2f ms alone vs %.2f ms/step" %
-                          (roof["launches"], roof["ms"], total_ms / args.steps),
+    step_s = total_ms / args.steps / 1e3
+    gflop = roof["gflop"]
+    whole = gflop / 1e3 / step_s
+    fwd_factor = {"h3": 1.5, "x3": 3.0, "tf32": 1.0}[eng.precision]
+    issued = gflop * (2.0 + fwd_factor) / 3.0             # forward = 1/3 of the step's GEMM work, backward 2/3
+    kernel = {"h3": "tc_gemm_tma_kernel<.., H3> forward (tcgen05 kind::f16 on fp16 hi/lo split operands, 3 products) + "
+                    "tc_gemm_tma_kernel backward (kind::tf32)",
+              "x3": "tc_gemm_x3_kernel forward (3xTF32) + tc_gemm_tma_kernel backward (kind::tf32)",
+              "tf32": "tc_gemm_tma_kernel (tcgen05 kind::tf32)"}[eng.precision]
+    roofline = {"bound": "tensor", "achieved": whole, "peak": tf32_peak, "unit": "TFLOP/s", "frac": whole / tf32_peak,
+                "traffic": ncu_traffic_per_launch(),
+                "traffic_source": "profiles/r2_launch_shares.txt: ncu dram__bytes_read+write of the GEMM launches of one "
+                                  "step / launches (bytes per launch; ncu flushes caches between launches)",
+                "kernel": kernel, "launches_per_step": roof["launches"], "launch_kinds": roof["kinds"],
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (%s)" % which,
-                "algorithmic_gflop_per_step": roof["gflop"],
-                "whole_step_frac": (value * FLOP_PER_CROP_FWD_BWD / 1e12) / (tf32_peak * world)}
+                "algorithmic_gflop_per_step": gflop,
+                "alone": {"ms": roof["ms"], "tflops": roof["tflops"], "frac": roof["tflops"] / tf32_peak,
+                          "note": "the GEMM launches replayed serially on one stream; exceeds ms_per_step by design"},
+                "tensor_busy_frac": issued / 1e3 / step_s / tf32_peak}
 
+    precision = {"h3": "fp16 hi/lo split forward (3 products, fp32 accumulate: every forward output within 1e-3 of the "
+                       "fp32 graph, measured <= 4e-5), single-pass tf32 backward",
+                 "x3": "3xTF32 forward, single-pass tf32 backward",
+                 "tf32": "single-pass tf32 (FAST mode: misses the 1e-3 parity bar on the decoder maps)"}[eng.precision]
     line = {
         "metric": "instance-crops/sec fwd+bwd", "value": value, "unit": "crops/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"h3": "f16x3+tf32", "x3": "tf32x3+tf32", "tf32": "tf32"}[eng.precision], "data": "synthetic",
         "config": {"workload": "cfg2: 32 crops 48x48x3 + 160x608 full image per GPU, monopsr_model_000 "
                                "fwd+bwd+train-op (clip+Adam+EMA)", "crops_per_gpu": CROPS_PER_SAMPLE,
-                   "precision": "3xTF32 forward (MPB_PRECISION=x3), single-pass tf32 backward" if getattr(eng, "x3", False)
-                                else "single-pass tf32",
+                   "precision": precision, "precision_mode": eng.precision,
                    "points_per_instance": 2304, "parallelism": "dp%d" % world, "l2": "flushed between timed steps",
                    "weights": "random-init, seed 0"},
         "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -329,6 +464,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
     }
+    eng.check_overflow()
     if not args.no_ops:
         line["ops"] = tfops_micro(dev)
     if not args.no_cpu_baseline and world == 1:

@@ -56,6 +56,17 @@ typedef struct mpb_tc_gemm_params {
     float* out_r;        /* optional second output [rows][ldor]: the tf32-rounded value (GEMM operand of the next
                           * layer) while `out` keeps the unrounded one (fp32 residual stream) */
     int ldor;
+    /* ---- fp16 hi/lo split forward ("h3", mpb_tc_gemm_h3; ignored by the other entry points) ----
+     * A "split copy" of an fp32 matrix has the SAME byte geometry (4 bytes per element, same pitch): every group of
+     * 32 consecutive elements of a row (128 bytes) holds 32 fp16 `hi` = fp16(x) followed by 32 fp16 `lo` =
+     * fp16(x - hi) -- for the weights the other way round, `lo` first -- so that one 128-byte shared-memory row is
+     * at once the K=64 operand of the two cross products and, half of it, the K=32 operand of hi*hi. */
+    const void* X16;     /* split copy of X ([hi | lo] blocks, pitch ldx floats) */
+    const void* W16;     /* split copy of Wt ([lo | hi] blocks, pitch ldw floats), each output channel optionally
+                          * pre-scaled by a power of two (undone by `scale`) */
+    void* out16;         /* optional third output: the stored value ALSO as a split copy ([hi | lo], pitch ldo16 floats) */
+    int ldo16;
+    int* overflow;       /* optional sticky flag, set to 1 when a value beyond the fp16 range (|v| > 65504) was split */
 } mpb_tc_gemm_params;
 
 /* BN: tile width in output columns (64, 128 or 256). */
@@ -66,6 +77,28 @@ int mpb_tc_gemm(const mpb_tc_gemm_params* p, int BN, void* stream);
  * MMAs per k-step, for fp32-level accuracy (the reference's convolutions / matmuls are fp32: net_builder.py:44-89,
  * monopsr_output_builder.py:166-283) at the memory traffic of the single-pass kernel.  Same epilogue options. */
 int mpb_tc_gemm_x3(const mpb_tc_gemm_params* p, int BN, void* stream);
+/* fp16-split forward variant ("h3"): op must be MPB_TC_FWD, operands are the split copies X16 / W16 (see the struct).
+ *   acc = A_hi*B_lo + A_lo*B_hi  (one K=64 kind::f16 block)  +  A_hi*B_hi  (K=32)   -- fp32 accumulation in TMEM;
+ * the dropped lo*lo term is 2^-22 relative.  Accuracy is that of the 3xTF32 kernel (fp32-level, the reference's
+ * convolutions / matmuls are fp32: net_builder.py:44-89, monopsr_output_builder.py:166-283) for 1.5x instead of
+ * 3x the tensor work of a single tf32 pass, with the shared-memory / TMA traffic of the single pass.
+ * BN 64, 128 or 256; split-K as in mpb_tc_gemm.  Same epilogue options plus `out16`. */
+int mpb_tc_gemm_h3(const mpb_tc_gemm_params* p, int BN, void* stream);
+/* split copy of a row-major fp32 matrix: rows x C (C % 32 == 0), pitches in floats; b_operand = 1 writes [lo | hi]
+ * blocks (weights), 0 writes [hi | lo] (activations).  overflow: optional sticky flag (see the struct). */
+int mpb_split16(long rows, int C, const float* src, int lds, void* dst16, int ldd, int b_operand, int* overflow,
+                void* stream);
+/* whole-model weight preparation for the h3 kernel: one warp per (layer, output channel) row computes
+ * v = w * s (s = gamma * rsqrt(var + eps) for a frozen-BN conv, 1 otherwise), scales the row by the power of two
+ * that puts its largest |v| into [2^13, 2^14) -- so that the lo halves stay in fp16's normal range -- writes the
+ * [lo | hi] split copy and 1 / scale to inv_scale[row]. */
+typedef struct mpb_w16_layer {
+    const float* w; const float* gamma; const float* var;     /* gamma / var NULL: no BN fold */
+    void* w16; float* inv_scale;
+    int cout; int K; int row0; int pad_;
+} mpb_w16_layer;
+int mpb_split16_weights_multi(int total_rows, const mpb_w16_layer* layers, const int* row2layer, float eps, void* stream);
+
 /* 1 (default): the elementwise / weight-preparation kernels round every GEMM operand they produce to tf32;
  * 0: they leave it as computed (what mpb_tc_gemm_x3 wants).  Synchronous; set it outside graph capture. */
 int mpb_set_operand_rounding(int on);
@@ -195,11 +228,29 @@ typedef struct mpb_heads_io {
     float* d_prop_y; float* d_prop_z; /* scratch [N] */
     const float* d_feat2; int ldd2;   /* gradient of the regression concat buffer (from the fc0 data-gradient) */
     float* maskstats;                 /* [N+1]: valid pixels per box, total */
+    /* loss of the local xyz map (yaml loss_config.inst_xyz_map_local = [type, weight]; loss_builder.py:19-84):
+     * xyz_loss_mode 0 = smooth_l1_nonzero, evaluated (value and gradient) inside mpb_heads_final;
+     * 1 = a point-set loss (chamfer_dist / emd): mpb_heads_final leaves that term out, the caller adds it with
+     * mpb_pointset_* and the point-set ops of monopsr_b200_tfops.h. */
+    int xyz_loss_mode;
+    float xyz_loss_weight;
 } mpb_heads_io;
 int mpb_heads_static(const mpb_heads_io* io, void* stream);        /* once per sample */
 int mpb_heads_mid(const mpb_heads_io* io, void* stream);           /* after lwh / alpha heads */
 int mpb_heads_final(const mpb_heads_io* io, int train, void* stream); /* after cen_y / cen_z heads */
 int mpb_heads_bwd_mid(const mpb_heads_io* io, void* stream);       /* after the regression fc0 data-gradient */
+
+/* ---- glue of the point-set training losses (ChamferDistance / EarthMoversDistance as loss_config entries;
+ * core/losses_custom.py:135-198, builders/loss_builder.py:60-84, monopsr_model.py:580-586) ----
+ * clouds: p = pred * mask, t = gt * mask for npts points (mask is per point: masked points become (0,0,0) on both
+ * sides, quirk Q8).  */
+int mpb_pointset_mask(long npts, const float* pred, const float* gt, const float* mask, float* p, float* t, void* stream);
+/* losses[slot] += scale * (sum(a[0..na)) + sum(b[0..nb))) and the same into losses[total_slot]; b may be NULL.
+ * fill (may be NULL): fill[0..nfill) = fill_value (the constant upstream gradient of the distances). */
+int mpb_pointset_loss_add(long na, const float* a, long nb, const float* b, float scale, float* losses, int slot,
+                          int total_slot, float* fill, long nfill, float fill_value, void* stream);
+/* d_pred[i][c] += scale * grad[i][c] * mask[i]   (d p / d pred = mask) */
+int mpb_pointset_grad_add(long npts, const float* grad, const float* mask, float scale, float* d_pred, void* stream);
 
 /* ---- fused train-op: per-variable clip_by_norm + Adam + EMA (csrc/optimizer.cu) ----
  * Replaces slim.learning.create_train_op(..., clip_gradient_norm=1.0) (core/trainer.py:76-81) with

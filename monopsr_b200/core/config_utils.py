@@ -91,7 +91,10 @@ def validate_for_engine(cfg):
     for k, v in expect.items():
         need(getattr(oc, k, None) == v, "output_config.%s must be %r" % (k, v))
     lc = m.loss_config
-    expect_l = dict(inst_xyz_map_local=["smooth_l1_nonzero", 100.0], lwh=["smooth_l1", 1.0],
+    xyz = list(getattr(lc, "inst_xyz_map_local", []))
+    need(len(xyz) >= 2 and xyz[0] in ("smooth_l1_nonzero", "chamfer_dist", "emd"),
+         "loss_config.inst_xyz_map_local must be [smooth_l1_nonzero | chamfer_dist | emd, weight]")
+    expect_l = dict(lwh=["smooth_l1", 1.0],
                     alpha_cls=["softmax", 0.3, 0.001], alpha_reg=["smooth_l1", 1.0], cen_y=["smooth_l1", 0.1],
                     cen_z=["smooth_l1", 0.1], inst_xyz_map_global=["smooth_l1_nonzero", 0.1],
                     inst_depth_map_global=["smooth_l1_nonzero", 10.0])

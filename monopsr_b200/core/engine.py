@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from .. import lib as _lib
-from ..lib_net import TC_DGRAD, TC_FWD, TC_WGRAD, BnLayer, HeadsIO, OptChunk, TcGemmParams
+from ..lib_net import TC_DGRAD, TC_FWD, TC_WGRAD, BnLayer, HeadsIO, OptChunk, TcGemmParams, W16Layer
 from . import model_spec as ms
 
 BN_EPS_RESNET = 1e-5
@@ -35,6 +35,7 @@ ADAM_BETA1, ADAM_BETA2, ADAM_EPSILON = 0.9, 0.999, 1e-8                   # tf.t
 EMA_DECAY = 0.9999                                                        # MovingAverageOptimizer(average_decay)
 CLIP_GRADIENT_NORM = 1.0                                                  # per variable (slim.learning.create_train_op)
 KPAD = 1088          # 1043 / 1060 concat widths padded to a multiple of 64
+DEFAULT_PRECISION = "h3"
 
 
 def _ptr(t):
@@ -43,24 +44,44 @@ def _ptr(t):
 
 class Engine:
     _rounding_now = {}          # device index -> operand-rounding state of the library (starts at 1)
+    # train-op hyper-parameters: class defaults = monopsr_model_000.yaml's; configure() overrides them per engine
+    lr_initial, lr_decay_steps, lr_decay_factor, lr_staircase, ema_decay = LR_INITIAL, LR_DECAY_STEPS, LR_DECAY_FACTOR, True, EMA_DECAY
 
-    def __init__(self, device, params=None, num_boxes=ms.NUM_BOXES, seed=0, sms=148, precision=None):
+    def __init__(self, device, params=None, num_boxes=ms.NUM_BOXES, seed=0, sms=148, precision=None,
+                 xyz_loss=("smooth_l1_nonzero", 100.0)):
         self.dev = torch.device(device)
         self.N = num_boxes
         self.L = _lib.load()
         self.sms = sms
         self._launch_checks = True
-        # Forward precision.  "x3" (default): forward GEMMs as 3xTF32 on UNROUNDED operands
-        # (csrc/tc_gemm.cu::tc_gemm_x3_kernel) -- every forward output within 1e-3 of the fp32 reference (measured
-        # <= 1e-4, profiles/r2_notes.md) for ~3x the forward MMA work.  "tf32": single pass on operands rounded to
-        # nearest at their producers -- the documented FAST mode, misses the 1e-3 bar on the decoder maps (2.6e-3).
-        # The operand-rounding switch is a __constant__ of the library: _enter() re-asserts it whenever engines of
-        # different precision alternate inside one process (they may not run concurrently).
-        self.precision = (precision or os.environ.get("MPB_PRECISION", "x3")).lower()
-        if self.precision not in ("x3", "tf32"):
-            raise ValueError("precision must be 'x3' or 'tf32' (got %r)" % self.precision)
+        # Forward precision -- all three keep fp32 accumulation in TMEM:
+        #   "h3"   forward GEMMs on fp16 hi/lo SPLIT COPIES of both operands, three products as six kind::f16 MMAs per
+        #          k-block (csrc/tc_gemm.cu H3 branch, csrc/split16.cu): fp32-level accuracy -- every forward output
+        #          within 1e-3 of the fp32 reference -- for 1.5x the tensor work of one tf32 pass at unchanged operand
+        #          traffic.  fp16's range is watched: Engine.check_overflow() raises if an activation beyond 65504 was split.
+        #   "x3"   3xTF32 on unrounded operands, lo tiles derived on chip (tc_gemm_x3_kernel): same accuracy, 3x the
+        #          forward tensor work, no range limit -- the fallback when h3 overflows.
+        #   "tf32" single pass on operands rounded to nearest at their producers: the documented FAST mode, misses the
+        #          1e-3 bar on the decoder maps (2.6e-3).
+        # The backward pass is single-pass tf32 in every mode.  The operand-rounding switch is a __constant__ of the
+        # library: _enter() re-asserts it whenever engines of different precision alternate inside one process.
+        self.precision = (precision or os.environ.get("MPB_PRECISION", DEFAULT_PRECISION)).lower()
+        if self.precision not in ("h3", "x3", "tf32"):
+            raise ValueError("precision must be 'h3', 'x3' or 'tf32' (got %r)" % self.precision)
         self.x3 = self.precision == "x3"
-        self.rounding = 0 if self.x3 else 1
+        self.h3 = self.precision == "h3"
+        # x3 / h3 read their forward operands unrounded (h3: the split copies are taken from the unrounded values), so
+        # every producer leaves its result as computed; the single-pass backward then sees fp32 words whose low 13 bits
+        # the tensor core drops (truncation; measured gradient error in these modes: median 4e-3, below tf32 mode's)
+        self.rounding = 1 if self.precision == "tf32" else 0
+        self._s16 = {}              # storage pointer -> split copy (h3)
+        # loss of the local xyz map: yaml loss_config.inst_xyz_map_local = [type, weight] (loss_builder.py:19-84,
+        # monopsr_model.py:580-586).  'smooth_l1_nonzero' is fused into the heads kernel; 'chamfer_dist' / 'emd' run
+        # the point-set ops inside the step (value AND gradient: nn_distance_grad / matchcostgrad feed d_xyz).
+        self.xyz_loss_type, self.xyz_loss_weight = str(xyz_loss[0]), float(xyz_loss[1])
+        if self.xyz_loss_type not in ("smooth_l1_nonzero", "chamfer_dist", "emd"):
+            raise NotImplementedError("loss type %r for inst_xyz_map_local has no sm_100a kernel" % self.xyz_loss_type)
+        self._ps = None             # buffers of the point-set loss, allocated on first use
         self._enter()
         with torch.cuda.device(self.dev):
             self._build_param_layout()
@@ -142,6 +163,8 @@ class Engine:
         self.adam_v = z(self.n_train)
         self.ema = z(self.n_train)
         self.prep = z(self.n_train)            # folded / tf32-rounded weights (same offsets as params)
+        self.prep16 = z(self.n_train) if self.h3 else None     # [lo | hi] fp16 split copies of the forward GEMM weights
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.hyper = z(4)
         # optimizer chunk table
         chunks = []
@@ -179,23 +202,34 @@ class Engine:
     def pview(self, name):
         return self.view(name, self.prep)
 
-    def load_params(self, P):
-        """P: name -> numpy array in TF layout (conv HWIO, fc [in,out])."""
-        for n, (s, k) in self.ptable.items():
-            a = np.asarray(P[n], np.float32)
-            assert tuple(a.shape) == tuple(s), (n, a.shape, s)
-            if k == "weights":
-                if a.ndim == 4:
-                    a = a.transpose(3, 0, 1, 2).reshape(a.shape[3], -1)       # HWIO -> O,(H,W,I)
-                else:
-                    a = a.T                                                     # [in,out] -> [out,in]
-                    ds = self.layout[n][2]
-                    if a.shape[1] != ds[1]:
-                        a = np.concatenate([a, np.zeros((a.shape[0], ds[1] - a.shape[1]), np.float32)], 1)
-            self.view(n).copy_(torch.from_numpy(np.ascontiguousarray(a)))
+    def _to_dev_layout(self, n, a):
+        s, k = self.ptable[n]
+        a = np.asarray(a, np.float32)
+        assert tuple(a.shape) == tuple(s), (n, a.shape, s)
+        if k == "weights":
+            if a.ndim == 4:
+                a = a.transpose(3, 0, 1, 2).reshape(a.shape[3], -1)       # HWIO -> O,(H,W,I)
+            else:
+                a = a.T                                                     # [in,out] -> [out,in]
+                ds = self.layout[n][2]
+                if a.shape[1] != ds[1]:
+                    a = np.concatenate([a, np.zeros((a.shape[0], ds[1] - a.shape[1]), np.float32)], 1)
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+    def load_params(self, P, slots=None):
+        """P: name -> numpy array in TF layout (conv HWIO, fc [in,out]).  The optimizer state is re-initialised (Adam
+        moments 0, EMA shadows = the variables, as a fresh TF graph does) except for the variables in `slots`
+        (name -> (adam_m, adam_v, ema) in TF layout): a training resume restores those as tf.train.Saver does."""
+        for n in self.ptable:
+            self.view(n).copy_(self._to_dev_layout(n, P[n]))
         self.ema.copy_(self.params)
         self.adam_m.zero_()
         self.adam_v.zero_()
+        for n, (m_, v_, e_) in (slots or {}).items():
+            if self.layout[n][0] == "T":
+                self.view(n, self.adam_m).copy_(self._to_dev_layout(n, m_))
+                self.view(n, self.adam_v).copy_(self._to_dev_layout(n, v_))
+                self.view(n, self.ema).copy_(self._to_dev_layout(n, e_))
         self._prepared = False
 
     def export_params(self, arena=None):
@@ -214,17 +248,20 @@ class Engine:
     def export_grads(self):
         return self.export_params(self.grads)
 
-    def load_checkpoint(self, prefix, kind="monopsr", use_ema=False):
+    def load_checkpoint(self, prefix, kind="monopsr", use_ema=False, resume=False):
         """Restore variables from a TensorFlow checkpoint `prefix` (core/tf_checkpoint.py): kind 'monopsr' = a MonoPSR
         training checkpoint (use_ema: the MovingAverageOptimizer shadows, as evaluation does), 'detection' = the
         pre-trained object-detection-API ResNet-101 for both encoders (core/checkpoint_utils.py:64-117).  Variables
         absent from the checkpoint (or of another shape) keep their current values; returns the mapping report."""
         from . import tf_checkpoint
         table = [(n, s, k) for n, (s, k) in self.ptable.items()]
-        loaded, report = tf_checkpoint.load_checkpoint(prefix, table, kind=kind, use_ema=use_ema)
+        loaded, report = tf_checkpoint.load_checkpoint(prefix, table, kind=kind, use_ema=use_ema,
+                                                        with_slots=resume and kind == "monopsr")
         P = self.export_params()
         P.update(loaded)
-        self.load_params(P)
+        # resume=True (the trainer): Adam moments and EMA shadows come back too -- restarting them at 0 / at the
+        # variables would make the first updates after a resume ~3x too large (bias correction uses t = step + 1)
+        self.load_params(P, slots=report.get("slots") if resume else None)
         return report
 
     def save_checkpoint(self, prefix, global_step=None):
@@ -232,11 +269,13 @@ class Engine:
         from . import tf_checkpoint
         T = self.export_params()
         trainable = set(self.trainable_names)
-        for n, v in self.export_params(self.ema).items():
-            if n in trainable:
-                T[n + tf_checkpoint.EMA_SUFFIX] = v
+        for arena, sfx in ((self.ema, tf_checkpoint.EMA_SUFFIX), (self.adam_m, tf_checkpoint.ADAM_M_SUFFIX),
+                           (self.adam_v, tf_checkpoint.ADAM_V_SUFFIX)):
+            for n, v in self.export_params(arena).items():
+                if n in trainable:
+                    T[n + sfx] = v
         if global_step is not None:
-            T["global_step"] = np.array(int(global_step), np.int64)
+            T["global_step"] = np.array(int(global_step), np.int32)       # the reference's global_step is int32
         tf_checkpoint.write_bundle(prefix, T, with_data_crc=True)
 
     # ------------------------------------------------------------------ activations
@@ -339,14 +378,20 @@ class Engine:
     def _cur(self):
         return torch.cuda.current_stream(self.dev)
 
+    @staticmethod
+    def set_library_rounding(dev, on):
+        """the library's process-wide operand-rounding switch (a __constant__), tracked per device"""
+        dev = torch.device(dev)
+        key = dev.index or 0
+        if Engine._rounding_now.get(key, 1) != int(on):
+            with torch.cuda.device(dev):
+                torch.cuda.synchronize(dev)
+                _lib.check(_lib.load().mpb_set_operand_rounding(int(on)), "mpb_set_operand_rounding")
+            Engine._rounding_now[key] = int(on)
+
     def _enter(self):
         """make the library's operand-rounding switch match this engine (no-op in the common single-engine case)"""
-        key = self.dev.index or 0
-        if Engine._rounding_now.get(key, 1) != self.rounding:
-            with torch.cuda.device(self.dev):
-                torch.cuda.synchronize(self.dev)
-                _lib.check(self.L.mpb_set_operand_rounding(self.rounding), "mpb_set_operand_rounding")
-            Engine._rounding_now[key] = self.rounding
+        Engine.set_library_rounding(self.dev, self.rounding)
 
     def _side(self, stream):
         """context: run on `stream` after everything issued so far on the current stream"""
@@ -359,6 +404,29 @@ class Engine:
         if self.overlap:
             for st_ in streams:
                 self._cur().wait_stream(st_)
+
+    def s16(self, t):
+        """the fp16 hi/lo split copy that shadows fp32 tensor `t` (same storage geometry; views map to views)"""
+        st = t.untyped_storage()
+        key = st.data_ptr()
+        sh = self._s16.get(key)
+        if sh is None:
+            sh = torch.empty(st.nbytes() // 4, dtype=torch.float32, device=self.dev)
+            self._s16[key] = sh
+        return torch.as_strided(sh, t.shape, t.stride(), t.storage_offset())
+
+    def _split(self, t, rows, C, ld):
+        """h3: write the split copy of a GEMM operand produced by a non-GEMM kernel (pools, resizes, batch norm, FC glue)"""
+        if self.h3:
+            self._chk(self.L.mpb_split16(rows, C, _ptr(t), ld, _ptr(self.s16(t)), ld, 0, _ptr(self.overflow), self._st()),
+                      "split16")
+
+    def check_overflow(self):
+        """h3 only: raise if a forward activation left fp16's range since the last check (then use precision='x3')"""
+        if self.h3 and int(self.overflow.item()) != 0:
+            self.overflow.zero_()
+            raise _lib.MpbError("h3 forward: an activation beyond +-65504 was split into fp16 halves; "
+                                "results are invalid -- run this model with precision='x3'")
 
     def _plan_tiles(self, mtiles, ncols, nkb, csk=None):
         """(tile width, split-K) of a FWD / DGRAD launch; rules read off tools/gemm_sweep.py on B200
@@ -385,7 +453,8 @@ class Engine:
 
     def gemm(self, op, M, H, W, k, dil, Cin, Cout, X, ldx, Wt, ldw, out, ldo, Y=None, ldy=0, tapmask=None,
              shift=None, res=None, ldr=0, mask=None, ldm=0, rowscale=None, colsum=None, relu=0, round_tf32=0,
-             atomic=0, ksplit=1, bn=None, out_r=None, ldor=0):
+             atomic=0, ksplit=1, bn=None, out_r=None, ldor=0, out16=False):
+        """out16 (h3 only): also write the split copy of `out` -- set it where the result feeds a forward GEMM"""
         p = TcGemmParams()
         p.op, p.H, p.W, p.kh, p.kw, p.dil, p.M, p.Cin, p.Cout = op, H, W, k, k, dil, M, Cin, Cout
         p.X, p.ldx, p.Y, p.ldy, p.Wt, p.ldw, p.out, p.ldo = _ptr(X), ldx, _ptr(Y), ldy, _ptr(Wt), ldw, _ptr(out), ldo
@@ -404,6 +473,24 @@ class Engine:
                                           csk=self.csk_fwd if op == TC_FWD else self.csk)
                 if ksplit == 1 and not atomic and M % (H * W) == 0:
                     p.ksplit = ks
+        if self.h3 and op == TC_FWD:
+            # operands = split copies; results stay unrounded (pools / resizes / batch norm read them), the rounded
+            # second copy of the residual stream is replaced by the split copy
+            p.round_tf32 = 0
+            off = (Wt.data_ptr() - self.prep.data_ptr()) // 4
+            p.X16 = _ptr(self.s16(X))
+            p.W16 = ctypes.c_void_p(self.prep16.data_ptr() + 4 * off)
+            p.scale = _ptr(self.w16_inv[off])
+            p.overflow = _ptr(self.overflow)
+            if out16 or out_r is not None:
+                p.out16, p.ldo16 = _ptr(self.s16(out)), ldo
+            p.out_r, p.ldor = None, 0
+            if not atomic:
+                p.ksplit = 1
+            if getattr(self, "_record", None) is not None:
+                self._record.append((p, bn, 2.0 * M * Cin * Cout * k * k, "h3"))
+            self._chk(self.L.mpb_tc_gemm_h3(ctypes.byref(p), bn, self._st()), "mpb_tc_gemm_h3")
+            return
         if self.x3 and op == TC_FWD:
             # operands stay unrounded: no rounding in the epilogue, no rounded second copy (callers read `out`)
             p.round_tf32, p.out_r, p.ldor = 0, None, 0
@@ -411,11 +498,11 @@ class Engine:
                 p.ksplit = 1
             bn3 = 128 if Cout % 128 == 0 else 64
             if getattr(self, "_record", None) is not None:
-                self._record.append((p, -bn3, 2.0 * M * Cin * Cout * k * k))      # negative tile width = x3 launch
+                self._record.append((p, bn3, 2.0 * M * Cin * Cout * k * k, "x3"))
             self._chk(self.L.mpb_tc_gemm_x3(ctypes.byref(p), bn3, self._st()), "mpb_tc_gemm_x3")
             return
         if getattr(self, "_record", None) is not None:
-            self._record.append((p, bn, 2.0 * M * Cin * Cout * k * k))
+            self._record.append((p, bn, 2.0 * M * Cin * Cout * k * k, "tf32"))
         self._chk(self.L.mpb_tc_gemm(ctypes.byref(p), bn, self._st()), "mpb_tc_gemm")
 
     def gemm_only_roofline(self, flush=None, iters=10):
@@ -430,11 +517,9 @@ class Engine:
         with torch.cuda.stream(s):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
-                for p, bn, _ in rec:
-                    if bn < 0:
-                        self._chk(self.L.mpb_tc_gemm_x3(ctypes.byref(p), -bn, self._st()), "mpb_tc_gemm_x3")
-                    else:
-                        self._chk(self.L.mpb_tc_gemm(ctypes.byref(p), bn, self._st()), "mpb_tc_gemm")
+                fns = {"tf32": self.L.mpb_tc_gemm, "x3": self.L.mpb_tc_gemm_x3, "h3": self.L.mpb_tc_gemm_h3}
+                for p, bn, _, kind in rec:
+                    self._chk(fns[kind](ctypes.byref(p), bn, self._st()), "mpb_tc_gemm (%s)" % kind)
         torch.cuda.synchronize(self.dev)
         g.replay()
         torch.cuda.synchronize(self.dev)
@@ -450,7 +535,10 @@ class Engine:
             ts.append(a.elapsed_time(b))
         ms_ = float(np.median(ts))
         flop = float(sum(r[2] for r in rec))
-        return {"ms": ms_, "gflop": flop / 1e9, "tflops": flop / (ms_ * 1e-3) / 1e12, "launches": len(rec)}
+        kinds = {}
+        for r in rec:
+            kinds[r[3]] = kinds.get(r[3], 0) + 1
+        return {"ms": ms_, "gflop": flop / 1e9, "tflops": flop / (ms_ * 1e-3) / 1e12, "launches": len(rec), "kinds": kinds}
 
     def wgrad(self, M, H, W, k, dil, Cin, Cout, X, ldx, dY, ldy, dW, tapmask=None, rowscale=None):
         # widest tile that divides Cin, then enough K slices (RED.ADD into the zeroed gradient arena) to put
@@ -491,6 +579,41 @@ class Engine:
         first = min(self.layout[n][1] for n in self.trainable_names if not n.startswith("FirstStage"))
         self.round_off, self.round_len = first, self.n_train - first
 
+    def _build_w16_table(self):
+        """h3: device tables of every forward tensor-core GEMM weight (tower convs with their frozen BN, squash, decoder
+        convs, the six FC layers) for the one-launch split / scale pass; `w16_inv[arena offset]` = 1 / row scale"""
+        self.w16_inv, self.w16_tabs = {}, {}
+        tower, head = [], []
+        for enc in ms.ENCODERS:
+            for scope, k, cin, cout, _ in ms.conv_layers(enc):
+                if k * k * cin % 32:
+                    continue                                    # the 7x7x3 stem is a SIMT kernel
+                b = scope + "/BatchNorm/"
+                tower.append((scope + "/weights", self.view(b + "gamma"), self.view(b + "moving_variance")))
+        gemm_heads = ["squash/1x1_conv"] + [D["scope"] for D in self.dec] + \
+                     ["output/%s_fc/%s_fc/%s" % (a, a, l) for a in ("proposal", "regression") for l in ("img_fc", "fc0", "fc1")]
+        for sc in gemm_heads:
+            head.append((sc + "/weights", None, None))
+        for key, rows_ in (("towers", tower), ("head", head)):
+            arr = (W16Layer * len(rows_))()
+            row2layer, row = [], 0
+            for i, (name, gamma, var) in enumerate(rows_):
+                _, off, ds = self.layout[name]
+                cout, K = ds
+                inv = torch.empty(cout, device=self.dev)
+                self.w16_inv[off] = inv
+                e = arr[i]
+                e.w = self.params.data_ptr() + 4 * off
+                e.gamma = gamma.data_ptr() if gamma is not None else None
+                e.var = var.data_ptr() if var is not None else None
+                e.w16 = self.prep16.data_ptr() + 4 * off
+                e.inv_scale = inv.data_ptr()
+                e.cout, e.K, e.row0 = cout, K, row
+                row2layer += [i] * cout
+                row += cout
+            self.w16_tabs[key] = (row, torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev),
+                                  torch.tensor(row2layer, dtype=torch.int32, device=self.dev))
+
     def prepare_weights(self, part="all"):
         """fold frozen BN into the tower convs, tf32-round every GEMM weight (run after each update)."""
         self._enter()
@@ -503,6 +626,13 @@ class Engine:
         if part in ("all", "head"):
             self._chk(L.mpb_round_copy(self.round_len, _ptr(self.params[self.round_off:]), _ptr(self.prep[self.round_off:]),
                                        st), "round_copy")
+        if self.h3:
+            if getattr(self, "w16_tabs", None) is None:
+                self._build_w16_table()
+            for key in ("towers", "head"):
+                if part in ("all", key):
+                    rows_, tab, r2l = self.w16_tabs[key]
+                    self._chk(L.mpb_split16_weights_multi(rows_, _ptr(tab), _ptr(r2l), BN_EPS_RESNET, st), "split16_weights")
         if part in ("all", "towers"):
             self._prepared = True
 
@@ -556,6 +686,8 @@ class Engine:
                   "d_cen_y_offs", "d_cen_z_offs", "d_prop_y", "d_prop_z", "maskstats"):
             setattr(io, k, h[k].data_ptr())
         io.xyz_local, io.d_xyz_local = self.xyz.data_ptr(), self.d_xyz.data_ptr()
+        io.xyz_loss_mode = 0 if self.xyz_loss_type == "smooth_l1_nonzero" else 1
+        io.xyz_loss_weight = self.xyz_loss_weight
         io.feat1, io.ld1 = self.fc["proposal"]["feat"].data_ptr(), KPAD
         io.feat2, io.ld2 = self.fc["regression"]["feat"].data_ptr(), KPAD
         io.d_feat2, io.ldd2 = self.fc["regression"]["d_feat"].data_ptr(), KPAD
@@ -571,6 +703,7 @@ class Engine:
                                  _ptr(self.bnfold[s0][1]), _ptr(T["stem"]), st), "stem_fwd")
         self._chk(L.mpb_maxpool3s2_fwd(T["nimg"], T["H2"], T["W2"], 64, _ptr(T["stem"]), _ptr(T["pool"]), st), "pool1")
         x, ldx = T["pool"], 64
+        self._split(T["pool"], T["M"], 64, 64)
         xr = x                      # tf32-rounded view of x (the pooled stem output is already rounded)
         M, h, w = T["M"], T["h"], T["w"]
         for U in T["units"]:
@@ -586,16 +719,17 @@ class Engine:
             else:
                 res, ldr = x, ldx
             self.gemm(TC_FWD, M, h, w, 1, 1, cin, base, xr, ldx, self.pview(s + "/conv1/weights"), cin, U["y1"], base,
-                      shift=self.bnfold[s + "/conv1"][1], relu=1, round_tf32=1)
+                      shift=self.bnfold[s + "/conv1"][1], relu=1, round_tf32=1, out16=True)
             self.gemm(TC_FWD, M, h, w, 3, rate, base, base, U["y1"], base, self.pview(s + "/conv2/weights"), 9 * base,
-                      U["y2"], base, tapmask=T["tapmask"][rate], shift=self.bnfold[s + "/conv2"][1], relu=1, round_tf32=1)
+                      U["y2"], base, tapmask=T["tapmask"][rate], shift=self.bnfold[s + "/conv2"][1], relu=1, round_tf32=1,
+                      out16=True)
             last_crop = U["out"] is None       # written straight into the concat buffer: rounded (squash operand)
             self.gemm(TC_FWD, M, h, w, 1, 1, base, cout, U["y2"], base, self.pview(s + "/conv3/weights"), base, out, ldo,
                       shift=self.bnfold[s + "/conv3"][1], res=res, ldr=ldr, relu=1, round_tf32=1 if last_crop else 0,
-                      out_r=U["out_r"], ldor=cout)
+                      out_r=U["out_r"], ldor=cout, out16=last_crop)
             U["x"], U["ldx"], U["xr"], U["o"], U["ldo"] = x, ldx, xr, out, ldo
             x, ldx = out, ldo
-            xr = U["out_r"] if (U["out_r"] is not None and not self.x3) else out
+            xr = U["out_r"] if (U["out_r"] is not None and not (self.x3 or self.h3)) else out
         return x, ldx
 
     def _fc_layer(self, x, ldx, K, wname, out, ldo, acc):
@@ -608,6 +742,7 @@ class Engine:
                   ksplit=ksplit, bn=64)
         self._chk(self.L.mpb_bias_relu(N, 1024, _ptr(acc), 1024, _ptr(self.view(wname + "/biases")), 1, 1, _ptr(out), ldo,
                                        self._st()), "bias_relu")
+        self._split(out, N, ldo, ldo)        # (the concat tails of `feat` were written before this layer ran)
 
     def forward(self, train=True, compute_losses=None, features_only=False):
         """train: the reference's is_training (decoder batch norm with batch statistics + moving-average update, and
@@ -631,20 +766,24 @@ class Engine:
             ff, _ = self._tower_fwd(Tf, I["full_img"])
             self._chk(L.mpb_crop_pool_fwd(Tf["h"], Tf["w"], 1024, _ptr(ff), N, _ptr(I["boxes_2d_norm"]), 24,
                                           _ptr(self.concat[:, 1024:]), 2048, self._st()), "crop_pool_fwd")
+            self._split(self.concat[:, 1024:], self.Mc, 1024, 2048)
         self._tower_fwd(Tc, I["rgb_crops"])
         self._join(self.s_full)
         Mc = self.Mc
         self.gemm(TC_FWD, Mc, 12, 12, 1, 1, 2048, 512, self.concat, 2048, self.pview("squash/1x1_conv/weights"), 2048,
                   self.squashed, 512, shift=self.view("squash/1x1_conv/biases"), relu=1, round_tf32=1)
         self._chk(L.mpb_maxpool2_fwd(N, 12, 12, 512, _ptr(self.squashed), 512, _ptr(self.pooled), 512, st), "pool")
+        self._split(self.pooled, N * 36, 512, 512)
         if not features_only:
             with self._side(self.s_fc):
                 self._fc_forward()
         self._chk(L.mpb_resize_ac_fwd(N, 12, 12, 512, _ptr(self.squashed), 24, 24, _ptr(self.r1), st), "resize1")
+        self._split(self.r1, N * 576, 512, 512)
         x = self.r1
         for i, D in enumerate(self.dec):
             if i == 2:
                 self._chk(L.mpb_resize_ac_fwd(N, 24, 24, 256, _ptr(x), 48, 48, _ptr(self.r2), st), "resize2")
+                self._split(self.r2, N * 2304, 256, 256)
                 x = self.r2
             side = D["side"]
             self.gemm(TC_FWD, D["M"], side, side, 3, 1, D["cin"], D["cout"], x, D["cin"], self.pview(D["scope"] + "/weights"),
@@ -661,6 +800,8 @@ class Engine:
                                              BN_EPS_DECODER, _ptr(D["y"]), st), "bn_infer_fwd")
             D["x"] = x
             x = D["y"]
+            if i < 3:
+                self._split(x, D["M"], D["cout"], D["cout"])
         if features_only:
             return {"features_for_map": x.view(N, 48, 48, 128), "features_for_box_3d": self.pooled.view(N, 6, 6, 512)}
         sx = "output/inst_xyz_map_local/inst_xyz_map_local"
@@ -669,6 +810,45 @@ class Engine:
         self._join(self.s_fc)            # the FC stacks ran beside the decoder
         io = self.heads_io()
         self._chk(L.mpb_heads_final(ctypes.byref(io), 1 if compute_losses else 0, st), "heads_final")
+        if compute_losses and io.xyz_loss_mode == 1:
+            self._pointset_loss()
+
+    def _pointset_loss(self):
+        """ChamferDistance / EarthMoversDistance as the training loss of the local xyz map (losses_custom.py:135-198):
+        clouds = pred * mask and gt * mask as (N, 2304, 3); loss = weight * sum_b(dist_b) / B / num_boxes
+        (loss_builder.py:60-84 then monopsr_model.py:585), B = num_boxes; its gradient goes into d_xyz next to the
+        projection / depth terms that mpb_heads_final left there."""
+        L, st, N, I = self.L, self._st(), self.N, self.inputs
+        n = 2304
+        npts = N * n
+        if self._ps is None:
+            e = lambda *s_, dt=torch.float32: torch.empty(*s_, dtype=dt, device=self.dev)
+            ps = dict(p=e(N, n, 3), t=e(N, n, 3), g1=e(N, n, 3), g2=e(N, n, 3))
+            if self.xyz_loss_type == "chamfer_dist":
+                ps.update(d1=e(N, n), d2=e(N, n), i1=e(N, n, dt=torch.int32), i2=e(N, n, dt=torch.int32), c=e(N, n))
+            else:
+                ps.update(match=e(N, n, n), cost=e(N))
+            self._ps = ps
+        ps = self._ps
+        scale = self.xyz_loss_weight / float(N) / float(N)
+        self._chk(L.mpb_pointset_mask(npts, _ptr(self.xyz), _ptr(I["gt_inst_xyz_maps_local"]), _ptr(I["gt_valid_mask_maps"]),
+                                      _ptr(ps["p"]), _ptr(ps["t"]), st), "pointset_mask")
+        if self.xyz_loss_type == "chamfer_dist":
+            self._chk(L.mpb_nn_distance(N, n, _ptr(ps["p"]), n, _ptr(ps["t"]), _ptr(ps["d1"]), _ptr(ps["i1"]), _ptr(ps["d2"]),
+                                        _ptr(ps["i2"]), st), "nn_distance")
+            self._chk(L.mpb_pointset_loss_add(npts, _ptr(ps["d1"]), npts, _ptr(ps["d2"]), scale, _ptr(self.h["losses"]), 0, 8,
+                                              _ptr(ps["c"]), npts, 1.0, st), "pointset_loss_add")
+            self._chk(L.mpb_nn_distance_grad(N, n, _ptr(ps["p"]), n, _ptr(ps["t"]), _ptr(ps["c"]), _ptr(ps["i1"]), _ptr(ps["c"]),
+                                             _ptr(ps["i2"]), _ptr(ps["g1"]), _ptr(ps["g2"]), st), "nn_distance_grad")
+        else:
+            self._chk(L.mpb_approxmatch(N, n, n, _ptr(ps["p"]), _ptr(ps["t"]), _ptr(ps["match"]), None, st), "approxmatch")
+            self._chk(L.mpb_matchcost(N, n, n, _ptr(ps["p"]), _ptr(ps["t"]), _ptr(ps["match"]), _ptr(ps["cost"]), st), "matchcost")
+            self._chk(L.mpb_pointset_loss_add(N, _ptr(ps["cost"]), 0, None, scale, _ptr(self.h["losses"]), 0, 8, None, 0, 0.0,
+                                              st), "pointset_loss_add")
+            self._chk(L.mpb_matchcostgrad(N, n, n, _ptr(ps["p"]), _ptr(ps["t"]), _ptr(ps["match"]), _ptr(ps["g1"]),
+                                          _ptr(ps["g2"]), st), "matchcostgrad")
+        self._chk(L.mpb_pointset_grad_add(npts, _ptr(ps["g1"]), _ptr(I["gt_valid_mask_maps"]), scale, _ptr(self.d_xyz), st),
+                  "pointset_grad_add")
 
     def _fc_forward(self):
         """heads_static, proposal stack, lwh/alpha heads, heads_mid, regression stack, cen_y/cen_z heads"""
@@ -901,15 +1081,53 @@ class Engine:
                   "bn_param_grad_multi")
 
     # ------------------------------------------------------------------ train-op
+    @classmethod
+    def from_config(cls, device, config, **kw):
+        """Engine for a parsed yaml config (core/config_utils.parse_yaml_config): the xyz-map loss type / weight and the
+        train-op hyper-parameters come from the config instead of the built-in monopsr_model_000 defaults."""
+        from . import config_utils
+        config_utils.validate_for_engine(config)
+        xyz = list(config.model_config.loss_config.inst_xyz_map_local)
+        eng = cls(device, xyz_loss=(xyz[0], float(xyz[1])), **kw)
+        eng.configure(config.train_config)
+        return eng
+
+    def configure(self, train_config):
+        """optimizer_builder.build / _create_learning_rate (builders/optimizer_builder.py:23-118) on
+        train_config.optimizer.adam_optimizer: exponential_decay (staircase or not) or constant learning rate, the EMA
+        decay of MovingAverageOptimizer (use_moving_average: false -> the shadows simply track the variables)."""
+        a = train_config.optimizer.adam_optimizer
+        kind = getattr(a, "learning_rate_type", "exponential_decay")
+        if kind == "exponential_decay":
+            self.lr_initial, self.lr_decay_steps = float(a.initial_learning_rate), int(a.decay_steps)
+            self.lr_decay_factor, self.lr_staircase = float(a.decay_factor), bool(getattr(a, "staircase", False))
+        elif kind == "constant":
+            self.lr_initial, self.lr_decay_steps, self.lr_decay_factor, self.lr_staircase = float(a.learning_rate), 1, 1.0, True
+        else:
+            raise NotImplementedError("learning_rate_type %r" % kind)
+        self.ema_decay = float(a.moving_average_decay) if getattr(a, "use_moving_average", False) else 0.0
+        self._graph = self._g_fb = None          # the EMA decay is baked into a captured train-op launch
+
     def learning_rate(self, step):
-        return LR_INITIAL * (LR_DECAY_FACTOR ** (step // LR_DECAY_STEPS))        # exponential_decay, staircase (yaml:145-150)
+        """tf.train.exponential_decay (yaml:145-150): lr * factor ^ (step / decay_steps), floored when staircase"""
+        e = step / float(self.lr_decay_steps)
+        return self.lr_initial * (self.lr_decay_factor ** (math.floor(e) if self.lr_staircase else e))
 
     def set_hyper(self, step):
         t = step + 1
         lr_t = self.learning_rate(step) * math.sqrt(1.0 - ADAM_BETA2 ** t) / (1.0 - ADAM_BETA1 ** t)
-        self.hyper_host = getattr(self, "hyper_host", torch.zeros(4, pin_memory=True))
-        self.hyper_host[0] = lr_t
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        # ring of pinned slots with an event each: the copy of step k may still be queued when the host prepares
+        # step k + 1 (graph replays are asynchronous), so one reused buffer could hand step k a later lr_t
+        ring = getattr(self, "_hyper_ring", None)
+        if ring is None:
+            ring = self._hyper_ring = [(torch.zeros(4, pin_memory=True), torch.cuda.Event()) for _ in range(8)]
+            self._hyper_i = 0
+        host, ev = ring[self._hyper_i % len(ring)]
+        self._hyper_i += 1
+        ev.synchronize()                     # (no-op unless the host is 8 steps ahead of the device)
+        host[0] = lr_t
+        self.hyper.copy_(host, non_blocking=True)
+        ev.record(self._cur())
 
     def optimizer_step(self, grad_scale=1.0, part="all"):
         c0, nc, t0, nt = self.opt_parts[part]
@@ -918,7 +1136,7 @@ class Engine:
                                             _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
                                             _ptr(self.ema), ctypes.c_void_p(self.norm2.data_ptr() + 4 * c0), _ptr(self.hyper),
                                             grad_scale, CLIP_GRADIENT_NORM, ADAM_BETA1,
-                                            ADAM_BETA2, ADAM_EPSILON, EMA_DECAY, self._st()), "opt_step")
+                                            ADAM_BETA2, ADAM_EPSILON, self.ema_decay, self._st()), "opt_step")
         self._prepared = False
 
     def allreduce_grads(self):

@@ -55,9 +55,12 @@ class Evaluator(object):
                                             inputs["gt_valid_mask_maps"], int(sample_dict[P.SAMPLE_NUM_OBJS]))
         return {k: v.detach().cpu().numpy() for k, v in r.items()}
 
-    def run_checkpoint_once(self, checkpoint_prefix, samples, use_ema=True):
+    def run_checkpoint_once(self, checkpoint_prefix, samples, use_ema=False):
         """samples: iterable of (sample, sample_dict).  Returns {'num_samples', 'mean_losses' (val), 'metrics' (val:
-        name -> list of per-object values, for evaluator_utils.save_metrics), 'seconds'}"""
+        name -> list of per-object values, for evaluator_utils.save_metrics), 'seconds'}.
+        use_ema=False is the reference's behaviour: its Evaluator restores with a plain tf.train.Saver() built on the
+        eval graph (core/evaluator.py:125,144), i.e. the RAW variables -- the MovingAverageOptimizer shadows are
+        saved but never consumed.  use_ema=True is an explicit opt-in to evaluate the averaged weights instead."""
         if checkpoint_prefix is not None:
             self.engine.load_checkpoint(checkpoint_prefix, use_ema=use_ema)
         t0, n, sums = time.time(), 0, {}

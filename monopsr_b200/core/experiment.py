@@ -26,9 +26,20 @@ def output_types_list(output_config):
     return sorted(k for k in output_config.__dict__.keys() if not k.startswith("__"))
 
 
-def _default_engine(device):
+def _default_engine(device, config=None):
+    """the engine of an experiment: loss type of the xyz map and the train-op hyper-parameters from the yaml"""
     from .engine import Engine
-    return Engine(device)
+    return Engine(device) if config is None else Engine.from_config(device, config)
+
+
+def _make_engine(engine_factory, device, config):
+    """engine_factory(device) or engine_factory(device, config) -- older injected factories take the device only"""
+    import inspect
+    try:
+        takes_config = len(inspect.signature(engine_factory).parameters) >= 2
+    except (TypeError, ValueError):
+        takes_config = False
+    return engine_factory(device, config) if takes_config else engine_factory(device)
 
 
 def checkpoints_in(checkpoint_dir, model_type):
@@ -174,7 +185,7 @@ def train(config, device="cuda:0", engine_factory=_default_engine, data_dir=None
     rank, world, device = data_parallel_setup(device)
     rng = np.random if (seed is None and rank == 0) else np.random.RandomState((seed or 0) + rank)
     dataset = KittiDataset(config.dataset_config, "train", data_dir=data_dir, rng=rng)
-    engine = engine_factory(device)
+    engine = _make_engine(engine_factory, device, config)
     with PrefetchLoader(dataset, shuffle=True, workers=LOADER_WORKERS) as loader:
         return trainer_mod.train(engine, config, loader.sample_fn, pretrained_checkpoint=pretrained_checkpoint, log=log,
                                  chief=rank == 0)
@@ -189,7 +200,8 @@ def evaluate(config, device="cuda:0", engine_factory=_default_engine, data_dir=N
         d.data_split_dir, d.has_kitti_labels = "training", True
     d.aug_list = []
     dataset = KittiDataset(d, "val", data_dir=data_dir)
-    ev = ExperimentEvaluator(engine_factory(device), dataset, config, eval_mode="val", skip_evaluated_checkpoints=True,
+    config_utils.validate_for_engine(config)
+    ev = ExperimentEvaluator(_make_engine(engine_factory, device, config), dataset, config, eval_mode="val", skip_evaluated_checkpoints=True,
                              do_kitti_native_eval=True, log=log)
     return ev.repeated_checkpoint_run(max_polls=max_polls)
 
@@ -204,6 +216,7 @@ def inference(config, data_split, ckpt_indices, device="cuda:0", engine_factory=
     d.aug_config.box_jitter_type = None
     dataset = DatasetBuilder.build_kitti_dataset(d, train_val_test="test", data_dir=data_dir)
     every = isinstance(ckpt_indices, str) and ckpt_indices == "all"
-    ev = ExperimentEvaluator(engine_factory(device), dataset, config, eval_mode="test", skip_evaluated_checkpoints=every,
+    config_utils.validate_for_engine(config)
+    ev = ExperimentEvaluator(_make_engine(engine_factory, device, config), dataset, config, eval_mode="test", skip_evaluated_checkpoints=every,
                              do_kitti_native_eval=False, log=log)
     return ev.repeated_checkpoint_run(max_polls=max_polls) if every else ev.run_latest_checkpoints(ckpt_indices)

@@ -321,7 +321,11 @@ def write_bundle(prefix, tensors, block_entries=64, with_data_crc=True):
     """write {name: ndarray} as <prefix>.index + <prefix>.data-00000-of-00001 (one shard, uncompressed blocks)"""
     os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
     pairs, offset = [], 0
-    with open(prefix + ".data-00000-of-00001", "wb") as f:
+    # like TensorFlow's BundleWriter: both files are written under temporary names and renamed into place, the index
+    # LAST -- a reader that globs '*.index' (the evaluator's polling loop, other data-parallel ranks) never sees a
+    # half-written checkpoint
+    tmp = "%s.tmp%d" % (prefix, os.getpid())
+    with open(tmp + ".data", "wb") as f:
         for name in sorted(tensors, key=lambda s: s.encode("utf-8")):
             a = np.asarray(tensors[name]).copy(order="C")        # (ascontiguousarray would turn a scalar into shape (1,))
             a = a.astype(a.dtype.newbyteorder("<")) if a.dtype.byteorder == ">" else a
@@ -345,12 +349,35 @@ def write_bundle(prefix, tensors, block_entries=64, with_data_crc=True):
     out += idx_body + idx_trailer
     footer = meta_handle + idx_handle
     out += footer + b"\x00" * (40 - len(footer)) + struct.pack("<Q", MAGIC)
-    with open(prefix + ".index", "wb") as f:
+    with open(tmp + ".index", "wb") as f:
         f.write(bytes(out))
+    os.replace(tmp + ".data", prefix + ".data-00000-of-00001")
+    os.replace(tmp + ".index", prefix + ".index")
 
 
 # ------------------------------------------------------------------------------------------------- variable mapping
 EMA_SUFFIX = "/ExponentialMovingAverage"
+ADAM_M_SUFFIX, ADAM_V_SUFFIX = "/Adam", "/Adam_1"          # tf.train.AdamOptimizer slot variables
+SLOT_SCOPES = ("", "train_op/")                              # slot variables may live under the train-op's name scope
+
+
+def _find(ckpt_vars, name):
+    for sc in SLOT_SCOPES:
+        if sc + name in ckpt_vars:
+            return sc + name
+    return None
+
+
+def map_slots(ckpt_vars, param_table):
+    """Optimizer state of a MonoPSR training checkpoint: {name: (adam_m, adam_v, ema)} for the variables whose three slot
+    tensors ('<var>/Adam', '<var>/Adam_1', '<var>/ExponentialMovingAverage', optionally below 'train_op/') are all
+    present with the variable's shape.  tf.train.Saver restores them on resume (core/trainer.py:148-153)."""
+    out = {}
+    for name, shape, _ in param_table:
+        keys = [_find(ckpt_vars, name + sfx) for sfx in (ADAM_M_SUFFIX, ADAM_V_SUFFIX, EMA_SUFFIX)]
+        if all(k is not None and tuple(ckpt_vars[k].shape) == tuple(shape) for k in keys):
+            out[name] = tuple(np.asarray(ckpt_vars[k], np.float32) for k in keys)
+    return out
 
 
 def map_monopsr_checkpoint(ckpt_vars, param_table, use_ema=False):
@@ -360,7 +387,8 @@ def map_monopsr_checkpoint(ckpt_vars, param_table, use_ema=False):
     params, report = {}, {"loaded": [], "missing": [], "shape_mismatch": [], "unused": []}
     used = set()
     for name, shape, _ in param_table:
-        src = name + EMA_SUFFIX if use_ema and (name + EMA_SUFFIX) in ckpt_vars else name
+        ema_key = _find(ckpt_vars, name + EMA_SUFFIX) if use_ema else None
+        src = ema_key if ema_key is not None else name
         if src not in ckpt_vars:
             report["missing"].append(name)
             continue
@@ -389,16 +417,26 @@ def map_detection_checkpoint(ckpt_vars, param_table, encoders=("FirstStageFeatur
     return map_monopsr_checkpoint(renamed, [t for t in param_table if t[0] in renamed])
 
 
-def load_checkpoint(prefix, param_table, kind="monopsr", use_ema=False):
+def load_checkpoint(prefix, param_table, kind="monopsr", use_ema=False, with_slots=False):
     """read `prefix` and map it; kind 'monopsr' (a MonoPSR training checkpoint) or 'detection' (the pre-trained
-    object-detection-API ResNet-101).  The result feeds Engine.load_params (missing variables keep their values)."""
+    object-detection-API ResNet-101).  The result feeds Engine.load_params (missing variables keep their values).
+    with_slots (kind 'monopsr'): report['slots'] = map_slots(...) and report['global_step'] for a training resume."""
     want = None
     if kind == "monopsr":
         names = {n for n, _, _ in param_table}
-        want = names | {n + EMA_SUFFIX for n in names}
+        want = set(names)
+        for sc in SLOT_SCOPES:
+            want |= {sc + n + EMA_SUFFIX for n in names}
+            if with_slots:
+                want |= {sc + n + sfx for n in names for sfx in (ADAM_M_SUFFIX, ADAM_V_SUFFIX)}
+        want.add("global_step")
     ckpt = read_bundle(prefix, names=want) if want is not None else read_bundle(prefix)
     if kind == "monopsr":
-        return map_monopsr_checkpoint(ckpt, param_table, use_ema)
+        params, report = map_monopsr_checkpoint(ckpt, param_table, use_ema)
+        if with_slots:
+            report["slots"] = map_slots(ckpt, param_table)
+            report["global_step"] = int(ckpt["global_step"]) if "global_step" in ckpt else None
+        return params, report
     if kind == "detection":
         return map_detection_checkpoint(ckpt, param_table)
     raise ValueError("Invalid checkpoint kind", kind)

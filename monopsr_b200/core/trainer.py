@@ -35,6 +35,20 @@ def prune_checkpoints(checkpoint_dir, model_type, keep):
             os.remove(f)
 
 
+def _broadcast_resume(prefix, step):
+    """under torch.distributed every rank resumes from what rank 0 found (a rank that globs the directory a moment
+    later could otherwise pick up the chief's fresh step-0 save)"""
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return prefix, step
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return prefix, step
+    box = [(prefix, step)]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
 def train(engine, config, sample_fn, pretrained_checkpoint=None, log=print, chief=True):
     """trainer.train(model, config).  config: parse_yaml_config result (config_name, model_config.model_type,
     train_config.{max_iterations, summary_interval, checkpoint_interval, max_checkpoints_to_keep,
@@ -51,8 +65,9 @@ def train(engine, config, sample_fn, pretrained_checkpoint=None, log=print, chie
     log("Training", config.config_name)
     start = 0
     resume, step0 = (None, 0) if tc.overwrite_checkpoints else latest_checkpoint(ckpt_dir, model_type)
+    resume, step0 = _broadcast_resume(resume, step0)      # data parallel: every rank follows rank 0's decision
     if resume is not None:
-        engine.load_checkpoint(resume)
+        engine.load_checkpoint(resume, resume=True)       # variables, Adam moments and EMA shadows (tf.train.Saver)
         start = step0
     elif pretrained_checkpoint is not None:
         engine.load_checkpoint(pretrained_checkpoint, kind="detection")
@@ -63,7 +78,8 @@ def train(engine, config, sample_fn, pretrained_checkpoint=None, log=print, chie
     log("Starting from step {} / {}".format(start, tc.max_iterations))
     last_time, last_loss = time.time(), None
     for step in range(start, tc.max_iterations + 1):
-        if step % tc.checkpoint_interval == 0 and chief:
+        if step % tc.checkpoint_interval == 0 and chief and not (resume is not None and step == start):
+            # (the checkpoint a run resumed from is not written again)
             engine.save_checkpoint("{}-{:08d}".format(prefix, step), global_step=step)
             prune_checkpoints(ckpt_dir, model_type, tc.max_checkpoints_to_keep)
             log("{}: Step {} / {}: Checkpoint saved to {}-{:08d}".format(config.config_name, step, tc.max_iterations,

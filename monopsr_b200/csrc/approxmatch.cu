@@ -23,6 +23,7 @@
 #include "../../include/monopsr_b200_tfops.h"
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -474,6 +475,265 @@ matchcostgrad2_kernel(int n, int m, const float* __restrict__ xyz1,
     }
 }
 
+
+// =====================================================================================
+// Streaming versions of matchcost / matchcostgrad for n % 4 == 0 (the HBM-bound pair: `match` is b*m*n*4 bytes,
+// 134 MB at 32 x 1024^2, everything else is KBs).  `match` is read exactly ONCE with 16-byte streaming loads,
+// eight rows (eight independent LDG.128) in flight per thread:
+//   * a CTA owns kMsRows... rows x one slab of 1024 columns; thread t owns columns 4t..4t+3 of the slab, so the
+//     dataset points and the column accumulators (grad1) live in registers for the whole tile;
+//   * matchcostgrad is FUSED (the reference, tf_approxmatch_g.cu:229-295, and the first version here read `match`
+//     twice): w = match * rsqrt(max(d2, 1e-20)) is evaluated once per element and feeds both
+//     grad1[k] += (p1_k - p2_l) w  (column sums: registers) and grad2[l] -= (p1_k - p2_l) w (row sums);
+//   * row sums of 8 rows x 3 coordinates are reduced across the warp with a halving butterfly (27 SHFL for 24
+//     values instead of 120), across warps through shared memory in a fixed order;
+//   * per-tile column partials / per-slab row partials go to a stream-ordered scratch and are summed by a small
+//     second kernel in a FIXED order: deterministic, no atomics (the reference's grad kernels are deterministic
+//     too; only its nn_distance gradient uses atomics).
+// FP32 work is issued as packed f32x2 (two columns per instruction): ~9 instructions per element, which keeps
+// the kernel under the HBM time (20.5 us at 6555 GB/s for 134 MB).
+// =====================================================================================
+constexpr int kMsThreads = 256;
+constexpr int kMsSlab = kMsThreads * 4;      // columns per CTA
+constexpr int kMsBatch = 8;                  // rows in flight per thread
+
+__device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// kMsBatch rows of this thread's 4 columns.  The full-batch path has NO predicates: ptxas then issues all eight
+// LDG.128 back to back (with per-row predicates it sank each load next to its use: 1-2 loads in flight per thread,
+// 3 TB/s); the ordering fence keeps the loads ahead of the arithmetic.
+__device__ __forceinline__ void ms_load_batch(float4 (&w)[kMsBatch], const float* p, int n, int rows_left) {
+    if (rows_left >= kMsBatch) {
+#pragma unroll
+        for (int r = 0; r < kMsBatch; r++) w[r] = ldcs4(p + (size_t)r * n);
+    } else {
+#pragma unroll
+        for (int r = 0; r < kMsBatch; r++) w[r] = r < rows_left ? ldcs4(p + (size_t)r * n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("" ::: "memory");
+}
+
+// the four dataset points of this thread as packed pairs: X01 = {x0,x1}, X23 = {x2,x3}, ...
+struct MsCols { uint64_t x01, x23, y01, y23, z01, z23; };
+__device__ __forceinline__ MsCols ms_load_cols(const float* p1, int k, bool act) {
+    MsCols c;
+    if (act) {      // 12 consecutive floats, 16-byte aligned (k % 4 == 0)
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p1 + (size_t)k * 3));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p1 + (size_t)k * 3 + 4));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(p1 + (size_t)k * 3 + 8));
+        c.x01 = pk(a.x, a.w); c.y01 = pk(a.y, b.x); c.z01 = pk(a.z, b.y);
+        c.x23 = pk(b.z, d.y); c.y23 = pk(b.w, d.z); c.z23 = pk(d.x, d.w);
+    } else {
+        c.x01 = c.x23 = c.y01 = c.y23 = c.z01 = c.z23 = pk(0.f, 0.f);
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(kMsThreads)
+matchcost_stream_kernel(int n, int m, int rows_per_tile, const float* __restrict__ xyz1,
+                        const float* __restrict__ xyz2, const float* __restrict__ match,
+                        float* __restrict__ partial, int* __restrict__ counters, float* __restrict__ out) {
+    extern __shared__ __align__(16) float4 ms_q[];           // [rows_per_tile] query points of the tile
+    __shared__ float red[kMsThreads / 32];
+    const int tile = blockIdx.x, slab = blockIdx.y, bi = blockIdx.z, tid = threadIdx.x;
+    const int l0 = tile * rows_per_tile, rows = min(rows_per_tile, m - l0);
+    const float* p1 = xyz1 + (size_t)bi * n * 3;
+    const float* p2 = xyz2 + (size_t)bi * m * 3;
+    const int k = slab * kMsSlab + tid * 4;
+    const bool act = k < n;
+    const float* mt = match + ((size_t)bi * m + l0) * n + (act ? k : 0);
+    for (int t = tid; t < rows_per_tile; t += kMsThreads) {
+        const int l = l0 + min(t, rows - 1);
+        ms_q[t] = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
+    }
+    const MsCols c = ms_load_cols(p1, k, act);
+    __syncthreads();
+    uint64_t acc = pk(0.f, 0.f);
+    for (int r0 = 0; r0 < rows; r0 += kMsBatch) {
+        float4 w[kMsBatch];
+        ms_load_batch(w, mt + (size_t)r0 * n, n, act ? rows - r0 : 0);
+#pragma unroll
+        for (int r = 0; r < kMsBatch; r++) {
+            const float4 q = ms_q[r0 + r];
+            const uint64_t qx = pk(q.x, q.x), qy = pk(q.y, q.y), qz = pk(q.z, q.z);
+            uint64_t dx = sub2(c.x01, qx), dy = sub2(c.y01, qy), dz = sub2(c.z01, qz);
+            float a0, a1, a2, a3;
+            upk(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), a0, a1);
+            dx = sub2(c.x23, qx); dy = sub2(c.y23, qy); dz = sub2(c.z23, qz);
+            upk(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), a2, a3);
+            acc = fma2(pk(sqrt_approx(a0), sqrt_approx(a1)), pk(w[r].x, w[r].y), acc);
+            acc = fma2(pk(sqrt_approx(a2), sqrt_approx(a3)), pk(w[r].z, w[r].w), acc);
+        }
+    }
+    float lo, hi;
+    upk(acc, lo, hi);
+    float v = lo + hi;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    // the LAST CTA of this batch element to arrive sums all partials in a fixed order (deterministic, one launch)
+    const int per_elem = gridDim.x * gridDim.y;
+    __shared__ int s_last;
+    if (tid == 0) {
+        float s_ = 0.f;
+        for (int w_ = 0; w_ < kMsThreads / 32; w_++) s_ += red[w_];
+        partial[(size_t)bi * per_elem + slab * gridDim.x + tile] = s_;
+        __threadfence();
+        s_last = atomicAdd(&counters[bi], 1) == per_elem - 1;
+    }
+    __syncthreads();
+    if (s_last && tid < 32) {
+        __threadfence();
+        float a = 0.f;
+        for (int t = tid; t < per_elem; t += 32) a += __ldcg(&partial[(size_t)bi * per_elem + t]);
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (tid == 0) out[bi] = a;
+    }
+}
+
+// keep-or-send halving step of the butterfly: after it, u[i] (i < H) holds the sum over the lane pair
+// {lane, lane ^ BIT} of value (lane & BIT ? H + i : i)
+template <int H, int BIT>
+__device__ __forceinline__ void ms_halve(const float* v, float* u, int lane) {
+    const bool up = (lane & BIT) != 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+        const float keep = up ? v[H + i] : v[i];
+        const float send = up ? v[i] : v[H + i];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
+    }
+}
+
+__global__ void __launch_bounds__(kMsThreads, 3)
+matchcostgrad_stream_kernel(int n, int m, int rows_per_tile, const float* __restrict__ xyz1,
+                            const float* __restrict__ xyz2, const float* __restrict__ match,
+                            float* __restrict__ part1,     // [b][tiles][n][3]   column partials (grad1)
+                            float* __restrict__ part2,     // [b][slabs][m][3]   row partials (grad2, sign included)
+                            int* __restrict__ counters, float* __restrict__ grad1, float* __restrict__ grad2) {
+    extern __shared__ __align__(16) float4 ms_q[];           // [rows_per_tile] query points, then [warps][rows][3] row sums
+    const int tile = blockIdx.x, slab = blockIdx.y, bi = blockIdx.z, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int l0 = tile * rows_per_tile, rows = min(rows_per_tile, m - l0);
+    float* rsum = reinterpret_cast<float*>(ms_q + rows_per_tile);      // [8 warps][rows_per_tile][3]
+    const float* p1 = xyz1 + (size_t)bi * n * 3;
+    const float* p2 = xyz2 + (size_t)bi * m * 3;
+    const int k = slab * kMsSlab + tid * 4;
+    const bool act = k < n;
+    const float* mt = match + ((size_t)bi * m + l0) * n + (act ? k : 0);
+    for (int t = tid; t < rows_per_tile; t += kMsThreads) {
+        const int l = l0 + min(t, rows - 1);
+        ms_q[t] = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
+    }
+    const MsCols c = ms_load_cols(p1, k, act);
+    __syncthreads();
+    uint64_t gx01 = pk(0.f, 0.f), gx23 = gx01, gy01 = gx01, gy23 = gx01, gz01 = gx01, gz23 = gx01;
+    for (int r0 = 0; r0 < rows; r0 += kMsBatch) {
+        float4 w[kMsBatch];
+        ms_load_batch(w, mt + (size_t)r0 * n, n, act ? rows - r0 : 0);
+        float v[kMsBatch * 3];
+#pragma unroll
+        for (int r = 0; r < kMsBatch; r++) {
+            const float4 q = ms_q[min(r0 + r, rows_per_tile - 1)];
+            const uint64_t qx = pk(q.x, q.x), qy = pk(q.y, q.y), qz = pk(q.z, q.z);
+            const uint64_t dx0 = sub2(c.x01, qx), dy0 = sub2(c.y01, qy), dz0 = sub2(c.z01, qz);
+            const uint64_t dx1 = sub2(c.x23, qx), dy1 = sub2(c.y23, qy), dz1 = sub2(c.z23, qz);
+            float a0, a1, a2, a3;
+            upk(fma2(dz0, dz0, fma2(dx0, dx0, mul2(dy0, dy0))), a0, a1);
+            upk(fma2(dz1, dz1, fma2(dx1, dx1, mul2(dy1, dy1))), a2, a3);
+            const uint64_t w01 = pk(w[r].x * rsqrt_approx(fmaxf(a0, 1e-20f)), w[r].y * rsqrt_approx(fmaxf(a1, 1e-20f)));
+            const uint64_t w23 = pk(w[r].z * rsqrt_approx(fmaxf(a2, 1e-20f)), w[r].w * rsqrt_approx(fmaxf(a3, 1e-20f)));
+            gx01 = fma2(dx0, w01, gx01); gy01 = fma2(dy0, w01, gy01); gz01 = fma2(dz0, w01, gz01);
+            gx23 = fma2(dx1, w23, gx23); gy23 = fma2(dy1, w23, gy23); gz23 = fma2(dz1, w23, gz23);
+            float s0, s1;
+            upk(fma2(dx1, w23, mul2(dx0, w01)), s0, s1); v[r * 3 + 0] = s0 + s1;
+            upk(fma2(dy1, w23, mul2(dy0, w01)), s0, s1); v[r * 3 + 1] = s0 + s1;
+            upk(fma2(dz1, w23, mul2(dz0, w01)), s0, s1); v[r * 3 + 2] = s0 + s1;
+        }
+        // 24 row sums across the 32 lanes: 12 + 6 + 3 keep-or-send steps, then 2 plain steps on 3 values
+        float u12[12], u6[6], u3[3];
+        ms_halve<12, 16>(v, u12, lane);
+        ms_halve<6, 8>(u12, u6, lane);
+        ms_halve<3, 4>(u6, u3, lane);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            u3[i] += __shfl_xor_sync(0xffffffffu, u3[i], 2);
+            u3[i] += __shfl_xor_sync(0xffffffffu, u3[i], 1);
+        }
+        // lanes 4j..4j+3 now hold row j: index = (lane & 16 ? 12 : 0) + (lane & 8 ? 6 : 0) + (lane & 4 ? 3 : 0) = 3 * (lane >> 2)
+        if ((lane & 3) == 0) {
+            const int r = r0 + (lane >> 2);
+            if (r < rows_per_tile) {
+                float* d = rsum + ((size_t)warp * rows_per_tile + r) * 3;
+                d[0] = u3[0]; d[1] = u3[1]; d[2] = u3[2];
+            }
+        }
+    }
+    if (act) {          // column partials of this tile: 12 consecutive floats per thread
+        float x0, x1, x2, x3, y0, y1, y2, y3, z0, z1, z2, z3;
+        upk(gx01, x0, x1); upk(gx23, x2, x3); upk(gy01, y0, y1); upk(gy23, y2, y3); upk(gz01, z0, z1); upk(gz23, z2, z3);
+        float4* d = reinterpret_cast<float4*>(part1 + (((size_t)bi * gridDim.x + tile) * n + k) * 3);
+        d[0] = make_float4(x0, y0, z0, x1);
+        d[1] = make_float4(y1, z1, x2, y2);
+        d[2] = make_float4(z2, x3, y3, z3);
+    }
+    __syncthreads();
+    for (int t = tid; t < rows * 3; t += kMsThreads) {       // fixed order over the 8 warps
+        float s_ = 0.f;
+#pragma unroll
+        for (int w_ = 0; w_ < kMsThreads / 32; w_++) s_ += rsum[(size_t)w_ * rows_per_tile * 3 + t];
+        part2[(((size_t)bi * gridDim.y + slab) * m + l0) * 3 + t] = -s_;          // grad2 uses (p2 - p1)
+    }
+    // the LAST CTA of this batch element to arrive sums the per-tile column partials (and, with several slabs, the
+    // per-slab row partials) in a fixed order: deterministic, no second launch
+    const int per_elem = gridDim.x * gridDim.y;
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&counters[bi], 1) == per_elem - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int T = gridDim.x, S = gridDim.y;
+    const float4* q1 = reinterpret_cast<const float4*>(part1 + (size_t)bi * T * n * 3);
+    float4* o1 = reinterpret_cast<float4*>(grad1 + (size_t)bi * n * 3);
+    const int n4 = n * 3 / 4;                                  // n % 4 == 0
+    for (int i = tid; i < n4; i += kMsThreads) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < T; t++) {
+            const float4 v = __ldcg(q1 + (size_t)t * n4 + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        o1[i] = a;
+    }
+    if (S > 1) {
+        const float* q2 = part2 + (size_t)bi * S * m * 3;
+        for (int i = tid; i < m * 3; i += kMsThreads) {
+            float a = 0.f;
+            for (int t = 0; t < S; t++) a += __ldcg(q2 + (size_t)t * m * 3 + i);
+            grad2[(size_t)bi * m * 3 + i] = a;
+        }
+    }
+}
+
+// rows per tile: a multiple of 8, at most 64, small enough that the launch has >= ~6 CTAs per SM to balance on
+inline int ms_rows_per_tile(int b, int m, int slabs) {
+    const char* e = getenv("MPB_MS_ROWS");
+    if (e && atoi(e) >= 8) return min(64, atoi(e) / 8 * 8);
+    int rt = 64;
+    while (rt > 8 && (long)b * slabs * ceil_div(m, rt) < 6L * num_sms()) rt -= 8;
+    return rt;
+}
+
 }  // namespace mpb
 
 MPB_API int mpb_approxmatch(int b, int n, int m, const float* xyz1, const float* xyz2,
@@ -545,6 +805,19 @@ MPB_API int mpb_matchcost(int b, int n, int m, const float* xyz1, const float* x
     if (n == 0 || m == 0) return cuda_status(cudaMemsetAsync(out, 0, sizeof(float) * b, s));
     if (!xyz1 || !xyz2 || !match) return -1;
     if (b > 65535) return -1;
+    if (n % 4 == 0 && (reinterpret_cast<uintptr_t>(match) & 15u) == 0 && (reinterpret_cast<uintptr_t>(xyz1) & 15u) == 0) {
+        const int slabs = ceil_div(n, kMsSlab), rt = ms_rows_per_tile(b, m, slabs), tiles = ceil_div(m, rt);
+        float* partial = nullptr;
+        MPB_CUDA_TRY(scratch_alloc((void**)&partial, sizeof(float) * ((size_t)b * slabs * tiles + b), s));
+        int* counters = reinterpret_cast<int*>(partial + (size_t)b * slabs * tiles);
+        MPB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * b, s));
+        matchcost_stream_kernel<<<dim3(tiles, slabs, b), kMsThreads, sizeof(float4) * rt, s>>>(n, m, rt, xyz1, xyz2, match,
+                                                                                              partial, counters, out);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        scratch_free(partial, s);
+        return cuda_status(e);
+    }
     const int tiles = ceil_div(m, kMcRows);
     float* partial = nullptr;
     MPB_CUDA_TRY(scratch_alloc((void**)&partial, sizeof(float) * (size_t)b * tiles, s));
@@ -570,6 +843,23 @@ MPB_API int mpb_matchcostgrad(int b, int n, int m, const float* xyz1, const floa
     }
     if (!xyz1 || !xyz2 || !match || !grad1 || !grad2) return -1;
     if (b > 65535) return -1;
+    if (n % 4 == 0 && (reinterpret_cast<uintptr_t>(match) & 15u) == 0 && (reinterpret_cast<uintptr_t>(xyz1) & 15u) == 0) {
+        // fused single pass over `match` (see matchcostgrad_stream_kernel)
+        const int slabs = ceil_div(n, kMsSlab), rt = ms_rows_per_tile(b, m, slabs), tiles = ceil_div(m, rt);
+        float *part1 = nullptr, *part2 = nullptr;
+        const size_t n1 = (size_t)b * tiles * n * 3, n2 = (size_t)b * slabs * m * 3;
+        MPB_CUDA_TRY(scratch_alloc((void**)&part1, sizeof(float) * (n1 + (slabs > 1 ? n2 : 0) + b), s));
+        part2 = slabs > 1 ? part1 + n1 : grad2;         // one slab: the row sums ARE grad2
+        int* counters = reinterpret_cast<int*>(part1 + n1 + (slabs > 1 ? n2 : 0));
+        MPB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * b, s));
+        const size_t smem = sizeof(float4) * rt + sizeof(float) * (kMsThreads / 32) * rt * 3;
+        matchcostgrad_stream_kernel<<<dim3(tiles, slabs, b), kMsThreads, smem, s>>>(n, m, rt, xyz1, xyz2, match, part1, part2,
+                                                                                   counters, grad1, grad2);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        scratch_free(part1, s);
+        return cuda_status(e);
+    }
     size_t sm1 = sizeof(float) * 4 * 1024;   // float4[1024] >= [4][64][3] floats
     matchcostgrad1_kernel<<<dim3(ceil_div(n, kG1Cols), b), kG1Cols * kG1Groups, sm1, s>>>(
         n, m, xyz1, xyz2, match, grad1);

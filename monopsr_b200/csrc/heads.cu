@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(256) heads_final_kernel(mpb_heads_io io, int t
 
     const float nv_b = fmaxf(io.maskstats[b], 1.f);     // tf.where(num_valid < 1, 1, num_valid)
     const float nv_all = io.maskstats[N];
-    const float inv_xyz = nv_all > 0.f ? 100.f / N / (3.f * nv_all) : 0.f;   // SUM_BY_NONZERO over (N,48,48,3)
+    // SUM_BY_NONZERO over (N,48,48,3); a point-set loss for this output (xyz_loss_mode 1) is added by the caller
+    const float inv_xyz = (nv_all > 0.f && io.xyz_loss_mode == 0) ? io.xyz_loss_weight / N / (3.f * nv_all) : 0.f;
     const float inv_dep = nv_all > 0.f ? 10.f / N / nv_all : 0.f;
 
     // geometry constants of this box
@@ -282,9 +283,71 @@ __global__ void heads_bwd_mid_kernel(mpb_heads_io io) {
     for (int c = 0; c < 24; c++) io.d_alpha[b * 24 + c] += t[3 + c];
 }
 
+// ---- glue of the point-set training losses (see include/monopsr_b200_net.h)
+__global__ void pointset_mask_kernel(long npts, const float* __restrict__ pred, const float* __restrict__ gt,
+                                     const float* __restrict__ mask, float* __restrict__ p, float* __restrict__ t) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npts * 3; i += (long)gridDim.x * blockDim.x) {
+        const float m = mask[i / 3];
+        p[i] = pred[i] * m;
+        t[i] = gt[i] * m;
+    }
+}
+// ONE CTA: fixed summation order (deterministic loss value), then two plain adds by one thread
+__global__ void __launch_bounds__(1024)
+pointset_loss_add_kernel(long na, const float* __restrict__ a, long nb, const float* __restrict__ b, float scale,
+                         float* __restrict__ losses, int slot, int total_slot, float* __restrict__ fill, long nfill,
+                         float fill_value) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (long i = threadIdx.x; i < na; i += blockDim.x) acc += (double)a[i];
+    if (b) for (long i = threadIdx.x; i < nb; i += blockDim.x) acc += (double)b[i];
+    if (fill) for (long i = threadIdx.x; i < nfill; i += blockDim.x) fill[i] = fill_value;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+        const float v = (float)(s * (double)scale);
+        losses[slot] += v;
+        losses[total_slot] += v;
+    }
+}
+__global__ void pointset_grad_add_kernel(long npts, const float* __restrict__ grad, const float* __restrict__ mask,
+                                         float scale, float* __restrict__ d_pred) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npts * 3; i += (long)gridDim.x * blockDim.x)
+        d_pred[i] += scale * grad[i] * mask[i / 3];
+}
+
 }  // namespace mpb
 
 using namespace mpb;
+MPB_API int mpb_pointset_mask(long npts, const float* pred, const float* gt, const float* mask, float* p, float* t,
+                              void* stream) {
+    if (npts < 0 || !pred || !gt || !mask || !p || !t) return -1;
+    if (npts == 0) return 0;
+    const long blocks = (npts * 3 + 255) / 256;
+    pointset_mask_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, (cudaStream_t)stream>>>(npts, pred, gt, mask, p, t);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_pointset_loss_add(long na, const float* a, long nb, const float* b, float scale, float* losses, int slot,
+                                  int total_slot, float* fill, long nfill, float fill_value, void* stream) {
+    if (na < 0 || nb < 0 || !a || !losses || slot < 0 || total_slot < 0) return -1;
+    pointset_loss_add_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(na, a, b ? nb : 0, b, scale, losses, slot, total_slot, fill,
+                                                                  nfill, fill_value);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_pointset_grad_add(long npts, const float* grad, const float* mask, float scale, float* d_pred, void* stream) {
+    if (npts < 0 || !grad || !mask || !d_pred) return -1;
+    if (npts == 0) return 0;
+    const long blocks = (npts * 3 + 255) / 256;
+    pointset_grad_add_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, (cudaStream_t)stream>>>(npts, grad, mask, scale,
+                                                                                                       d_pred);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
 MPB_API int mpb_heads_static(const mpb_heads_io* io, void* stream) {
     if (!io || io->nbox <= 0) return -1;
     MPB_CUDA_TRY(cudaMemsetAsync(io->maskstats + io->nbox, 0, sizeof(float), (cudaStream_t)stream));

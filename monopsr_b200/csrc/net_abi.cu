@@ -25,6 +25,11 @@ MPB_API int mpb_tc_gemm_x3(const mpb_tc_gemm_params* p, int BN, void* stream) {
     return mpb::tc_gemm_x3_launch(*p, BN, (cudaStream_t)stream);
 }
 
+MPB_API int mpb_tc_gemm_h3(const mpb_tc_gemm_params* p, int BN, void* stream) {
+    if (!p) return -1;
+    return mpb::tc_gemm_h3_launch(*p, BN, (cudaStream_t)stream);
+}
+
 MPB_API int mpb_build_tapmask(int nimg, int H, int W, int kh, int kw, int dil, unsigned short* out,
                               void* stream) {
     if (nimg <= 0 || H <= 0 || W <= 0 || kh * kw > 16 || !out) return -1;

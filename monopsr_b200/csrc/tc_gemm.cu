@@ -1,6 +1,7 @@
 // monopsr_b200/csrc/tc_gemm.cu -- see tc_gemm.cuh for the design.
 #include "tc_gemm.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace mpb {
@@ -68,6 +69,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// fp16 hi/lo split of two fp32 values: hi = fp16(x) (round to nearest), lo = fp16(x - hi); x - hi is exact in fp32
+__device__ __forceinline__ void split16_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -181,7 +199,7 @@ struct EpiCtx {
     int quad, row0, nvalid, ldo, ks, rank;
     uint32_t trow;
     float rs;
-    bool has_res, has_mask, do_round, has_outr, is_atomic;
+    bool has_res, has_mask, do_round, has_outr, is_atomic, has_out16;
     float* stg_base;
     float* scratch;            // this warp's 4 KB transposition tile
     int nepi;
@@ -286,6 +304,26 @@ __device__ __forceinline__ void epi_chunk(const TcGemmParams& p, const EpiCtx& c
                 x[4 * i] *= s2.x; x[4 * i + 1] *= s2.y; x[4 * i + 2] *= s2.z; x[4 * i + 3] *= s2.w;
             }
         }
+        if (c.has_out16) {
+            // split copy of the (unrounded) result for the next h3 GEMM: 4 hi halves at the column's place in the
+            // [hi | lo] block of its 32-column group, 4 lo halves 64 bytes further
+            unsigned char* o16 = reinterpret_cast<unsigned char*>(p.out16) + ((size_t)(c.row0 + g) * p.ldo16 + (col & ~31)) * 4 +
+                                 (col & 31) * 2;
+            const size_t step16 = (size_t)16 * p.ldo16;
+            float mx = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t h0, l0, h1, l1;
+                split16_pair(x[4 * i], x[4 * i + 1], h0, l0);
+                split16_pair(x[4 * i + 2], x[4 * i + 3], h1, l1);
+                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(x[4 * i]), fabsf(x[4 * i + 1]))), fmaxf(fabsf(x[4 * i + 2]), fabsf(x[4 * i + 3])));
+                if (4 * i + g < c.nvalid) {
+                    *reinterpret_cast<uint2*>(o16 + i * step16) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(o16 + i * step16 + 64) = make_uint2(l0, l1);
+                }
+            }
+            if (mx > 65504.f && p.overflow) *p.overflow = 1;
+        }
         if (c.do_round) {
 #pragma unroll
             for (int e = 0; e < 32; e++) x[e] = round_tf32(x[e]);
@@ -353,7 +391,7 @@ __device__ __forceinline__ void epi_setup(EpiCtx& c, const TcGemmParams& p, uint
     c.rs = 1.f;
     if (p.rowscale && c.row0 + lane < nrows) c.rs = __ldg(p.rowscale + c.row0 + lane);
     c.has_res = p.res != nullptr; c.has_mask = p.mask != nullptr; c.do_round = p.round_tf32 != 0;
-    c.has_outr = p.out_r != nullptr; c.is_atomic = p.atomic != 0;
+    c.has_outr = p.out_r != nullptr; c.is_atomic = p.atomic != 0; c.has_out16 = p.out16 != nullptr;
     c.stg_base = stg_base;
     c.scratch = stg_base + (quad + 4 * half) * 1024;
     c.nepi = nepi;
@@ -665,7 +703,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 // for A drops by CN (the GEMMs of this network are bound by exactly that traffic).
 // CSK: cluster split-K -- the cluster spans gridDim.z (= p.ksplit CTAs, disjoint K ranges of one tile) and the
 // partial accumulators are reduced through distributed shared memory in the epilogue (see tc_epilogue_dump).
-template <int BN, int OP, int CN, bool CSK>
+// H3: fp16 hi/lo split forward (mpb_tc_gemm_h3): the maps address the split copies X16 / W16 -- same byte geometry as
+// the fp32 operands, so producer, stages and barriers are untouched; only the MMA issue differs (six kind::f16
+// instructions per k-block instead of four kind::tf32).
+template <int BN, int OP, int CN, bool CSK, bool H3 = false>
 __global__ void __launch_bounds__(tma_threads<BN>(), tma_min_blocks<BN>())
 tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant__ CUtensorMap mapA,
                    const __grid_constant__ CUtensorMap mapB) {
@@ -867,9 +908,21 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                 if (i < 16) TC_TR(20 + i);
                 const uint64_t ad = ad0 + (uint64_t)((stage * kStage) >> 4);
                 const uint64_t bd = bd0 + (uint64_t)((stage * kStage) >> 4);
+                if (H3) {
+                    // a 128-byte row of A is [hi(32) | lo(32)] fp16, of B [lo(32) | hi(32)]: the four K=16 steps over
+                    // the whole row give A_hi*B_lo + A_lo*B_hi, then A's first half against B's second half is
+                    // A_hi*B_hi.  Small terms first.  (descriptor address units are 16 bytes: +2 = one K=16 step)
+                    constexpr uint32_t idesc_h = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 #pragma unroll
-                for (int k = 0; k < kTcBK / 8; k++)
-                    umma_tf32(tmem_acc, ad + k * ka, bd + k * kb_, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; k++)
+                        umma_f16(tmem_acc, ad + k * 2, bd + k * 2, idesc_h, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_f16(tmem_acc, ad, bd + 4, idesc_h, 1u);
+                    umma_f16(tmem_acc, ad + 2, bd + 6, idesc_h, 1u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kTcBK / 8; k++)
+                        umma_tf32(tmem_acc, ad + k * ka, bd + k * kb_, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
                 if (CN > 1) umma_commit_mc(empty_bar(stage), kMask);   // frees this stage in every CTA
                 else umma_commit(empty_bar(stage));
                 if (i == nk - 1) {
@@ -1208,7 +1261,7 @@ static int csk_cluster_x(unsigned gx, unsigned ks) {
     return 2;
 }
 
-template <int BN, int OP, int CN, bool CSK = false>
+template <int BN, int OP, int CN, bool CSK = false, bool H3 = false>
 static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     alignas(64) CUtensorMap mapA, mapB;
     const int taps = p.kh * p.kw;
@@ -1216,9 +1269,13 @@ static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     bool ok = true;
     if (OP == TC_FWD || OP == TC_DGRAD) {
         const int Ck = (OP == TC_FWD) ? p.Cin : p.Cout;
-        if (taps == 1) ok &= make_map_2d(&mapA, p.X, Ck, p.M, p.ldx, kTcBM / CN, false);
-        else ok &= make_map_im2col(&mapA, p.X, Ck, p.W, p.H, nimg, p.ldx, p.kh, p.kw, p.dil, kTcBM / CN, false);
-        if (OP == TC_FWD) ok &= make_map_2d(&mapB, p.Wt, (long)taps * p.Cin, p.Cout, p.ldw, BN, false);
+        // h3: the split copies have the byte geometry of the fp32 operands (32 floats = 64 halves = one 128-byte
+        // block), so the fp32 maps address them unchanged
+        const float* Xp = H3 ? reinterpret_cast<const float*>(p.X16) : p.X;
+        const float* Wp = H3 ? reinterpret_cast<const float*>(p.W16) : p.Wt;
+        if (taps == 1) ok &= make_map_2d(&mapA, Xp, Ck, p.M, p.ldx, kTcBM / CN, false);
+        else ok &= make_map_im2col(&mapA, Xp, Ck, p.W, p.H, nimg, p.ldx, p.kh, p.kw, p.dil, kTcBM / CN, false);
+        if (OP == TC_FWD) ok &= make_map_2d(&mapB, Wp, (long)taps * p.Cin, p.Cout, p.ldw, BN, false);
         else ok &= make_map_2d(&mapB, p.Wt, (long)taps * p.Cin, p.Cout, p.ldw, 32, true);
     } else {
         ok &= make_map_2d(&mapA, p.Y, p.Cout, p.M, p.ldy, 32, true);
@@ -1229,12 +1286,12 @@ static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     constexpr int smem = tc_smem_bytes<BN>();
     static bool attr_set = false;
     if (!attr_set) {
-        MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN, OP, CN, CSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MPB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_tma_kernel<BN, OP, CN, CSK, H3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const bool pdl = tc_gemm_pdl();
     if (CN == 1 && !CSK && !pdl) {
-        tc_gemm_tma_kernel<BN, OP, CN, CSK><<<grid, tma_threads<BN>(), smem, s>>>(p, mapA, mapB);
+        tc_gemm_tma_kernel<BN, OP, CN, CSK, H3><<<grid, tma_threads<BN>(), smem, s>>>(p, mapA, mapB);
         MPB_LAUNCH_CHECK();
         return 0;
     }
@@ -1259,7 +1316,7 @@ static int launch_tma_cn(const TcGemmParams& p, dim3 grid, cudaStream_t s) {
     }
     cfg.attrs = at;
     cfg.numAttrs = na;
-    MPB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_tma_kernel<BN, OP, CN, CSK>, p, mapA, mapB));
+    MPB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_tma_kernel<BN, OP, CN, CSK, H3>, p, mapA, mapB));
     count_launch();
     return 0;
 }
@@ -1334,6 +1391,30 @@ int tc_gemm_x3_launch(const TcGemmParams& p, int BN, cudaStream_t s) {
     dim3 grid(ceil_div(p.M, kTcBM), p.Cout / BN, p.ksplit);
     if (grid.y > 65535 || grid.z > 65535) return -1;
     return BN == 64 ? launch_x3<64>(p, grid, s) : launch_x3<128>(p, grid, s);
+}
+
+// fp16-split forward GEMM (see the H3 branch of tc_gemm_tma_kernel): FWD only, whole images in the pixel grid (TMA
+// path), split-K in both forms of the single-pass kernel.
+int tc_gemm_h3_launch(const TcGemmParams& p, int BN, cudaStream_t s) {
+    if (p.op != TC_FWD || p.M <= 0 || p.Cin <= 0 || p.Cout <= 0 || p.ksplit < 1) return -1;
+    if (BN != 64 && BN != 128 && BN != 256) return -1;
+    if (!p.X16 || !p.W16 || !p.out) return -1;
+    if (p.Cin % kTcBK || p.Cout % BN || p.ldo % 4 || p.ldx % 4 || p.ldw % 4) return -1;
+    if (p.M % (p.H * p.W) != 0 || !tma_api_ready()) return -1;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    if (!al16(p.out) || !al16(p.out_r) || !al16(p.res) || !al16(p.mask) || !al16(p.scale) || !al16(p.shift) ||
+        !al16(p.scale2) || !al16(p.colsum) || !al16(p.out16) || !al16(p.X16) || !al16(p.W16))
+        return -1;
+    if ((p.res && p.ldr % 4) || (p.mask && p.ldm % 4) || (p.out_r && p.ldor % 4) || (p.out16 && p.ldo16 % 32)) return -1;
+    const int taps = p.kh * p.kw;
+    const int nkb_ = taps * (p.Cin / kTcBK);
+    if (p.ksplit > 1 && (p.ksplit - 1) * ceil_div(nkb_, p.ksplit) >= nkb_) return -1;
+    if (p.ksplit > 1 && !p.atomic) return -1;      // cluster split-K: not instantiated for h3
+    dim3 grid(ceil_div(p.M, kTcBM), p.Cout / BN, p.ksplit);
+    if (grid.y > 65535 || grid.z > 65535) return -1;
+    if (BN == 64) return launch_tma_cn<64, TC_FWD, 1, false, true>(p, grid, s);
+    if (BN == 128) return launch_tma_cn<128, TC_FWD, 1, false, true>(p, grid, s);
+    return launch_tma_cn<256, TC_FWD, 1, false, true>(p, grid, s);
 }
 
 static int g_tc_mode = -1;   // 0 = cp.async producers, 1 = TMA producers

@@ -55,7 +55,8 @@ constexpr int tc_smem_bytes() {
 }
 
 int tc_gemm_launch(const TcGemmParams& p, int BN, cudaStream_t s);
-int tc_gemm_x3_launch(const TcGemmParams& p, int BN, cudaStream_t s);   // 3xTF32 forward variant (opt-in)
+int tc_gemm_x3_launch(const TcGemmParams& p, int BN, cudaStream_t s);   // 3xTF32 forward variant
+int tc_gemm_h3_launch(const TcGemmParams& p, int BN, cudaStream_t s);   // fp16 hi/lo split forward variant
 int tc_gemm_mode();            // 0 = cp.async producers, 1 = TMA producers (default)
 void tc_gemm_set_mode(int m);
 void tc_gemm_set_cluster(int c);  // max CTAs per cluster for A-tile multicast (1 = off, default)

@@ -24,6 +24,7 @@ class TcGemmParams(ctypes.Structure):
         ("scale2", c_p), ("rowscale", c_p), ("colsum", c_p),
         ("relu", c_i), ("round_tf32", c_i), ("atomic", c_i), ("ksplit", c_i),
         ("out_r", c_p), ("ldor", c_i),
+        ("X16", c_p), ("W16", c_p), ("out16", c_p), ("ldo16", c_i), ("overflow", c_p),
     ]
 
 
@@ -43,6 +44,7 @@ class HeadsIO(ctypes.Structure):
         ("d_prop_y", c_p), ("d_prop_z", c_p),
         ("d_feat2", c_p), ("ldd2", c_i),
         ("maskstats", c_p),
+        ("xyz_loss_mode", c_i), ("xyz_loss_weight", c_f),
     ]
 
 
@@ -50,6 +52,11 @@ class BnLayer(ctypes.Structure):
     _fields_ = [("w", c_p), ("gamma", c_p), ("beta", c_p), ("mean", c_p), ("var", c_p), ("wf", c_p), ("scale", c_p),
                 ("shift", c_p), ("dw", c_p), ("dbeta", c_p), ("dgamma", c_p), ("cout", c_i), ("K", c_i), ("row0", c_i),
                 ("pad_", c_i)]
+
+
+class W16Layer(ctypes.Structure):
+    _fields_ = [("w", c_p), ("gamma", c_p), ("var", c_p), ("w16", c_p), ("inv_scale", c_p), ("cout", c_i), ("K", c_i),
+                ("row0", c_i), ("pad_", c_i)]
 
 
 class OptChunk(ctypes.Structure):
@@ -79,6 +86,9 @@ _SIGS = {
     "mpb_resize_ac_bwd": [c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
     "mpb_bn_train_fwd": [c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
     "mpb_tc_gemm_x3": [c_p, c_i, c_p],
+    "mpb_tc_gemm_h3": [c_p, c_i, c_p],
+    "mpb_split16": [c_l, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p],
+    "mpb_split16_weights_multi": [c_i, c_p, c_p, c_f, c_p],
     "mpb_set_operand_rounding": [c_i],
     "mpb_bn_infer_fwd": [c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
     "mpb_bn_train_bwd": [c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
@@ -95,6 +105,9 @@ _SIGS = {
     "mpb_heads_mid": [ctypes.POINTER(HeadsIO), c_p],
     "mpb_heads_final": [ctypes.POINTER(HeadsIO), c_i, c_p],
     "mpb_heads_bwd_mid": [ctypes.POINTER(HeadsIO), c_p],
+    "mpb_pointset_mask": [c_l, c_p, c_p, c_p, c_p, c_p, c_p],
+    "mpb_pointset_loss_add": [c_l, c_p, c_l, c_p, c_f, c_p, c_i, c_i, c_p, c_l, c_f, c_p],
+    "mpb_pointset_grad_add": [c_l, c_p, c_p, c_f, c_p, c_p],
     "mpb_gt_xyz_from_depth": [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p],
     "mpb_image_inputs": [c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p],
     "mpb_opt_step_range": [c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_f, c_f, c_p],

@@ -428,13 +428,49 @@ def regression_targets(out, S):
     }
 
 
-def loss(out, S):
-    """monopsr_model.py:554-958 with the weights of monopsr_model_000.yaml:102-118."""
+def chamfer_loss(pred, gt, valid):
+    """losses_custom.ChamferDistance (losses_custom.py:169-198): both maps times the mask, (B, h*w, 3) clouds, squared
+    nearest-neighbour distances in both directions, sum / B"""
+    B = pred.shape[0]
+    p, t = (pred * valid).reshape(B, -1, 3), (gt * valid).reshape(B, -1, 3)
+    tot = 0.0
+    for b in range(B):
+        d = ((p[b][:, None, :] - t[b][None, :, :]) ** 2).sum(-1)
+        tot = tot + d.min(1).values.sum() + d.min(0).values.sum()
+    return tot / B
+
+
+def emd_loss(pred, gt, valid, match_fn):
+    """losses_custom.EarthMoversDistance (losses_custom.py:135-166): match = approx_match(p, t) is a constant
+    (ops.NoGradient), cost_b = sum_{l,k} match[l,k] * ||t_l - p_k||, sum / B.  match_fn(p, t) -> (B, m, n) supplies the
+    matching (the CPU oracle of the op, or the op itself, which is checked against that oracle separately)"""
+    B = pred.shape[0]
+    p, t = (pred * valid).reshape(B, -1, 3), (gt * valid).reshape(B, -1, 3)
+    match = match_fn(p.detach(), t.detach())
+    tot = 0.0
+    for b in range(B):
+        d2 = ((t[b][:, None, :] - p[b][None, :, :]) ** 2).sum(-1)
+        # the gradient of the op clamps the squared distance at 1e-20 (tf_approxmatch_g.cu:243,281): sqrt(0) has none
+        tot = tot + (match[b].to(d2.dtype) * torch.sqrt(d2.clamp_min(1e-20))).sum()
+    return tot / B
+
+
+def loss(out, S, xyz_loss=("smooth_l1_nonzero", 100.0), match_fn=None):
+    """monopsr_model.py:554-958 with the weights of monopsr_model_000.yaml:102-118.  xyz_loss: the yaml entry
+    loss_config.inst_xyz_map_local = [type, weight] (loss_builder.py:19-84)."""
     N = NUM_BOXES
     valid = S["gt_valid_mask_maps"]
     L = {}
-    L["inst_xyz_map_local"] = 100.0 * smooth_l1_nonzero(out["inst_xyz_map_local"],
-                                                        S["gt_inst_xyz_maps_local"], valid) / N
+    kind, weight = xyz_loss
+    if kind == "smooth_l1_nonzero":
+        xl = smooth_l1_nonzero(out["inst_xyz_map_local"], S["gt_inst_xyz_maps_local"], valid)
+    elif kind == "chamfer_dist":
+        xl = chamfer_loss(out["inst_xyz_map_local"], S["gt_inst_xyz_maps_local"], valid)
+    elif kind == "emd":
+        xl = emd_loss(out["inst_xyz_map_local"], S["gt_inst_xyz_maps_local"], valid, match_fn)
+    else:
+        raise ValueError("Invalid loss type", kind)
+    L["inst_xyz_map_local"] = weight * xl / N
     T = regression_targets(out, S)
     L["lwh_offs"] = 1.0 * huber(out["lwh_offs"] - T["lwh_offs"]).sum() / N
     eps = 0.001

@@ -24,3 +24,12 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.fail("this test is marked gpu but no CUDA device is visible")
     return torch.device("cuda:0")
+
+
+@pytest.fixture
+def tf32_rounding(cuda):
+    """kernel unit tests that pin the tf32 rounding of operand producers: put the library's process-wide switch into
+    its default state (an x3 / h3 engine of an earlier test leaves it off)"""
+    from monopsr_b200.core.engine import Engine
+    Engine.set_library_rounding(cuda, 1)
+    return cuda

@@ -30,7 +30,7 @@ class StubEngine(object):
             open(prefix + ext, "wb").close()
         self.calls.append(("save", global_step))
 
-    def load_checkpoint(self, prefix, kind="monopsr", use_ema=False):
+    def load_checkpoint(self, prefix, kind="monopsr", use_ema=False, resume=False):
         self.loaded.append((os.path.basename(prefix), kind, use_ema))
         return {"loaded": [], "missing": []}
 
@@ -97,7 +97,8 @@ def test_evaluator_writes_predictions(tmp_path):
           P.SAMPLE_CAM_P: S["cam_p"], P.SAMPLE_LABEL_SCORES: np.linspace(0.3, 0.9, 32).astype(np.float32),
           P.SAMPLE_LABEL_BOXES_2D: S["boxes_2d"]}
     res = ev.run_checkpoint_once("/ckpts/monopsr_model-00120000", [(S, sd)])
-    assert res["num_samples"] == 1 and eng.loaded == [("monopsr_model-00120000", "monopsr", True)]
+    # the RAW variables, as the reference's evaluator restores them (plain tf.train.Saver: core/evaluator.py:125,144)
+    assert res["num_samples"] == 1 and eng.loaded == [("monopsr_model-00120000", "monopsr", False)]
     assert ("forward", False) in eng.calls
     b3 = np.loadtxt(os.path.join(dirs[P.OUT_DIR_BOX_3D], "000007.txt"))
     b2 = np.loadtxt(os.path.join(dirs[P.OUT_DIR_BOX_2D], "000007.txt"))

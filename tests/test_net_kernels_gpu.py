@@ -9,7 +9,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("tf32_rounding")]
 
 from monopsr_b200 import lib as mlib  # noqa: E402
 from monopsr_b200.lib_net import HeadsIO, OptChunk  # noqa: E402
@@ -275,6 +275,7 @@ def test_heads_losses_and_gradients_vs_oracle(cuda):
     feat1, feat2 = e(N, 1088), e(N, 1088)
     d_feat2 = rnd(N, 1088, seed=6, scale=0.01)
     io = HeadsIO()
+    io.xyz_loss_mode, io.xyz_loss_weight = 0, 100.0
     io.nbox = N
     for k in ("boxes_2d", "cam_p", "class_indices", "mean_lwh", "prop_cen_z_offset", "est_view_angs", "boxes_3d",
               "gt_alpha_bins", "gt_alpha_regs", "gt_alpha_valid_bins", "gt_view_angs"):

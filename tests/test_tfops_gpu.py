@@ -177,6 +177,7 @@ def _match_close(got, exp, what):
 @pytest.mark.parametrize("b,n,m,seed,masked", [
     (1, 1, 1, 0, 0), (2, 3, 3, 1, 0), (3, 37, 53, 11, 0), (2, 64, 64, 12, 0.4), (2, 128, 256, 13, 0),
     (4, 512, 512, 14, 0), (32, 200, 200, 15, 0), (1, 1024, 1024, 200, 0), (3, 700, 100, 16, 0),
+    (2, 2304, 72, 17, 0.4), (1, 1028, 37, 18, 0), (2, 1026, 50, 19, 0),      # column slabs > 1, row-tile tails, n % 4 != 0
 ])
 def test_emd_vs_oracle(cuda, b, n, m, seed, masked):
     x, y = _clouds(b, n, m, seed, masked)

@@ -10,6 +10,7 @@ def planner(csk=1, csk_bn=128, ctas128=2, fill=0.9, sms=148):
     e = Engine.__new__(Engine)          # no device: only the planning attributes
     e.sms, e.fill, e.csk, e.csk_bn = sms, fill, csk, csk_bn
     e.ctas_per_sm = {64: 2, 128: ctas128, 256: 1}
+    e.h3 = e.x3 = False
     return e
 
 
@@ -82,7 +83,7 @@ def test_x3_mode_dispatch_of_forward_gemms():
     assert e.L.calls[0][1:] == (128, 0, None, 1, 0)          # planner would have asked for a 2-CTA cluster: dropped
     assert e.L.calls[1][1] == 64 and e.L.calls[2][1:] == (128, 0, None, 4, 1)      # atomic split-K is kept
     assert e.L.calls[3][2] == 1 and e.L.calls[3][4] == 2     # the backward launch is planned as before
-    assert [r[1] for r in e._record] == [-128, -64, -128, 128]
+    assert [(r[1], r[3]) for r in e._record] == [(128, "x3"), (64, "x3"), (128, "x3"), (128, "tf32")]
     e.x3 = False
     e.gemm(TC_FWD, 6080, 40, 152, 3, 2, 256, 256, x, 256, w, 2304, o, 256, relu=1, round_tf32=1, out_r=o2, ldor=256)
     assert e.L.calls[-1][0] == "tf32" and e.L.calls[-1][2] == 1 and e.L.calls[-1][3] == o2.data_ptr()

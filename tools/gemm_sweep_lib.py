@@ -29,12 +29,14 @@ spin_up()
 _side = torch.cuda.Stream(device=dev)
 
 
-def time_it(p, bn, n=20, x3=False):
+def time_it(p, bn, n=20, x3=False, kind=None):
     """n back-to-back launches replayed as ONE CUDA graph (the ctypes + tensor-map-encode launch path costs
     ~10 us of CPU per call, more than the shorter kernels run), timed with CUDA events; us per launch.
     x3: the 3xTF32 forward variant (mpb_tc_gemm_x3) instead of the single-pass kernel"""
     st = ctypes.c_void_p(_side.cuda_stream)
     launch = L.mpb_tc_gemm_x3 if x3 else L.mpb_tc_gemm
+    if kind is not None:
+        launch = {"tf32": L.mpb_tc_gemm, "x3": L.mpb_tc_gemm_x3, "h3": L.mpb_tc_gemm_h3}[kind]
     with torch.cuda.stream(_side):
         for _ in range(2):
             if launch(ctypes.byref(p), bn, st) != 0:
