@@ -137,6 +137,10 @@ typedef struct mpb_bn_layer {
 } mpb_bn_layer;
 int mpb_fold_bn_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream);
 int mpb_bn_param_grad_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream);
+/* the same over rows [row_begin, row_end) of the table: d(gamma) of a group of layers as soon as their weight gradients
+ * are final (the data-parallel step all-reduces the tower gradients bucket by bucket under the backward pass) */
+int mpb_bn_param_grad_range(int row_begin, int row_end, const mpb_bn_layer* layers, const int* row2layer, float eps,
+                            void* stream);
 
 /* ---- stem: conv2d_same(7x7, stride 2) + frozen BN + ReLU  (nets/resnet_v1.py:234) ---- */
 int mpb_stem_fwd(int nimg, int Hin, int Win, const float* x, const float* wf, const float* shift, float* y, void* stream);
@@ -157,6 +161,15 @@ int mpb_crop_pool_bwd(int H, int W, int C, const float* feat, int nbox, const fl
 
 /* ---- tf.image.resize_images(align_corners=True) (net_builder.py:73-75,82-84) ---- */
 int mpb_resize_ac_fwd(int nimg, int H, int W, int C, const float* x, int OH, int OW, float* y, void* stream);
+/* ...16: the same kernels, writing ALSO the fp16 hi/lo split copy of y (y16, same geometry, [hi | lo] blocks; C % 32 == 0)
+ * that the h3 forward GEMM consumes -- saves a separate mpb_split16 pass over the decoder activations. */
+int mpb_resize_ac_fwd16(int nimg, int H, int W, int C, const float* x, int OH, int OW, float* y, void* y16, int* overflow,
+                        void* stream);
+int mpb_bn_train_fwd16(int M, int C, const float* z, const float* beta, float eps, float* y, float* mean, float* var,
+                       float* moving_mean, float* moving_var, float decay, double* scratch, void* y16, int* overflow,
+                       void* stream);
+int mpb_bn_infer_fwd16(int M, int C, const float* z, const float* beta, const float* moving_mean, const float* moving_var,
+                       float eps, float* y, void* y16, int* overflow, void* stream);
 int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, int OH, int OW, float* dx, void* stream); /* overwrites dx (gather form, no atomics) */
 
 /* ---- slim.batch_norm(is_training=True) + ReLU of the map decoder (net_builder.py:77-89) ----

@@ -105,11 +105,13 @@ class Engine:
         self.s_wc = torch.cuda.Stream(device=self.dev)
         self.s_wf = torch.cuda.Stream(device=self.dev)
         self.s_opt = torch.cuda.Stream(device=self.dev)
+        self.s_ar = torch.cuda.Stream(device=self.dev)      # d(gamma) + all-reduce issue of the gradient buckets
         self.early_opt = False      # set by the single-GPU train step: head train-op under the towers' backward
         self._grads_zeroed = False
         self.overlap = True
         self.fill = float(os.environ.get("MPB_TILE_FILL", "0.9"))   # min fraction of SMs a launch must fill before widening tiles
         self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
+        self.shortk_bn = int(os.environ.get("MPB_SHORTK_BN", "64"))      # tile width of short, epilogue-bound reductions
         self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "128"))
         self.wgrad_fill = float(os.environ.get("MPB_WGRAD_FILL", "0.5"))   # target CTAs / SMs when choosing split-K
         # cluster split-K (DSMEM reduce) for long reductions: faster per launch (profiles/r1_gemm_sweep.txt), but the
@@ -443,8 +445,8 @@ class Engine:
             if bn in tiles and tiles[bn] >= lo:
                 # short reductions are epilogue-bound: once the grid needs a second wave anyway, 64-wide
                 # tiles (two CTAs per SM, one's epilogue under the other's main loop) win
-                if nkb <= 8 and tiles[bn] > self.sms and 64 in tiles:
-                    break
+                if nkb <= 8 and tiles[bn] > self.sms and self.shortk_bn in tiles:
+                    return self.shortk_bn, 1
                 return bn, 1
         for bn in (64, 128, 256):
             if bn in tiles:
@@ -553,7 +555,7 @@ class Engine:
     # ------------------------------------------------------------------ weight preparation
     def _build_bn_table(self):
         """device table of every frozen-BN conv of both towers (one launch folds / differentiates them all)"""
-        self.bnfold = {}
+        self.bnfold, self.bn_row0 = {}, {}
         layers = []
         for enc in ms.ENCODERS:
             for scope, k, cin, cout, _ in ms.conv_layers(enc):
@@ -570,6 +572,7 @@ class Engine:
             e.wf, e.scale, e.shift = self.pview(scope + "/weights").data_ptr(), self.bnfold[scope][0].data_ptr(), self.bnfold[scope][1].data_ptr()
             e.dw, e.dbeta, e.dgamma = self.gview(scope + "/weights").data_ptr(), self.gview(b + "beta").data_ptr(), self.gview(b + "gamma").data_ptr()
             e.cout, e.K, e.row0 = cout, K, row
+            self.bn_row0[scope] = row
             row2layer += [i] * cout
             row += cout
         self.bn_rows = row
@@ -777,31 +780,32 @@ class Engine:
         if not features_only:
             with self._side(self.s_fc):
                 self._fc_forward()
-        self._chk(L.mpb_resize_ac_fwd(N, 12, 12, 512, _ptr(self.squashed), 24, 24, _ptr(self.r1), st), "resize1")
-        self._split(self.r1, N * 576, 512, 512)
+        s16 = (lambda t: _ptr(self.s16(t))) if self.h3 else (lambda t: None)      # split copies written by the producers
+        ovf = _ptr(self.overflow) if self.h3 else None
+        self._chk(L.mpb_resize_ac_fwd16(N, 12, 12, 512, _ptr(self.squashed), 24, 24, _ptr(self.r1), s16(self.r1), ovf, st),
+                  "resize1")
         x = self.r1
         for i, D in enumerate(self.dec):
             if i == 2:
-                self._chk(L.mpb_resize_ac_fwd(N, 24, 24, 256, _ptr(x), 48, 48, _ptr(self.r2), st), "resize2")
-                self._split(self.r2, N * 2304, 256, 256)
+                self._chk(L.mpb_resize_ac_fwd16(N, 24, 24, 256, _ptr(x), 48, 48, _ptr(self.r2), s16(self.r2), ovf, st),
+                          "resize2")
                 x = self.r2
             side = D["side"]
             self.gemm(TC_FWD, D["M"], side, side, 3, 1, D["cin"], D["cout"], x, D["cin"], self.pview(D["scope"] + "/weights"),
                       9 * D["cin"], D["z"], D["cout"], tapmask=self.tm24 if side == 24 else self.tm48)
             b = D["scope"] + "/BatchNorm/"
+            y16 = s16(D["y"]) if i < 3 else None         # the last decoder output feeds the (SIMT) xyz head only
             if train:      # batch statistics + moving-average update (UPDATE_OPS)
-                self._chk(L.mpb_bn_train_fwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")), BN_EPS_DECODER,
-                                             _ptr(D["y"]), _ptr(D["mean"]), _ptr(D["var"]),
-                                             _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
-                                             BN_DECAY_DECODER, _ptr(self.bn_scratch), st), "bn_train_fwd")
+                self._chk(L.mpb_bn_train_fwd16(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")), BN_EPS_DECODER,
+                                               _ptr(D["y"]), _ptr(D["mean"]), _ptr(D["var"]),
+                                               _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
+                                               BN_DECAY_DECODER, _ptr(self.bn_scratch), y16, ovf, st), "bn_train_fwd")
             else:          # validation / inference graphs are built with is_training=False: moving statistics
-                self._chk(L.mpb_bn_infer_fwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")),
-                                             _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
-                                             BN_EPS_DECODER, _ptr(D["y"]), st), "bn_infer_fwd")
+                self._chk(L.mpb_bn_infer_fwd16(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")),
+                                               _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
+                                               BN_EPS_DECODER, _ptr(D["y"]), y16, ovf, st), "bn_infer_fwd")
             D["x"] = x
             x = D["y"]
-            if i < 3:
-                self._split(x, D["M"], D["cout"], D["cout"])
         if features_only:
             return {"features_for_map": x.view(N, 48, 48, 128), "features_for_box_3d": self.pooled.view(N, 6, 6, 512)}
         sx = "output/inst_xyz_map_local/inst_xyz_map_local"
@@ -935,9 +939,10 @@ class Engine:
         self._fc_bwd(P["feat"], KPAD, P["d_feat"], KPAD, P["g_img"], self.pooled, 18432, 18432, p + "/img_fc",
                      self.d_flat, 18432, res=self.d_flat, ldr=18432)
 
-    def _tower_bwd(self, T, x_in, ws):
+    def _tower_bwd(self, T, x_in, ws, on_done=None):
         """T['units'][-1]['g_out'] holds g = dL/d(out)*(out>0) of the last unit (and its d(beta3) is set).
-        The data-gradient chain runs on the current stream, the weight gradients on `ws`."""
+        The data-gradient chain runs on the current stream, the weight gradients on `ws`.
+        on_done(ui): called when everything of unit ui (and, with ui = -1, of the stem) has been issued."""
         L = self.L
         M, h, w = T["M"], T["h"], T["w"]
         units = T["units"]
@@ -981,6 +986,8 @@ class Engine:
                 dst, colsum = T["g_pool"], None
             self.gemm(TC_DGRAD, M, h, w, 1, 1, cin, base, U["g1"], base, self.pview(s + "/conv1/weights"), cin, dst, cin,
                       res=res, ldr=ldr, mask=x, ldm=ldx, colsum=colsum, round_tf32=1)
+            if on_done is not None:
+                on_done(ui)
         # stem
         st = self._st()
         s0 = T["enc"] + "/resnet_v1_101/conv1"
@@ -991,6 +998,8 @@ class Engine:
                                         _ptr(self.gview(s0 + "/BatchNorm/beta")), st), "stem_colsum")
         self._chk(L.mpb_stem_wgrad(T["nimg"], T["Hin"], T["Win"], _ptr(x_in), _ptr(T["g_stem"]), _ptr(self.bnfold[s0][0]),
                                    _ptr(self.gview(s0 + "/weights")), st), "stem_wgrad")
+        if on_done is not None:
+            on_done(-1)
 
     def backward(self):
         """head part (FC stacks, decoder, squash: every gradient outside the towers), then the two towers"""
@@ -1062,10 +1071,87 @@ class Engine:
         if join:        # the gradients of the head variables are complete on THIS stream (bucketed all-reduce)
             self._join(self.s_wf, self.s_fc)
 
-    def _backward_towers(self):
+    # ---- data parallelism: the tower gradients leave in buckets, under the rest of the backward pass
+    def _dp_plan(self, nbuckets):
+        """Buckets of the towers' gradient arena in the order the backward pass completes them.  Bucket j = the units
+        cut[j] <= u < cut[j-1] of BOTH towers (the same units of the two towers finish at about the same time; the last
+        bucket ends with the stems): per tower one contiguous arena range and one contiguous range of rows of the
+        frozen-BN table.  Cuts are placed so that every bucket carries about the same number of bytes."""
+        if getattr(self, "bn_layers", None) is None:
+            self._build_bn_table()
+        towers = []
+        for ti, enc in enumerate(ms.ENCODERS):
+            units = self.towers[enc]["units"]
+            first = lambda U: U["scope"] + ("/shortcut" if U["proj"] else "/conv1")
+            start = self.layout[enc + "/resnet_v1_101/conv1/weights"][1]
+            end = self.layout[ms.ENCODERS[1] + "/resnet_v1_101/conv1/weights"][1] if ti == 0 else self.round_off
+            offs = [self.layout[first(U) + "/weights"][1] for U in units] + [end]
+            rows = [self.bn_row0[first(U)] for U in units]
+            row_start = self.bn_row0[enc + "/resnet_v1_101/conv1"]
+            row_end = self.bn_row0[ms.ENCODERS[1] + "/resnet_v1_101/conv1"] if ti == 0 else self.bn_rows
+            towers.append(dict(start=start, offs=offs, rows=rows + [row_end], row_start=row_start))
+        t0 = towers[0]
+        nu = len(t0["offs"]) - 1
+        total = t0["offs"][-1] - t0["start"]
+        cuts, acc, hi = [], 0, nu
+        for u in range(nu - 1, 0, -1):
+            acc = t0["offs"][hi] - t0["offs"][u]
+            if len(cuts) < nbuckets - 1 and acc >= total / nbuckets:
+                cuts.append(u)
+                hi = u
+        plan = []
+        prev = nu
+        for c in cuts + [None]:
+            rng, rws = [], []
+            for t in towers:
+                a = t["start"] if c is None else t["offs"][c]
+                rng.append((a, t["offs"][prev]))
+                rws.append((t["row_start"] if c is None else t["rows"][c], t["rows"][prev]))
+            plan.append(dict(unit=-1 if c is None else c, ranges=rng, rows=rws))
+            prev = c
+        return plan
+
+    def _dp_issue(self, bucket, events):
+        """d(gamma) of the bucket's layers, then its all-reduce, on the side stream s_ar -- after the events that mark
+        the bucket's gradients final on the data-gradient and weight-gradient streams of both towers"""
+        import torch.distributed as dist
+        with torch.cuda.stream(self.s_ar):
+            for ev in events:
+                self.s_ar.wait_event(ev)
+            for r0, r1 in bucket["rows"]:
+                self._chk(self.L.mpb_bn_param_grad_range(r0, r1, _ptr(self.bn_layers), _ptr(self.bn_row2layer), BN_EPS_RESNET,
+                                                         self._st()), "bn_param_grad_range")
+            for a, b in bucket["ranges"]:
+                self._dp_works.append(dist.all_reduce(self.grads[a:b], op=dist.ReduceOp.SUM, async_op=True))
+
+    def _backward_towers(self, dp_plan=None):
         L, st, N, I = self.L, self._st(), self.N, self.inputs
         Tc, Tf = self.towers[ms.ENCODERS[0]], self.towers[ms.ENCODERS[1]]
         lastf = Tf["units"][-1]
+        if dp_plan is not None:
+            by_unit = {bk["unit"]: j for j, bk in enumerate(dp_plan)}
+            marks = {}
+
+            def cb(ti, ws):
+                def on_done(ui):
+                    j = by_unit.get(ui)
+                    if j is None:
+                        return
+                    marks.setdefault(j, []).extend([self._cur().record_event(), ws.record_event()])
+                    if ti == 0:                       # the crop tower is issued last: both towers' marks exist now
+                        self._dp_issue(dp_plan[j], marks[j])
+                return on_done
+            with self._side(self.s_full):
+                self._chk(L.mpb_crop_pool_bwd(Tf["h"], Tf["w"], 1024, _ptr(lastf["o"]), N, _ptr(I["boxes_2d_norm"]), 24,
+                                              _ptr(self.g_fullcrop), 1024, _ptr(self.d_fullfeat), self._st()), "crop_pool_bwd")
+                self._chk(L.mpb_relu_bwd_colsum(Tf["M"], 1024, _ptr(lastf["o"]), 1024, _ptr(self.d_fullfeat), 1024,
+                                                _ptr(lastf["g_out"]), 1024,
+                                                _ptr(self.gview(lastf["scope"] + "/conv3/BatchNorm/beta")), self._st()),
+                          "full_relu_bwd")
+                self._tower_bwd(Tf, I["full_img"], self.s_wf, on_done=cb(1, self.s_wf))
+            self._tower_bwd(Tc, I["rgb_crops"], self.s_wc, on_done=cb(0, self.s_wc))
+            self._join(self.s_full, self.s_wf, self.s_wc)
+            return
         with self._side(self.s_full):
             self._chk(L.mpb_crop_pool_bwd(Tf["h"], Tf["w"], 1024, _ptr(lastf["o"]), N, _ptr(I["boxes_2d_norm"]), 24,
                                           _ptr(self.g_fullcrop), 1024, _ptr(self.d_fullfeat), self._st()), "crop_pool_bwd")
@@ -1106,7 +1192,7 @@ class Engine:
         else:
             raise NotImplementedError("learning_rate_type %r" % kind)
         self.ema_decay = float(a.moving_average_decay) if getattr(a, "use_moving_average", False) else 0.0
-        self._graph = self._g_fb = None          # the EMA decay is baked into a captured train-op launch
+        self._graph = self._g_fb = self._g_dp = None          # the EMA decay is baked into a captured train-op launch
 
     def learning_rate(self, step):
         """tf.train.exponential_decay (yaml:145-150): lr * factor ^ (step / decay_steps), floored when staircase"""
@@ -1161,8 +1247,15 @@ class Engine:
         self.set_hyper(self.step_count)
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if distributed:
-            # graphs around the NCCL all-reduces (kept out of capture for portability)
+        if distributed and int(os.environ.get("MPB_DP_GRAPH", "1")):
+            # ONE graph for the whole data-parallel step, NCCL all-reduces captured inside it: the head bucket leaves
+            # under the towers' backward pass, the tower gradients leave in MPB_DP_BUCKETS buckets (d(gamma) + all-reduce
+            # on a side stream) as the backward pass completes them; only the last bucket is exposed
+            if getattr(self, "_g_dp", None) is None:
+                self._capture_dp()
+            self._g_dp.replay()
+        elif distributed:
+            # three graphs around two NCCL all-reduces issued from the host (MPB_DP_GRAPH=0)
             if getattr(self, "_g_fb", None) is None:
                 self._capture_split()
             from . import dp
@@ -1210,6 +1303,38 @@ class Engine:
                 self.prepare_weights()
         self.launches_per_step = _lib.launch_count() - c0
         self._graph = g
+
+    def dp_step_eager(self, nbuckets=None):
+        """the data-parallel step, launch by launch (also what _capture_dp records): forward, head backward, head bucket
+        all-reduce || towers' backward with bucketed all-reduces, train-op on the mean gradient"""
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        plan = self._dp_plan(nbuckets or int(os.environ.get("MPB_DP_BUCKETS", "4")))
+        self.forward(train=True)
+        self._backward_head(join=True)
+        self._dp_works = []
+        self._dp_issue(dict(rows=[], ranges=[(self.round_off, self.n_train)]), [self._cur().record_event()])
+        self._backward_towers(dp_plan=plan)
+        for w in self._dp_works:
+            w.wait()                                   # the current stream waits for NCCL's
+        self._cur().wait_stream(self.s_ar)
+        self._dp_works = []
+        self.optimizer_step(1.0 / world)
+        self.prepare_weights()
+
+    def _capture_dp(self):
+        import torch.distributed as dist
+        if not self._prepared:
+            self.prepare_weights()
+        warm = torch.zeros(8, device=self.dev)
+        dist.all_reduce(warm)                          # communicator set-up outside the capture
+        self._warm()
+        g = torch.cuda.CUDAGraph()
+        c0 = _lib.launch_count()
+        with torch.cuda.graph(g, stream=self.s_main, capture_error_mode="thread_local"):
+            self.dp_step_eager()
+        self.launches_per_step = _lib.launch_count() - c0
+        self._g_dp = g
 
     def _capture_split(self):
         import torch.distributed as dist

@@ -509,18 +509,17 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return y;
 }
 
-// kMsBatch rows of this thread's 4 columns.  The full-batch path has NO predicates: ptxas then issues all eight
-// LDG.128 back to back (with per-row predicates it sank each load next to its use: 1-2 loads in flight per thread,
-// 3 TB/s); the ordering fence keeps the loads ahead of the arithmetic.
-__device__ __forceinline__ void ms_load_batch(float4 (&w)[kMsBatch], const float* p, int n, int rows_left) {
-    if (rows_left >= kMsBatch) {
-#pragma unroll
-        for (int r = 0; r < kMsBatch; r++) w[r] = ldcs4(p + (size_t)r * n);
-    } else {
-#pragma unroll
-        for (int r = 0; r < kMsBatch; r++) w[r] = r < rows_left ? ldcs4(p + (size_t)r * n) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    asm volatile("" ::: "memory");
+// One row of this thread's 4 columns (zero beyond the tile).  The kernels keep a RING of kMsBatch such loads per thread:
+// slot j is consumed and immediately refilled with the row kMsBatch further down, so eight LDG.128 per thread are in
+// flight at every moment of the CTA's life -- including its prologue, because the ring is primed before the query
+// points are staged.  (The first version loaded eight rows, waited, computed, loaded the next eight: 3.8 TB/s.)
+// The load itself is UNCONDITIONAL (row clamped into the tile, inactive threads point at column 0): ptxas sinks
+// predicated loads down to their first use, which would serialise the ring; out-of-range values are zeroed at use.
+__device__ __forceinline__ float4 ms_ld(const float* mt, int r, int rows, int n) {
+    return ldcs4(mt + (size_t)min(r, rows - 1) * n);
+}
+__device__ __forceinline__ float4 ms_use(float4 v, bool valid) {
+    return valid ? v : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // the four dataset points of this thread as packed pairs: X01 = {x0,x1}, X23 = {x2,x3}, ...
@@ -552,6 +551,9 @@ matchcost_stream_kernel(int n, int m, int rows_per_tile, const float* __restrict
     const int k = slab * kMsSlab + tid * 4;
     const bool act = k < n;
     const float* mt = match + ((size_t)bi * m + l0) * n + (act ? k : 0);
+    float4 w[kMsBatch];
+#pragma unroll
+    for (int j = 0; j < kMsBatch; j++) w[j] = ms_ld(mt, j, rows, n);
     for (int t = tid; t < rows_per_tile; t += kMsThreads) {
         const int l = l0 + min(t, rows - 1);
         ms_q[t] = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
@@ -560,19 +562,20 @@ matchcost_stream_kernel(int n, int m, int rows_per_tile, const float* __restrict
     __syncthreads();
     uint64_t acc = pk(0.f, 0.f);
     for (int r0 = 0; r0 < rows; r0 += kMsBatch) {
-        float4 w[kMsBatch];
-        ms_load_batch(w, mt + (size_t)r0 * n, n, act ? rows - r0 : 0);
 #pragma unroll
-        for (int r = 0; r < kMsBatch; r++) {
-            const float4 q = ms_q[r0 + r];
+        for (int j = 0; j < kMsBatch; j++) {
+            const float4 cur = ms_use(w[j], act && r0 + j < rows);
+            w[j] = ms_ld(mt, r0 + kMsBatch + j, rows, n);
+            asm volatile("" ::: "memory");        // keep the refill HERE: eight rows ahead of its use
+            const float4 q = ms_q[min(r0 + j, rows_per_tile - 1)];
             const uint64_t qx = pk(q.x, q.x), qy = pk(q.y, q.y), qz = pk(q.z, q.z);
             uint64_t dx = sub2(c.x01, qx), dy = sub2(c.y01, qy), dz = sub2(c.z01, qz);
             float a0, a1, a2, a3;
             upk(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), a0, a1);
             dx = sub2(c.x23, qx); dy = sub2(c.y23, qy); dz = sub2(c.z23, qz);
             upk(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), a2, a3);
-            acc = fma2(pk(sqrt_approx(a0), sqrt_approx(a1)), pk(w[r].x, w[r].y), acc);
-            acc = fma2(pk(sqrt_approx(a2), sqrt_approx(a3)), pk(w[r].z, w[r].w), acc);
+            acc = fma2(pk(sqrt_approx(a0), sqrt_approx(a1)), pk(cur.x, cur.y), acc);
+            acc = fma2(pk(sqrt_approx(a2), sqrt_approx(a3)), pk(cur.z, cur.w), acc);
         }
     }
     float lo, hi;
@@ -630,6 +633,9 @@ matchcostgrad_stream_kernel(int n, int m, int rows_per_tile, const float* __rest
     const int k = slab * kMsSlab + tid * 4;
     const bool act = k < n;
     const float* mt = match + ((size_t)bi * m + l0) * n + (act ? k : 0);
+    float4 w[kMsBatch];
+#pragma unroll
+    for (int j = 0; j < kMsBatch; j++) w[j] = ms_ld(mt, j, rows, n);
     for (int t = tid; t < rows_per_tile; t += kMsThreads) {
         const int l = l0 + min(t, rows - 1);
         ms_q[t] = make_float4(p2[l * 3], p2[l * 3 + 1], p2[l * 3 + 2], 0.f);
@@ -638,11 +644,12 @@ matchcostgrad_stream_kernel(int n, int m, int rows_per_tile, const float* __rest
     __syncthreads();
     uint64_t gx01 = pk(0.f, 0.f), gx23 = gx01, gy01 = gx01, gy23 = gx01, gz01 = gx01, gz23 = gx01;
     for (int r0 = 0; r0 < rows; r0 += kMsBatch) {
-        float4 w[kMsBatch];
-        ms_load_batch(w, mt + (size_t)r0 * n, n, act ? rows - r0 : 0);
         float v[kMsBatch * 3];
 #pragma unroll
         for (int r = 0; r < kMsBatch; r++) {
+            const float4 cur = ms_use(w[r], act && r0 + r < rows);
+            w[r] = ms_ld(mt, r0 + kMsBatch + r, rows, n);
+            asm volatile("" ::: "memory");        // keep the refill HERE: eight rows ahead of its use
             const float4 q = ms_q[min(r0 + r, rows_per_tile - 1)];
             const uint64_t qx = pk(q.x, q.x), qy = pk(q.y, q.y), qz = pk(q.z, q.z);
             const uint64_t dx0 = sub2(c.x01, qx), dy0 = sub2(c.y01, qy), dz0 = sub2(c.z01, qz);
@@ -650,8 +657,8 @@ matchcostgrad_stream_kernel(int n, int m, int rows_per_tile, const float* __rest
             float a0, a1, a2, a3;
             upk(fma2(dz0, dz0, fma2(dx0, dx0, mul2(dy0, dy0))), a0, a1);
             upk(fma2(dz1, dz1, fma2(dx1, dx1, mul2(dy1, dy1))), a2, a3);
-            const uint64_t w01 = pk(w[r].x * rsqrt_approx(fmaxf(a0, 1e-20f)), w[r].y * rsqrt_approx(fmaxf(a1, 1e-20f)));
-            const uint64_t w23 = pk(w[r].z * rsqrt_approx(fmaxf(a2, 1e-20f)), w[r].w * rsqrt_approx(fmaxf(a3, 1e-20f)));
+            const uint64_t w01 = mul2(pk(cur.x, cur.y), pk(rsqrt_approx(fmaxf(a0, 1e-20f)), rsqrt_approx(fmaxf(a1, 1e-20f))));
+            const uint64_t w23 = mul2(pk(cur.z, cur.w), pk(rsqrt_approx(fmaxf(a2, 1e-20f)), rsqrt_approx(fmaxf(a3, 1e-20f))));
             gx01 = fma2(dx0, w01, gx01); gy01 = fma2(dy0, w01, gy01); gz01 = fma2(dz0, w01, gz01);
             gx23 = fma2(dx1, w23, gx23); gy23 = fma2(dy1, w23, gy23); gz23 = fma2(dz1, w23, gz23);
             float s0, s1;
@@ -725,13 +732,16 @@ matchcostgrad_stream_kernel(int n, int m, int rows_per_tile, const float* __rest
     }
 }
 
-// rows per tile: a multiple of 8, at most 64, small enough that the launch has >= ~6 CTAs per SM to balance on
+// rows per tile: a multiple of 8, chosen so that the whole launch is ONE wave of long-lived CTAs where possible
+// (3 CTAs of 256 threads per SM): T = slots / (b * slabs) tiles per batch element; capped at 128 rows (shared memory
+// of the row sums), below which several waves run -- the primed ring keeps the loads flowing across CTA boundaries
 inline int ms_rows_per_tile(int b, int m, int slabs) {
     const char* e = getenv("MPB_MS_ROWS");
-    if (e && atoi(e) >= 8) return min(64, atoi(e) / 8 * 8);
-    int rt = 64;
-    while (rt > 8 && (long)b * slabs * ceil_div(m, rt) < 6L * num_sms()) rt -= 8;
-    return rt;
+    if (e && atoi(e) >= 8) return min(128, atoi(e) / 8 * 8);
+    const long slots = 3L * num_sms();
+    const int T = (int)max(1L, slots / ((long)b * slabs));
+    int rt = (ceil_div(m, T) + 7) / 8 * 8;
+    return max(8, min(128, rt));
 }
 
 }  // namespace mpb

@@ -3,6 +3,7 @@
 // NHWC fp32 everywhere.  Each kernel cites the reference graph op it replaces (the reference
 // obtains all of these from TensorFlow 1.8 / TF-slim; semantics restated from TF defaults).
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "../../include/monopsr_b200_net.h"
 #include <math.h>
 
@@ -17,6 +18,18 @@ __device__ __forceinline__ float rtf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return c_round_operands ? __uint_as_float(u) : x;
 }
+// h3 forward: optional fp16 hi/lo split copy ([hi | lo] per 32-channel block, see csrc/split16.cu) written by the
+// producer itself next to its fp32 result.  v = 4 consecutive channels c..c+3 of pixel `row` (pitch ld floats).
+__device__ __forceinline__ void store_split16(unsigned char* y16, long row, int ld, int c, float4 v, int* overflow) {
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    unsigned char* d = y16 + ((size_t)row * ld + (c & ~31)) * 4 + (c & 31) * 2;
+    *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(d + 64) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    if (overflow && fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) > 65504.f) *overflow = 1;
+}
+
 
 // ---------------------------------------------------------------- weight preparation
 // Frozen (inference-mode) BN folded into the conv weights (feature_extractor.py:228-242:
@@ -122,9 +135,9 @@ fold_bn_multi_kernel(int total_rows, const mpb_bn_layer* __restrict__ layers, co
     }
 }
 __global__ void __launch_bounds__(256)
-bn_param_grad_multi_kernel(int total_rows, const mpb_bn_layer* __restrict__ layers, const int* __restrict__ row2layer,
-                           float eps) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+bn_param_grad_multi_kernel(int row_begin, int total_rows, const mpb_bn_layer* __restrict__ layers,
+                           const int* __restrict__ row2layer, float eps) {
+    const int row = row_begin + blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= total_rows) return;
     const mpb_bn_layer L = layers[row2layer[row]];
     const int co = row - L.row0;
@@ -453,7 +466,8 @@ __global__ void crop_pool_bwd_kernel(int H, int W, int C, const float* __restric
 // ---------------------------------------------------------------- bilinear resize, align_corners=True
 // tf.image.resize_images(x, (OH,OW), align_corners=True) (builders/net_builder.py:73-75,82-84)
 __global__ void resize_ac_fwd_kernel(int nimg, int H, int W, int C4, int OH, int OW,
-                                     const float4* __restrict__ x, float4* __restrict__ y) {
+                                     const float4* __restrict__ x, float4* __restrict__ y,
+                                     unsigned char* __restrict__ y16, int* __restrict__ overflow) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long total = (long)nimg * OH * OW * C4;
     if (i >= total) return;
@@ -473,6 +487,7 @@ __global__ void resize_ac_fwd_kernel(int nimg, int H, int W, int C4, int OH, int
     MPB_LERP(x) MPB_LERP(y) MPB_LERP(z) MPB_LERP(w)
 #undef MPB_LERP
     y[i] = o;
+    if (y16) store_split16(y16, i / C4, C4 * 4, c * 4, o, overflow);
 }
 
 // Backward of the bilinear align-corners resize in GATHER form: one thread per input pixel x 4 channels sums the
@@ -584,7 +599,7 @@ __global__ void bn_finalize_kernel(int M, int C, const double* __restrict__ psum
 }
 __global__ void bn_apply_kernel(long total4, int C4, const float4* __restrict__ z, const float* __restrict__ mean,
                                 const float* __restrict__ var, const float* __restrict__ beta, float eps,
-                                float4* __restrict__ y) {
+                                float4* __restrict__ y, unsigned char* __restrict__ y16, int* __restrict__ overflow) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)(i % C4) * 4;
@@ -595,6 +610,7 @@ __global__ void bn_apply_kernel(long total4, int C4, const float4* __restrict__ 
     o.z = rtf32(fmaxf((v.z - mean[c + 2]) * rsqrtf(var[c + 2] + eps) + beta[c + 2], 0.f));
     o.w = rtf32(fmaxf((v.w - mean[c + 3]) * rsqrtf(var[c + 3] + eps) + beta[c + 3], 0.f));
     y[i] = o;
+    if (y16) store_split16(y16, i / C4, C4 * 4, c, o, overflow);
 }
 // backward: g = dy*(y>0); s1 = sum g; s2 = sum g*xhat; dz = rstd*(g - s1/M - xhat*s2/M); dbeta = s1
 // same thread layout as bn_stats_kernel (4 channels per thread, 2 rows in flight: three tensors are read)
@@ -874,11 +890,17 @@ MPB_API int mpb_fold_bn_multi(int total_rows, const mpb_bn_layer* layers, const 
     MPB_LAUNCH_CHECK();
     return 0;
 }
-MPB_API int mpb_bn_param_grad_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream) {
-    if (total_rows <= 0 || !layers || !row2layer) return -1;
-    bn_param_grad_multi_kernel<<<ceil_div(total_rows, 8), 256, 0, ST>>>(total_rows, layers, row2layer, eps);
+MPB_API int mpb_bn_param_grad_range(int row_begin, int row_end, const mpb_bn_layer* layers, const int* row2layer, float eps,
+                                    void* stream) {
+    if (row_begin < 0 || row_end < row_begin || !layers || !row2layer) return -1;
+    if (row_end == row_begin) return 0;
+    bn_param_grad_multi_kernel<<<ceil_div(row_end - row_begin, 8), 256, 0, ST>>>(row_begin, row_end, layers, row2layer, eps);
     MPB_LAUNCH_CHECK();
     return 0;
+}
+MPB_API int mpb_bn_param_grad_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream) {
+    if (total_rows <= 0) return -1;
+    return mpb_bn_param_grad_range(0, total_rows, layers, row2layer, eps, stream);
 }
 MPB_API int mpb_stem_fwd(int nimg, int Hin, int Win, const float* x, const float* wf, const float* shift, float* y,
                          void* stream) {
@@ -936,11 +958,17 @@ MPB_API int mpb_crop_pool_bwd(int H, int W, int C, const float* feat, int nbox, 
     MPB_LAUNCH_CHECK();
     return 0;
 }
-MPB_API int mpb_resize_ac_fwd(int nimg, int H, int W, int C, const float* x, int OH, int OW, float* y, void* stream) {
+MPB_API int mpb_resize_ac_fwd16(int nimg, int H, int W, int C, const float* x, int OH, int OW, float* y, void* y16,
+                                int* overflow, void* stream) {
+    if (y16 && C % 32) return -1;
     resize_ac_fwd_kernel<<<nblk((long)nimg * OH * OW * (C / 4), 256), 256, 0, ST>>>(nimg, H, W, C / 4, OH, OW,
-                                                                                  (const float4*)x, (float4*)y);
+                                                                                  (const float4*)x, (float4*)y,
+                                                                                  (unsigned char*)y16, overflow);
     MPB_LAUNCH_CHECK();
     return 0;
+}
+MPB_API int mpb_resize_ac_fwd(int nimg, int H, int W, int C, const float* x, int OH, int OW, float* y, void* stream) {
+    return mpb_resize_ac_fwd16(nimg, H, W, C, x, OH, OW, y, nullptr, nullptr, stream);
 }
 MPB_API int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, int OH, int OW, float* dx, void* stream) {
     if (C % 4 || H < 2 || W < 2 || OH < H || OW < W || OH > 3 * H || OW > 3 * W) return -1;   // <= 6 taps per axis
@@ -949,9 +977,10 @@ MPB_API int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, in
     MPB_LAUNCH_CHECK();
     return 0;
 }
-MPB_API int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, float eps, float* y, float* mean,
-                             float* var, float* moving_mean, float* moving_var, float decay, double* scratch,
-                             void* stream) {
+MPB_API int mpb_bn_train_fwd16(int M, int C, const float* z, const float* beta, float eps, float* y, float* mean,
+                               float* var, float* moving_mean, float* moving_var, float decay, double* scratch,
+                               void* y16, int* overflow, void* stream) {
+    if (y16 && C % 32) return -1;
     MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, ST));
     if (C % 4) return -1;
     dim3 g(ceil_div(C, 128), min(num_sms() * 4, ceil_div(M, 64)));
@@ -960,9 +989,15 @@ MPB_API int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, fl
     bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(M, C, scratch, scratch + C, mean, var, moving_mean, moving_var, decay);
     MPB_LAUNCH_CHECK();
     bn_apply_kernel<<<nblk((long)M * C / 4, 256), 256, 0, ST>>>((long)M * C / 4, C / 4, (const float4*)z, mean, var, beta, eps,
-                                                              (float4*)y);
+                                                              (float4*)y, (unsigned char*)y16, overflow);
     MPB_LAUNCH_CHECK();
     return 0;
+}
+MPB_API int mpb_bn_train_fwd(int M, int C, const float* z, const float* beta, float eps, float* y, float* mean,
+                             float* var, float* moving_mean, float* moving_var, float decay, double* scratch,
+                             void* stream) {
+    return mpb_bn_train_fwd16(M, C, z, beta, eps, y, mean, var, moving_mean, moving_var, decay, scratch, nullptr, nullptr,
+                              stream);
 }
 MPB_API int mpb_set_operand_rounding(int on) {
     const int v = on ? 1 : 0;
@@ -971,13 +1006,17 @@ MPB_API int mpb_set_operand_rounding(int on) {
 }
 // slim.batch_norm(is_training=False): the moving statistics instead of the batch's (validation / inference graphs:
 // MonoPSRModel is built with is_training = (train_val_test == 'train'), monopsr_model.py:139, net_builder.py:39,79,87)
-MPB_API int mpb_bn_infer_fwd(int M, int C, const float* z, const float* beta, const float* moving_mean,
-                             const float* moving_var, float eps, float* y, void* stream) {
-    if (M <= 0 || C <= 0 || C % 4 || !z || !beta || !moving_mean || !moving_var || !y) return -1;
+MPB_API int mpb_bn_infer_fwd16(int M, int C, const float* z, const float* beta, const float* moving_mean,
+                               const float* moving_var, float eps, float* y, void* y16, int* overflow, void* stream) {
+    if (M <= 0 || C <= 0 || C % 4 || !z || !beta || !moving_mean || !moving_var || !y || (y16 && C % 32)) return -1;
     bn_apply_kernel<<<nblk((long)M * C / 4, 256), 256, 0, ST>>>((long)M * C / 4, C / 4, (const float4*)z, moving_mean,
-                                                              moving_var, beta, eps, (float4*)y);
+                                                              moving_var, beta, eps, (float4*)y, (unsigned char*)y16, overflow);
     MPB_LAUNCH_CHECK();
     return 0;
+}
+MPB_API int mpb_bn_infer_fwd(int M, int C, const float* z, const float* beta, const float* moving_mean,
+                             const float* moving_var, float eps, float* y, void* stream) {
+    return mpb_bn_infer_fwd16(M, C, z, beta, moving_mean, moving_var, eps, y, nullptr, nullptr, stream);
 }
 MPB_API int mpb_bn_train_bwd(int M, int C, const float* z, const float* mean, const float* var, float eps, const float* y,
                              const float* dy, float* dz, float* dbeta, double* scratch, void* stream) {

@@ -72,6 +72,7 @@ _SIGS = {
     "mpb_fold_bn": [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
     "mpb_fold_bn_multi": [c_i, c_p, c_p, c_f, c_p],
     "mpb_bn_param_grad_multi": [c_i, c_p, c_p, c_f, c_p],
+    "mpb_bn_param_grad_range": [c_i, c_i, c_p, c_p, c_f, c_p],
     "mpb_round_copy": [c_l, c_p, c_p, c_p],
     "mpb_bn_param_grad": [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p],
     "mpb_stem_fwd": [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
@@ -85,6 +86,9 @@ _SIGS = {
     "mpb_resize_ac_fwd": [c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
     "mpb_resize_ac_bwd": [c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p],
     "mpb_bn_train_fwd": [c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
+    "mpb_resize_ac_fwd16": [c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p],
+    "mpb_bn_train_fwd16": [c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
+    "mpb_bn_infer_fwd16": [c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
     "mpb_tc_gemm_x3": [c_p, c_i, c_p],
     "mpb_tc_gemm_h3": [c_p, c_i, c_p],
     "mpb_split16": [c_l, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p],

@@ -11,6 +11,7 @@ def planner(csk=1, csk_bn=128, ctas128=2, fill=0.9, sms=148):
     e.sms, e.fill, e.csk, e.csk_bn = sms, fill, csk, csk_bn
     e.ctas_per_sm = {64: 2, 128: ctas128, 256: 1}
     e.h3 = e.x3 = False
+    e.shortk_bn = 64
     return e
 
 

@@ -18,7 +18,7 @@ a, b = Engine(dev, params=P), Engine(dev, params=P)
 a.set_inputs(S); b.set_inputs(S)
 ok = True
 for step in range(3):
-    a.train_step()                            # three CUDA graphs around two gradient buckets
+    a.train_step()                            # ONE graph, NCCL inside: head bucket + MPB_DP_BUCKETS tower buckets
     b.set_hyper(b.step_count); b.train_step_eager(); b.step_count += 1
     torch.cuda.synchronize()
     pa, pb = a.params, b.params
@@ -30,6 +30,24 @@ for step in range(3):
         print("step %d: ranks identical %s; graph/bucketed vs eager/one all-reduce rel diff %.3e; finite %s" % (
             step, ident, rel, bool(torch.isfinite(pa).all())))
     ok = ok and ident and rel < 1e-3      # graph vs eager differ by the order of fp32 RED.ADDs, amplified by Adam
+# timing of the three variants on this box (device events, max over ranks)
+def timed(fn, n=20):
+    for _ in range(3):
+        fn()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+t_graph = timed(a.train_step)
+os.environ["MPB_DP_GRAPH"] = "0"
+c = Engine(dev, params=P); c.set_inputs(S)
+t_split = timed(c.train_step)
 if rank == 0:
+    print("ms/step at %d ranks: one graph with bucketed all-reduces %.3f | three graphs, two all-reduces %.3f" % (world, t_graph, t_split))
     print("DP CHECK", "OK" if ok else "FAILED")
 dist.destroy_process_group()
