@@ -410,8 +410,7 @@ def main():
     e2e_value = crops / (e2e_ms / 1e3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM):
@@ -472,9 +471,18 @@ def main():
         ts = cpu_reference_step(P, S, threads, 1)
         line["cpu_baseline"] = {"value": CROPS_PER_SAMPLE / ts[0], "unit": "crops/s", "cores": threads, "kind": "port",
                                 "sample": "1 full step of 32 crops (restated TF1 graph, torch-CPU fp32)"}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """multi-rank exit: tearing an NCCL communicator down while CUDA graphs that ran on it are still alive can block
+    for minutes (seen on the 2-GPU box); the work is done and printed, so leave without the teardown"""
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

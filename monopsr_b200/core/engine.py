@@ -666,9 +666,18 @@ class Engine:
                 t = t.float()
             if k in self.inputs and self.inputs[k].shape == t.shape:
                 self.inputs[k].copy_(t, non_blocking=True)
+            elif k in self.inputs and self._captured():
+                # the captured graphs (and the heads' pointer table) hold the ADDRESS of the first buffer: a reallocation
+                # would leave them reading stale memory
+                raise _lib.MpbError("input %r changed shape from %s to %s after the step was captured into a CUDA graph; "
+                                    "create a new Engine for another input geometry" % (k, tuple(self.inputs[k].shape),
+                                                                                       tuple(t.shape)))
             else:
                 self.inputs[k] = t.to(self.dev).contiguous()
         self._heads_io = None
+
+    def _captured(self):
+        return any(getattr(self, g, None) is not None for g in ("_graph", "_g_fb", "_g_dp"))
 
     def heads_io(self):
         if getattr(self, "_heads_io", None) is not None:
@@ -1192,7 +1201,7 @@ class Engine:
         else:
             raise NotImplementedError("learning_rate_type %r" % kind)
         self.ema_decay = float(a.moving_average_decay) if getattr(a, "use_moving_average", False) else 0.0
-        self._graph = self._g_fb = self._g_dp = None          # the EMA decay is baked into a captured train-op launch
+        self._graph = self._g_fb = self._g_dp = None          # (the EMA decay is baked into a captured train-op launch
 
     def learning_rate(self, step):
         """tf.train.exponential_decay (yaml:145-150): lr * factor ^ (step / decay_steps), floored when staircase"""
@@ -1247,15 +1256,19 @@ class Engine:
         self.set_hyper(self.step_count)
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if distributed and int(os.environ.get("MPB_DP_GRAPH", "1")):
-            # ONE graph for the whole data-parallel step, NCCL all-reduces captured inside it: the head bucket leaves
-            # under the towers' backward pass, the tower gradients leave in MPB_DP_BUCKETS buckets (d(gamma) + all-reduce
-            # on a side stream) as the backward pass completes them; only the last bucket is exposed
+        if distributed and int(os.environ.get("MPB_DP_GRAPH", "0")):
+            # opt-in (MPB_DP_GRAPH=1): ONE graph for the whole data-parallel step, NCCL all-reduces captured inside it:
+            # the head bucket leaves under the towers' backward pass, the tower gradients leave in MPB_DP_BUCKETS buckets
+            # (d(gamma) + all-reduce on a side stream) as the backward pass completes them.  Measured on 2 B200: bit-
+            # identical replicas, 9.90 vs 9.86 ms/step for the default below -- the all-reduce kernels slow the GEMMs
+            # they run beside by as much as the overlap hides (profiles/r2_notes.md), so it is not the default
             if getattr(self, "_g_dp", None) is None:
                 self._capture_dp()
             self._g_dp.replay()
         elif distributed:
-            # three graphs around two NCCL all-reduces issued from the host (MPB_DP_GRAPH=0)
+            # four graphs around two NCCL all-reduces issued from the host: the head bucket (arena tail, 45 %) is
+            # reduced under the towers' backward pass, the tower bucket under the train-op of the head variables
+            # (NVLink traffic beside an HBM-bound pass: different resources), then the towers' train-op
             if getattr(self, "_g_fb", None) is None:
                 self._capture_split()
             from . import dp
@@ -1263,7 +1276,9 @@ class Engine:
             head = dp.allreduce_start(self.grads[self.round_off:])     # on NCCL's stream, beside the towers' backward
             self._g_bt.replay()
             dp.allreduce_finish(head)
-            dp.allreduce_flat(self.grads[:self.round_off])
+            towers = dp.allreduce_start(self.grads[:self.round_off])   # beside the head variables' train-op
+            self._g_opt_head.replay()
+            dp.allreduce_finish(towers)
             self._g_opt.replay()
         else:
             if getattr(self, "_graph", None) is None:
@@ -1343,15 +1358,19 @@ class Engine:
         self._warm()
         # three graphs around two gradient buckets: [forward + head backward] -> all-reduce of the head variables'
         # gradients (arena tail, 45 %) UNDER [towers' backward] -> all-reduce of the tower gradients -> [train-op]
-        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        g1, g2, g3, g4 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         c0 = _lib.launch_count()
         with torch.cuda.graph(g1, stream=self.s_main, capture_error_mode="thread_local"):
             self.forward(train=True)
             self._backward_head(join=True)
         with torch.cuda.graph(g2, stream=self.s_main, capture_error_mode="thread_local"):
             self._backward_towers()
+        scale = 1.0 / dist.get_world_size()
+        with torch.cuda.graph(g4, stream=self.s_main, capture_error_mode="thread_local"):
+            self.optimizer_step(scale, part="head")
+            self.prepare_weights(part="head")
         with torch.cuda.graph(g3, stream=self.s_main, capture_error_mode="thread_local"):
-            self.optimizer_step(1.0 / dist.get_world_size())
-            self.prepare_weights()
+            self.optimizer_step(scale, part="towers")
+            self.prepare_weights(part="towers")
         self.launches_per_step = _lib.launch_count() - c0
-        self._g_fb, self._g_bt, self._g_opt = g1, g2, g3
+        self._g_fb, self._g_bt, self._g_opt_head, self._g_opt = g1, g2, g4, g3

@@ -224,19 +224,30 @@ __device__ __forceinline__ void epi_load_mask(const TcGemmParams& p, const EpiCt
         mv[i] = (4 * i + (lane >> 3) < c.nvalid) ? ldg4(mp + (size_t)(4 * i) * p.ldm) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// fused epilogue of one 32-column chunk: accumulator from TMEM (+ the cluster peers' partials).  rv / mv hold
-// this chunk's residual / mask values on entry and the ones of chunk cc_next (if < BN/32) on exit.
+// per-column scale / shift of chunk cc (this lane's 4 columns): like the residual they do not depend on the accumulator,
+// so the first chunk's are fetched before the wait for the main loop and the next chunk's while this one is finished
+// (they used to be loaded at the top of every chunk and waited for ~500 clk each time: an L2 round trip per chunk)
+struct EpiCols { float4 sc, sh; };
+__device__ __forceinline__ void epi_load_cols(const TcGemmParams& p, int cc, int lane, int n0, EpiCols& cv) {
+    const int col = n0 + cc * 32 + (lane & 7) * 4;
+    cv.sc = p.scale ? ldg4(p.scale + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+    cv.sh = p.shift ? ldg4(p.shift + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// fused epilogue of one 32-column chunk: accumulator from TMEM (+ the cluster peers' partials).  rv / mv / cv hold
+// this chunk's residual / mask / column values on entry and the ones of chunk cc_next (if < BN/32) on exit.
 template <int BN, int OP>
 __device__ __forceinline__ void epi_chunk(const TcGemmParams& p, const EpiCtx& c, int cc, int cc_next, int lane, int n0,
-                                          float4 (&rv)[8], float4 (&mv)[8]) {
+                                          float4 (&rv)[8], float4 (&mv)[8], EpiCols& cv) {
     const int g = lane >> 3, q = lane & 7;         // after the transpose: rows 4i+g, columns 4q..4q+3
     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int c0 = cc * 32;
     float4* stg4 = reinterpret_cast<float4*>(c.scratch);
     (void)stg4;
         const int col = n0 + c0 + q * 4;
-        const float4 sc = p.scale ? ldg4(p.scale + col) : one4;
-        const float4 sh = p.shift ? ldg4(p.shift + col) : zero4;
+        const float4 sc = cv.sc, sh = cv.sh;
+        if (cc_next < BN / 32) epi_load_cols(p, cc_next, lane, n0, cv);
+        (void)one4;
         float x[32];
         {
             tmem_ld32(c.trow + c0, x);
@@ -402,11 +413,11 @@ __device__ __forceinline__ void epi_setup(EpiCtx& c, const TcGemmParams& p, uint
 // owned chunks: rank, rank + ks, ...; the j-th of them goes to the warp with half == j % nhalf
 template <int BN, int OP>
 __device__ __forceinline__ void tc_epilogue(const TcGemmParams& p, const EpiCtx& c, int half, int nhalf, int lane, int n0,
-                                            float4 (&rv)[8], float4 (&mv)[8] TC_TR_ARG) {
+                                            float4 (&rv)[8], float4 (&mv)[8], EpiCols& cv TC_TR_ARG) {
     const int step = nhalf * c.ks;
 #pragma unroll 1
     for (int cc = c.rank + half * c.ks; cc < BN / 32; cc += step) {
-        epi_chunk<BN, OP>(p, c, cc, cc + step, lane, n0, rv, mv);
+        epi_chunk<BN, OP>(p, c, cc, cc + step, lane, n0, rv, mv, cv);
         if (c.quad == 0 && lane == 0 && half == 0 && cc == c.rank) TC_TR(53);
     }
     if (c.quad == 0 && half == 0 && lane == 0) TC_TR(54);
@@ -563,10 +574,12 @@ tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
         EpiCtx ec;
         float4 rv[8], mv[8];
         epi_setup<OP>(ec, p, tmem_acc, warp, 0, lane, m0, stg_base, 1, 0, 4, 0, 1);
+        EpiCols cv;
         epi_load_res(p, ec, 0, lane, n0, rv);
         epi_load_mask(p, ec, 0, lane, n0, mv);
+        epi_load_cols(p, 0, lane, n0, cv);
         tc_epilogue_dump<BN, OP>(p, tmem_full_bar, tmem_acc, warp, 0, 1, lane, m0, stg_base, 4, 1, 0 TC_TR_PASS);
-        tc_epilogue<BN, OP>(p, ec, 0, 1, lane, n0, rv, mv TC_TR_PASS);
+        tc_epilogue<BN, OP>(p, ec, 0, 1, lane, n0, rv, mv, cv TC_TR_PASS);
     } else {
         // =========================== MMA ISSUER (warp 4) ===========================
         constexpr bool a_mn = (OP == TC_WGRAD);
@@ -950,13 +963,15 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
     }
     EpiCtx ec;
     float4 rv[8], mv[8];
+    EpiCols cv;
     if (warp >= 2) {
         const int half = (warp - 2) >> 2;
         epi_setup<OP>(ec, p, tmem_acc, warp & 3, half, lane, m0, stg_base, ks, krank, EW, cl_x, cl_nx);
-        // residual / mask of this warp's first chunk: in flight while the main loop runs
+        // residual / mask / column values of this warp's first chunk: in flight while the main loop runs
         if (krank + half * ks < BN / 32) {
             epi_load_res(p, ec, krank + half * ks, lane, n0, rv);
             epi_load_mask(p, ec, krank + half * ks, lane, n0, mv);
+            epi_load_cols(p, krank + half * ks, lane, n0, cv);
         }
         if (kTwoProducers && warp == 2) {      // second issuing warp: the odd k-blocks (see above)
             for (int i = 0; i < npre; i++) produce(i, false, false);
@@ -966,7 +981,7 @@ tc_gemm_tma_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant
                                  TC_TR_PASS);
     }
     if (CSK) cluster_sync_all();         // every peer's partial chunks are in its shared memory
-    if (warp >= 2) tc_epilogue<BN, OP>(p, ec, (warp - 2) >> 2, EW / 4, lane, n0, rv, mv TC_TR_PASS);
+    if (warp >= 2) tc_epilogue<BN, OP>(p, ec, (warp - 2) >> 2, EW / 4, lane, n0, rv, mv, cv TC_TR_PASS);
     __syncthreads();
     if (tid == 0) TC_TR(55);
     if (CN > 1 || CSK) cluster_sync_all();   // no CTA leaves while peers may still multicast into it / read its smem
@@ -1121,6 +1136,7 @@ tc_gemm_x3_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant_
     float* stg_base = reinterpret_cast<float*>(smem_raw + (base - raw));
     EpiCtx ec;
     float4 rv[8], mv[8];
+    EpiCols cv;
     if (warp == 0) {
         for (int i = npre; i < nk; i++) produce(true);
     } else if (warp == 1) {
@@ -1159,6 +1175,7 @@ tc_gemm_x3_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant_
         epi_setup<TC_FWD>(ec, p, tmem_acc, warp & 3, 0, lane, m0, stg_base, 1, 0, 4, 0, 1);
         epi_load_res(p, ec, 0, lane, n0, rv);
         epi_load_mask(p, ec, 0, lane, n0, mv);
+        epi_load_cols(p, 0, lane, n0, cv);
         const int t = tid - 64;
         constexpr int n4 = (int)(kHalf / 16);          // float4s of [A | B]; a multiple of 128
         int st = 0;
@@ -1176,7 +1193,7 @@ tc_gemm_x3_kernel(const __grid_constant__ TcGemmParams p, const __grid_constant_
             if (++st == kX3Stages) { st = 0; ph ^= 1u; }
         }
         tc_epilogue_dump<BN, TC_FWD>(p, tmem_full_bar, tmem_acc, warp & 3, 0, 1, lane, m0, stg_base, 4, 1, 0 TC_TR_PASS);
-        tc_epilogue<BN, TC_FWD>(p, ec, 0, 1, lane, n0, rv, mv TC_TR_PASS);
+        tc_epilogue<BN, TC_FWD>(p, ec, 0, 1, lane, n0, rv, mv, cv TC_TR_PASS);
     }
     __syncthreads();
     if (warp == 1) {

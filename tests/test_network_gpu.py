@@ -3,8 +3,8 @@
 Forward bar = the north star's: EVERY forward output within 1e-3 relative (l2) of the fp32 reference graph, in the
 engine's DEFAULT precision (measured on a B200: <= 1e-4, profiles/r2_notes.md).  The single-pass tf32 FAST mode
 (precision="tf32") is checked against its documented envelope only -- it misses the bar on the decoder maps.
-Gradients come from a single-pass tf32 backward: ~1e-2 (late layers) .. 1e-1 (the stems, 100 layers of
-backward); a wiring error shows up as O(1).
+Gradients come from a single-pass tf32 backward on that accurate forward pass: 4e-3 median, < 1e-2 at the stems
+(100 layers of backward); a wiring error shows up as O(1).
 """
 import numpy as np
 import pytest
@@ -83,13 +83,16 @@ def test_gradients_all_parameters(setup):
     for n in eng.trainable_names:
         errs[n] = l2rel(torch.from_numpy(G[n]).to(eng.dev), Pt[n].grad)
     vals = np.array(list(errs.values()))
-    assert np.median(vals) < 4e-2, np.median(vals)
+    # measured on a B200 in the default precision (profiles/r2_check_network_h3.txt): median 4.2e-3, worst 8.5e-3 (the
+    # stems, after ~100 layers of single-pass tf32 backward on an accurate forward pass).  Round 1's tf32 forward gave
+    # 1e-2 / 1e-1 and this test allowed 4e-2 / 0.25.
+    assert np.median(vals) < 1e-2, np.median(vals)
     worst = max(errs, key=errs.get)
-    assert errs[worst] < 0.25, (worst, errs[worst])
+    assert errs[worst] < 3e-2, (worst, errs[worst])
     # late layers (few tf32 roundings between loss and parameter) are tight
     for n in ("output/alpha/weights", "output/lwh/lwh/weights", "output/cen_y/cen_y/weights",
               "output/regression_fc/regression_fc/fc1/weights", "output/inst_xyz_map_local/inst_xyz_map_local/weights"):
-        assert errs[n] < 1.5e-2, (n, errs[n])
+        assert errs[n] < 8e-3, (n, errs[n])
 
 
 def test_bn_moving_statistics_updated(setup):

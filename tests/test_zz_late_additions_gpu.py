@@ -114,3 +114,16 @@ def test_validation_pass_on_the_engine(cuda, tmp_path):
     assert min(res["metrics"][M.METRIC_EMD]) >= 0 and min(res["metrics"][M.METRIC_CHAMFER]) >= 0
     out = ev.convert_and_evaluate(ds, base, 0, kitti_score_threshold=0.0)
     assert out and any(l.startswith("car_detection AP:") for l in out[0]["lines"])
+
+
+def test_inputs_may_not_change_shape_after_capture(cuda):
+    """the captured step holds raw pointers to the input buffers: a different geometry afterwards must fail loudly"""
+    from monopsr_b200 import lib as mlib
+    S = ms.synthetic_sample(0)
+    eng = Engine(cuda, params=ms.init_params(0))
+    eng.train_step(S)
+    eng.train_step(S)                                   # same shapes: copied into the captured buffers
+    bad = dict(S)
+    bad["full_img"] = np.zeros((1, 80, 304, 3), np.float32)
+    with pytest.raises(mlib.MpbError):
+        eng.set_inputs(bad)
