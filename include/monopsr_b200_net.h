@@ -96,6 +96,9 @@ typedef struct mpb_w16_layer {
     const float* w; const float* gamma; const float* var;     /* gamma / var NULL: no BN fold */
     void* w16; float* inv_scale;
     int cout; int K; int row0; int pad_;
+    /* optional: the same pass also does the work of mpb_fold_bn_multi for this layer -- wf = w * s (fp32, the
+     * backward pass's operand), scale[co] = s, shift[co] = beta[co] - mean[co] * s -- so the weights are read once */
+    float* wf; float* scale; float* shift; const float* beta; const float* mean;
 } mpb_w16_layer;
 int mpb_split16_weights_multi(int total_rows, const mpb_w16_layer* layers, const int* row2layer, float eps, void* stream);
 

@@ -109,9 +109,13 @@ class Engine:
         self.early_opt = False      # set by the single-GPU train step: head train-op under the towers' backward
         self._grads_zeroed = False
         self.overlap = True
-        self.fill = float(os.environ.get("MPB_TILE_FILL", "0.9"))   # min fraction of SMs a launch must fill before widening tiles
+        # tile planning knobs (tools/r2_call_f.sh / r2_call_h.sh sweeps, profiles/r2_notes.md).  The h3 forward does 1.5x
+        # the MMA work per operand byte, which moves the balance towards wider tiles: 128-wide tiles already at 0.6 of
+        # the SMs and for the short epilogue-bound reductions measured 9.11 vs 9.40 ms/step (tf32 mode keeps 0.9 / 64)
+        wide = self.precision != "tf32"
+        self.fill = float(os.environ.get("MPB_TILE_FILL", "0.6" if wide else "0.9"))   # min fraction of SMs a launch must fill before widening tiles
         self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
-        self.shortk_bn = int(os.environ.get("MPB_SHORTK_BN", "64"))      # tile width of short, epilogue-bound reductions
+        self.shortk_bn = int(os.environ.get("MPB_SHORTK_BN", "128" if wide else "64"))   # tile width of short, epilogue-bound reductions
         self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "128"))
         self.wgrad_fill = float(os.environ.get("MPB_WGRAD_FILL", "0.5"))   # target CTAs / SMs when choosing split-K
         # cluster split-K (DSMEM reduce) for long reductions: faster per launch (profiles/r1_gemm_sweep.txt), but the
@@ -202,7 +206,19 @@ class Engine:
         return self.view(name, self.grads)
 
     def pview(self, name):
+        """the prepared form of a GEMM weight: BN-folded (towers) / tf32-rounded.  With unrounded operands (h3 / x3) the
+        prepared form of a weight WITHOUT batch norm is the weight itself: no copy is kept of those"""
+        if self.rounding == 0 and not name.startswith("FirstStage"):
+            return self.view(name)
         return self.view(name, self.prep)
+
+    def _arena_off(self, t):
+        """float offset of a weight view inside its arena (params and prep share the layout)"""
+        for base in (self.prep, self.params):
+            d = t.data_ptr() - base.data_ptr()
+            if 0 <= d < base.numel() * 4:
+                return d // 4
+        raise ValueError("not a view of the parameter arenas")
 
     def _to_dev_layout(self, n, a):
         s, k = self.ptable[n]
@@ -479,7 +495,7 @@ class Engine:
             # operands = split copies; results stay unrounded (pools / resizes / batch norm read them), the rounded
             # second copy of the residual stream is replaced by the split copy
             p.round_tf32 = 0
-            off = (Wt.data_ptr() - self.prep.data_ptr()) // 4
+            off = self._arena_off(Wt)
             p.X16 = _ptr(self.s16(X))
             p.W16 = ctypes.c_void_p(self.prep16.data_ptr() + 4 * off)
             p.scale = _ptr(self.w16_inv[off])
@@ -578,6 +594,17 @@ class Engine:
         self.bn_rows = row
         self.bn_layers = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev)
         self.bn_row2layer = torch.tensor(row2layer, dtype=torch.int32, device=self.dev)
+        # the two 7x7x3 stems alone (h3: every other tower conv is folded by the split-copy pass)
+        stems = [i for i, (scope, K, cout) in enumerate(layers) if K % 32]
+        sarr = (BnLayer * len(stems))()
+        s2l, srow = [], 0
+        for j, i in enumerate(stems):
+            ctypes.memmove(ctypes.addressof(sarr[j]), ctypes.addressof(arr[i]), ctypes.sizeof(BnLayer))
+            sarr[j].row0 = srow
+            s2l += [j] * sarr[j].cout
+            srow += sarr[j].cout
+        self.bn_stem = (srow, torch.frombuffer(bytearray(bytes(sarr)), dtype=torch.uint8).to(self.dev),
+                        torch.tensor(s2l, dtype=torch.int32, device=self.dev))
         # the non-tower GEMM weights only need tf32 rounding: they are contiguous at the end of the arena
         first = min(self.layout[n][1] for n in self.trainable_names if not n.startswith("FirstStage"))
         self.round_off, self.round_len = first, self.n_train - first
@@ -592,15 +619,15 @@ class Engine:
                 if k * k * cin % 32:
                     continue                                    # the 7x7x3 stem is a SIMT kernel
                 b = scope + "/BatchNorm/"
-                tower.append((scope + "/weights", self.view(b + "gamma"), self.view(b + "moving_variance")))
+                tower.append((scope + "/weights", self.view(b + "gamma"), self.view(b + "moving_variance"), scope))
         gemm_heads = ["squash/1x1_conv"] + [D["scope"] for D in self.dec] + \
                      ["output/%s_fc/%s_fc/%s" % (a, a, l) for a in ("proposal", "regression") for l in ("img_fc", "fc0", "fc1")]
         for sc in gemm_heads:
-            head.append((sc + "/weights", None, None))
+            head.append((sc + "/weights", None, None, None))
         for key, rows_ in (("towers", tower), ("head", head)):
             arr = (W16Layer * len(rows_))()
             row2layer, row = [], 0
-            for i, (name, gamma, var) in enumerate(rows_):
+            for i, (name, gamma, var, scope) in enumerate(rows_):
                 _, off, ds = self.layout[name]
                 cout, K = ds
                 inv = torch.empty(cout, device=self.dev)
@@ -611,6 +638,11 @@ class Engine:
                 e.var = var.data_ptr() if var is not None else None
                 e.w16 = self.prep16.data_ptr() + 4 * off
                 e.inv_scale = inv.data_ptr()
+                if scope is not None:        # frozen-BN conv: this pass also folds (wf, scale, shift) -- one read of w
+                    b = scope + "/BatchNorm/"
+                    e.wf = self.prep.data_ptr() + 4 * off
+                    e.scale, e.shift = self.bnfold[scope][0].data_ptr(), self.bnfold[scope][1].data_ptr()
+                    e.beta, e.mean = self.view(b + "beta").data_ptr(), self.view(b + "moving_mean").data_ptr()
                 e.cout, e.K, e.row0 = cout, K, row
                 row2layer += [i] * cout
                 row += cout
@@ -624,9 +656,13 @@ class Engine:
         if getattr(self, "bn_layers", None) is None:
             self._build_bn_table()
         if part in ("all", "towers"):
-            self._chk(L.mpb_fold_bn_multi(self.bn_rows, _ptr(self.bn_layers), _ptr(self.bn_row2layer), BN_EPS_RESNET, st),
-                      "fold_bn_multi")
-        if part in ("all", "head"):
+            if self.h3:      # the split-copy pass below folds every tensor-core conv; only the two stems are left
+                rows_, tab, r2l = self.bn_stem
+                self._chk(L.mpb_fold_bn_multi(rows_, _ptr(tab), _ptr(r2l), BN_EPS_RESNET, st), "fold_bn_multi (stems)")
+            else:
+                self._chk(L.mpb_fold_bn_multi(self.bn_rows, _ptr(self.bn_layers), _ptr(self.bn_row2layer), BN_EPS_RESNET, st),
+                          "fold_bn_multi")
+        if part in ("all", "head") and self.rounding:      # (unrounded operands: pview() hands out the weights themselves)
             self._chk(L.mpb_round_copy(self.round_len, _ptr(self.params[self.round_off:]), _ptr(self.prep[self.round_off:]),
                                        st), "round_copy")
         if self.h3:

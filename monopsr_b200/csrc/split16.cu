@@ -71,11 +71,17 @@ split16_weights_multi_kernel(int total_rows, const mpb_w16_layer* __restrict__ l
         frexpf(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
         sc = ldexpf(1.f, max(-100, min(100, 14 - e)));
     }
-    if (lane == 0) L.inv_scale[co] = 1.f / sc;
+    if (lane == 0) {
+        L.inv_scale[co] = 1.f / sc;
+        if (L.scale) L.scale[co] = s;
+        if (L.shift) L.shift[co] = L.beta[co] - L.mean[co] * s;
+    }
     const float m = s * sc;
     unsigned char* d = reinterpret_cast<unsigned char*>(L.w16) + (size_t)co * L.K * 4;
+    float4* wf4 = L.wf ? reinterpret_cast<float4*>(L.wf + (size_t)co * L.K) : nullptr;
     for (int k = lane; k < n4; k += 32) {
         const float4 v = __ldg(w4 + k);
+        if (wf4) wf4[k] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);      // folded fp32 weights (backward operand)
         uint32_t h0, l0, h1, l1;
         split16_pair_(v.x * m, v.y * m, h0, l0);
         split16_pair_(v.z * m, v.w * m, h1, l1);

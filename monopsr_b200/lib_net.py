@@ -56,7 +56,7 @@ class BnLayer(ctypes.Structure):
 
 class W16Layer(ctypes.Structure):
     _fields_ = [("w", c_p), ("gamma", c_p), ("var", c_p), ("w16", c_p), ("inv_scale", c_p), ("cout", c_i), ("K", c_i),
-                ("row0", c_i), ("pad_", c_i)]
+                ("row0", c_i), ("pad_", c_i), ("wf", c_p), ("scale", c_p), ("shift", c_p), ("beta", c_p), ("mean", c_p)]
 
 
 class OptChunk(ctypes.Structure):
