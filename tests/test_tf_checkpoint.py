@@ -206,3 +206,50 @@ def test_detection_checkpoint_mapping_equals_the_reference_restore_logic():
         assert enc + "/resnet_v1_101/conv1/weights" not in loaded       # foreign shape: skipped by both
         assert enc + "/resnet_v1_101/conv1/BatchNorm/gamma" in loaded
     assert not any(n.startswith(("squash/", "map_decoder/", "output/")) for n in loaded)
+
+
+def test_training_resume_restores_adam_and_ema_slots(tmp_path):
+    """a training checkpoint carries '<var>/Adam', '<var>/Adam_1', '<var>/ExponentialMovingAverage' (tf.train.Saver saves
+    the optimizer's slot variables; core/trainer.py:85,148-153 restores them): map_slots finds them, also below the
+    train-op's name scope, and load_checkpoint(with_slots=True) reports them with the int32 global step"""
+    rng = np.random.RandomState(3)
+    table = [("x/weights", (3, 3, 4, 8), "weights"), ("x/BatchNorm/gamma", (8,), "gamma"), ("y/weights", (16, 5), "weights")]
+    T = {}
+    for n, s, _ in table:
+        T[n] = rng.randn(*s).astype(np.float32)
+    for n, s, _ in table[:2]:
+        for sfx in (C.ADAM_M_SUFFIX, C.ADAM_V_SUFFIX, C.EMA_SUFFIX):
+            T[n + sfx] = rng.randn(*s).astype(np.float32)
+    for sfx in (C.ADAM_M_SUFFIX, C.ADAM_V_SUFFIX, C.EMA_SUFFIX):          # the third variable: slots under 'train_op/'
+        T["train_op/y/weights" + sfx] = rng.randn(16, 5).astype(np.float32)
+    T["global_step"] = np.array(4000, np.int32)
+    prefix = str(tmp_path / "m-00004000")
+    C.write_bundle(prefix, T)
+    assert sorted(os.listdir(tmp_path)) == ["m-00004000.data-00000-of-00001", "m-00004000.index"]     # no temporary files left
+    params, report = C.load_checkpoint(prefix, table, with_slots=True)
+    assert report["global_step"] == 4000 and not report["missing"]
+    assert sorted(report["slots"]) == sorted(n for n, _, _ in table)
+    for n, _, _ in table:
+        m, v, e = report["slots"][n]
+        src = n if n != "y/weights" else "train_op/" + n
+        assert np.array_equal(m, T[src + C.ADAM_M_SUFFIX]) and np.array_equal(v, T[src + C.ADAM_V_SUFFIX])
+        assert np.array_equal(e, T[src + C.EMA_SUFFIX]) and np.array_equal(params[n], T[n])
+    # the shadows win only on request, and are found below the name scope too
+    ema, _ = C.load_checkpoint(prefix, table, use_ema=True)
+    assert np.array_equal(ema["y/weights"], T["train_op/y/weights" + C.EMA_SUFFIX])
+    raw, rep = C.load_checkpoint(prefix, table)
+    assert np.array_equal(raw["y/weights"], T["y/weights"]) and "slots" not in rep
+    # a variable with an incomplete slot set is left to re-initialisation
+    del T["x/weights" + C.ADAM_V_SUFFIX]
+    C.write_bundle(prefix, T)
+    assert "x/weights" not in C.load_checkpoint(prefix, table, with_slots=True)[1]["slots"]
+
+
+def test_a_reader_never_sees_a_half_written_checkpoint(tmp_path, monkeypatch):
+    """data and index are written under temporary names and renamed into place, the index last"""
+    order = []
+    real = os.replace
+    monkeypatch.setattr(os, "replace", lambda a, b: (order.append(os.path.basename(b)), real(a, b))[1])
+    C.write_bundle(str(tmp_path / "c"), {"v": np.arange(4, dtype=np.float32)})
+    assert order == ["c.data-00000-of-00001", "c.index"]
+    assert np.array_equal(C.read_bundle(str(tmp_path / "c"))["v"], np.arange(4, dtype=np.float32))

@@ -127,3 +127,24 @@ def test_inputs_may_not_change_shape_after_capture(cuda):
     bad["full_img"] = np.zeros((1, 80, 304, 3), np.float32)
     with pytest.raises(mlib.MpbError):
         eng.set_inputs(bad)
+
+
+def test_training_resume_restores_optimizer_state(cuda, tmp_path):
+    """save after two steps, resume into a fresh engine: variables, Adam moments and EMA shadows are back bit for bit
+    (tf.train.Saver semantics; a resume that zeroed the moments would over-step ~3x on its first updates)"""
+    S = ms.synthetic_sample(3)
+    a = Engine(cuda, params=ms.init_params(3))
+    a.train_step(S)
+    a.train_step(S)
+    torch.cuda.synchronize()
+    prefix = str(tmp_path / "monopsr_model-00000002")
+    a.save_checkpoint(prefix, global_step=2)
+    b = Engine(cuda, params=ms.init_params(4))
+    rep = b.load_checkpoint(prefix, resume=True)
+    assert rep["global_step"] == 2 and len(rep["slots"]) == len(b.trainable_names)
+    for x, y in ((a.params, b.params), (a.adam_m, b.adam_m), (a.adam_v, b.adam_v), (a.ema, b.ema), (a.state, b.state)):
+        assert torch.equal(x, y)
+    assert float(b.adam_v.abs().max()) > 0
+    c = Engine(cuda, params=ms.init_params(4))
+    c.load_checkpoint(prefix)                      # plain restore (evaluation): fresh optimizer state, raw variables
+    assert torch.equal(c.params, a.params) and float(c.adam_m.abs().max()) == 0 and torch.equal(c.ema, c.params)
