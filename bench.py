@@ -464,7 +464,7 @@ def main():
         "roofline": roofline,
     }
     eng.check_overflow()
-    if not args.no_ops:
+    if not args.no_ops and world == 1:        # the op configurations are single-GPU measurements
         line["ops"] = tfops_micro(dev)
     if not args.no_cpu_baseline and world == 1:
         threads = cpu_threads()

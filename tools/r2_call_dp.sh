@@ -10,7 +10,7 @@ timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 python - <<PY
 import json
 try:
-    d = json.load(open("$OUT/bench.json"))
+    d = json.loads([l for l in open("$OUT/bench.json") if l.startswith("{")][-1])
     print("N=%d %.3f ms/step %.0f crops/s e2e %.0f" % (d["n_gpus"], d["ms_per_step"], d["value"], d["e2e"]["value"]))
 except Exception as e:
     print("bench failed", e); print(open("$OUT/bench.err").read()[-1500:])
