@@ -98,10 +98,13 @@ class Engine:
         # CTAs of a bulk launch from another stream.  The dependent chains (main, full-image tower, FC stacks) run
         # at high priority; weight gradients, zero-fills and the side train-op are filler at default priority.
         # Measured: 9.09 vs 8.55 ms/step -- the starved weight-gradient streams finish late -- so OFF by default.
-        hi = -1 if int(os.environ.get("MPB_STREAM_PRIO", "0")) else 0
+        # MPB_STREAM_PRIO=2: only the FC stacks' stream -- a chain of SMALL kernels whose backward half gates the towers'
+        # backward pass and which the timeline shows waiting 20-100 us at a time behind the decoder's bulk weight gradients
+        prio = int(os.environ.get("MPB_STREAM_PRIO", "0"))
+        hi = -1 if prio == 1 else 0
         self.s_main = torch.cuda.Stream(device=self.dev, priority=hi)     # capture stream of the step
         self.s_full = torch.cuda.Stream(device=self.dev, priority=hi)
-        self.s_fc = torch.cuda.Stream(device=self.dev, priority=hi)
+        self.s_fc = torch.cuda.Stream(device=self.dev, priority=-1 if prio in (1, 2) else 0)
         self.s_wc = torch.cuda.Stream(device=self.dev)
         self.s_wf = torch.cuda.Stream(device=self.dev)
         self.s_opt = torch.cuda.Stream(device=self.dev)

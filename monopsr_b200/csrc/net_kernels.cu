@@ -414,53 +414,85 @@ __device__ __forceinline__ float crop_sample(const float* feat, int W, int C, in
     return top + (bot - top) * c.ly;
 }
 
-__global__ void crop_pool_fwd_kernel(int H, int W, int C, const float* __restrict__ feat, int nbox,
-                                     const float* __restrict__ boxes, int crop, float* __restrict__ out, int ldo) {
-    const int P = crop / 2;
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)nbox * P * P * C;
-    if (i >= total) return;
-    const int ch = (int)(i % C);
-    long p = i / C;
-    const int pw = (int)(p % P); p /= P;
-    const int ph = (int)(p % P);
-    const int b = (int)(p / P);
-    float m = -INFINITY;
-    for (int k = 0; k < 4; k++) {
-        CropCoord c = crop_coord(boxes + b * 4, ph * 2 + (k >> 1), pw * 2 + (k & 1), crop, H, W);
-        m = fmaxf(m, crop_sample(feat, W, C, ch, c));
-    }
-    out[(((size_t)b * P + ph) * P + pw) * ldo + ch] = rtf32(m);
+// thread = (box, pooled pixel, 4 channels): 16-byte loads of the four bilinear corners (the one-channel-per-thread
+// versions took 75 / 103 us on the critical path either side of the full-image tower, profiles/r2_notes.md)
+__device__ __forceinline__ float4 crop_sample4(const float* feat, int W, int C, int ch, const CropCoord& c) {
+    if (!c.valid) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 tl = *reinterpret_cast<const float4*>(feat + ((size_t)c.y0 * W + c.x0) * C + ch);
+    const float4 tr = *reinterpret_cast<const float4*>(feat + ((size_t)c.y0 * W + c.x1i) * C + ch);
+    const float4 bl = *reinterpret_cast<const float4*>(feat + ((size_t)c.y1i * W + c.x0) * C + ch);
+    const float4 br = *reinterpret_cast<const float4*>(feat + ((size_t)c.y1i * W + c.x1i) * C + ch);
+    float4 o;
+#define MPB_BIL(f) { const float top = tl.f + (tr.f - tl.f) * c.lx, bot = bl.f + (br.f - bl.f) * c.lx; o.f = top + (bot - top) * c.ly; }
+    MPB_BIL(x) MPB_BIL(y) MPB_BIL(z) MPB_BIL(w)
+#undef MPB_BIL
+    return o;
 }
 
-__global__ void crop_pool_bwd_kernel(int H, int W, int C, const float* __restrict__ feat, int nbox,
-                                     const float* __restrict__ boxes, int crop, const float* __restrict__ dout,
-                                     int ldd, float* __restrict__ dfeat) {
-    const int P = crop / 2;
+__global__ void __launch_bounds__(256)
+crop_pool_fwd_kernel(int H, int W, int C, const float* __restrict__ feat, int nbox,
+                     const float* __restrict__ boxes, int crop, float* __restrict__ out, int ldo) {
+    const int P = crop / 2, C4 = C >> 2;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)nbox * P * P * C;
+    const long total = (long)nbox * P * P * C4;
     if (i >= total) return;
-    const int ch = (int)(i % C);
-    long p = i / C;
+    const int ch = (int)(i % C4) * 4;
+    long p = i / C4;
     const int pw = (int)(p % P); p /= P;
     const int ph = (int)(p % P);
     const int b = (int)(p / P);
-    const float g = dout[(((size_t)b * P + ph) * P + pw) * ldd + ch];
-    if (g == 0.f) return;
-    float m = -INFINITY;
-    int best = 0;
-    CropCoord bc;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
     for (int k = 0; k < 4; k++) {
-        CropCoord c = crop_coord(boxes + b * 4, ph * 2 + (k >> 1), pw * 2 + (k & 1), crop, H, W);
-        const float v = crop_sample(feat, W, C, ch, c);
-        if (v > m) { m = v; best = k; bc = c; }
+        const CropCoord c = crop_coord(boxes + b * 4, ph * 2 + (k >> 1), pw * 2 + (k & 1), crop, H, W);
+        const float4 v = crop_sample4(feat, W, C, ch, c);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
-    (void)best;
-    if (!bc.valid) return;
-    atomicAdd(&dfeat[((size_t)bc.y0 * W + bc.x0) * C + ch], g * (1.f - bc.ly) * (1.f - bc.lx));
-    atomicAdd(&dfeat[((size_t)bc.y0 * W + bc.x1i) * C + ch], g * (1.f - bc.ly) * bc.lx);
-    atomicAdd(&dfeat[((size_t)bc.y1i * W + bc.x0) * C + ch], g * bc.ly * (1.f - bc.lx));
-    atomicAdd(&dfeat[((size_t)bc.y1i * W + bc.x1i) * C + ch], g * bc.ly * bc.lx);
+    *reinterpret_cast<float4*>(out + (((size_t)b * P + ph) * P + pw) * ldo + ch) =
+        make_float4(rtf32(m.x), rtf32(m.y), rtf32(m.z), rtf32(m.w));
+}
+
+__global__ void __launch_bounds__(256)
+crop_pool_bwd_kernel(int H, int W, int C, const float* __restrict__ feat, int nbox,
+                     const float* __restrict__ boxes, int crop, const float* __restrict__ dout,
+                     int ldd, float* __restrict__ dfeat) {
+    const int P = crop / 2, C4 = C >> 2;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)nbox * P * P * C4;
+    if (i >= total) return;
+    const int ch = (int)(i % C4) * 4;
+    long p = i / C4;
+    const int pw = (int)(p % P); p /= P;
+    const int ph = (int)(p % P);
+    const int b = (int)(p / P);
+    const float4 g4 = *reinterpret_cast<const float4*>(dout + (((size_t)b * P + ph) * P + pw) * ldd + ch);
+    if (g4.x == 0.f && g4.y == 0.f && g4.z == 0.f && g4.w == 0.f) return;
+    // first maximum of the four samples, per channel (strict >: the forward's fmaxf keeps the first of equals)
+    CropCoord cs[4];
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    int bx = 0, by = 0, bz = 0, bw = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        cs[k] = crop_coord(boxes + b * 4, ph * 2 + (k >> 1), pw * 2 + (k & 1), crop, H, W);
+        const float4 v = crop_sample4(feat, W, C, ch, cs[k]);
+        if (v.x > m.x) { m.x = v.x; bx = k; }
+        if (v.y > m.y) { m.y = v.y; by = k; }
+        if (v.z > m.z) { m.z = v.z; bz = k; }
+        if (v.w > m.w) { m.w = v.w; bw = k; }
+    }
+    // the gradient of each channel goes to the corners of ITS winning sample: per sample k, one vector RED per corner
+    // with the channels that did not pick k zeroed (channels mostly agree, so most vectors are skipped)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float4 g = make_float4(bx == k ? g4.x : 0.f, by == k ? g4.y : 0.f, bz == k ? g4.z : 0.f, bw == k ? g4.w : 0.f);
+        if ((g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) || !cs[k].valid) continue;
+        const CropCoord& c = cs[k];
+        const float w00 = (1.f - c.ly) * (1.f - c.lx), w01 = (1.f - c.ly) * c.lx, w10 = c.ly * (1.f - c.lx), w11 = c.ly * c.lx;
+        atomicAdd(reinterpret_cast<float4*>(dfeat + ((size_t)c.y0 * W + c.x0) * C + ch), make_float4(g.x * w00, g.y * w00, g.z * w00, g.w * w00));
+        atomicAdd(reinterpret_cast<float4*>(dfeat + ((size_t)c.y0 * W + c.x1i) * C + ch), make_float4(g.x * w01, g.y * w01, g.z * w01, g.w * w01));
+        atomicAdd(reinterpret_cast<float4*>(dfeat + ((size_t)c.y1i * W + c.x0) * C + ch), make_float4(g.x * w10, g.y * w10, g.z * w10, g.w * w10));
+        atomicAdd(reinterpret_cast<float4*>(dfeat + ((size_t)c.y1i * W + c.x1i) * C + ch), make_float4(g.x * w11, g.y * w11, g.z * w11, g.w * w11));
+    }
 }
 
 // ---------------------------------------------------------------- bilinear resize, align_corners=True
@@ -690,6 +722,21 @@ bn_bwd_apply_kernel(long total4, int M, int C, const float* __restrict__ z, cons
 // add_inst_xyz_maps_local (monopsr_output_builder.py:95-108).  N=3 output channels: bandwidth
 // bound on the (32,48,48,128) map features; one warp per output pixel, lanes over the 128
 // channels (float4 each), weights [3][9][128] in shared memory.
+// A warp owns kXyzPx = 8 consecutive pixels of one image row (W % 8 == 0): the 3 x 10 input pixels it needs are loaded
+// once (30 LDG.128 per lane instead of 72), the nine (tap, output) weight vectors of a filter row sit in registers for
+// the ten columns, and the 24 partial sums are reduced across the lanes with a halving butterfly (27 SHFL, not 120).
+// (One warp per pixel re-read every input pixel nine times: 340 MB through L1/L2 for a 38 MB tensor, 62 us.)
+constexpr int kXyzPx = 8;
+template <int H_, int BIT>
+__device__ __forceinline__ void xyz_halve(const float* v, float* u, int lane) {
+    const bool up = (lane & BIT) != 0;
+#pragma unroll
+    for (int i = 0; i < H_; i++) {
+        const float keep = up ? v[H_ + i] : v[i];
+        const float send = up ? v[i] : v[H_ + i];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
+    }
+}
 __global__ void __launch_bounds__(256)
 xyzhead_fwd_kernel(int nimg, int H, int W, const float* __restrict__ x, const float* __restrict__ w,
                    const float* __restrict__ bias, float* __restrict__ y) {
@@ -697,31 +744,58 @@ xyzhead_fwd_kernel(int nimg, int H, int W, const float* __restrict__ x, const fl
     for (int i = threadIdx.x; i < 3 * 9 * 32; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pix >= (long)nimg * H * W) return;
-    const int n = (int)(pix / (H * W)), rem = (int)(pix % (H * W)), h = rem / W, ww = rem % W;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int t = 0; t < 9; t++) {
-        const int ih = h + t / 3 - 1, iw = ww + t % 3 - 1;
-        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-        const float4 v = reinterpret_cast<const float4*>(x + (((size_t)n * H + ih) * W + iw) * 128)[lane];
-        const float4 w0 = sw[(0 * 9 + t) * 32 + lane], w1 = sw[(1 * 9 + t) * 32 + lane], w2 = sw[(2 * 9 + t) * 32 + lane];
-        a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
-        a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
-        a2 += v.x * w2.x + v.y * w2.y + v.z * w2.z + v.w * w2.w;
+    const int wpr = W / kXyzPx;                                      // warps per image row
+    const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= (long)nimg * H * wpr) return;
+    const int n = (int)(wid / ((long)H * wpr)), rem = (int)(wid % ((long)H * wpr)), h = rem / wpr, w0 = (rem % wpr) * kXyzPx;
+    float acc[kXyzPx * 3];
+#pragma unroll
+    for (int i = 0; i < kXyzPx * 3; i++) acc[i] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+        const int ih = h + ky - 1;
+        if (ih < 0 || ih >= H) continue;                             // warp-uniform
+        float4 wt[3][3];                                             // [kx][output]
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++)
+#pragma unroll
+            for (int o = 0; o < 3; o++) wt[kx][o] = sw[(o * 9 + ky * 3 + kx) * 32 + lane];
+        const float4* row = reinterpret_cast<const float4*>(x + (((size_t)n * H + ih) * W) * 128) + lane;
+#pragma unroll
+        for (int cx = -1; cx <= kXyzPx; cx++) {
+            const int iw = w0 + cx;
+            if (iw < 0 || iw >= W) continue;                         // warp-uniform
+            const float4 v = row[(size_t)iw * 32];
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const int p = cx - kx + 1;                           // output pixel that sees column cx through tap kx
+                if (p < 0 || p >= kXyzPx) continue;                  // compile-time after unrolling
+#pragma unroll
+                for (int o = 0; o < 3; o++) {
+                    const float4 q = wt[kx][o];
+                    acc[p * 3 + o] += v.x * q.x + v.y * q.y + v.z * q.z + v.w * q.w;
+                }
+            }
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    float u12[12], u6[6], u3[3];
+    xyz_halve<12, 16>(acc, u12, lane);
+    xyz_halve<6, 8>(u12, u6, lane);
+    xyz_halve<3, 4>(u6, u3, lane);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        u3[i] += __shfl_xor_sync(0xffffffffu, u3[i], 2);
+        u3[i] += __shfl_xor_sync(0xffffffffu, u3[i], 1);
     }
-    if (lane == 0) {
-        y[pix * 3 + 0] = a0 + bias[0];
-        y[pix * 3 + 1] = a1 + bias[1];
-        y[pix * 3 + 2] = a2 + bias[2];
+    if ((lane & 3) == 0) {                                           // lanes 4j .. 4j+3 hold pixel j
+        float* d = y + ((((size_t)n * H + h) * W) + w0 + (lane >> 2)) * 3;
+        d[0] = u3[0] + bias[0];
+        d[1] = u3[1] + bias[1];
+        d[2] = u3[2] + bias[2];
     }
 }
-// dX[p][ci] = sum_{t,co} dY[p - off(t)][co] * w[co][t][ci]   (thread = (pixel, 4 channels))
+// dX[p][ci] = sum_{t,co} dY[p - off(t)][co] * w[co][t][ci]   (thread = 4 channels; a warp owns 8 consecutive pixels of a
+// row, so the 27 weight vectors are fetched from shared memory once per 8 pixels and dY comes from 3 x 10 x 3 broadcast loads)
 __global__ void __launch_bounds__(256)
 xyzhead_dgrad_kernel(int nimg, int H, int W, const float* __restrict__ dy, const float* __restrict__ w,
                      float* __restrict__ dx) {
@@ -729,22 +803,43 @@ xyzhead_dgrad_kernel(int nimg, int H, int W, const float* __restrict__ dy, const
     for (int i = threadIdx.x; i < 3 * 9 * 32; i += blockDim.x) sw[i] = reinterpret_cast<const float4*>(w)[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pix >= (long)nimg * H * W) return;
-    const int n = (int)(pix / (H * W)), rem = (int)(pix % (H * W)), h = rem / W, ww = rem % W;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = 0; t < 9; t++) {
-        const int ih = h - (t / 3 - 1), iw = ww - (t % 3 - 1);
-        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-        const float* g = dy + (((size_t)n * H + ih) * W + iw) * 3;
-        const float g0 = g[0], g1 = g[1], g2 = g[2];
-        const float4 w0 = sw[(0 * 9 + t) * 32 + lane], w1 = sw[(1 * 9 + t) * 32 + lane], w2 = sw[(2 * 9 + t) * 32 + lane];
-        acc.x += g0 * w0.x + g1 * w1.x + g2 * w2.x;
-        acc.y += g0 * w0.y + g1 * w1.y + g2 * w2.y;
-        acc.z += g0 * w0.z + g1 * w1.z + g2 * w2.z;
-        acc.w += g0 * w0.w + g1 * w1.w + g2 * w2.w;
+    const int wpr = W / kXyzPx;
+    const long wid = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= (long)nimg * H * wpr) return;
+    const int n = (int)(wid / ((long)H * wpr)), rem = (int)(wid % ((long)H * wpr)), h = rem / wpr, w0 = (rem % wpr) * kXyzPx;
+    float4 acc[kXyzPx];
+#pragma unroll
+    for (int i = 0; i < kXyzPx; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+        const int ih = h - (ky - 1);                                 // dY row that reaches this row through filter row ky
+        if (ih < 0 || ih >= H) continue;
+        float4 wt[3][3];
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++)
+#pragma unroll
+            for (int o = 0; o < 3; o++) wt[kx][o] = sw[(o * 9 + ky * 3 + kx) * 32 + lane];
+        const float* grow = dy + (((size_t)n * H + ih) * W) * 3;
+#pragma unroll
+        for (int cx = -1; cx <= kXyzPx; cx++) {
+            const int iw = w0 + cx;
+            if (iw < 0 || iw >= W) continue;
+            const float g0 = __ldg(grow + (size_t)iw * 3), g1 = __ldg(grow + (size_t)iw * 3 + 1), g2 = __ldg(grow + (size_t)iw * 3 + 2);
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const int p = cx + kx - 1;                           // dX pixel p reads dY[p - (kx - 1)] through tap kx
+                if (p < 0 || p >= kXyzPx) continue;
+                const float4 q0 = wt[kx][0], q1 = wt[kx][1], q2 = wt[kx][2];
+                acc[p].x += g0 * q0.x + g1 * q1.x + g2 * q2.x;
+                acc[p].y += g0 * q0.y + g1 * q1.y + g2 * q2.y;
+                acc[p].z += g0 * q0.z + g1 * q1.z + g2 * q2.z;
+                acc[p].w += g0 * q0.w + g1 * q1.w + g2 * q2.w;
+            }
+        }
     }
-    reinterpret_cast<float4*>(dx + (size_t)pix * 128)[lane] = acc;
+    float4* d = reinterpret_cast<float4*>(dx + ((((size_t)n * H + h) * W) + w0) * 128) + lane;
+#pragma unroll
+    for (int i = 0; i < kXyzPx; i++) d[(size_t)i * 32] = acc[i];
 }
 // dW[co][t][ci] += sum_p dY[p][co] * x[p + off(t)][ci];  db[co] += sum_p dY[p][co]
 // CTA = 128 threads (ci) x a strip of pixels; 27 accumulators per thread.
@@ -793,28 +888,38 @@ __global__ void fc_small_fwd_kernel(int B, int K, int N, const float* __restrict
     if (lane == 0) y[(size_t)b * ldy + n] = acc + bias[n];
 }
 // dx[b][k] (+)= sum_n dy[b][n] w[n][k];  dw[n][k] += sum_b dy[b][n] x[b][k];  db[n] += sum_b dy[b][n]
-__global__ void fc_small_bwd_kernel(int B, int K, int N, const float* __restrict__ x, int ldx,
-                                    const float* __restrict__ w, const float* __restrict__ dy, int ldy,
-                                    float* __restrict__ dx, int lddx, int accumulate_dx,
-                                    float* __restrict__ dw, float* __restrict__ db) {
+// grid (K tiles, B + N): row r < B of the grid computes dx[r][:], row B + n computes dw[n][:]; dy (B x N, a few hundred
+// floats) is staged in shared memory.  (The first version looped over B x N + N x B dependent global loads in 8 CTAs:
+// 16-119 us per call, four calls on the FC stacks' backward chain, which gates the towers' backward pass.)
+__global__ void __launch_bounds__(128)
+fc_small_bwd_kernel(int B, int K, int N, const float* __restrict__ x, int ldx,
+                    const float* __restrict__ w, const float* __restrict__ dy, int ldy,
+                    float* __restrict__ dx, int lddx, int accumulate_dx,
+                    float* __restrict__ dw, float* __restrict__ db) {
+    extern __shared__ float sdy[];                       // [B][N]
+    for (int i = threadIdx.x; i < B * N; i += blockDim.x) sdy[i] = dy[(size_t)(i / N) * ldy + i % N];
+    __syncthreads();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < K) {
-        for (int b = 0; b < B; b++) {
+    const int r = blockIdx.y;
+    if (r < B) {
+        if (k < K) {
             float acc = 0.f;
-            for (int n = 0; n < N; n++) acc = fmaf(dy[(size_t)b * ldy + n], w[(size_t)n * K + k], acc);
-            float* d = dx + (size_t)b * lddx + k;
+            for (int n = 0; n < N; n++) acc = fmaf(sdy[r * N + n], w[(size_t)n * K + k], acc);
+            float* d = dx + (size_t)r * lddx + k;
             *d = accumulate_dx ? (*d + acc) : acc;
         }
-        for (int n = 0; n < N; n++) {
+    } else {
+        const int n = r - B;
+        if (k < K) {
             float acc = 0.f;
-            for (int b = 0; b < B; b++) acc = fmaf(dy[(size_t)b * ldy + n], x[(size_t)b * ldx + k], acc);
+            for (int b = 0; b < B; b++) acc = fmaf(sdy[b * N + n], x[(size_t)b * ldx + k], acc);
             dw[(size_t)n * K + k] += acc;
         }
-    }
-    if (k < N) {
-        float acc = 0.f;
-        for (int b = 0; b < B; b++) acc += dy[(size_t)b * ldy + k];
-        db[k] += acc;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            float acc = 0.f;
+            for (int b = 0; b < B; b++) acc += sdy[b * N + n];
+            db[n] += acc;
+        }
     }
 }
 
@@ -945,16 +1050,20 @@ MPB_API int mpb_maxpool2_bwd(int nimg, int H, int W, int C, const float* x, int 
 }
 MPB_API int mpb_crop_pool_fwd(int H, int W, int C, const float* feat, int nbox, const float* boxes_norm, int crop,
                               float* out, int ldo, void* stream) {
-    crop_pool_fwd_kernel<<<nblk((long)nbox * (crop / 2) * (crop / 2) * C, 256), 256, 0, ST>>>(H, W, C, feat, nbox,
-                                                                                            boxes_norm, crop, out, ldo);
+    if (C % 4 || ldo % 4 || (reinterpret_cast<uintptr_t>(feat) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return -1;
+    crop_pool_fwd_kernel<<<nblk((long)nbox * (crop / 2) * (crop / 2) * (C / 4), 256), 256, 0, ST>>>(H, W, C, feat, nbox,
+                                                                                                  boxes_norm, crop, out, ldo);
     MPB_LAUNCH_CHECK();
     return 0;
 }
 MPB_API int mpb_crop_pool_bwd(int H, int W, int C, const float* feat, int nbox, const float* boxes_norm, int crop,
                               const float* dout, int ldd, float* dfeat, void* stream) {
+    if (C % 4 || ldd % 4 || (reinterpret_cast<uintptr_t>(feat) & 15u) || (reinterpret_cast<uintptr_t>(dout) & 15u) ||
+        (reinterpret_cast<uintptr_t>(dfeat) & 15u))
+        return -1;
     MPB_CUDA_TRY(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)H * W * C, ST));
-    crop_pool_bwd_kernel<<<nblk((long)nbox * (crop / 2) * (crop / 2) * C, 256), 256, 0, ST>>>(H, W, C, feat, nbox,
-                                                                                            boxes_norm, crop, dout, ldd, dfeat);
+    crop_pool_bwd_kernel<<<nblk((long)nbox * (crop / 2) * (crop / 2) * (C / 4), 256), 256, 0, ST>>>(H, W, C, feat, nbox,
+                                                                                                  boxes_norm, crop, dout, ldd, dfeat);
     MPB_LAUNCH_CHECK();
     return 0;
 }
@@ -1031,12 +1140,14 @@ MPB_API int mpb_bn_train_bwd(int M, int C, const float* z, const float* mean, co
     return 0;
 }
 MPB_API int mpb_xyzhead_fwd(int nimg, int H, int W, const float* x, const float* w, const float* bias, float* y, void* stream) {
-    xyzhead_fwd_kernel<<<nblk((long)nimg * H * W, 8), 256, 0, ST>>>(nimg, H, W, x, w, bias, y);
+    if (W % kXyzPx) return -1;
+    xyzhead_fwd_kernel<<<nblk((long)nimg * H * (W / kXyzPx), 8), 256, 0, ST>>>(nimg, H, W, x, w, bias, y);
     MPB_LAUNCH_CHECK();
     return 0;
 }
 MPB_API int mpb_xyzhead_dgrad(int nimg, int H, int W, const float* w, const float* dy, float* dx, void* stream) {
-    xyzhead_dgrad_kernel<<<nblk((long)nimg * H * W, 8), 256, 0, ST>>>(nimg, H, W, dy, w, dx);
+    if (W % kXyzPx) return -1;
+    xyzhead_dgrad_kernel<<<nblk((long)nimg * H * (W / kXyzPx), 8), 256, 0, ST>>>(nimg, H, W, dy, w, dx);
     MPB_LAUNCH_CHECK();
     return 0;
 }
@@ -1059,7 +1170,9 @@ MPB_API int mpb_fc_small_fwd(int B, int K, int N, const float* x, int ldx, const
 }
 MPB_API int mpb_fc_small_bwd(int B, int K, int N, const float* x, int ldx, const float* w, const float* dy, int ldy,
                              float* dx, int lddx, int accumulate_dx, float* dw, float* db, void* stream) {
-    fc_small_bwd_kernel<<<nblk(K > N ? K : N, 128), 128, 0, ST>>>(B, K, N, x, ldx, w, dy, ldy, dx, lddx, accumulate_dx, dw, db);
+    if (B <= 0 || K <= 0 || N <= 0 || (size_t)B * N * sizeof(float) > 48 * 1024) return -1;
+    fc_small_bwd_kernel<<<dim3(ceil_div(K, 128), B + N), 128, sizeof(float) * B * N, ST>>>(B, K, N, x, ldx, w, dy, ldy, dx, lddx,
+                                                                                       accumulate_dx, dw, db);
     MPB_LAUNCH_CHECK();
     return 0;
 }
