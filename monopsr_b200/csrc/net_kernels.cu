@@ -167,46 +167,70 @@ bn_param_grad_multi_kernel(int row_begin, int total_rows, const mpb_bn_layer* __
 
 // ---------------------------------------------------------------- stem: conv 7x7/2 + BN + ReLU
 // resnet_utils.conv2d_same(net, 64, 7, stride=2) (nets/resnet_v1.py:234): pad 3|3, VALID.
-// Cin=3 -> K=147: bandwidth-bound, kept off the tensor cores.  One thread = one output pixel x
-// 16 channels; folded weights in shared memory.
+// Cin=3 -> K=147: kept off the tensor cores.  One thread = FOUR consecutive output pixels of a row x 8 channels: the 24
+// weights of a tap (two LDS.128 per input channel from a k-major copy in shared memory) are used for four pixels, the
+// 13 x 3 input values of a filter row for all seven taps.  (One pixel x 16 channels per thread issued one LDS per FMA:
+// 134 us for the full image at the head of the full-image tower's chain, with nothing else to run beside it.)
 constexpr int kStemK = 147;
+constexpr int kStemPx = 4, kStemCg = 8;
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(int nimg, int Hin, int Win, int Ho, int Wo, const float* __restrict__ x,
                 const float* __restrict__ wf, const float* __restrict__ shift, float* __restrict__ y) {
-    __shared__ float sw[64 * kStemK];
-    for (int i = threadIdx.x; i < 64 * kStemK; i += blockDim.x) sw[i] = wf[i];
+    __shared__ __align__(16) float swt[kStemK * 64];                 // [k][co]
+    for (int i = threadIdx.x; i < 64 * kStemK; i += blockDim.x)      // conflict-free stores; the strided reads hit L2
+        swt[i] = __ldg(wf + (size_t)(i & 63) * kStemK + (i >> 6));
     __syncthreads();
-    const int cg = threadIdx.x & 3;                       // 4 groups of 16 output channels
-    const long pix = (long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
-    const long total = (long)nimg * Ho * Wo;
-    if (pix >= total) return;
-    const int n = (int)(pix / (Ho * Wo)), rem = (int)(pix % (Ho * Wo)), oh = rem / Wo, ow = rem % Wo;
-    float acc[16];
+    const int cg = threadIdx.x & 7;                                  // 8 groups of 8 output channels
+    const int qpr = (Wo + kStemPx - 1) / kStemPx;                    // pixel quads per output row
+    const long quad = (long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+    if (quad >= (long)nimg * Ho * qpr) return;
+    const int n = (int)(quad / ((long)Ho * qpr)), rem = (int)(quad % ((long)Ho * qpr)), oh = rem / qpr, ow0 = (rem % qpr) * kStemPx;
+    float acc[kStemPx][kStemCg];
 #pragma unroll
-    for (int c = 0; c < 16; c++) acc[c] = 0.f;
+    for (int p = 0; p < kStemPx; p++)
+#pragma unroll
+        for (int c = 0; c < kStemCg; c++) acc[p][c] = 0.f;
     for (int kh = 0; kh < 7; kh++) {
         const int ih = oh * 2 - 3 + kh;
         if (ih < 0 || ih >= Hin) continue;
-        for (int kw = 0; kw < 7; kw++) {
-            const int iw = ow * 2 - 3 + kw;
-            if (iw < 0 || iw >= Win) continue;
-            const float* xp = x + (((size_t)n * Hin + ih) * Win + iw) * 3;
-            const float x0 = xp[0], x1 = xp[1], x2 = xp[2];
-            const float* wp = sw + (cg * 16) * kStemK + (kh * 7 + kw) * 3;
+        const float* xr = x + ((size_t)n * Hin + ih) * Win * 3;
+        float px[2 * kStemPx + 5][3];                                // input columns ow0*2-3 .. ow0*2+9
 #pragma unroll
-            for (int c = 0; c < 16; c++)
-                acc[c] = fmaf(x2, wp[c * kStemK + 2], fmaf(x1, wp[c * kStemK + 1], fmaf(x0, wp[c * kStemK], acc[c])));
+        for (int j = 0; j < 2 * kStemPx + 5; j++) {
+            const int iw = ow0 * 2 - 3 + j;
+            const bool in = iw >= 0 && iw < Win;
+            px[j][0] = in ? __ldg(xr + (size_t)iw * 3) : 0.f;
+            px[j][1] = in ? __ldg(xr + (size_t)iw * 3 + 1) : 0.f;
+            px[j][2] = in ? __ldg(xr + (size_t)iw * 3 + 2) : 0.f;
+        }
+#pragma unroll
+        for (int kw = 0; kw < 7; kw++) {
+            float wv[3][kStemCg];
+#pragma unroll
+            for (int ci = 0; ci < 3; ci++) {
+                const float4* wp = reinterpret_cast<const float4*>(swt + ((kh * 7 + kw) * 3 + ci) * 64 + cg * kStemCg);
+                const float4 a = wp[0], b = wp[1];
+                wv[ci][0] = a.x; wv[ci][1] = a.y; wv[ci][2] = a.z; wv[ci][3] = a.w;
+                wv[ci][4] = b.x; wv[ci][5] = b.y; wv[ci][6] = b.z; wv[ci][7] = b.w;
+            }
+#pragma unroll
+            for (int p = 0; p < kStemPx; p++) {
+                const int j = kw + 2 * p;
+#pragma unroll
+                for (int c = 0; c < kStemCg; c++)
+                    acc[p][c] = fmaf(px[j][2], wv[2][c], fmaf(px[j][1], wv[1][c], fmaf(px[j][0], wv[0][c], acc[p][c])));
+            }
         }
     }
-    float* yp = y + (size_t)pix * 64 + cg * 16;
+    const float4 s0 = *reinterpret_cast<const float4*>(shift + cg * kStemCg), s1 = *reinterpret_cast<const float4*>(shift + cg * kStemCg + 4);
 #pragma unroll
-    for (int c = 0; c < 16; c += 4) {
-        float4 o;
-        o.x = rtf32(fmaxf(acc[c] + shift[cg * 16 + c], 0.f));
-        o.y = rtf32(fmaxf(acc[c + 1] + shift[cg * 16 + c + 1], 0.f));
-        o.z = rtf32(fmaxf(acc[c + 2] + shift[cg * 16 + c + 2], 0.f));
-        o.w = rtf32(fmaxf(acc[c + 3] + shift[cg * 16 + c + 3], 0.f));
-        *reinterpret_cast<float4*>(yp + c) = o;
+    for (int p = 0; p < kStemPx; p++) {
+        if (ow0 + p >= Wo) break;
+        float* yp = y + ((((size_t)n * Ho + oh) * Wo) + ow0 + p) * 64 + cg * kStemCg;
+        *reinterpret_cast<float4*>(yp) = make_float4(rtf32(fmaxf(acc[p][0] + s0.x, 0.f)), rtf32(fmaxf(acc[p][1] + s0.y, 0.f)),
+                                                     rtf32(fmaxf(acc[p][2] + s0.z, 0.f)), rtf32(fmaxf(acc[p][3] + s0.w, 0.f)));
+        *reinterpret_cast<float4*>(yp + 4) = make_float4(rtf32(fmaxf(acc[p][4] + s1.x, 0.f)), rtf32(fmaxf(acc[p][5] + s1.y, 0.f)),
+                                                         rtf32(fmaxf(acc[p][6] + s1.z, 0.f)), rtf32(fmaxf(acc[p][7] + s1.w, 0.f)));
     }
 }
 
@@ -1010,7 +1034,8 @@ MPB_API int mpb_bn_param_grad_multi(int total_rows, const mpb_bn_layer* layers, 
 MPB_API int mpb_stem_fwd(int nimg, int Hin, int Win, const float* x, const float* wf, const float* shift, float* y,
                          void* stream) {
     const int Ho = (Hin + 6 - 7) / 2 + 1, Wo = (Win + 6 - 7) / 2 + 1;
-    stem_fwd_kernel<<<nblk((long)nimg * Ho * Wo, 64), 256, 0, ST>>>(nimg, Hin, Win, Ho, Wo, x, wf, shift, y);
+    const int qpr = (Wo + kStemPx - 1) / kStemPx;
+    stem_fwd_kernel<<<nblk((long)nimg * Ho * qpr, 32), 256, 0, ST>>>(nimg, Hin, Win, Ho, Wo, x, wf, shift, y);
     MPB_LAUNCH_CHECK();
     return 0;
 }
