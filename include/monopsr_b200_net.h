@@ -101,6 +101,11 @@ typedef struct mpb_w16_layer {
     float* wf; float* scale; float* shift; const float* beta; const float* mean;
 } mpb_w16_layer;
 int mpb_split16_weights_multi(int total_rows, const mpb_w16_layer* layers, const int* row2layer, float eps, void* stream);
+/* the same over a LIST of global rows (DEVICE array; NULL = rows 0..nrows-1) none longer than max_row_floats: rows up to
+ * 256 / 1024 / 2304 floats are kept in registers between the two passes (the weights are read once, and short rows do
+ * not pay the register footprint of long ones) */
+int mpb_split16_weights_rows(int nrows, const int* rowlist, int max_row_floats, const mpb_w16_layer* layers,
+                             const int* row2layer, float eps, void* stream);
 
 /* 1 (default): the elementwise / weight-preparation kernels round every GEMM operand they produce to tf32;
  * 0: they leave it as computed (what mpb_tc_gemm_x3 wants).  Synchronous; set it outside graph capture. */
@@ -139,6 +144,8 @@ typedef struct mpb_bn_layer {
     int cout; int K; int row0; int pad_;
 } mpb_bn_layer;
 int mpb_fold_bn_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream);
+/* p[0..n) = 0 with one CTA per SM (the gradient arena is zeroed beside the forward pass without taking its CTA slots) */
+int mpb_zero_fill(long n, float* p, void* stream);
 int mpb_bn_param_grad_multi(int total_rows, const mpb_bn_layer* layers, const int* row2layer, float eps, void* stream);
 /* the same over rows [row_begin, row_end) of the table: d(gamma) of a group of layers as soon as their weight gradients
  * are final (the data-parallel step all-reduces the tower gradients bucket by bucket under the backward pass) */

@@ -110,6 +110,7 @@ class Engine:
         self.s_opt = torch.cuda.Stream(device=self.dev)
         self.s_ar = torch.cuda.Stream(device=self.dev)      # d(gamma) + all-reduce issue of the gradient buckets
         self.early_opt = False      # set by the single-GPU train step: head train-op under the towers' backward
+        self.early_opt_unit = None  # ... started when the full-image tower's backward chain reaches this unit
         self._grads_zeroed = False
         self.overlap = True
         # tile planning knobs (tools/r2_call_f.sh / r2_call_h.sh sweeps, profiles/r2_notes.md).  The h3 forward does 1.5x
@@ -649,7 +650,15 @@ class Engine:
                 e.cout, e.K, e.row0 = cout, K, row
                 row2layer += [i] * cout
                 row += cout
-            self.w16_tabs[key] = (row, torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev),
+            # rows in classes by length: the kernel keeps a row in registers between its two passes
+            Ks = np.array([arr[i].K for i in row2layer])
+            classes, lo = [], 0
+            for cap in (256, 1024, 2304, 1 << 30):
+                idx = np.nonzero((Ks > lo) & (Ks <= cap))[0].astype(np.int32)
+                if len(idx):
+                    classes.append((len(idx), torch.from_numpy(idx).to(self.dev), int(min(cap, Ks[idx].max()))))
+                lo = cap
+            self.w16_tabs[key] = (classes, torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev),
                                   torch.tensor(row2layer, dtype=torch.int32, device=self.dev))
 
     def prepare_weights(self, part="all"):
@@ -673,8 +682,10 @@ class Engine:
                 self._build_w16_table()
             for key in ("towers", "head"):
                 if part in ("all", key):
-                    rows_, tab, r2l = self.w16_tabs[key]
-                    self._chk(L.mpb_split16_weights_multi(rows_, _ptr(tab), _ptr(r2l), BN_EPS_RESNET, st), "split16_weights")
+                    classes, tab, r2l = self.w16_tabs[key]
+                    for nrows, rowlist, cap in classes:
+                        self._chk(L.mpb_split16_weights_rows(nrows, _ptr(rowlist), cap, _ptr(tab), _ptr(r2l), BN_EPS_RESNET, st),
+                                  "split16_weights")
         if part in ("all", "towers"):
             self._prepared = True
 
@@ -811,7 +822,7 @@ class Engine:
         Tc, Tf = self.towers[ms.ENCODERS[0]], self.towers[ms.ENCODERS[1]]
         if train and self.overlap:
             with self._side(self.s_wf):      # 400 MB zero-fill of the gradient arena, beside the forward pass
-                self.grads.zero_()
+                self._chk(L.mpb_zero_fill(self.n_train, _ptr(self.grads), self._st()), "zero_fill")
             self._grads_zeroed = True
         with self._side(self.s_full):
             ff, _ = self._tower_fwd(Tf, I["full_img"])
@@ -1052,14 +1063,25 @@ class Engine:
     def backward(self):
         """head part (FC stacks, decoder, squash: every gradient outside the towers), then the two towers"""
         self._backward_head()
+        head_opt = None
         if self.early_opt:
-            # every gradient outside the towers is final (FC stacks on s_fc, decoder wgrads on s_wf, the rest here)
-            for s_ in (self._cur(), self.s_wf, self.s_fc):
-                self.s_opt.wait_stream(s_)
-            with torch.cuda.stream(self.s_opt):
-                self.optimizer_step(1.0, part="head")
-                self.prepare_weights(part="head")
-        self._backward_towers()
+            # every gradient outside the towers is final (FC stacks on s_fc, decoder wgrads on s_wf, the rest here): the
+            # train-op of those variables may run under the towers' backward pass.  Started at once it competes with the
+            # busiest part of that pass for HBM (measured slower); started when the full-image tower's chain reaches
+            # unit `early_opt_unit` it fills the thin tail of the pass (block1 / block2 and the stems) instead
+            evs = [s_.record_event() for s_ in (self._cur(), self.s_wf, self.s_fc)]
+
+            def launch_head_opt():
+                with torch.cuda.stream(self.s_opt):
+                    for e in evs:
+                        self.s_opt.wait_event(e)
+                    self.optimizer_step(1.0, part="head")
+                    self.prepare_weights(part="head")
+            if self.early_opt_unit is None:
+                launch_head_opt()
+            else:
+                head_opt = (self.early_opt_unit, launch_head_opt)
+        self._backward_towers(head_opt=head_opt)
 
     def _backward_head(self, join=False):
         L, st, N, I, h = self.L, self._st(), self.N, self.inputs, self.h
@@ -1172,7 +1194,7 @@ class Engine:
             for a, b in bucket["ranges"]:
                 self._dp_works.append(dist.all_reduce(self.grads[a:b], op=dist.ReduceOp.SUM, async_op=True))
 
-    def _backward_towers(self, dp_plan=None):
+    def _backward_towers(self, dp_plan=None, head_opt=None):
         L, st, N, I = self.L, self._st(), self.N, self.inputs
         Tc, Tf = self.towers[ms.ENCODERS[0]], self.towers[ms.ENCODERS[1]]
         lastf = Tf["units"][-1]
@@ -1207,7 +1229,15 @@ class Engine:
                                             _ptr(lastf["g_out"]), 1024,
                                             _ptr(self.gview(lastf["scope"] + "/conv3/BatchNorm/beta")), self._st()),
                       "full_relu_bwd")
-            self._tower_bwd(Tf, I["full_img"], self.s_wf)
+            cb = None
+            if head_opt is not None:
+                unit, launch = head_opt
+
+                def cb(ui):
+                    if ui == unit:
+                        self.s_opt.wait_event(self._cur().record_event())
+                        launch()
+            self._tower_bwd(Tf, I["full_img"], self.s_wf, on_done=cb)
         self._tower_bwd(Tc, I["rgb_crops"], self.s_wc)
         self._join(self.s_full, self.s_wf, self.s_wc)
         # d(gamma) of every frozen BN from (w, dw, dbeta), both towers in one launch
@@ -1343,6 +1373,8 @@ class Engine:
         # measured: stepping the head variables under the towers' backward pass is ~1.5 % SLOWER than one train-op
         # at the end (the HBM-bound Adam pass slows the concurrent GEMMs more than the overlap saves): off
         early = int(os.environ.get("MPB_EARLY_OPT", "0")) != 0
+        u = os.environ.get("MPB_EARLY_OPT_UNIT", "")
+        self.early_opt_unit = int(u) if u != "" else None
         with torch.cuda.graph(g, stream=self.s_main, capture_error_mode="thread_local"):
             self.forward(train=True)
             self.early_opt = early

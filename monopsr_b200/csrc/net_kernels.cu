@@ -245,14 +245,14 @@ stem_wgrad_kernel(int nimg, int Hin, int Win, int Ho, int Wo, const float* __res
     // synchronisations instead of 37
     constexpr int PT = 16;
     __shared__ float sg[PT][64];
-    __shared__ float sx[PT][kStemK + 1];
+    __shared__ __align__(16) float sx[PT][4 * 40];       // 4 parts of 37 taps, each padded to 40: a part is 10 LDS.128
     __shared__ int spix[PT][3];
     const long total = (long)nimg * Ho * Wo;
     const long p0 = (long)blockIdx.x * pix_per_cta, pend = min(total, p0 + pix_per_cta);
     const int co = threadIdx.x & 63, part = threadIdx.x >> 6;   // 4 parts over the 147 taps
-    float acc[37];
+    float acc[40];
 #pragma unroll
-    for (int i = 0; i < 37; i++) acc[i] = 0.f;
+    for (int i = 0; i < 40; i++) acc[i] = 0.f;
     for (long pix0 = p0; pix0 < pend; pix0 += PT) {
         __syncthreads();
         if (threadIdx.x < PT) {
@@ -269,17 +269,21 @@ stem_wgrad_kernel(int nimg, int Hin, int Win, int Ho, int Wo, const float* __res
             const int q = i / kStemK, k = i - q * kStemK;
             const int t = k / 3, ci = k - t * 3;
             const int n = spix[q][0], ih = spix[q][1] * 2 - 3 + t / 7, iw = spix[q][2] * 2 - 3 + t % 7;
-            sx[q][k] = (pix0 + q < pend && ih >= 0 && ih < Hin && iw >= 0 && iw < Win)
-                           ? x[(((size_t)n * Hin + ih) * Win + iw) * 3 + ci] : 0.f;
+            sx[q][(k / 37) * 40 + k % 37] = (pix0 + q < pend && ih >= 0 && ih < Hin && iw >= 0 && iw < Win)
+                                                ? x[(((size_t)n * Hin + ih) * Win + iw) * 3 + ci] : 0.f;
         }
         __syncthreads();
 #pragma unroll 4
         for (int q = 0; q < PT; q++) {
             const float gv = sg[q][co];
+            const float4* xp = reinterpret_cast<const float4*>(&sx[q][part * 40]);
 #pragma unroll
-            for (int i = 0; i < 37; i++) {
-                const int k = part * 37 + i;
-                if (k < kStemK) acc[i] = fmaf(gv, sx[q][k], acc[i]);
+            for (int i4 = 0; i4 < 10; i4++) {                  // (the 3 padding slots of a part hold garbage: never written back)
+                const float4 v = xp[i4];
+                acc[4 * i4] = fmaf(gv, v.x, acc[4 * i4]);
+                acc[4 * i4 + 1] = fmaf(gv, v.y, acc[4 * i4 + 1]);
+                acc[4 * i4 + 2] = fmaf(gv, v.z, acc[4 * i4 + 2]);
+                acc[4 * i4 + 3] = fmaf(gv, v.w, acc[4 * i4 + 3]);
             }
         }
     }
@@ -320,42 +324,51 @@ __global__ void maxpool3s2_fwd_kernel(int nimg, int H, int W, int C4, int Ho, in
 
 // gather form (deterministic): dx[in] = (x[in]>0) * sum over the <=4 windows containing `in` whose
 // FIRST maximum is `in`.  The (x>0) factor is the ReLU of the stem that produced x.
-__global__ void maxpool3s2_bwd_kernel(int nimg, int H, int W, int C, int Ho, int Wo,
-                                      const float* __restrict__ x, const float* __restrict__ dy,
-                                      float* __restrict__ dx) {
+// thread = (input pixel, 4 channels): the <= 4 windows x 9 taps are 16-byte loads and the "first maximum" test runs on
+// the four channels at once (the one-channel version: 57-63 us at the very end of the full-image tower's backward chain)
+__global__ void __launch_bounds__(256)
+maxpool3s2_bwd_kernel(int nimg, int H, int W, int C4, int Ho, int Wo,
+                      const float4* __restrict__ x, const float4* __restrict__ dy, float4* __restrict__ dx) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)nimg * H * W * C;
+    const long total = (long)nimg * H * W * C4;
     if (i >= total) return;
-    const int c = (int)(i % C);
-    long p = i / C;
+    const int c = (int)(i % C4);
+    long p = i / C4;
     const int iw = (int)(p % W); p /= W;
     const int ih = (int)(p % H);
     const int n = (int)(p / H);
-    const float xv = x[i];
-    float acc = 0.f;
-    if (xv > 0.f) {
+    const float4 xv = x[i];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xv.x > 0.f || xv.y > 0.f || xv.z > 0.f || xv.w > 0.f) {
         for (int oh = max(0, (ih - 1) / 2); oh <= min(Ho - 1, ih / 2); oh++) {
             if (ih < oh * 2 || ih > oh * 2 + 2) continue;
             for (int ow = max(0, (iw - 1) / 2); ow <= min(Wo - 1, iw / 2); ow++) {
                 if (iw < ow * 2 || iw > ow * 2 + 2) continue;
-                // is (ih,iw) the first max of window (oh,ow)?
-                bool first = true;
-                for (int dh = 0; dh < 3 && first; dh++) {
+                // per channel: is (ih,iw) the FIRST maximum of window (oh,ow)?
+                bool fx = true, fy = true, fz = true, fw = true;
+                for (int dh = 0; dh < 3; dh++) {
                     const int jh = oh * 2 + dh;
                     if (jh >= H) break;
                     for (int dw = 0; dw < 3; dw++) {
                         const int jw = ow * 2 + dw;
                         if (jw >= W) break;
-                        const float v = x[(((size_t)n * H + jh) * W + jw) * C + c];
+                        const float4 v = x[(((size_t)n * H + jh) * W + jw) * C4 + c];
                         const bool before = (jh < ih) || (jh == ih && jw < iw);
-                        if (v > xv || (before && v == xv)) { first = false; break; }
+                        fx = fx && !(v.x > xv.x || (before && v.x == xv.x));
+                        fy = fy && !(v.y > xv.y || (before && v.y == xv.y));
+                        fz = fz && !(v.z > xv.z || (before && v.z == xv.z));
+                        fw = fw && !(v.w > xv.w || (before && v.w == xv.w));
                     }
                 }
-                if (first) acc += dy[(((size_t)n * Ho + oh) * Wo + ow) * C + c];
+                const float4 g = dy[(((size_t)n * Ho + oh) * Wo + ow) * C4 + c];
+                if (fx) acc.x += g.x;
+                if (fy) acc.y += g.y;
+                if (fz) acc.z += g.z;
+                if (fw) acc.w += g.w;
             }
         }
     }
-    dx[i] = acc;
+    dx[i] = make_float4(xv.x > 0.f ? acc.x : 0.f, xv.y > 0.f ? acc.y : 0.f, xv.z > 0.f ? acc.z : 0.f, xv.w > 0.f ? acc.w : 0.f);
 }
 
 // slim.max_pool2d([2,2]) (builders/net_builder.py:60,68): VALID, stride 2
@@ -984,6 +997,18 @@ relu_bwd_colsum_kernel(int M, int C, const float* __restrict__ y, int ldy, const
         atomicAdd(&colsum[c], a);
     }
 }
+__global__ void __launch_bounds__(256) zero_fill_kernel(long n, float* __restrict__ p) {
+    const long n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long stride = (long)gridDim.x * blockDim.x;
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        p4[i] = z; p4[i + stride] = z; p4[i + 2 * stride] = z; p4[i + 3 * stride] = z;
+    }
+    for (; i < n4; i += stride) p4[i] = z;
+    for (long j = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) p[j] = 0.f;
+}
 __global__ void add_inplace_kernel(long n, float* __restrict__ a, const float* __restrict__ b) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] += b[i];
@@ -1057,7 +1082,10 @@ MPB_API int mpb_maxpool3s2_fwd(int nimg, int H, int W, int C, const float* x, fl
 }
 MPB_API int mpb_maxpool3s2_bwd(int nimg, int H, int W, int C, const float* x, const float* dy, float* dx, void* stream) {
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-    maxpool3s2_bwd_kernel<<<nblk((long)nimg * H * W * C, 256), 256, 0, ST>>>(nimg, H, W, C, Ho, Wo, x, dy, dx);
+    if (C % 4) return -1;
+    maxpool3s2_bwd_kernel<<<nblk((long)nimg * H * W * (C / 4), 256), 256, 0, ST>>>(
+        nimg, H, W, C / 4, Ho, Wo, reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy),
+        reinterpret_cast<float4*>(dx));
     MPB_LAUNCH_CHECK();
     return 0;
 }
@@ -1211,6 +1239,15 @@ MPB_API int mpb_relu_bwd_colsum(int M, int C, const float* y, int ldy, const flo
                                 float* colsum, void* stream) {
     dim3 grid(ceil_div(C, 32), min(256, ceil_div(M, 64)));
     relu_bwd_colsum_kernel<<<grid, 256, 0, ST>>>(M, C, y, ldy, dy, lddy, g, ldg, colsum);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+// zero-fill that leaves the SMs to others: ONE 256-thread CTA per SM streaming 16-byte stores.  (A framework fill kernel
+// with ~100k CTAs takes every CTA slot of the chip for its 55 us, and the step's first kernels queue behind it.)
+MPB_API int mpb_zero_fill(long n, float* p, void* stream) {
+    if (n < 0 || (n && !p) || (reinterpret_cast<uintptr_t>(p) & 15u)) return -1;
+    if (n == 0) return 0;
+    zero_fill_kernel<<<num_sms(), 256, 0, ST>>>(n, p);
     MPB_LAUNCH_CHECK();
     return 0;
 }

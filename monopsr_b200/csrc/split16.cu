@@ -47,20 +47,38 @@ split16_kernel(long total4, int C4, const float* __restrict__ src, int lds, unsi
 
 // One warp per (layer, output channel) row: pass 1 = row maximum of |w * s|, pass 2 = scaled [lo | hi] split copy.
 // (The second read of the row comes from L1/L2: rows are 256 B .. 72 KB.)
+// CH = float4 chunks per lane kept in registers between the passes (rows of <= 128 * CH floats); 0 = re-read path.
+// The rows are handed over in classes by length (rowlist): short rows take a few registers and run at full occupancy,
+// and no warp carries 72 registers of buffer for a 256-float row.
+template <int CH>
 __global__ void __launch_bounds__(256)
-split16_weights_multi_kernel(int total_rows, const mpb_w16_layer* __restrict__ layers, const int* __restrict__ row2layer,
-                             float eps) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= total_rows) return;
+split16_weights_multi_kernel(int nrows, const int* __restrict__ rowlist, const mpb_w16_layer* __restrict__ layers,
+                             const int* __restrict__ row2layer, float eps) {
+    const int ri = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ri >= nrows) return;
+    const int row = rowlist ? rowlist[ri] : ri;
     const mpb_w16_layer L = layers[row2layer[row]];
     const int co = row - L.row0;
     const float s = L.gamma ? L.gamma[co] * rsqrtf(L.var[co] + eps) : 1.f;
     const float4* w4 = reinterpret_cast<const float4*>(L.w + (size_t)co * L.K);
     const int n4 = L.K >> 2;
+    // rows of up to 2304 floats (every tower conv) stay in registers between the two passes: the weights are read once
+    constexpr int kRegChunks = CH > 0 ? CH : 1;
+    const bool in_regs = CH > 0 && n4 <= kRegChunks * 32;
+    float4 buf[kRegChunks];
     float mx = 0.f;
-    for (int k = lane; k < n4; k += 32) {
-        const float4 v = __ldg(w4 + k);
-        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < kRegChunks; j++) {
+            const int k = lane + 32 * j;
+            buf[j] = k < n4 ? __ldg(w4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(buf[j].x), fabsf(buf[j].y))), fmaxf(fabsf(buf[j].z), fabsf(buf[j].w)));
+        }
+    } else {
+        for (int k = lane; k < n4; k += 32) {
+            const float4 v = __ldg(w4 + k);
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     mx *= fabsf(s);
@@ -79,8 +97,7 @@ split16_weights_multi_kernel(int total_rows, const mpb_w16_layer* __restrict__ l
     const float m = s * sc;
     unsigned char* d = reinterpret_cast<unsigned char*>(L.w16) + (size_t)co * L.K * 4;
     float4* wf4 = L.wf ? reinterpret_cast<float4*>(L.wf + (size_t)co * L.K) : nullptr;
-    for (int k = lane; k < n4; k += 32) {
-        const float4 v = __ldg(w4 + k);
+    auto emit = [&](int k, const float4 v) {
         if (wf4) wf4[k] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);      // folded fp32 weights (backward operand)
         uint32_t h0, l0, h1, l1;
         split16_pair_(v.x * m, v.y * m, h0, l0);
@@ -89,6 +106,15 @@ split16_weights_multi_kernel(int total_rows, const mpb_w16_layer* __restrict__ l
         unsigned char* q = d + (size_t)(c & ~31) * 4 + (c & 31) * 2;
         *reinterpret_cast<uint2*>(q) = make_uint2(l0, l1);            // [lo | hi]
         *reinterpret_cast<uint2*>(q + 64) = make_uint2(h0, h1);
+    };
+    if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < kRegChunks; j++) {
+            const int k = lane + 32 * j;
+            if (k < n4) emit(k, buf[j]);
+        }
+    } else {
+        for (int k = lane; k < n4; k += 32) emit(k, __ldg(w4 + k));
     }
 }
 
@@ -109,11 +135,22 @@ MPB_API int mpb_split16(long rows, int C, const float* src, int lds, void* dst16
     return 0;
 }
 
-MPB_API int mpb_split16_weights_multi(int total_rows, const mpb_w16_layer* layers, const int* row2layer, float eps,
-                                      void* stream) {
+MPB_API int mpb_split16_weights_rows(int nrows, const int* rowlist, int max_row_floats, const mpb_w16_layer* layers,
+                                     const int* row2layer, float eps, void* stream) {
     using namespace mpb;
-    if (total_rows <= 0 || !layers || !row2layer) return -1;
-    split16_weights_multi_kernel<<<ceil_div(total_rows, 8), 256, 0, (cudaStream_t)stream>>>(total_rows, layers, row2layer, eps);
+    if (nrows < 0 || !layers || !row2layer) return -1;
+    if (nrows == 0) return 0;
+    const dim3 g(ceil_div(nrows, 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (max_row_floats <= 256) split16_weights_multi_kernel<2><<<g, 256, 0, st>>>(nrows, rowlist, layers, row2layer, eps);
+    else if (max_row_floats <= 1024) split16_weights_multi_kernel<8><<<g, 256, 0, st>>>(nrows, rowlist, layers, row2layer, eps);
+    else if (max_row_floats <= 2304) split16_weights_multi_kernel<18><<<g, 256, 0, st>>>(nrows, rowlist, layers, row2layer, eps);
+    else split16_weights_multi_kernel<0><<<g, 256, 0, st>>>(nrows, rowlist, layers, row2layer, eps);
     MPB_LAUNCH_CHECK();
     return 0;
+}
+MPB_API int mpb_split16_weights_multi(int total_rows, const mpb_w16_layer* layers, const int* row2layer, float eps,
+                                      void* stream) {
+    if (total_rows <= 0) return -1;
+    return mpb_split16_weights_rows(total_rows, nullptr, 1 << 30, layers, row2layer, eps, stream);
 }

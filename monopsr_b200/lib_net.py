@@ -93,6 +93,7 @@ _SIGS = {
     "mpb_tc_gemm_h3": [c_p, c_i, c_p],
     "mpb_split16": [c_l, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p],
     "mpb_split16_weights_multi": [c_i, c_p, c_p, c_f, c_p],
+    "mpb_split16_weights_rows": [c_i, c_p, c_i, c_p, c_p, c_f, c_p],
     "mpb_set_operand_rounding": [c_i],
     "mpb_bn_infer_fwd": [c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_p, c_p],
     "mpb_bn_train_bwd": [c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
@@ -105,6 +106,7 @@ _SIGS = {
     "mpb_bias_relu": [c_l, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_i, c_p],
     "mpb_relu_bwd_colsum": [c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p],
     "mpb_add_inplace": [c_l, c_p, c_p, c_p],
+    "mpb_zero_fill": [c_l, c_p, c_p],
     "mpb_heads_static": [ctypes.POINTER(HeadsIO), c_p],
     "mpb_heads_mid": [ctypes.POINTER(HeadsIO), c_p],
     "mpb_heads_final": [ctypes.POINTER(HeadsIO), c_i, c_p],

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call I: critical-path SIMT kernels (crop+pool, xyz head, small FC backward) rewritten; FC-stream priority
-OUT=gpurun_out/r2_i
+OUT=gpurun_out/r2_j
 mkdir -p $OUT
 timeout 900 python -m pytest tests/test_net_kernels_gpu.py tests/test_network_gpu.py tests/test_h3_gpu.py tests/test_zz_late_additions_gpu.py tests/test_pointset_loss_gpu.py -q -x -p no:cacheprovider 2>&1 | tail -4
 run() { # tag, env...
@@ -16,9 +16,9 @@ except Exception as e:
 PY
 }
 run base A=1
-run prio2 MPB_STREAM_PRIO=2
+
 run base2 A=1
-run prio2b MPB_STREAM_PRIO=2
+
 run tf32 MPB_PRECISION=tf32
 timeout 200 python tools/step_timeline.py > $OUT/step_timeline.txt 2>&1; grep "step span\|concurrency" $OUT/step_timeline.txt
 cp gpurun_out/step_kernels.csv $OUT/ 2>/dev/null
