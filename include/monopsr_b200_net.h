@@ -180,6 +180,14 @@ int mpb_bn_train_fwd16(int M, int C, const float* z, const float* beta, float ep
                        void* stream);
 int mpb_bn_infer_fwd16(int M, int C, const float* z, const float* beta, const float* moving_mean, const float* moving_var,
                        float eps, float* y, void* y16, int* overflow, void* stream);
+/* train-mode batch norm in ONE launch per direction: statistics, a grid barrier, then the apply phase re-reading from L2
+ * what the same CTA just streamed (2 CTAs per SM, all resident).  Same arithmetic and outputs as mpb_bn_train_fwd16 /
+ * mpb_bn_train_bwd; scratch must hold 2C + 2 doubles (the barrier counter sits behind the accumulators). */
+int mpb_bn_train_fwd_fused(int M, int C, const float* z, const float* beta, float eps, float* y, float* mean, float* var,
+                           float* moving_mean, float* moving_var, float decay, double* scratch, void* y16, int* overflow,
+                           void* stream);
+int mpb_bn_train_bwd_fused(int M, int C, const float* z, const float* mean, const float* var, float eps, const float* y,
+                           const float* dy, float* dz, float* dbeta, double* scratch, void* stream);
 int mpb_resize_ac_bwd(int nimg, int H, int W, int C, const float* dy, int OH, int OW, float* dx, void* stream); /* overwrites dx (gather form, no atomics) */
 
 /* ---- slim.batch_norm(is_training=True) + ReLU of the map decoder (net_builder.py:77-89) ----

@@ -118,6 +118,7 @@ class Engine:
         # the SMs and for the short epilogue-bound reductions measured 9.11 vs 9.40 ms/step (tf32 mode keeps 0.9 / 64)
         wide = self.precision != "tf32"
         self.fill = float(os.environ.get("MPB_TILE_FILL", "0.6" if wide else "0.9"))   # min fraction of SMs a launch must fill before widening tiles
+        self.bn_fused = int(os.environ.get("MPB_BN_FUSED", "1")) != 0      # decoder batch norm: one launch per direction
         self.shortk = int(os.environ.get("MPB_SHORTK", "512"))
         self.shortk_bn = int(os.environ.get("MPB_SHORTK_BN", "128" if wide else "64"))   # tile width of short, epilogue-bound reductions
         self.wgrad_bn = int(os.environ.get("MPB_WGRAD_BN", "128"))
@@ -855,10 +856,11 @@ class Engine:
             b = D["scope"] + "/BatchNorm/"
             y16 = s16(D["y"]) if i < 3 else None         # the last decoder output feeds the (SIMT) xyz head only
             if train:      # batch statistics + moving-average update (UPDATE_OPS)
-                self._chk(L.mpb_bn_train_fwd16(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")), BN_EPS_DECODER,
-                                               _ptr(D["y"]), _ptr(D["mean"]), _ptr(D["var"]),
-                                               _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
-                                               BN_DECAY_DECODER, _ptr(self.bn_scratch), y16, ovf, st), "bn_train_fwd")
+                fwd = L.mpb_bn_train_fwd_fused if self.bn_fused else L.mpb_bn_train_fwd16
+                self._chk(fwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")), BN_EPS_DECODER,
+                              _ptr(D["y"]), _ptr(D["mean"]), _ptr(D["var"]),
+                              _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
+                              BN_DECAY_DECODER, _ptr(self.bn_scratch), y16, ovf, st), "bn_train_fwd")
             else:          # validation / inference graphs are built with is_training=False: moving statistics
                 self._chk(L.mpb_bn_infer_fwd16(D["M"], D["cout"], _ptr(D["z"]), _ptr(self.view(b + "beta")),
                                                _ptr(self.view(b + "moving_mean")), _ptr(self.view(b + "moving_variance")),
@@ -1106,9 +1108,10 @@ class Engine:
             D = self.dec[i]
             side, b = D["side"], D["scope"] + "/BatchNorm/"
             tm = self.tm24 if side == 24 else self.tm48
-            self._chk(L.mpb_bn_train_bwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(D["mean"]), _ptr(D["var"]), BN_EPS_DECODER,
-                                         _ptr(D["y"]), _ptr(D["dy"]), _ptr(D["dz"]), _ptr(self.gview(b + "beta")),
-                                         _ptr(self.bn_scratch), st), "bn_train_bwd")
+            bwd = L.mpb_bn_train_bwd_fused if self.bn_fused else L.mpb_bn_train_bwd
+            self._chk(bwd(D["M"], D["cout"], _ptr(D["z"]), _ptr(D["mean"]), _ptr(D["var"]), BN_EPS_DECODER,
+                          _ptr(D["y"]), _ptr(D["dy"]), _ptr(D["dz"]), _ptr(self.gview(b + "beta")),
+                          _ptr(self.bn_scratch), st), "bn_train_bwd")
             with self._side(self.s_wf):
                 self.wgrad(D["M"], side, side, 3, 1, D["cin"], D["cout"], D["x"], D["cin"], D["dz"], D["cout"],
                            self.gview(D["scope"] + "/weights"), tapmask=tm)

@@ -755,6 +755,180 @@ bn_bwd_apply_kernel(long total4, int M, int C, const float* __restrict__ z, cons
         for (int j = 0; j < 4; j++) dbeta[i * 4 + j] = (float)s1[i * 4 + j];
 }
 
+// ---------------------------------------------------------------- train-mode batch norm, ONE launch per direction
+// statistics -> grid barrier -> apply in the same kernel: the apply phase re-reads from L2 what the same CTA streamed a
+// moment ago (the 48x48x128 tensors are 38 MB each, L2 is 126 MB), the finalize kernel disappears, and the decoder chain
+// -- which runs alone on the GPU -- loses two launches and their gaps per layer and direction.  The grid is 2 CTAs per SM
+// (fits beside anything the other streams run), so all CTAs are resident and a counter barrier is safe; the counter
+// lives behind the 2C accumulators in `scratch` (2C + 2 doubles, zeroed by the memset that precedes the launch).
+__device__ __forceinline__ void bn_grid_barrier(unsigned long long* counter, unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull);
+        while (*reinterpret_cast<volatile unsigned long long*>(counter) < nblocks) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+bn_train_fwd_fused_kernel(int M, int C, const float* __restrict__ z, const float* __restrict__ beta, float eps,
+                          float* __restrict__ y, float* __restrict__ mean, float* __restrict__ var,
+                          float* __restrict__ mmean, float* __restrict__ mvar, float decay, double* __restrict__ scratch,
+                          unsigned char* __restrict__ y16, int* __restrict__ overflow) {
+    double* psum = scratch;
+    double* psq = scratch + C;
+    const int lane32 = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane32) * 4;
+    const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (c < C) {
+        int r = r0 + rg;
+        for (; r + 56 < r1; r += 64) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = *reinterpret_cast<const float4*>(z + (size_t)(r + 8 * u) * C + c);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+                q.x = fmaf(v[u].x, v[u].x, q.x); q.y = fmaf(v[u].y, v[u].y, q.y);
+                q.z = fmaf(v[u].z, v[u].z, q.z); q.w = fmaf(v[u].w, v[u].w, q.w);
+            }
+        }
+        for (; r < r1; r += 8) {
+            const float4 v = *reinterpret_cast<const float4*>(z + (size_t)r * C + c);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+        }
+    }
+    __shared__ float4 ss[8][32], sq[8][32];
+    ss[rg][lane32] = s;
+    sq[rg][lane32] = q;
+    __syncthreads();
+    if (rg == 0 && c < C) {
+        double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 8; k++) {
+            const float4 x = ss[k][lane32], w = sq[k][lane32];
+            a[0] += x.x; a[1] += x.y; a[2] += x.z; a[3] += x.w;
+            b[0] += w.x; b[1] += w.y; b[2] += w.z; b[3] += w.w;
+        }
+        for (int j = 0; j < 4; j++) { atomicAdd(&psum[c + j], a[j]); atomicAdd(&psq[c + j], b[j]); }
+    }
+    bn_grid_barrier(reinterpret_cast<unsigned long long*>(scratch + 2 * C), gridDim.x * gridDim.y);
+    if (c >= C) return;
+    float mu[4], rs[4], bt[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {        // the arithmetic of bn_finalize_kernel + bn_apply_kernel
+        const double m = __ldcg(psum + c + j) / M;
+        const double v = fmax(__ldcg(psq + c + j) / M - m * m, 0.0);
+        mu[j] = (float)m;
+        rs[j] = rsqrtf((float)v + eps);
+        bt[j] = beta[c + j];
+        if (blockIdx.y == 0 && rg == 0) {
+            mean[c + j] = (float)m;
+            var[c + j] = (float)v;
+            if (mmean) {   // UPDATE_OPS: moving = moving*decay + batch*(1-decay)  (batch var as TF: biased)
+                mmean[c + j] = mmean[c + j] * decay + (float)m * (1.f - decay);
+                mvar[c + j] = mvar[c + j] * decay + (float)v * (1.f - decay);
+            }
+        }
+    }
+    for (int r = r0 + rg; r < r1; r += 8) {
+        const float4 v = *reinterpret_cast<const float4*>(z + (size_t)r * C + c);
+        float4 o;
+        o.x = rtf32(fmaxf((v.x - mu[0]) * rs[0] + bt[0], 0.f));
+        o.y = rtf32(fmaxf((v.y - mu[1]) * rs[1] + bt[1], 0.f));
+        o.z = rtf32(fmaxf((v.z - mu[2]) * rs[2] + bt[2], 0.f));
+        o.w = rtf32(fmaxf((v.w - mu[3]) * rs[3] + bt[3], 0.f));
+        *reinterpret_cast<float4*>(y + (size_t)r * C + c) = o;
+        if (y16) store_split16(y16, r, C, c, o, overflow);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_train_bwd_fused_kernel(int M, int C, const float* __restrict__ z, const float* __restrict__ y,
+                          const float* __restrict__ dy, const float* __restrict__ mean, const float* __restrict__ var,
+                          float eps, double* __restrict__ scratch, float* __restrict__ dz, float* __restrict__ dbeta) {
+    double* s1 = scratch;
+    double* s2 = scratch + C;
+    const int lane32 = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane32) * 4;
+    const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    float4 mu = a, rs = a;
+    if (c < C) {
+        mu = *reinterpret_cast<const float4*>(mean + c);
+        const float4 vr = *reinterpret_cast<const float4*>(var + c);
+        rs = make_float4(rsqrtf(vr.x + eps), rsqrtf(vr.y + eps), rsqrtf(vr.z + eps), rsqrtf(vr.w + eps));
+        auto acc = [&](const float4& zz, const float4& yy, const float4& dd) {
+            const float gx = yy.x > 0.f ? dd.x : 0.f, gy = yy.y > 0.f ? dd.y : 0.f;
+            const float gz = yy.z > 0.f ? dd.z : 0.f, gw = yy.w > 0.f ? dd.w : 0.f;
+            a.x += gx; a.y += gy; a.z += gz; a.w += gw;
+            b.x = fmaf(gx, (zz.x - mu.x) * rs.x, b.x); b.y = fmaf(gy, (zz.y - mu.y) * rs.y, b.y);
+            b.z = fmaf(gz, (zz.z - mu.z) * rs.z, b.z); b.w = fmaf(gw, (zz.w - mu.w) * rs.w, b.w);
+        };
+        int r = r0 + rg;
+        for (; r + 16 < r1; r += 24) {
+            float4 zv[3], yv[3], dv[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const size_t o = (size_t)(r + 8 * u) * C + c;
+                zv[u] = *reinterpret_cast<const float4*>(z + o);
+                yv[u] = *reinterpret_cast<const float4*>(y + o);
+                dv[u] = *reinterpret_cast<const float4*>(dy + o);
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++) acc(zv[u], yv[u], dv[u]);
+        }
+        for (; r < r1; r += 8) {
+            const size_t o = (size_t)r * C + c;
+            acc(*reinterpret_cast<const float4*>(z + o), *reinterpret_cast<const float4*>(y + o),
+                *reinterpret_cast<const float4*>(dy + o));
+        }
+    }
+    __shared__ float4 sa[8][32], sb[8][32];
+    sa[rg][lane32] = a;
+    sb[rg][lane32] = b;
+    __syncthreads();
+    if (rg == 0 && c < C) {
+        double p[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 8; k++) {
+            const float4 x = sa[k][lane32], w = sb[k][lane32];
+            p[0] += x.x; p[1] += x.y; p[2] += x.z; p[3] += x.w;
+            q[0] += w.x; q[1] += w.y; q[2] += w.z; q[3] += w.w;
+        }
+        for (int j = 0; j < 4; j++) { atomicAdd(&s1[c + j], p[j]); atomicAdd(&s2[c + j], q[j]); }
+    }
+    bn_grid_barrier(reinterpret_cast<unsigned long long*>(scratch + 2 * C), gridDim.x * gridDim.y);
+    if (c >= C) return;
+    float m1[4], m2[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {        // the arithmetic of bn_bwd_apply_kernel
+        const double t1 = __ldcg(s1 + c + j), t2 = __ldcg(s2 + c + j);
+        m1[j] = (float)(t1 / M);
+        m2[j] = (float)(t2 / M);
+        if (blockIdx.y == 0 && rg == 0) dbeta[c + j] = (float)t1;
+    }
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+    for (int r = r0 + rg; r < r1; r += 8) {
+        const size_t o = (size_t)r * C + c;
+        const float4 zz = *reinterpret_cast<const float4*>(z + o), yy = *reinterpret_cast<const float4*>(y + o);
+        const float4 dd = *reinterpret_cast<const float4*>(dy + o);
+        const float zc[4] = {zz.x, zz.y, zz.z, zz.w}, yc[4] = {yy.x, yy.y, yy.z, yy.w}, dc[4] = {dd.x, dd.y, dd.z, dd.w};
+        float ov[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float xh = (zc[j] - muv[j]) * rsv[j];
+            const float g = yc[j] > 0.f ? dc[j] : 0.f;
+            ov[j] = rtf32(rsv[j] * (g - m1[j] - xh * m2[j]));
+        }
+        *reinterpret_cast<float4*>(dz + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    }
+}
+
 // ---------------------------------------------------------------- xyz head: conv3x3 128 -> 3 (+bias)
 // add_inst_xyz_maps_local (monopsr_output_builder.py:95-108).  N=3 output channels: bandwidth
 // bound on the (32,48,48,128) map features; one warp per output pixel, lanes over the 128
@@ -1152,6 +1326,31 @@ MPB_API int mpb_bn_train_fwd16(int M, int C, const float* z, const float* beta, 
     MPB_LAUNCH_CHECK();
     bn_apply_kernel<<<nblk((long)M * C / 4, 256), 256, 0, ST>>>((long)M * C / 4, C / 4, (const float4*)z, mean, var, beta, eps,
                                                               (float4*)y, (unsigned char*)y16, overflow);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+// single-launch variants (see bn_train_fwd_fused_kernel): scratch = 2C + 2 doubles
+static dim3 bn_fused_grid(int M, int C) {
+    const int gx = ceil_div(C, 128);
+    int gy = max(1, (2 * num_sms()) / gx);                  // 2 CTAs per SM in total: resident beside anything
+    gy = min(gy, ceil_div(M, 8));
+    return dim3(gx, gy);
+}
+MPB_API int mpb_bn_train_fwd_fused(int M, int C, const float* z, const float* beta, float eps, float* y, float* mean,
+                                   float* var, float* moving_mean, float* moving_var, float decay, double* scratch,
+                                   void* y16, int* overflow, void* stream) {
+    if (M <= 0 || C <= 0 || C % 4 || (y16 && C % 32) || !z || !beta || !y || !mean || !var || !scratch) return -1;
+    MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * C + 2), ST));
+    bn_train_fwd_fused_kernel<<<bn_fused_grid(M, C), 256, 0, ST>>>(M, C, z, beta, eps, y, mean, var, moving_mean, moving_var,
+                                                                  decay, scratch, (unsigned char*)y16, overflow);
+    MPB_LAUNCH_CHECK();
+    return 0;
+}
+MPB_API int mpb_bn_train_bwd_fused(int M, int C, const float* z, const float* mean, const float* var, float eps,
+                                   const float* y, const float* dy, float* dz, float* dbeta, double* scratch, void* stream) {
+    if (M <= 0 || C <= 0 || C % 4 || !z || !mean || !var || !y || !dy || !dz || !dbeta || !scratch) return -1;
+    MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * C + 2), ST));
+    bn_train_bwd_fused_kernel<<<bn_fused_grid(M, C), 256, 0, ST>>>(M, C, z, y, dy, mean, var, eps, scratch, dz, dbeta);
     MPB_LAUNCH_CHECK();
     return 0;
 }

@@ -89,6 +89,8 @@ _SIGS = {
     "mpb_resize_ac_fwd16": [c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p],
     "mpb_bn_train_fwd16": [c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
     "mpb_bn_infer_fwd16": [c_i, c_i, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
+    "mpb_bn_train_fwd_fused": [c_i, c_i, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
+    "mpb_bn_train_bwd_fused": [c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
     "mpb_tc_gemm_x3": [c_p, c_i, c_p],
     "mpb_tc_gemm_h3": [c_p, c_i, c_p],
     "mpb_split16": [c_l, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p],

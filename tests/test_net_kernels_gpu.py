@@ -374,3 +374,45 @@ def _oracle_tail(out, S):
     off = (-off_l)[:, None] + ((-off_r) - (-off_l))[:, None] * lin[None, :]
     out["inst_depth_map_global"] = xyz_local[..., 2:3] + cen_z.reshape(N, 1, 1, 1) + off.reshape(N, 48, 1, 1)
     return out
+
+
+@pytest.mark.parametrize("M,C", [(2048, 128), (18432, 256), (73728, 128), (37, 64)])
+def test_bn_train_single_launch_variants_match_the_three_kernel_path(cuda, M, C):
+    """mpb_bn_train_fwd_fused / _bwd_fused (statistics -> grid barrier -> apply in one launch) against the separate
+    stats / finalize / apply kernels: same arithmetic, sums differ only in the order of the double atomics"""
+    L = mlib.load()
+    z = rnd(M, C, seed=11) * 2 + 0.7
+    beta = rnd(C, seed=12, scale=0.3)
+    outs = []
+    for fused in (False, True):
+        y, mean, var = torch.empty_like(z), torch.empty(C, device=cuda), torch.empty(C, device=cuda)
+        mm, mv = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
+        scr = torch.zeros(2 * C + 2, dtype=torch.float64, device=cuda)
+        y16 = torch.empty_like(z) if C % 32 == 0 else None
+        flag = torch.zeros(1, dtype=torch.int32, device=cuda)
+        fn = L.mpb_bn_train_fwd_fused if fused else L.mpb_bn_train_fwd16
+        ok(fn(M, C, P(z), P(beta), 1e-3, P(y), P(mean), P(var), P(mm), P(mv), 0.999, P(scr),
+              None if y16 is None else P(y16), P(flag), mlib.stream_ptr()))
+        dy = rnd(M, C, seed=13)
+        dz, dbeta = torch.empty_like(z), torch.empty(C, device=cuda)
+        fb = L.mpb_bn_train_bwd_fused if fused else L.mpb_bn_train_bwd
+        ok(fb(M, C, P(z), P(mean), P(var), 1e-3, P(y), P(dy), P(dz), P(dbeta), P(scr), mlib.stream_ptr()))
+        torch.cuda.synchronize()
+        outs.append((y, mean, var, mm, mv, dz, dbeta, y16))
+    a, b = outs
+    for i, name in enumerate(("y", "mean", "var", "moving_mean", "moving_var", "dz", "dbeta")):
+        # the statistics are summed in a different order (fp32 ulps); y is then rounded to the operand grid of the
+        # library's rounding mode, where an ulp of difference before rounding can flip one tf32 step (2^-10)
+        # (dz is a backward GEMM operand and is rounded the same way)
+        close(b[i], a[i].double(), 1.1e-3 if name in ("y", "dz") else 2e-5,
+              atol=1e-5 * max(1.0, float(a[i].abs().max())))
+    if a[7] is not None:
+        # the split copies ([hi | lo] halves per 32 columns) both reconstruct y
+        for t in (a[7], b[7]):
+            h = t.view(torch.float16).reshape(M, C // 32, 2, 32).double()
+            close((h[:, :, 0] + h[:, :, 1]).reshape(M, C), b[0].double(), 1.1e-3,
+                  atol=1e-5 * max(1.0, float(b[0].abs().max())))
+    # and against the definition
+    zz = z.double()
+    ref = torch.relu((zz - zz.mean(0)) / torch.sqrt(zz.var(0, unbiased=False) + 1e-3) + beta.double())
+    close(b[0], ref, 1.5e-3, atol=1e-5)
