@@ -377,9 +377,10 @@ matchcost_partial_kernel(int n, int m, const float* __restrict__ xyz1,
 
 __global__ void matchcost_final_kernel(int tiles, const float* __restrict__ partial,
                                        float* __restrict__ out) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // (a no-op unless launched as a programmatic dependent)
     const int bi = blockIdx.x;
     float acc = 0.f;
-    for (int t = threadIdx.x; t < tiles; t += 32) acc += partial[(size_t)bi * tiles + t];
+    for (int t = threadIdx.x; t < tiles; t += 32) acc += __ldcg(&partial[(size_t)bi * tiles + t]);
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (threadIdx.x == 0) out[bi] = acc;
 }
@@ -607,6 +608,39 @@ matchcost_stream_kernel(int n, int m, int rows_per_tile, const float* __restrict
     }
 }
 
+// fixed-order sum of T partial planes of n4 float4 each (the tail of the last CTA of a batch element): four planes
+// and two outputs per thread in flight, so the tail is a few L2 round trips instead of T of them
+__device__ __forceinline__ void ms_sum_planes(const float4* __restrict__ q, float4* __restrict__ o, int n4, int T, int tid,
+                                              int nthr = kMsThreads) {
+    for (int i0 = tid; i0 < n4; i0 += 2 * nthr) {
+        const int i1 = i0 + nthr;
+        const bool two = i1 < n4;
+        const int j1 = two ? i1 : i0;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+        int t = 0;
+        for (; t + 4 <= T; t += 4) {
+            float4 v[4], u[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                v[j] = __ldcg(q + (size_t)(t + j) * n4 + i0);
+                u[j] = __ldcg(q + (size_t)(t + j) * n4 + j1);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w;
+                c.x += u[j].x; c.y += u[j].y; c.z += u[j].z; c.w += u[j].w;
+            }
+        }
+        for (; t < T; t++) {
+            const float4 v = __ldcg(q + (size_t)t * n4 + i0), u = __ldcg(q + (size_t)t * n4 + j1);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            c.x += u.x; c.y += u.y; c.z += u.z; c.w += u.w;
+        }
+        o[i0] = a;
+        if (two) o[i1] = c;
+    }
+}
+
 // keep-or-send halving step of the butterfly: after it, u[i] (i < H) holds the sum over the lane pair
 // {lane, lane ^ BIT} of value (lane & BIT ? H + i : i)
 template <int H, int BIT>
@@ -714,17 +748,8 @@ matchcostgrad_stream_kernel(int n, int m, int rows_per_tile, const float* __rest
     if (!s_last) return;
     __threadfence();
     const int T = gridDim.x, S = gridDim.y;
-    const float4* q1 = reinterpret_cast<const float4*>(part1 + (size_t)bi * T * n * 3);
-    float4* o1 = reinterpret_cast<float4*>(grad1 + (size_t)bi * n * 3);
-    const int n4 = n * 3 / 4;                                  // n % 4 == 0
-    for (int i = tid; i < n4; i += kMsThreads) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = 0; t < T; t++) {
-            const float4 v = __ldcg(q1 + (size_t)t * n4 + i);
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        }
-        o1[i] = a;
-    }
+    ms_sum_planes(reinterpret_cast<const float4*>(part1 + (size_t)bi * T * n * 3),
+                  reinterpret_cast<float4*>(grad1 + (size_t)bi * n * 3), n * 3 / 4, T, tid);      // n % 4 == 0
     if (S > 1) {
         const float* q2 = part2 + (size_t)bi * S * m * 3;
         for (int i = tid; i < m * 3; i += kMsThreads) {
@@ -735,16 +760,414 @@ matchcostgrad_stream_kernel(int n, int m, int rows_per_tile, const float* __rest
     }
 }
 
+// ---------------------------------------------------------------- match_cost_grad with the bulk-copy engine feeding it
+// The register ring above cannot be both deep and cheap: eight LDG.128 per thread are 32 registers that ptxas refills
+// only at the end of a batch, so the loads of a warp arrive in bursts and every row pays address, clamp and select
+// instructions.  Here `match` is moved by cp.async.bulk (1-D TMA, no tensor map: a tile row is `slabw` contiguous floats)
+// into a ring of kMtStages shared-memory stages of kMtRows rows each, completion on mbarriers.  Loads in flight no longer
+// occupy registers, the warps take turns issuing four copies per stage and re-arm a stage two blocks after it was
+// consumed (so the issuer never waits for a slow warp), and the inner loop is arithmetic only:
+//  * every thread owns CG groups of four columns of a slab of `slabw` = 4 * CG * blockDim.x columns (all threads active:
+//    slabw divides n); with CG = 2 the per-row overheads -- query point, row-sum butterfly, barrier checks -- are shared
+//    by eight elements instead of four;
+//  * tiles hold whole 8-row batches (m % 8 == 0) and are walked in sub-tiles of <= kMtSubRows rows: the per-warp row sums
+//    of a sub-tile are combined (fixed order) and written out at its end, so a tile can be hundreds of rows tall and
+//    the number of column-partial planes the last CTA has to add stays small;
+//  * query points are staged pre-duplicated ({x,x,y,y} {z,z,-,-}: the packed operands come straight out of LDS.128 +
+//    LDS.64), the next sub-tile's points wait in registers;
+//  * the zero-distance guard is folded into the distance as an additive 1e-37 (for d = 0 every difference is 0 as well
+//    and the product is 0, as with the reference's max(d, 1e-20)).
+#ifndef MPB_MT_ROWS
+#define MPB_MT_ROWS 4
+#endif
+#ifndef MPB_MT_STAGES
+#define MPB_MT_STAGES 3
+#endif
+#ifndef MPB_MT_LAG
+#define MPB_MT_LAG 2
+#endif
+constexpr int kMtRows = MPB_MT_ROWS;        // rows per stage
+constexpr int kMtStages = MPB_MT_STAGES;
+constexpr int kMtSubRows = 80;              // rows per sub-tile (shared memory of the per-warp row sums)
+constexpr int kMtLag = MPB_MT_LAG;          // a stage is re-armed kMtLag blocks after its block was consumed:
+                                            // kMtStages - kMtLag blocks are in flight while one is being consumed
+static_assert(kMtLag >= 1 && kMtLag < kMtStages && kMsBatch % kMtRows == 0, "stage ring geometry");
+
+__device__ __forceinline__ uint32_t ms_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ms_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;      // bounded spin: a protocol bug must trap, not hang the GPU
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void ms_issue_block(uint32_t full_bar, uint32_t dst, const float* src, size_t row_stride,
+                                               uint32_t row_bytes, uint64_t policy) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar), "r"(row_bytes * kMtRows) : "memory");
+    if (row_stride * 4 == row_bytes) {       // the slab is the whole row: the block is one contiguous piece
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+            ::"r"(dst), "l"(src), "r"(row_bytes * kMtRows), "r"(full_bar), "l"(policy)
+            : "memory");
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < kMtRows; r++)
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+            ::"r"(dst + r * row_bytes), "l"(src + (size_t)r * row_stride), "r"(row_bytes), "r"(full_bar), "l"(policy)
+            : "memory");
+}
+
+template <int CG> struct MtCfg;
+template <> struct MtCfg<1> { static constexpr int kThreads = 256, kMinBlocks = 3; };
+template <> struct MtCfg<2> { static constexpr int kThreads = 128, kMinBlocks = 4; };
+
+template <int CG>
+__global__ void __launch_bounds__(MtCfg<CG>::kThreads, MtCfg<CG>::kMinBlocks)
+matchcostgrad_tma_kernel(int n, int m, int rows_per_tile, int sub_rows, const float* __restrict__ xyz1,
+                         const float* __restrict__ xyz2, const float* __restrict__ match,
+                         float* __restrict__ part1,     // [b][tiles][n][3]   column partials (grad1)
+                         float* __restrict__ part2) {   // [b][slabs][m][3]   row partials (grad2, sign included)
+    extern __shared__ __align__(128) unsigned char mt_smem[];
+    const int tile = blockIdx.x, slab = blockIdx.y, bi = blockIdx.z, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarps = nthr >> 5;
+    const int slabw = nthr * 4 * CG;
+    const uint32_t row_bytes = (uint32_t)slabw * 4u, stage_bytes = row_bytes * kMtRows;
+    const int l0 = tile * rows_per_tile, rows = min(rows_per_tile, m - l0);        // a multiple of 8, >= 8
+    float4* qd = reinterpret_cast<float4*>(mt_smem + (size_t)kMtStages * stage_bytes);       // [sub_rows][2]
+    float* rsum = reinterpret_cast<float*>(qd + 2 * sub_rows);                              // [warps][sub_rows][3]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rsum + (size_t)nwarps * sub_rows * 3);      // (sub_rows % 8 == 0: aligned)
+    const uint32_t full0 = ms_smem_u32(bars), empty0 = full0 + 8 * kMtStages, stage0 = ms_smem_u32(mt_smem);
+    const float* p1 = xyz1 + (size_t)bi * n * 3;
+    const float* p2 = xyz2 + ((size_t)bi * m + l0) * 3;                               // the tile's query points
+    const size_t ns = (size_t)n;
+    const float* mt = match + ((size_t)bi * m + l0) * ns + (size_t)slab * slabw;     // the tile's row 0, this slab
+    const int nblk = rows / kMtRows;
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (tid == 0) {
+        for (int s_ = 0; s_ < kMtStages; s_++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s_), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s_), "r"(nwarps));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int j = 0; j < kMtStages && j < nblk; j++)
+            ms_issue_block(full0 + 8 * j, stage0 + j * stage_bytes, mt + (size_t)j * kMtRows * ns, ns, row_bytes, policy);
+    }
+    // query points: this sub-tile's into shared memory, the next one's into registers (sub_rows <= blockDim.x)
+    float nq0 = 0.f, nq1 = 0.f, nq2 = 0.f;
+    if (tid < min(sub_rows, rows)) {
+        const float x = p2[tid * 3], y = p2[tid * 3 + 1], z = p2[tid * 3 + 2];
+        qd[2 * tid] = make_float4(x, x, y, y);
+        qd[2 * tid + 1] = make_float4(z, z, 0.f, 0.f);
+    }
+    if (sub_rows + tid < rows && tid < sub_rows) {
+        nq0 = p2[(sub_rows + tid) * 3]; nq1 = p2[(sub_rows + tid) * 3 + 1]; nq2 = p2[(sub_rows + tid) * 3 + 2];
+    }
+    MsCols c[CG];
+#pragma unroll
+    for (int g = 0; g < CG; g++) c[g] = ms_load_cols(p1, slab * slabw + (tid + g * nthr) * 4, true);
+    __syncthreads();
+    const uint64_t eps2 = pk(1e-37f, 1e-37f), zero2 = pk(0.f, 0.f);
+    uint64_t gx01[CG], gx23[CG], gy01[CG], gy23[CG], gz01[CG], gz23[CG];
+#pragma unroll
+    for (int g = 0; g < CG; g++) gx01[g] = gx23[g] = gy01[g] = gy23[g] = gz01[g] = gz23[g] = zero2;
+    int stage = 0, j = 0, turn = 0;
+    uint32_t phase = 0;
+    for (int sub0 = 0; sub0 < rows; sub0 += sub_rows) {
+        const int srows = min(sub_rows, rows - sub0);
+        for (int rb = 0; rb < srows; rb += kMsBatch) {
+            float v[kMsBatch * 3];
+#pragma unroll
+            for (int h = 0; h < kMsBatch / kMtRows; h++, j++) {
+                {
+                    // block j - lag was consumed by every warp a while ago: re-arm its stage with block j - lag + stages
+                    // (operands computed in uniform control flow; the warps take turns, one lane issues)
+                    const int jo = j - kMtLag, so = (stage + kMtStages - kMtLag) % kMtStages;
+                    const uint32_t ebar = empty0 + 8 * so, fbar = full0 + 8 * so, dst = stage0 + so * stage_bytes;
+                    const uint32_t eph = (so > stage ? phase ^ 1u : phase);        // phase of block jo's use of its stage
+                    const float* src = mt + (size_t)(jo + kMtStages) * kMtRows * ns;
+                    if (jo >= 0 && jo + kMtStages < nblk && warp == turn && lane == 0) {
+                        ms_mbar_wait(ebar, eph);
+                        ms_issue_block(fbar, dst, src, ns, row_bytes, policy);
+                    }
+                    if (++turn == nwarps) turn = 0;
+                }
+                ms_mbar_wait(full0 + 8 * stage, phase);
+                const float4* st = reinterpret_cast<const float4*>(mt_smem + (size_t)stage * stage_bytes) + tid;
+                const float4* q = qd + 2 * (rb + h * kMtRows);
+#pragma unroll
+                for (int r = 0; r < kMtRows; r++) {
+                    const float4 qa = q[2 * r];
+                    const float2 qb = *reinterpret_cast<const float2*>(q + 2 * r + 1);
+                    const uint64_t qx = pk(qa.x, qa.y), qy = pk(qa.z, qa.w), qz = pk(qb.x, qb.y);
+                    uint64_t sx = zero2, sy = zero2, sz = zero2;
+#pragma unroll
+                    for (int g = 0; g < CG; g++) {
+                        const float4 cur = st[(size_t)r * nthr * CG + g * nthr];
+                        const uint64_t dx0 = sub2(c[g].x01, qx), dy0 = sub2(c[g].y01, qy), dz0 = sub2(c[g].z01, qz);
+                        const uint64_t dx1 = sub2(c[g].x23, qx), dy1 = sub2(c[g].y23, qy), dz1 = sub2(c[g].z23, qz);
+                        float a0, a1, a2, a3;
+                        upk(fma2(dz0, dz0, fma2(dx0, dx0, fma2(dy0, dy0, eps2))), a0, a1);
+                        upk(fma2(dz1, dz1, fma2(dx1, dx1, fma2(dy1, dy1, eps2))), a2, a3);
+                        const uint64_t w01 = mul2(pk(cur.x, cur.y), pk(rsqrt_approx(a0), rsqrt_approx(a1)));
+                        const uint64_t w23 = mul2(pk(cur.z, cur.w), pk(rsqrt_approx(a2), rsqrt_approx(a3)));
+                        gx01[g] = fma2(dx0, w01, gx01[g]); gy01[g] = fma2(dy0, w01, gy01[g]); gz01[g] = fma2(dz0, w01, gz01[g]);
+                        gx23[g] = fma2(dx1, w23, gx23[g]); gy23[g] = fma2(dy1, w23, gy23[g]); gz23[g] = fma2(dz1, w23, gz23[g]);
+                        if (g == 0) {
+                            sx = fma2(dx1, w23, mul2(dx0, w01)); sy = fma2(dy1, w23, mul2(dy0, w01)); sz = fma2(dz1, w23, mul2(dz0, w01));
+                        } else {
+                            sx = fma2(dx1, w23, fma2(dx0, w01, sx)); sy = fma2(dy1, w23, fma2(dy0, w01, sy));
+                            sz = fma2(dz1, w23, fma2(dz0, w01, sz));
+                        }
+                    }
+                    float s0, s1;
+                    const int vi = (h * kMtRows + r) * 3;
+                    upk(sx, s0, s1); v[vi + 0] = s0 + s1;
+                    upk(sy, s0, s1); v[vi + 1] = s0 + s1;
+                    upk(sz, s0, s1); v[vi + 2] = s0 + s1;
+                }
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * stage) : "memory");
+                if (++stage == kMtStages) { stage = 0; phase ^= 1u; }
+            }
+            // 24 row sums across the 32 lanes: 12 + 6 + 3 keep-or-send steps, then 2 plain steps on 3 values
+            float u12[12], u6[6], u3[3];
+            ms_halve<12, 16>(v, u12, lane);
+            ms_halve<6, 8>(u12, u6, lane);
+            ms_halve<3, 4>(u6, u3, lane);
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                u3[i] += __shfl_xor_sync(0xffffffffu, u3[i], 2);
+                u3[i] += __shfl_xor_sync(0xffffffffu, u3[i], 1);
+            }
+            if ((lane & 3) == 0) {       // lanes 4j..4j+3 hold row j of the batch
+                float* d = rsum + ((size_t)warp * sub_rows + rb + (lane >> 2)) * 3;
+                d[0] = u3[0]; d[1] = u3[1]; d[2] = u3[2];
+            }
+        }
+        // end of the sub-tile: row sums out (fixed order over the warps), next query points in
+        __syncthreads();
+        for (int t = tid; t < srows * 3; t += nthr) {
+            float s_ = 0.f;
+            for (int w_ = 0; w_ < nwarps; w_++) s_ += rsum[(size_t)w_ * sub_rows * 3 + t];
+            part2[(((size_t)bi * gridDim.y + slab) * m + l0 + sub0) * 3 + t] = -s_;          // grad2 uses (p2 - p1)
+        }
+        if (sub0 + sub_rows < rows) {
+            if (tid < sub_rows) {
+                qd[2 * tid] = make_float4(nq0, nq0, nq1, nq1);
+                qd[2 * tid + 1] = make_float4(nq2, nq2, 0.f, 0.f);
+                const int t2 = sub0 + 2 * sub_rows + tid;
+                if (t2 < rows) { nq0 = p2[t2 * 3]; nq1 = p2[t2 * 3 + 1]; nq2 = p2[t2 * 3 + 2]; }
+            }
+            __syncthreads();
+        }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the plane-summing launch may take its seats
+#pragma unroll
+    for (int g = 0; g < CG; g++) {       // column partials of this tile: 12 consecutive floats per column group
+        float x0, x1, x2, x3, y0, y1, y2, y3, z0, z1, z2, z3;
+        upk(gx01[g], x0, x1); upk(gx23[g], x2, x3); upk(gy01[g], y0, y1); upk(gy23[g], y2, y3);
+        upk(gz01[g], z0, z1); upk(gz23[g], z2, z3);
+        const int k = slab * slabw + (tid + g * nthr) * 4;
+        float4* d = reinterpret_cast<float4*>(part1 + (((size_t)bi * gridDim.x + tile) * n + k) * 3);
+        d[0] = make_float4(x0, y0, z0, x1);
+        d[1] = make_float4(y1, z1, x2, y2);
+        d[2] = make_float4(z2, x3, y3, z3);
+    }
+}
+
+// match_cost on the same feed: no row or column sums to keep, one partial per CTA, summed per batch element by
+// matchcost_final_kernel as a programmatic dependent launch (no counters to clear, no last-CTA tail)
+template <int CG>
+__global__ void __launch_bounds__(MtCfg<CG>::kThreads, MtCfg<CG>::kMinBlocks)
+matchcost_tma_kernel(int n, int m, int rows_per_tile, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                     const float* __restrict__ match, float* __restrict__ partial) {      // [b][slabs * tiles]
+    extern __shared__ __align__(128) unsigned char mt_smem[];
+    const int tile = blockIdx.x, slab = blockIdx.y, bi = blockIdx.z, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarps = nthr >> 5;
+    const int slabw = nthr * 4 * CG;
+    const uint32_t row_bytes = (uint32_t)slabw * 4u, stage_bytes = row_bytes * kMtRows;
+    const int l0 = tile * rows_per_tile, rows = min(rows_per_tile, m - l0);        // a multiple of 8, >= 8
+    float4* qd = reinterpret_cast<float4*>(mt_smem + (size_t)kMtStages * stage_bytes);       // [rows_per_tile][2]
+    float* red = reinterpret_cast<float*>(qd + 2 * rows_per_tile);                          // [8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8);
+    const uint32_t full0 = ms_smem_u32(bars), empty0 = full0 + 8 * kMtStages, stage0 = ms_smem_u32(mt_smem);
+    const float* p1 = xyz1 + (size_t)bi * n * 3;
+    const float* p2 = xyz2 + ((size_t)bi * m + l0) * 3;
+    const size_t ns = (size_t)n;
+    const float* mt = match + ((size_t)bi * m + l0) * ns + (size_t)slab * slabw;
+    const int nblk = rows / kMtRows;
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (tid == 0) {
+        for (int s_ = 0; s_ < kMtStages; s_++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s_), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s_), "r"(nwarps));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int j = 0; j < kMtStages && j < nblk; j++)
+            ms_issue_block(full0 + 8 * j, stage0 + j * stage_bytes, mt + (size_t)j * kMtRows * ns, ns, row_bytes, policy);
+    }
+    for (int t = tid; t < rows; t += nthr) {
+        const float x = p2[t * 3], y = p2[t * 3 + 1], z = p2[t * 3 + 2];
+        qd[2 * t] = make_float4(x, x, y, y);
+        qd[2 * t + 1] = make_float4(z, z, 0.f, 0.f);
+    }
+    MsCols c[CG];
+#pragma unroll
+    for (int g = 0; g < CG; g++) c[g] = ms_load_cols(p1, slab * slabw + (tid + g * nthr) * 4, true);
+    __syncthreads();
+    uint64_t acc = pk(0.f, 0.f);
+    int stage = 0, turn = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < nblk; j++) {
+        {
+            const int jo = j - kMtLag, so = (stage + kMtStages - kMtLag) % kMtStages;
+            const uint32_t ebar = empty0 + 8 * so, fbar = full0 + 8 * so, dst = stage0 + so * stage_bytes;
+            const uint32_t eph = (so > stage ? phase ^ 1u : phase);
+            const float* src = mt + (size_t)(jo + kMtStages) * kMtRows * ns;
+            if (jo >= 0 && jo + kMtStages < nblk && warp == turn && lane == 0) {
+                ms_mbar_wait(ebar, eph);
+                ms_issue_block(fbar, dst, src, ns, row_bytes, policy);
+            }
+            if (++turn == nwarps) turn = 0;
+        }
+        ms_mbar_wait(full0 + 8 * stage, phase);
+        const float4* st = reinterpret_cast<const float4*>(mt_smem + (size_t)stage * stage_bytes) + tid;
+        const float4* q = qd + 2 * (j * kMtRows);
+#pragma unroll
+        for (int r = 0; r < kMtRows; r++) {
+            const float4 qa = q[2 * r];
+            const float2 qb = *reinterpret_cast<const float2*>(q + 2 * r + 1);
+            const uint64_t qx = pk(qa.x, qa.y), qy = pk(qa.z, qa.w), qz = pk(qb.x, qb.y);
+#pragma unroll
+            for (int g = 0; g < CG; g++) {
+                const float4 cur = st[(size_t)r * nthr * CG + g * nthr];
+                uint64_t dx = sub2(c[g].x01, qx), dy = sub2(c[g].y01, qy), dz = sub2(c[g].z01, qz);
+                float a0, a1, a2, a3;
+                upk(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), a0, a1);
+                dx = sub2(c[g].x23, qx); dy = sub2(c[g].y23, qy); dz = sub2(c[g].z23, qz);
+                upk(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), a2, a3);
+                acc = fma2(pk(sqrt_approx(a0), sqrt_approx(a1)), pk(cur.x, cur.y), acc);
+                acc = fma2(pk(sqrt_approx(a2), sqrt_approx(a3)), pk(cur.z, cur.w), acc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * stage) : "memory");
+        if (++stage == kMtStages) { stage = 0; phase ^= 1u; }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    float lo, hi;
+    upk(acc, lo, hi);
+    float v = lo + hi;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+        float s_ = 0.f;
+        for (int w_ = 0; w_ < nwarps; w_++) s_ += red[w_];
+        partial[(size_t)bi * gridDim.x * gridDim.y + slab * gridDim.x + tile] = s_;
+    }
+}
+
+// the planes are added by a second, chip-wide launch (programmatic dependent launch: it is resident and waiting when
+// the last tile retires); a last-CTA-per-batch-element tail would leave 32 small CTAs chasing L2 latency alone
+// (measured: 4 us of 46 at 32 x 1024^2, 16 of 181 at 32 x 2304^2)
+__global__ void __launch_bounds__(256)
+ms_sum_planes_kernel(const float4* __restrict__ part1, float4* __restrict__ grad1, int n4a, int T,
+                     const float4* __restrict__ part2, float4* __restrict__ grad2, int n4b, int S) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int bi = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float4* q;
+    float4* o;
+    int n4, P;
+    const int na = T > 1 ? n4a : 0;
+    if (i < na) { q = part1 + (size_t)bi * T * n4a + i; o = grad1 + (size_t)bi * n4a + i; n4 = n4a; P = T; }
+    else {
+        i -= na;
+        if (S <= 1 || i >= n4b) return;
+        q = part2 + (size_t)bi * S * n4b + i; o = grad2 + (size_t)bi * n4b + i; n4 = n4b; P = S;
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int t = 0;
+    for (; t + 8 <= P; t += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __ldcg(q + (size_t)(t + j) * n4);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+    }
+    if (t + 4 <= P) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = __ldcg(q + (size_t)(t + j) * n4);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+        t += 4;
+    }
+    for (; t < P; t++) {
+        const float4 v = __ldcg(q + (size_t)t * n4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *o = a;
+}
+
 // rows per tile: a multiple of 8, chosen so that the whole launch is ONE wave of long-lived CTAs where possible
 // (3 CTAs of 256 threads per SM): T = slots / (b * slabs) tiles per batch element; capped at 128 rows (shared memory
 // of the row sums), below which several waves run -- the primed ring keeps the loads flowing across CTA boundaries
-inline int ms_rows_per_tile(int b, int m, int slabs, int ctas_per_sm) {
+inline int ms_rows_per_tile(int b, int m, int slabs, int ctas_per_sm, int cap = 128) {
     const char* e = getenv("MPB_MS_ROWS");
-    if (e && atoi(e) >= 8) return min(128, atoi(e) / 8 * 8);
+    if (e && atoi(e) >= 8) return min(cap, atoi(e) / 8 * 8);
     const long slots = (long)ctas_per_sm * num_sms();
     const int T = (int)max(1L, slots / ((long)b * slabs));
     int rt = (ceil_div(m, T) + 7) / 8 * 8;
-    return max(8, min(128, rt));
+    return max(8, min(cap, rt));
+}
+
+template <int CG>
+cudaError_t launch_matchcostgrad_tma(int b, int n, int m, int slabw, int rt, int tiles, const float* xyz1, const float* xyz2,
+                                     const float* match, float* part1, float* part2, float* grad1, float* grad2,
+                                     cudaStream_t s) {
+    const int nthr = slabw / (4 * CG), sub = min(kMtSubRows, nthr / 8 * 8), slabs = n / slabw;
+    auto smem_of = [](int slabw_, int sub_, int warps) {
+        return (size_t)kMtStages * kMtRows * slabw_ * 4 + 32 * (size_t)sub_ + 12 * (size_t)warps * sub_ + 16 * kMtStages;
+    };
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(matchcostgrad_tma_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem_of(kMsSlab, kMtSubRows, MtCfg<CG>::kThreads / 32));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    matchcostgrad_tma_kernel<CG><<<dim3(tiles, slabs, b), nthr, smem_of(slabw, sub, nthr / 32), s>>>(
+        n, m, rt, sub, xyz1, xyz2, match, part1, part2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || (tiles == 1 && slabs == 1)) return e;
+    count_launch();
+    const int n4a = n * 3 / 4, n4b = m * 3 / 4, work = (tiles > 1 ? n4a : 0) + (slabs > 1 ? n4b : 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ceil_div(work, 256), b);
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, ms_sum_planes_kernel, reinterpret_cast<const float4*>(part1),
+                              reinterpret_cast<float4*>(grad1), n4a, tiles, reinterpret_cast<const float4*>(part2),
+                              reinterpret_cast<float4*>(grad2), n4b, slabs);
 }
 
 }  // namespace mpb
@@ -818,6 +1241,49 @@ MPB_API int mpb_matchcost(int b, int n, int m, const float* xyz1, const float* x
     if (n == 0 || m == 0) return cuda_status(cudaMemsetAsync(out, 0, sizeof(float) * b, s));
     if (!xyz1 || !xyz2 || !match) return -1;
     if (b > 65535) return -1;
+    static const int cg_env = getenv("MPB_MC_CG") ? atoi(getenv("MPB_MC_CG")) : -1;      // 0: register-ring kernel
+    if (cg_env != 0 && n % 128 == 0 && m % 8 == 0 && (reinterpret_cast<uintptr_t>(match) & 15u) == 0 &&
+        (reinterpret_cast<uintptr_t>(xyz1) & 15u) == 0) {
+        // bulk-copy-fed kernel (matchcost_tma_kernel), per-CTA partials summed by a programmatic dependent launch
+        const int cg = (n % 256 == 0 && cg_env != 1) ? 2 : 1;
+        int slabw = 0;
+        for (int w_ = kMsSlab; w_ >= 128 * cg; w_ -= 128 * cg)
+            if (n % w_ == 0) { slabw = w_; break; }
+        const int slabs = n / slabw;
+        const char* e_ = getenv("MPB_MS_ROWS");
+        int rt = e_ && atoi(e_) >= 8 ? min(kMtSubRows, atoi(e_) / 8 * 8) : kMtSubRows;
+        while (!e_ && rt > 8 && (long)b * slabs * ceil_div(m, rt) < 2L * num_sms()) rt -= 8;
+        const int tiles = ceil_div(m, rt), nthr = slabw / (4 * cg);
+        float* partial = nullptr;
+        MPB_CUDA_TRY(scratch_alloc((void**)&partial, sizeof(float) * (size_t)b * slabs * tiles, s));
+        const size_t smem = (size_t)kMtStages * kMtRows * slabw * 4 + 32 * (size_t)rt + 32 + 16 * kMtStages;
+        static bool attr_set = false;
+        if (!attr_set) {
+            const int mx = kMtStages * kMtRows * kMsSlab * 4 + 32 * kMtSubRows + 32 + 16 * kMtStages;
+            MPB_CUDA_TRY(cudaFuncSetAttribute(matchcost_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            MPB_CUDA_TRY(cudaFuncSetAttribute(matchcost_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            attr_set = true;
+        }
+        if (cg == 2) matchcost_tma_kernel<2><<<dim3(tiles, slabs, b), nthr, smem, s>>>(n, m, rt, xyz1, xyz2, match, partial);
+        else matchcost_tma_kernel<1><<<dim3(tiles, slabs, b), nthr, smem, s>>>(n, m, rt, xyz1, xyz2, match, partial);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(b);
+            cfg.blockDim = dim3(32);
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, matchcost_final_kernel, slabs * tiles, (const float*)partial, out);
+            count_launch();
+        }
+        scratch_free(partial, s);
+        return cuda_status(e);
+    }
     if (n % 4 == 0 && (reinterpret_cast<uintptr_t>(match) & 15u) == 0 && (reinterpret_cast<uintptr_t>(xyz1) & 15u) == 0) {
         const int slabs = ceil_div(n, kMsSlab), rt = ms_rows_per_tile(b, m, slabs, MPB_MS_COST_MINB), tiles = ceil_div(m, rt);
         float* partial = nullptr;
@@ -857,20 +1323,50 @@ MPB_API int mpb_matchcostgrad(int b, int n, int m, const float* xyz1, const floa
     if (!xyz1 || !xyz2 || !match || !grad1 || !grad2) return -1;
     if (b > 65535) return -1;
     if (n % 4 == 0 && (reinterpret_cast<uintptr_t>(match) & 15u) == 0 && (reinterpret_cast<uintptr_t>(xyz1) & 15u) == 0) {
-        // fused single pass over `match` (see matchcostgrad_stream_kernel)
-        const int slabs = ceil_div(n, kMsSlab), rt = ms_rows_per_tile(b, m, slabs, 3), tiles = ceil_div(m, rt);
+        // fused single pass over `match`: fed by bulk copies where the geometry allows (matchcostgrad_tma_kernel: a slab
+        // width that divides n, all lanes of every warp busy, whole 8-row batches), else the register-ring kernel
+        static const int cg_env = getenv("MPB_MG_CG") ? atoi(getenv("MPB_MG_CG")) : -1;      // 0: ring kernel, 1 / 2: groups
+        int cg = 0, slabw = 0;
+        if (cg_env != 0 && m % 8 == 0) {
+            if (n % 256 == 0 && cg_env != 1) cg = 2;
+            else if (n % 128 == 0 && cg_env != 2) cg = 1;
+            if (cg)
+                for (int w_ = kMsSlab; w_ >= 128 * cg; w_ -= 128 * cg)
+                    if (n % w_ == 0) { slabw = w_; break; }
+        }
+        const int slabs = cg ? n / slabw : ceil_div(n, kMsSlab);
+        // bulk-copy kernel: tiles of one sub-tile (80 rows) measured best at both sizes -- 39.3 us at 32 x 1024^2 (13 tiles
+        // per element, one wave; 64 rows: 41.3, 96: 45.4) and 137.6 us at 32 x 2304^2 (29 tiles x 3 slabs, several waves;
+        // 336-row tiles in one wave: 162.1) -- shorter only when that would leave SMs without a CTA
+        int rt = ms_rows_per_tile(b, m, slabs, 3);
+        if (cg) {
+            const char* e_ = getenv("MPB_MS_ROWS");
+            rt = e_ && atoi(e_) >= 8 ? atoi(e_) / 8 * 8 : kMtSubRows;
+            while (!e_ && rt > 8 && (long)b * slabs * ceil_div(m, rt) < 2L * num_sms()) rt -= 8;
+        }
+        const int tiles = ceil_div(m, rt);
+        const bool direct1 = cg && tiles == 1;         // one tile: the column sums ARE grad1
         float *part1 = nullptr, *part2 = nullptr;
-        const size_t n1 = (size_t)b * tiles * n * 3, n2 = (size_t)b * slabs * m * 3;
-        MPB_CUDA_TRY(scratch_alloc((void**)&part1, sizeof(float) * (n1 + (slabs > 1 ? n2 : 0) + b), s));
-        part2 = slabs > 1 ? part1 + n1 : grad2;         // one slab: the row sums ARE grad2
-        int* counters = reinterpret_cast<int*>(part1 + n1 + (slabs > 1 ? n2 : 0));
-        MPB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * b, s));
-        const size_t smem = sizeof(float4) * rt + sizeof(float) * (kMsThreads / 32) * rt * 3;
-        matchcostgrad_stream_kernel<<<dim3(tiles, slabs, b), kMsThreads, smem, s>>>(n, m, rt, xyz1, xyz2, match, part1, part2,
-                                                                                   counters, grad1, grad2);
+        const size_t n1 = direct1 ? 0 : (size_t)b * tiles * n * 3, n2 = slabs > 1 ? (size_t)b * slabs * m * 3 : 0;
+        float* scratch = nullptr;
+        MPB_CUDA_TRY(scratch_alloc((void**)&scratch, sizeof(float) * (n1 + n2 + b), s));
+        part1 = direct1 ? grad1 : scratch;
+        part2 = slabs > 1 ? scratch + n1 : grad2;       // one slab: the row sums ARE grad2
+        cudaError_t e;
+        if (cg == 2) {
+            e = launch_matchcostgrad_tma<2>(b, n, m, slabw, rt, tiles, xyz1, xyz2, match, part1, part2, grad1, grad2, s);
+        } else if (cg == 1) {
+            e = launch_matchcostgrad_tma<1>(b, n, m, slabw, rt, tiles, xyz1, xyz2, match, part1, part2, grad1, grad2, s);
+        } else {
+            int* counters = reinterpret_cast<int*>(scratch + n1 + n2);
+            MPB_CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * b, s));
+            const size_t smem = sizeof(float4) * rt + sizeof(float) * (kMsThreads / 32) * rt * 3;
+            matchcostgrad_stream_kernel<<<dim3(tiles, slabs, b), kMsThreads, smem, s>>>(n, m, rt, xyz1, xyz2, match, part1,
+                                                                                       part2, counters, grad1, grad2);
+            e = cudaGetLastError();
+        }
         count_launch();
-        cudaError_t e = cudaGetLastError();
-        scratch_free(part1, s);
+        scratch_free(scratch, s);
         return cuda_status(e);
     }
     size_t sm1 = sizeof(float) * 4 * 1024;   // float4[1024] >= [4][64][3] floats

@@ -178,6 +178,8 @@ def _match_close(got, exp, what):
     (1, 1, 1, 0, 0), (2, 3, 3, 1, 0), (3, 37, 53, 11, 0), (2, 64, 64, 12, 0.4), (2, 128, 256, 13, 0),
     (4, 512, 512, 14, 0), (32, 200, 200, 15, 0), (1, 1024, 1024, 200, 0), (3, 700, 100, 16, 0),
     (2, 2304, 72, 17, 0.4), (1, 1028, 37, 18, 0), (2, 1026, 50, 19, 0),      # column slabs > 1, row-tile tails, n % 4 != 0
+    # bulk-copy-fed gradient kernel: one / two / three slabs of 1024 / 1024 / 384 columns, row tiles with tails
+    (3, 1024, 88, 22, 0), (2, 2048, 264, 23, 0.4), (2, 1152, 136, 24, 0),
 ])
 def test_emd_vs_oracle(cuda, b, n, m, seed, masked):
     x, y = _clouds(b, n, m, seed, masked)
@@ -245,6 +247,28 @@ def test_emd_full_size_properties(cuda):
             r = refgpu.approx_match(xt, yt)
             _match_close(mt.cpu().numpy(), r.cpu().numpy(), "cfg4 match vs reference GPU kernel")
             np.testing.assert_allclose(cost.cpu().numpy(), refgpu.match_cost(xt, yt, r).cpu().numpy(), rtol=1e-3)
+
+
+def test_emd_grad_full_size(cuda):
+    # the gradient kernel at BASELINE cfg4 and at the in-model size, on the match the product computed:
+    # against the reference's own kernels where available, and through linearity in `match` everywhere
+    for (b, n, seed) in [(32, 1024, 210), (32, 2304, 211)]:
+        x, y = _clouds(b, n, n, seed, 0.3)
+        xt, yt = _t(x, cuda), _t(y, cuda)
+        mt = tf_approxmatch.approx_match(xt, yt)
+        g1, g2 = tf_approxmatch.match_cost_grad(xt, yt, mt)
+        assert bool(torch.isfinite(g1).all()) and bool(torch.isfinite(g2).all())
+        # sum of all pulls is zero: grad1 and grad2 are the two ends of the same weighted unit vectors
+        s = float(g1.abs().sum(1).max())
+        assert float((g1.sum(1) + g2.sum(1)).abs().max()) < 1e-4 * s
+        h1, h2 = tf_approxmatch.match_cost_grad(xt, yt, mt * 0.25)
+        assert float((h1 * 4 - g1).abs().max()) <= 1e-5 * float(g1.abs().max())
+        assert float((h2 * 4 - g2).abs().max()) <= 1e-5 * float(g2.abs().max())
+        if refgpu.available() and n == 1024:
+            r1, r2 = refgpu.match_cost_grad(xt, yt, mt)
+            sc = max(float(r1.abs().max()), float(r2.abs().max()))
+            np.testing.assert_allclose(g1.cpu().numpy(), r1.cpu().numpy(), rtol=1e-3, atol=2e-5 * sc)
+            np.testing.assert_allclose(g2.cpu().numpy(), r2.cpu().numpy(), rtol=1e-3, atol=2e-5 * sc)
 
 
 def test_emd_large_fallback_path(cuda):

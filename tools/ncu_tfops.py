@@ -1,6 +1,6 @@
 """The point-set ops at BASELINE cfg3 / cfg4, launched three times each after a read-flush of L2, for
     ncu --set full --clock-control none --import-source on \
-        -k regex:'nn_distance_kernel|nn_distance_grad|approxmatch_cluster_kernel|matchcost_stream|matchcostgrad_stream' \
+        -k regex:'nn_distance_kernel|nn_distance_grad|approxmatch_cluster_kernel|matchcost_stream|matchcostgrad_stream|matchcostgrad_tma|ms_sum_planes' \
         -o gpurun_out/r2_ncu_tfops python tools/ncu_tfops.py
 (summary: ncu -i rep --page raw --csv > raw.csv; python tools/ncu_table.py raw.csv)."""
 import os, sys
