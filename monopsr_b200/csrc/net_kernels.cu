@@ -766,7 +766,12 @@ __device__ __forceinline__ void bn_grid_barrier(unsigned long long* counter, uns
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1ull);
-        while (*reinterpret_cast<volatile unsigned long long*>(counter) < nblocks) __nanosleep(64);
+        // bounded (~1 s): if the grid were ever not co-resident this must be an error, not a hung GPU
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned long long*>(counter) < nblocks) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();
+        }
         __threadfence();
     }
     __syncthreads();
@@ -1330,6 +1335,12 @@ MPB_API int mpb_bn_train_fwd16(int M, int C, const float* z, const float* beta, 
     return 0;
 }
 // single-launch variants (see bn_train_fwd_fused_kernel): scratch = 2C + 2 doubles
+// the launch is refused (-2) unless two CTAs of the kernel fit one SM: the barrier needs the whole grid resident
+template <typename K>
+static bool bn_fused_fits(K kernel) {
+    int per_sm = 0;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) == cudaSuccess && per_sm >= 2;
+}
 static dim3 bn_fused_grid(int M, int C) {
     const int gx = ceil_div(C, 128);
     int gy = max(1, (2 * num_sms()) / gx);                  // 2 CTAs per SM in total: resident beside anything
@@ -1340,6 +1351,8 @@ MPB_API int mpb_bn_train_fwd_fused(int M, int C, const float* z, const float* be
                                    float* var, float* moving_mean, float* moving_var, float decay, double* scratch,
                                    void* y16, int* overflow, void* stream) {
     if (M <= 0 || C <= 0 || C % 4 || (y16 && C % 32) || !z || !beta || !y || !mean || !var || !scratch) return -1;
+    static const bool fits = bn_fused_fits(bn_train_fwd_fused_kernel);
+    if (!fits) return -2;
     MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * C + 2), ST));
     bn_train_fwd_fused_kernel<<<bn_fused_grid(M, C), 256, 0, ST>>>(M, C, z, beta, eps, y, mean, var, moving_mean, moving_var,
                                                                   decay, scratch, (unsigned char*)y16, overflow);
@@ -1349,6 +1362,8 @@ MPB_API int mpb_bn_train_fwd_fused(int M, int C, const float* z, const float* be
 MPB_API int mpb_bn_train_bwd_fused(int M, int C, const float* z, const float* mean, const float* var, float eps,
                                    const float* y, const float* dy, float* dz, float* dbeta, double* scratch, void* stream) {
     if (M <= 0 || C <= 0 || C % 4 || !z || !mean || !var || !y || !dy || !dz || !dbeta || !scratch) return -1;
+    static const bool fits = bn_fused_fits(bn_train_bwd_fused_kernel);
+    if (!fits) return -2;
     MPB_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * C + 2), ST));
     bn_train_bwd_fused_kernel<<<bn_fused_grid(M, C), 256, 0, ST>>>(M, C, z, y, dy, mean, var, eps, scratch, dz, dbeta);
     MPB_LAUNCH_CHECK();
