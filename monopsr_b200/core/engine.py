@@ -201,6 +201,17 @@ class Engine:
         nt = len(self.trainable_names)
         self.opt_parts = {"all": (0, len(chunks), 0, nt), "towers": (0, c_head, 0, t_head),
                           "head": (c_head, len(chunks) - c_head, t_head, nt - t_head)}
+        # the towers' part again, one tower each (data parallelism: the second tower's gradients are still on NVLink
+        # while the first tower's variables are stepped)
+        second = self.trainable_names[0].split("/")[0]
+        t_mid = min(i for i, n in enumerate(self.trainable_names[:t_head]) if n.split("/")[0] != second)
+        assert all(n.split("/")[0] == second for n in self.trainable_names[:t_mid])
+        assert len({n.split("/")[0] for n in self.trainable_names[t_mid:t_head]}) == 1
+        c_mid = min(i for i, c in enumerate(chunks) if c[2] >= t_mid)
+        self.tower_mid = chunks[c_mid][0]              # arena offset where the second tower's variables start
+        assert all(c[0] + c[1] <= self.tower_mid for c in chunks[:c_mid])
+        self.opt_parts["tower0"] = (0, c_mid, 0, t_mid)
+        self.opt_parts["tower1"] = (c_mid, c_head - c_mid, t_mid, t_head - t_mid)
 
     def view(self, name, arena=None):
         a, off, ds = self.layout[name]
@@ -1348,10 +1359,21 @@ class Engine:
             head = dp.allreduce_start(self.grads[self.round_off:])     # on NCCL's stream, beside the towers' backward
             self._g_bt.replay()
             dp.allreduce_finish(head)
-            towers = dp.allreduce_start(self.grads[:self.round_off])   # beside the head variables' train-op
-            self._g_opt_head.replay()
-            dp.allreduce_finish(towers)
-            self._g_opt.replay()
+            if self._g_opt_t0 is not None:
+                # tower gradients in two buckets: the first travels beside the head variables' train-op, the second
+                # beside the first tower's train-op
+                t0 = dp.allreduce_start(self.grads[:self.tower_mid])
+                t1 = dp.allreduce_start(self.grads[self.tower_mid:self.round_off])
+                self._g_opt_head.replay()
+                dp.allreduce_finish(t0)
+                self._g_opt_t0.replay()
+                dp.allreduce_finish(t1)
+                self._g_opt.replay()
+            else:
+                towers = dp.allreduce_start(self.grads[:self.round_off])   # beside the head variables' train-op
+                self._g_opt_head.replay()
+                dp.allreduce_finish(towers)
+                self._g_opt.replay()
         else:
             if getattr(self, "_graph", None) is None:
                 self._capture()
@@ -1443,8 +1465,13 @@ class Engine:
         with torch.cuda.graph(g4, stream=self.s_main, capture_error_mode="thread_local"):
             self.optimizer_step(scale, part="head")
             self.prepare_weights(part="head")
+        self._g_opt_t0 = None
+        if int(os.environ.get("MPB_DP_TOWER_SPLIT", "1")):
+            self._g_opt_t0 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g_opt_t0, stream=self.s_main, capture_error_mode="thread_local"):
+                self.optimizer_step(scale, part="tower0")
         with torch.cuda.graph(g3, stream=self.s_main, capture_error_mode="thread_local"):
-            self.optimizer_step(scale, part="towers")
+            self.optimizer_step(scale, part="towers" if self._g_opt_t0 is None else "tower1")
             self.prepare_weights(part="towers")
         self.launches_per_step = _lib.launch_count() - c0
         self._g_fb, self._g_bt, self._g_opt_head, self._g_opt = g1, g2, g4, g3
