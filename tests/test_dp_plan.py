@@ -48,3 +48,18 @@ def test_bucket_boundaries_are_unit_boundaries():
         U = e.towers[ms.ENCODERS[0]]["units"][b["unit"]]
         first = U["scope"] + ("/shortcut" if U["proj"] else "/conv1") + "/weights"
         assert b["ranges"][0][0] == e.layout[first][1]
+
+
+def test_tower_variables_are_two_contiguous_runs_of_the_trainable_list():
+    """Engine.opt_parts['tower0' / 'tower1'] (data parallelism: one all-reduce and one train-op per tower) relies on the
+    trainable variables being ordered [first tower | second tower | everything else]"""
+    from monopsr_b200.core import model_spec as ms
+    names = [n for n, s, k in ms.param_table() if k in ms.TRAINABLE_KINDS]
+    t_head = min(i for i, n in enumerate(names) if not n.startswith("FirstStage"))
+    assert all(not n.startswith("FirstStage") for n in names[t_head:])
+    first = names[0].split("/")[0]
+    t_mid = min(i for i, n in enumerate(names[:t_head]) if n.split("/")[0] != first)
+    assert all(n.split("/")[0] == first for n in names[:t_mid])
+    assert len({n.split("/")[0] for n in names[t_mid:t_head]}) == 1
+    assert {first, names[t_mid].split("/")[0]} == set(ms.ENCODERS)
+    assert 0 < t_mid < t_head < len(names)
