@@ -30,6 +30,14 @@ namespace cg = cooperative_groups;
 namespace mpb {
 
 constexpr int kAmThreads = 512;
+#ifndef MPB_AM_UNROLL
+#define MPB_AM_UNROLL 8
+#endif
+constexpr int kAmUnroll = MPB_AM_UNROLL;     // candidate pairs in flight per lane in a sweep
+#ifndef MPB_AM_UNROLL_FINAL
+#define MPB_AM_UNROLL_FINAL 1
+#endif
+constexpr int kAmUnrollFinal = MPB_AM_UNROLL_FINAL;      // query rows in flight per lane in the final pass
 constexpr int kAmLevels = 10;   // j = 7 .. -2  (tf_approxmatch_g.cu:21)
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -114,7 +122,7 @@ __device__ __forceinline__ float am_sweep(const float4 me, const float* __restri
     const uint64_t mx = pk(me.x, me.x), my = pk(me.y, me.y), mz = pk(me.z, me.z), c2 = pk(c, c);
     uint64_t acc = pk(0.f, 0.f);
     const int npairs = (cnt + 1) >> 1;
-#pragma unroll 2
+#pragma unroll(kAmUnroll)
     for (int j = s; j < npairs; j += S) {
         const float4 a = o4[2 * j], b = o4[2 * j + 1];      // {x0,x1,y0,y1} {z0,z1,w0,w1}
         const uint64_t dx = sub2(pk(a.x, a.y), mx), dy = sub2(pk(a.z, a.w), my), dz = sub2(pk(b.x, b.y), mz);
@@ -250,6 +258,7 @@ approxmatch_cluster_kernel(int n, int m, const float* __restrict__ xyz1,
         float rl[kAmLevels];
 #pragma unroll
         for (int q = 0; q < kAmLevels; q++) rl[q] = act ? HL[(size_t)q * L.n_pad + k] : 0.f;
+#pragma unroll(kAmUnrollFinal)
         for (int l = l0; l < l1; l++) {
             const float4 o = am_point(P2, l);
             const float4* hr4 = reinterpret_cast<const float4*>(HR + (size_t)(l - l0) * 12);

@@ -1,6 +1,5 @@
 #!/bin/bash
-# round 2, call R: approxmatch skips the exact-zero terms of the fine levels
-OUT=gpurun_out/r2_r
-mkdir -p $OUT
-timeout 600 python -m pytest tests/test_tfops_gpu.py tests/test_pointset_loss_gpu.py -q -x -p no:cacheprovider > $OUT/tests.log 2>&1; tail -2 $OUT/tests.log
-timeout 200 python tools/am_quick.py 2>&1 | tail -4
+# round 2, call R: approxmatch unroll factors (sweeps / final pass)
+V=$PWD/monopsr_b200/build/variants
+echo "base (sweep unroll 8, final 1)"; timeout 100 python tools/am_quick.py 2>&1 | grep "scale 1.0"
+for u in u16f1 u8f2 u8f4 u16f2; do echo $u; MPB_LIB=$V/lib_$u.so timeout 100 python tools/am_quick.py 2>&1 | grep "scale 1.0"; done
