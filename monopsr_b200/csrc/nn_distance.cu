@@ -63,6 +63,11 @@ __device__ __forceinline__ uint64_t nn_d2x2(uint64_t qx, uint64_t qy, uint64_t q
     return fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
 }
 
+#ifndef MPB_NN_UNROLL
+#define MPB_NN_UNROLL 2
+#endif
+constexpr int kNnUnroll = MPB_NN_UNROLL;      // candidate groups (of 8) in flight per thread (4 / 8: 79.9 / 81.9 us vs 77.8 at cfg3)
+
 // candidates live in shared memory as structure-of-arrays blocks of 4: {x0..x3}{y0..y3}{z0..z3}
 struct Cand4 { float4 x, y, z; };
 
@@ -126,7 +131,7 @@ nn_distance_kernel(int n, int m, const float* __restrict__ xyz1, const float* __
             pgrp[q] = 0;
         }
         const int ngroups = cnt_pad / kNnGroup;
-#pragma unroll 2
+#pragma unroll(kNnUnroll)
         for (int g = 0; g < ngroups; g++) {
             const Cand4 a = cand[2 * g], b = cand[2 * g + 1];
             const uint64_t ax0 = pk(a.x.x, a.x.y), ax1 = pk(a.x.z, a.x.w), bx0 = pk(b.x.x, b.x.y), bx1 = pk(b.x.z, b.x.w);
